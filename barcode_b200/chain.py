@@ -1,0 +1,247 @@
+"""`Chain`: one HMC chain's device state behind the C ABI (one `bgpu_handle`).
+
+Thin Python view of include/barcode_gpu.h used by the tests and bench.py; the
+method names are the reference's (HMC.cc / HMC_momenta.cc / HMC_mass.cc).
+Arrays are numpy float64, shape (N1, N2, N3) or flat, z fastest.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, fields
+
+import numpy as np
+
+from . import _lib
+from ._lib import BGPU_CALC_H_EXACT, BgpuError, BgpuParams  # noqa: F401
+
+
+@dataclass
+class Params:
+    """input.par / DATA fields the path reads; defaults = bgpu_default_params()."""
+    N1: int = 64
+    L1: float = 200.0
+    xllc: float = 0.0
+    yllc: float = 0.0
+    zllc: float = 0.0
+    xobs: float = 90.0
+    yobs: float = 90.0
+    zobs: float = 90.0
+    planepar: bool = True
+    periodic: bool = True
+    masskernel: int = 1
+    likelihood: int = 1
+    sfmodel: int = 1
+    rsd_model: bool = False
+    calc_h: int = 0
+    mass_type: int = 1
+    D1: float = 1.0
+    D2: float = -3.0 / 7.0
+    ascale: float = 1.0
+    OM: float = 0.272
+    OL: float = 0.728
+    rho_c: float = 1.0
+    biasP: float = 1.0
+    biasE: float = 1.0
+    deltaQ_factor: float = 1.0
+    correct_delta: bool = True
+    mass_factor: float = 1.0
+    div_dH_by_N: bool = False
+    device: int = 0
+
+    def to_c(self) -> BgpuParams:
+        p = BgpuParams()
+        _lib.load().bgpu_default_params(C.byref(p))
+        for f in fields(self):
+            if f.name in ("N1", "L1"):
+                continue
+            setattr(p, f.name, type(getattr(p, f.name))(getattr(self, f.name)))
+        p.N1 = p.N2 = p.N3 = int(self.N1)
+        p.L1 = p.L2 = p.L3 = float(self.L1)
+        return p
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} elements, got {a.size}")
+    return a
+
+
+class Chain:
+    def __init__(self, params: Params):
+        self.params = params
+        self.L = _lib.load()
+        self.N1 = int(params.N1)
+        self.N = self.N1 ** 3
+        self.Nhalf = self.N1 * self.N1 * (self.N1 // 2 + 1)
+        self._h = C.c_void_p()
+        cp = params.to_c()
+        _lib.check(self.L.bgpu_create(C.byref(cp), C.byref(self._h)))
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if self._h:
+            self.L.bgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def shape(self):
+        return (self.N1, self.N1, self.N1)
+
+    # -- inputs -----------------------------------------------------------
+    def set_static(self, Power=None, nobs=None, noise=None, window=None):
+        arrs = [None if a is None else _f64(a, self.N) for a in (Power, nobs, noise, window)]
+        _lib.check(self.L.bgpu_set_static(self._h, *[None if a is None else _dp(a) for a in arrs]))
+
+    def set_mass(self, mass_f=None, mass_r=None):
+        arrs = [None if a is None else _f64(a, self.N) for a in (mass_f, mass_r)]
+        _lib.check(self.L.bgpu_set_mass(self._h, *[None if a is None else _dp(a) for a in arrs]))
+
+    def hamiltonian_mass(self):
+        """Hamiltonian_mass (HMC_mass.cc:315-368): returns (mass_f, mass_r)."""
+        mf, mr = np.zeros(self.N), np.zeros(self.N)
+        _lib.check(self.L.bgpu_hamiltonian_mass(self._h, _dp(mf), _dp(mr)))
+        return mf.reshape(self.shape), mr.reshape(self.shape)
+
+    # -- the seams S1..S5 -------------------------------------------------
+    def gradient_psi(self, signal):
+        s = _f64(signal, self.N)
+        out = np.empty(self.N)
+        _lib.check(self.L.bgpu_gradient_psi(self._h, _dp(s), _dp(out)))
+        return out.reshape(self.shape)
+
+    def psi(self, signal, want_deltaX=True):
+        s = _f64(signal, self.N)
+        a, b = C.c_double(), C.c_double()
+        dX = np.empty(self.N) if want_deltaX else None
+        _lib.check(self.L.bgpu_psi(self._h, _dp(s), C.byref(a), C.byref(b), _dp(dX) if want_deltaX else None))
+        return a.value, b.value, (dX.reshape(self.shape) if want_deltaX else None)
+
+    def kinetic_term(self, momenta):
+        p = _f64(momenta, self.N)
+        k = C.c_double()
+        _lib.check(self.L.bgpu_kinetic(self._h, _dp(p), C.byref(k)))
+        return k.value
+
+    def leapfrog(self, s_i, p_i, Neps: int, epsilon: float):
+        s, p = _f64(s_i, self.N), _f64(p_i, self.N)
+        sf, pf = np.empty(self.N), np.empty(self.N)
+        _lib.check(self.L.bgpu_leapfrog(self._h, _dp(s), _dp(p), int(Neps), float(epsilon), _dp(sf), _dp(pf)))
+        return sf.reshape(self.shape), pf.reshape(self.shape)
+
+    def delta_hamiltonian(self, s_i, p_i, s_f, p_f):
+        """delta_Hamiltonian (HMC.cc:209-248), host arithmetic on the six device-computed scalars."""
+        Ki = self.kinetic_term(p_i)
+        pri, lki, _ = self.psi(s_i, want_deltaX=False)
+        Kf = self.kinetic_term(p_f)
+        prf, lkf, dX = self.psi(s_f, want_deltaX=True)
+        Hi = Ki + (pri + lki)
+        Hf = Kf + (prf + lkf)
+        dH = Hf - Hi
+        if self.params.div_dH_by_N:
+            dH /= float(self.N)
+        return dH, dict(dK=Kf - Ki, dE=(prf + lkf) - (pri + lki), dprior=prf - pri, dlikeli=lkf - lki,
+                        psi_prior_i=pri, psi_prior_f=prf, psi_likeli_i=lki, psi_likeli_f=lkf,
+                        H_kin_i=Ki, H_kin_f=Kf), dX
+
+    def color_momenta(self, white=None, real_gauss=None):
+        w = None if white is None else np.ascontiguousarray(white, dtype=np.complex128).reshape(-1)
+        g = None if real_gauss is None else _f64(real_gauss, self.N)
+        if w is not None and w.size != self.N:
+            raise ValueError("white noise must be the full N1^3 complex grid")
+        out = np.empty(self.N)
+        _lib.check(self.L.bgpu_color_momenta(
+            self._h, None if w is None else w.view(np.float64).ctypes.data_as(C.POINTER(C.c_double)),
+            None if g is None else _dp(g), _dp(out)))
+        return out.reshape(self.shape)
+
+    def forward(self, signal, want_pos=False):
+        s = _f64(signal, self.N)
+        dX = np.empty(self.N)
+        if want_pos:
+            x, y, z = np.empty(self.N), np.empty(self.N), np.empty(self.N)
+            _lib.check(self.L.bgpu_forward(self._h, _dp(s), _dp(dX), _dp(x), _dp(y), _dp(z)))
+            return dX.reshape(self.shape), x, y, z
+        _lib.check(self.L.bgpu_forward(self._h, _dp(s), _dp(dX), None, None, None))
+        return dX.reshape(self.shape)
+
+    # -- building blocks for parity tests ---------------------------------
+    def assign_density(self, x, y, z):
+        x, y, z = _f64(x, self.N), _f64(y, self.N), _f64(z, self.N)
+        rho = np.empty(self.N)
+        _lib.check(self.L.bgpu_assign_density(self._h, _dp(x), _dp(y), _dp(z), _dp(rho)))
+        return rho.reshape(self.shape)
+
+    def cell_indices(self, x, y, z):
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        n = x.size
+        ci, cj, ck = (np.empty(n, dtype=np.int32) for _ in range(3))
+        ip = C.POINTER(C.c_int)
+        _lib.check(self.L.bgpu_cell_indices(self._h, _dp(x), _dp(y), _dp(z), n, ci.ctypes.data_as(ip),
+                                            cj.ctypes.data_as(ip), ck.ctypes.data_as(ip)))
+        return ci, cj, ck
+
+    def fft_r2c(self, a):
+        a = _f64(a, self.N)
+        out = np.empty(2 * self.Nhalf)
+        _lib.check(self.L.bgpu_fft_r2c(self._h, _dp(a), _dp(out)))
+        return out.view(np.complex128).reshape(self.N1, self.N1, self.N1 // 2 + 1)
+
+    def fft_c2r(self, c):
+        c = np.ascontiguousarray(c, dtype=np.complex128).reshape(-1)
+        if c.size != self.Nhalf:
+            raise ValueError("expected the half-complex array")
+        out = np.empty(self.N)
+        _lib.check(self.L.bgpu_fft_c2r(self._h, c.view(np.float64).ctypes.data_as(C.POINTER(C.c_double)), _dp(out)))
+        return out.reshape(self.shape)
+
+    def convolve_inv_corr(self, signal, corr):
+        s, c = _f64(signal, self.N), _f64(corr, self.N)
+        out = np.empty(self.N)
+        _lib.check(self.L.bgpu_convolve_inv_corr(self._h, _dp(s), _dp(c), _dp(out)))
+        return out.reshape(self.shape)
+
+    # -- device-pointer variants (torch tensors on this chain's device) -----
+    def set_stream(self, cuda_stream_ptr: int):
+        _lib.check(self.L.bgpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        _lib.check(self.L.bgpu_synchronize(self._h))
+
+    def gradient_psi_dev(self, d_signal_ptr: int, d_grad_ptr: int):
+        _lib.check(self.L.bgpu_gradient_psi_dev(self._h, C.c_void_p(d_signal_ptr), C.c_void_p(d_grad_ptr)))
+
+    def leapfrog_dev(self, d_signal_ptr: int, d_momenta_ptr: int, Neps: int, epsilon: float):
+        _lib.check(self.L.bgpu_leapfrog_dev(self._h, C.c_void_p(d_signal_ptr), C.c_void_p(d_momenta_ptr), int(Neps),
+                                            float(epsilon)))
+
+    def psi_dev(self, d_signal_ptr: int, d_deltaX_ptr: int = 0):
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self.L.bgpu_psi_dev(self._h, C.c_void_p(d_signal_ptr), C.byref(a), C.byref(b),
+                                       C.c_void_p(d_deltaX_ptr) if d_deltaX_ptr else None))
+        return a.value, b.value
+
+    def kinetic_dev(self, d_momenta_ptr: int):
+        k = C.c_double()
+        _lib.check(self.L.bgpu_kinetic_dev(self._h, C.c_void_p(d_momenta_ptr), C.byref(k)))
+        return k.value
+
+
+def kernel_launches() -> int:
+    return int(_lib.load().bgpu_kernel_launches())

@@ -1,0 +1,709 @@
+// barcode_b200/csrc/api.cu -- implementation of the C ABI in include/barcode_gpu.h:
+// the device-resident state of one HMC chain (the GPU counterpart of the
+// reference's HAMIL_DATA, struct_hamil.h:146-400) and the launch sequences for
+// gradient_psi / psi / kinetic_term / Hamiltonian_EoM / draw_momenta /
+// Hamiltonian_mass (HMC.cc, HMC_momenta.cc, HMC_mass.cc).
+#include "barcode_gpu.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "fft3d.h"
+#include "kernels.h"
+#include "util.h"
+
+namespace bgpu {
+std::atomic<uint64_t> g_kernel_launches{0};
+}
+
+using namespace bgpu;
+
+static thread_local std::string g_last_error;
+
+struct bgpu_handle {
+  bgpu_params p{};
+  int N = 0;
+  size_t n = 0;    // N^3
+  size_t nh = 0;   // N^2 (N/2+1)
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Fft3d fft;
+  GridGeom geom{};
+  LikeParams like{};
+  double kfac = 0.0, normFS = 0.0;
+  bool mass_fs = false, mass_rs = false;
+  bool have_power = false, have_obs = false, have_mass = false;
+
+  // static inputs
+  double *power = nullptr, *nobs = nullptr, *noise = nullptr, *window = nullptr;
+  double *inv_power = nullptr;               // half grid, (V/N)/P
+  double *mass_f = nullptr, *mass_r = nullptr;
+  double *inv_mass = nullptr;                // half grid, (V/N)/M_f
+  // state / scratch (real)
+  double *sig = nullptr, *mom = nullptr, *grad = nullptr;
+  double *psi[3] = {nullptr, nullptr, nullptr};
+  double *delta = nullptr, *resid = nullptr, *tmp = nullptr;
+  // scratch (half-complex)
+  double2 *shat = nullptr, *dhat = nullptr, *work = nullptr, *acc = nullptr;
+  // reductions
+  double *partials = nullptr, *dscal = nullptr;
+  double *hscal = nullptr;  // pinned
+};
+
+namespace {
+
+enum Scal { S_SUMRHO = 0, S_NLL = 1, S_PRIOR = 2, S_KIN = 3, S_P0 = 4, S_COUNT = 8 };
+
+template <class T>
+void dalloc(T *&ptr, size_t count) {
+  BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&ptr), count * sizeof(T)));
+}
+
+void h2d(bgpu_handle *h, double *dst, const double *src, size_t count) {
+  BGPU_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+}
+void d2h(bgpu_handle *h, double *dst, const double *src, size_t count) {
+  BGPU_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+}
+void sync(bgpu_handle *h) { BGPU_CUDA(cudaStreamSynchronize(h->stream)); }
+
+void require(bool ok, const char *msg) {
+  if (!ok) throw std::runtime_error(msg);
+}
+
+// E_Hubble_a, fgrow, c_pecvel: cosmo.cc:26-31,182-235
+double E_Hubble_a(double a, double OM, double OL) {
+  const double OK = 1. - OM - OL;
+  return std::sqrt(OM / (a * a * a) + OK / (a * a) + OL);
+}
+double fgrow1(double a, double OM, double OL) {
+  const double E = E_Hubble_a(a, OM, OL);
+  const double Omega = OM / ((E * E) * (a * a * a));
+  return std::pow(Omega, 5. / 9.);
+}
+
+void validate(const bgpu_params &p) {
+  require(p.N1 == p.N2 && p.N2 == p.N3, "bgpu: only cubic grids are supported (the reference sets N2=N3=N1, init_par.cc:116-122)");
+  require(Fft3d::supported(p.N1), "bgpu: N1 must be a power of two in [8, 1024]");
+  require(p.L1 == p.L2 && p.L2 == p.L3 && p.L1 > 0, "bgpu: only cubic boxes are supported");
+  require(p.masskernel >= 0 && p.masskernel <= 2,
+          "bgpu: masskernel must be 0 (NGP), 1 (CIC) or 2 (TSC); the SPH kernel (3) is not implemented on the GPU path yet");
+  require(p.likelihood == 0 || p.likelihood == 1,
+          "bgpu: likelihood must be 0 (Poisson) or 1 (Gaussian); lognormal / GRF are not implemented on the GPU path yet");
+  require(p.calc_h == 0 || p.calc_h == 1 || p.calc_h == BGPU_CALC_H_EXACT,
+          "bgpu: calc_h must be 0, 1 or 4 (exact adjoint); 2/3 need the SPH kernel (HMC_models.cc:316-319)");
+  require(p.mass_type == 0 || p.mass_type == 1 || p.mass_type == 4,
+          "bgpu: mass_type must be 0, 1 or 4 on the GPU path (2/3/5/6/60 are cold set-up paths)");
+  require(p.sfmodel == 1 || p.rsd_model,
+          "bgpu: sfmodel != 1 (2LPT/ALPT, Lag2Eul_non_zeldovich) is not implemented on the GPU path yet");
+  if (p.rsd_model) {
+    require(p.planepar != 0, "Non-plane-parallel RSD model is not yet implemented in calc_V! Use planepar = true.");
+    require(p.periodic != 0, "bgpu: RSD needs periodic boundary conditions (rsd.cc:59-64)");
+  }
+  require(p.periodic != 0, "bgpu: only periodic boundary conditions are supported (disp_part.cc:28)");
+}
+
+// ---------------------------------------------------------------------------
+// device pipelines
+// ---------------------------------------------------------------------------
+
+// Lag2Eul_zeldovich / _rsd_zeldovich from s^ (already in h->shat): Psi -> rho -> sum(rho).
+// dQ / rsd are arguments because the Poisson log-likelihood ignores both (poissonian.cpp:54-56).
+void forward_from_shat(bgpu_handle *h, double dQ, bool rsd, double *px, double *py, double *pz) {
+  const double inv_n = 1.0 / (double)h->n;
+  // in = dQ * s ; phi = -D1 * in (Lag2Eul.cc:88) ; Psi^_c = (k_c/k^2)(Im phi^, -Re phi^)
+  const double a = -h->p.D1 * dQ;
+  for (int c = 2; c >= 0; --c) {
+    KOp lop;
+    lop.kind = K_DISP;
+    lop.comp = c;
+    lop.a = a;
+    lop.kfac = h->kfac;
+    ROp sop;
+    sop.kind = R_SCALE;
+    sop.a = inv_n;
+    h->fft.c2r(h->shat, h->work, h->psi[c], lop, sop);
+  }
+  GridGeom g = h->geom;
+  g.rsd = rsd ? 1 : 0;
+  launch_scatter(g, h->psi[0], h->psi[1], h->psi[2], h->delta, px, py, pz, h->stream);
+  launch_sum(h->delta, h->n, h->partials, h->dscal + S_SUMRHO, h->stream);
+}
+
+void r2c_plain(bgpu_handle *h, const double *in, double2 *out) {
+  ROp lop;
+  lop.kind = R_LOAD;
+  h->fft.r2c(in, out, nullptr, lop, KOp{});
+}
+
+// likelihood_grad_log_like + prior + sum (HMC.cc:146-206, HMC_models.cc:377-471):
+// d_out (op) a_out * gradpsi(d_s), with op = set (R_SCALE) or accumulate (R_AXPY).
+void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
+  require(h->have_power && h->have_obs, "bgpu: bgpu_set_static (Power, nobs, noise, window) must be called first");
+  const bgpu_params &p = h->p;
+  const double inv_n = 1.0 / (double)h->n;
+  r2c_plain(h, d_s, h->shat);
+  forward_from_shat(h, p.deltaQ_factor, p.rsd_model != 0, nullptr, nullptr, nullptr);
+  LikeParams lp = h->like;
+  lp.exact_sign = (p.calc_h == BGPU_CALC_H_EXACT) ? 1 : 0;
+  launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->nobs, h->noise, h->window, h->resid, h->n,
+                           h->partials, h->dscal + S_NLL, h->stream);
+
+  // norm = -1 * deltaQ_factor * (D1 if correct_delta)   (HMC_models.cc:460-469)
+  double norm = -1.0;
+  norm *= p.deltaQ_factor;
+  if (p.correct_delta) norm *= p.D1;
+
+  if (p.calc_h == 1) {
+    // h = r (HMC_models.cc:413-415): gradpsi = IFFT[(V/N)/P s^] + norm * r
+    KOp lop;
+    lop.kind = K_MULREAL;
+    lop.real0 = h->inv_power;
+    ROp sop;
+    sop.kind = R_SCALE;
+    sop.a = inv_n;
+    h->fft.c2r(h->shat, h->work, d_out, lop, sop);
+    launch_axpy(d_out, h->resid, norm, h->n, h->stream);
+    return;
+  }
+
+  if (p.calc_h == 0) {
+    // likelihood_calc_h (HMC_models_testing.cpp:25-50): g_c = r * d_c(delta)
+    if (p.likelihood == 1) r2c_plain(h, h->delta, h->dhat);  // gradfft shares one forward transform
+    for (int c = 0; c < 3; ++c) {
+      if (p.likelihood == 1) {
+        KOp lop;
+        lop.kind = K_GRAD;
+        lop.comp = c;
+        lop.kfac = h->kfac;
+        ROp sop;
+        sop.kind = R_SCALE_MUL;
+        sop.a = inv_n;
+        sop.aux = h->resid;
+        h->fft.c2r(h->dhat, h->work, h->tmp, lop, sop);
+      } else {
+        launch_findif_product(h->delta, h->resid, h->tmp, h->N, p.L1, c, h->stream);
+      }
+      ROp lop2;
+      lop2.kind = R_LOAD;
+      KOp sop2;
+      sop2.kind = (c == 0) ? K_INVLAP_SET : K_INVLAP_ADD;
+      sop2.comp = c;
+      sop2.kfac = h->kfac;
+      h->fft.r2c(h->tmp, h->work, h->acc, lop2, sop2);
+    }
+  } else {
+    // exact adjoint: V = gather(r) in place over Psi, then the same back-projection
+    launch_gather_adjoint(h->geom, h->psi[0], h->psi[1], h->psi[2], h->resid, h->stream);
+    for (int c = 0; c < 3; ++c) {
+      ROp lop2;
+      lop2.kind = R_LOAD;
+      KOp sop2;
+      sop2.kind = (c == 0) ? K_INVLAP_SET : K_INVLAP_ADD;
+      sop2.comp = c;
+      sop2.kfac = h->kfac;
+      h->fft.r2c(h->psi[c], h->work, h->acc, lop2, sop2);
+    }
+  }
+  // gradpsi = IFFT[(V/N)/P s^ + norm * h^]
+  KOp lop;
+  lop.kind = K_FINAL;
+  lop.a = norm;
+  lop.real0 = h->inv_power;
+  lop.cplx0 = h->acc;
+  ROp sop;
+  sop.kind = R_SCALE;
+  sop.a = inv_n;
+  h->fft.c2r(h->shat, h->work, d_out, lop, sop);
+}
+
+// psi (HMC.cc:124-143): prior 1/2 s.S^-1 s (gaussian.cpp:20-35) and -lnL
+// (gaussian_independent.cpp:51-92 / poissonian.cpp:44-74); leaves deltaX in h->delta
+void psi_device(bgpu_handle *h, const double *d_s) {
+  require(h->have_power && h->have_obs, "bgpu: bgpu_set_static (Power, nobs, noise, window) must be called first");
+  const bgpu_params &p = h->p;
+  const double inv_n = 1.0 / (double)h->n;
+  r2c_plain(h, d_s, h->shat);
+  KOp lop;
+  lop.kind = K_MULREAL;
+  lop.real0 = h->inv_power;
+  ROp sop;
+  sop.kind = R_SCALE;
+  sop.a = inv_n;
+  h->fft.c2r(h->shat, h->work, h->tmp, lop, sop);
+  launch_half_dot(d_s, h->tmp, h->n, h->partials, h->dscal + S_PRIOR, h->stream);
+
+  const bool gauss = p.likelihood == 1;
+  forward_from_shat(h, gauss ? p.deltaQ_factor : 1.0, gauss ? (p.rsd_model != 0) : false, nullptr, nullptr, nullptr);
+  LikeParams lp = h->like;
+  lp.exact_sign = 0;
+  launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->nobs, h->noise, h->window, nullptr, h->n,
+                           h->partials, h->dscal + S_NLL, h->stream);
+}
+
+// M^-1 p (HMC.cc:298-327, :69-99) -> h->tmp ; returns false if there is no Fourier part
+void apply_inv_mass_fs(bgpu_handle *h, const double *d_p) {
+  require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
+  const double inv_n = 1.0 / (double)h->n;
+  r2c_plain(h, d_p, h->work);
+  KOp lop;
+  lop.kind = K_MULREAL;
+  lop.real0 = h->inv_mass;
+  ROp sop;
+  sop.kind = R_SCALE;
+  sop.a = inv_n;
+  h->fft.c2r(h->work, h->work, h->tmp, lop, sop);
+}
+
+void kinetic_device(bgpu_handle *h, const double *d_p) {
+  require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
+  if (h->mass_fs) apply_inv_mass_fs(h, d_p);
+  launch_kinetic(d_p, h->mass_fs ? h->tmp : nullptr, h->mass_rs ? h->mass_r : nullptr, h->n, h->partials,
+                 h->dscal + S_KIN, h->stream);
+}
+
+// Hamiltonian_EoM (HMC.cc:251-369) after the RNG draws, in place on device
+void leapfrog_device(bgpu_handle *h, double *d_s, double *d_p, uint64_t Neps, double eps) {
+  gradient_device(h, d_s, h->grad);
+  for (uint64_t jj = 0; jj < Neps; ++jj) {
+    launch_axpy(d_p, h->grad, -(0.5 * eps), h->n, h->stream);   // :293-294
+    if (h->mass_fs) {
+      apply_inv_mass_fs(h, d_p);                                 // :310
+      launch_axpy(d_s, h->tmp, eps, h->n, h->stream);            // :338-339
+    }
+    if (h->mass_rs) launch_axpy_div(d_s, d_p, h->mass_r, eps, h->n, h->stream);  // :317-327
+    gradient_device(h, d_s, h->grad);                            // :343-344
+    launch_axpy(d_p, h->grad, -(0.5 * eps), h->n, h->stream);   // :351-352
+    // :360-364 -- stop a trajectory whose momentum has run away
+    BGPU_CUDA(cudaMemcpyAsync(h->hscal + S_P0, d_p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    sync(h);
+    if (std::fabs(h->hscal[S_P0]) > 1e50) break;
+  }
+}
+
+void update_inverse(bgpu_handle *h, const double *full, double *half) {
+  launch_inverse_spectrum(full, half, h->N, h->normFS, h->stream);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+#define BGPU_TRY try {
+#define BGPU_CATCH                      \
+  }                                     \
+  catch (const std::exception &e) {     \
+    g_last_error = e.what();            \
+    return 1;                           \
+  }                                     \
+  catch (...) {                         \
+    g_last_error = "bgpu: unknown error"; \
+    return 1;                           \
+  }                                     \
+  return 0;
+
+extern "C" {
+
+int bgpu_abi_version(void) { return BGPU_ABI_VERSION; }
+const char *bgpu_last_error(void) { return g_last_error.c_str(); }
+uint64_t bgpu_kernel_launches(void) { return g_kernel_launches.load(); }
+
+void bgpu_default_params(bgpu_params *p) {
+  std::memset(p, 0, sizeof(*p));
+  p->N1 = p->N2 = p->N3 = 64;               // data/input.par:117-125
+  p->L1 = p->L2 = p->L3 = 200.0;
+  p->xobs = p->yobs = p->zobs = 90.0;
+  p->planepar = 1;
+  p->periodic = 1;
+  p->masskernel = 1;
+  p->likelihood = 1;
+  p->sfmodel = 1;
+  p->rsd_model = 0;
+  p->calc_h = 0;
+  p->mass_type = 1;
+  p->D1 = 1.0;
+  p->D2 = -3. / 7.;
+  p->ascale = 1.0;
+  p->OM = 0.272;                            // init_par.cc:38,480-483 (cmbcosm = 3)
+  p->OL = 0.728;
+  p->rho_c = p->biasP = p->biasE = 1.0;     // init_par.cc:574-578
+  p->deltaQ_factor = 1.0;
+  p->correct_delta = 1;
+  p->mass_factor = 1.0;
+  p->div_dH_by_N = 0;
+  p->device = 0;
+}
+
+int bgpu_create(const bgpu_params *p, bgpu_handle **out) {
+  bgpu_handle *h = nullptr;
+  BGPU_TRY
+  require(p && out, "bgpu_create: null argument");
+  *out = nullptr;
+  validate(*p);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw std::runtime_error(std::string("bgpu: no CUDA device available (") + cudaGetErrorString(e) +
+                             "); this path has no CPU fallback");
+  require(p->device >= 0 && p->device < ndev, "bgpu: device ordinal out of range");
+  BGPU_CUDA(cudaSetDevice(p->device));
+  h = new bgpu_handle;
+  h->p = *p;
+  h->N = p->N1;
+  h->n = (size_t)h->N * h->N * h->N;
+  h->nh = (size_t)h->N * h->N * (h->N / 2 + 1);
+  BGPU_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  h->fft.init(h->N, h->stream);
+  h->kfac = 2. * M_PI / p->L1;                                      // scale_space.cpp:42
+  h->normFS = (p->L1 * p->L2 * p->L3) / (double)h->n;               // HMC_help.cc:26
+  h->mass_fs = (p->mass_type == 1 || p->mass_type == 4);            // struct_hamil.h:276-296
+  h->mass_rs = (p->mass_type == 0);
+
+  GridGeom &g = h->geom;
+  g.N = h->N;
+  g.L = p->L1;
+  g.d = p->L1 / (double)h->N;                                       // init_par.cc:245
+  g.min1 = p->xllc; g.min2 = p->yllc; g.min3 = p->zllc;
+  g.masskernel = p->masskernel;
+  g.rsd = p->rsd_model ? 1 : 0;
+  g.fgrow = fgrow1(p->ascale, p->OM, p->OL);
+  g.cpecvel = g.fgrow * 100. * E_Hubble_a(p->ascale, p->OM, p->OL) * p->ascale;  // cosmo.cc:232
+  {
+    const double OC = 1. - p->OM - p->OL;                            // rsd.cc:27-28
+    const double Hub = 100. * std::sqrt(p->OM / p->ascale / p->ascale / p->ascale + p->OL + OC / p->ascale / p->ascale);
+    g.v_norm = 1. / Hub / p->ascale;                                 // rsd.cc:39
+  }
+  h->like.likelihood = p->likelihood;
+  h->like.rho_c = p->rho_c;
+  h->like.biasP = p->biasP;
+  h->like.biasE = p->biasE;
+  h->like.exact_sign = 0;
+
+  dalloc(h->power, h->n); dalloc(h->nobs, h->n); dalloc(h->noise, h->n); dalloc(h->window, h->n);
+  dalloc(h->inv_power, h->nh);
+  dalloc(h->mass_f, h->n); dalloc(h->mass_r, h->n); dalloc(h->inv_mass, h->nh);
+  dalloc(h->sig, h->n); dalloc(h->mom, h->n); dalloc(h->grad, h->n);
+  for (int c = 0; c < 3; ++c) dalloc(h->psi[c], h->n);
+  dalloc(h->delta, h->n); dalloc(h->resid, h->n); dalloc(h->tmp, h->n);
+  dalloc(h->shat, h->nh); dalloc(h->dhat, h->nh); dalloc(h->work, h->nh); dalloc(h->acc, h->nh);
+  dalloc(h->partials, (size_t)kReduceBlocks); dalloc(h->dscal, (size_t)S_COUNT);
+  BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hscal), S_COUNT * sizeof(double)));
+  BGPU_CUDA(cudaMemsetAsync(h->dscal, 0, S_COUNT * sizeof(double), h->stream));
+  sync(h);
+  *out = h;
+  h = nullptr;
+  }
+  catch (const std::exception &e) {
+    g_last_error = e.what();
+    if (h) bgpu_destroy(h);
+    return 1;
+  }
+  return 0;
+}
+
+void bgpu_destroy(bgpu_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->p.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->mass_f, h->mass_r, h->inv_mass,
+                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->delta, h->resid, h->tmp,
+                     h->partials, h->dscal};
+  for (double *q : reals)
+    if (q) cudaFree(q);
+  double2 *cplx[] = {h->shat, h->dhat, h->work, h->acc};
+  for (double2 *q : cplx)
+    if (q) cudaFree(q);
+  if (h->hscal) cudaFreeHost(h->hscal);
+  h->fft.destroy();
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int bgpu_set_stream(bgpu_handle *h, void *cuda_stream) {
+  BGPU_TRY
+  sync(h);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->own_stream = false;
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  h->fft.stream = h->stream;
+  BGPU_CATCH
+}
+
+int bgpu_synchronize(bgpu_handle *h) {
+  BGPU_TRY
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_set_static(bgpu_handle *h, const double *Power, const double *nobs, const double *noise,
+                    const double *window) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  if (Power) {
+    h2d(h, h->power, Power, h->n);
+    update_inverse(h, h->power, h->inv_power);
+    h->have_power = true;
+  }
+  if (nobs) h2d(h, h->nobs, nobs, h->n);
+  if (noise) h2d(h, h->noise, noise, h->n);
+  if (window) h2d(h, h->window, window, h->n);
+  if (nobs && noise && window) h->have_obs = true;
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_set_mass(bgpu_handle *h, const double *mass_f, const double *mass_r) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  if (h->mass_fs) {
+    require(mass_f != nullptr, "bgpu_set_mass: mass_f is required for this mass_type");
+    h2d(h, h->mass_f, mass_f, h->n);
+    update_inverse(h, h->mass_f, h->inv_mass);
+  }
+  if (h->mass_rs) {
+    require(mass_r != nullptr, "bgpu_set_mass: mass_r is required for this mass_type");
+    h2d(h, h->mass_r, mass_r, h->n);
+  }
+  h->have_mass = true;
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_hamiltonian_mass(bgpu_handle *h, double *mass_f_out, double *mass_r_out) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(h->have_power || h->p.mass_type == 0, "bgpu_hamiltonian_mass: Power must be set first");
+  launch_mass(h->power, h->mass_f, h->mass_r, h->p.mass_type, h->p.mass_factor, h->n, h->stream);
+  if (h->mass_fs) update_inverse(h, h->mass_f, h->inv_mass);
+  h->have_mass = true;
+  if (mass_f_out && h->mass_fs) d2h(h, mass_f_out, h->mass_f, h->n);
+  if (mass_r_out && h->mass_rs) d2h(h, mass_r_out, h->mass_r, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_gradient_psi_dev(bgpu_handle *h, const double *d_signal, double *d_gradpsi) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  gradient_device(h, d_signal, d_gradpsi);
+  BGPU_CATCH
+}
+
+int bgpu_gradient_psi(bgpu_handle *h, const double *signal, double *gradpsi) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, h->sig, signal, h->n);
+  gradient_device(h, h->sig, h->grad);
+  d2h(h, gradpsi, h->grad, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_psi_dev(bgpu_handle *h, const double *d_signal, double *psi_prior, double *psi_likeli, double *d_deltaX) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  psi_device(h, d_signal);
+  d2h(h, h->hscal, h->dscal, S_COUNT);
+  if (d_deltaX)
+    BGPU_CUDA(cudaMemcpyAsync(d_deltaX, h->delta, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  sync(h);
+  *psi_prior = h->hscal[S_PRIOR];
+  *psi_likeli = h->hscal[S_NLL];
+  BGPU_CATCH
+}
+
+int bgpu_psi(bgpu_handle *h, const double *signal, double *psi_prior, double *psi_likeli, double *deltaX_out) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, h->sig, signal, h->n);
+  psi_device(h, h->sig);
+  d2h(h, h->hscal, h->dscal, S_COUNT);
+  if (deltaX_out) d2h(h, deltaX_out, h->delta, h->n);
+  sync(h);
+  *psi_prior = h->hscal[S_PRIOR];
+  *psi_likeli = h->hscal[S_NLL];
+  BGPU_CATCH
+}
+
+int bgpu_kinetic_dev(bgpu_handle *h, const double *d_momenta, double *K) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  kinetic_device(h, d_momenta);
+  d2h(h, h->hscal, h->dscal, S_COUNT);
+  sync(h);
+  *K = h->hscal[S_KIN];
+  BGPU_CATCH
+}
+
+int bgpu_kinetic(bgpu_handle *h, const double *momenta, double *K) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, h->mom, momenta, h->n);
+  kinetic_device(h, h->mom);
+  d2h(h, h->hscal, h->dscal, S_COUNT);
+  sync(h);
+  *K = h->hscal[S_KIN];
+  BGPU_CATCH
+}
+
+int bgpu_leapfrog_dev(bgpu_handle *h, double *d_signal, double *d_momenta, uint64_t Neps, double epsilon) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  leapfrog_device(h, d_signal, d_momenta, Neps, epsilon);
+  BGPU_CATCH
+}
+
+int bgpu_leapfrog(bgpu_handle *h, const double *s_i, const double *p_i, uint64_t Neps, double epsilon, double *s_f,
+                  double *p_f) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, h->sig, s_i, h->n);
+  h2d(h, h->mom, p_i, h->n);
+  leapfrog_device(h, h->sig, h->mom, Neps, epsilon);
+  d2h(h, s_f, h->sig, h->n);
+  d2h(h, p_f, h->mom, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_color_momenta(bgpu_handle *h, const double *white, const double *real_gauss, double *momenta) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
+  if (h->mass_fs) {
+    require(white != nullptr, "bgpu_color_momenta: white noise is required for a Fourier-space mass");
+    // the full complex grid (2N doubles) is staged through dhat+acc's storage? no: own temporary
+    double2 *d_white = nullptr;
+    dalloc(d_white, h->n);
+    try {
+      BGPU_CUDA(cudaMemcpyAsync(d_white, white, h->n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+      const double amp = (double)h->n * (double)h->n / (h->p.L1 * h->p.L2 * h->p.L3);  // random.cpp:81-83
+      launch_colour_momenta(d_white, h->mass_f, h->work, h->N, amp, h->stream);
+      ROp sop;
+      sop.kind = R_SCALE;
+      sop.a = 1.0 / (double)h->n;
+      h->fft.c2r(h->work, h->work, h->mom, KOp{}, sop);
+      sync(h);
+    } catch (...) {
+      cudaFree(d_white);
+      throw;
+    }
+    cudaFree(d_white);
+  } else {
+    launch_fill(h->mom, 0.0, h->n, h->stream);                      // HMC_momenta.cc:60
+  }
+  if (h->mass_rs) {
+    require(real_gauss != nullptr, "bgpu_color_momenta: real_gauss is required for a real-space mass");
+    h2d(h, h->tmp, real_gauss, h->n);
+    launch_add_real_momenta(h->mom, h->mass_r, h->tmp, h->n, h->stream);
+  }
+  d2h(h, momenta, h->mom, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *posx, double *posy, double *posz) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, h->sig, signal, h->n);
+  r2c_plain(h, h->sig, h->shat);
+  const bool want_pos = posx && posy && posz;
+  // positions are staged in grad / resid / tmp (free during the forward model)
+  forward_from_shat(h, h->p.deltaQ_factor, h->p.rsd_model != 0, want_pos ? h->grad : nullptr,
+                    want_pos ? h->resid : nullptr, want_pos ? h->tmp : nullptr);
+  if (want_pos) {
+    d2h(h, posx, h->grad, h->n);
+    d2h(h, posy, h->resid, h->n);
+    d2h(h, posz, h->tmp, h->n);
+  }
+  // overdens only (massFunctions.cc:30-47): reuse the residual kernel in value-only mode with a unit window
+  LikeParams lp = h->like;
+  lp.exact_sign = 0;
+  launch_fill(h->mom, 1.0, h->n, h->stream);
+  launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->mom, h->mom, h->mom, nullptr, h->n, h->partials,
+                           h->dscal + S_NLL, h->stream);
+  d2h(h, deltaX, h->delta, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_assign_density(bgpu_handle *h, const double *x, const double *y, const double *z, double *rho) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, h->psi[0], x, h->n);
+  h2d(h, h->psi[1], y, h->n);
+  h2d(h, h->psi[2], z, h->n);
+  launch_scatter_positions(h->geom, h->psi[0], h->psi[1], h->psi[2], h->delta, h->stream);
+  d2h(h, rho, h->delta, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_cell_indices(bgpu_handle *h, const double *x, const double *y, const double *z, size_t n, int *ci, int *cj,
+                      int *ck) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(n <= h->n, "bgpu_cell_indices: at most N1*N2*N3 positions per call");
+  h2d(h, h->psi[0], x, n);
+  h2d(h, h->psi[1], y, n);
+  h2d(h, h->psi[2], z, n);
+  int *di = reinterpret_cast<int *>(h->delta), *dj = reinterpret_cast<int *>(h->resid),
+      *dk = reinterpret_cast<int *>(h->tmp);
+  launch_cell_indices(h->geom, h->psi[0], h->psi[1], h->psi[2], di, dj, dk, n, h->stream);
+  BGPU_CUDA(cudaMemcpyAsync(ci, di, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  BGPU_CUDA(cudaMemcpyAsync(cj, dj, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  BGPU_CUDA(cudaMemcpyAsync(ck, dk, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_fft_r2c(bgpu_handle *h, const double *in, double *out_complex) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, h->sig, in, h->n);
+  r2c_plain(h, h->sig, h->work);
+  d2h(h, out_complex, reinterpret_cast<double *>(h->work), 2 * h->nh);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_fft_c2r(bgpu_handle *h, const double *in_complex, double *out) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, reinterpret_cast<double *>(h->work), in_complex, 2 * h->nh);
+  ROp sop;
+  sop.kind = R_SCALE;
+  sop.a = 1.0 / (double)h->n;   // fftwrapper.cc:43-45
+  h->fft.c2r(h->work, h->work, h->tmp, KOp{}, sop);
+  d2h(h, out, h->tmp, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_convolve_inv_corr(bgpu_handle *h, const double *signal, const double *corr, double *out) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  h2d(h, h->sig, signal, h->n);
+  h2d(h, h->tmp, corr, h->n);
+  // the half-grid multiplier goes to the first half of h->acc's storage
+  double *half = reinterpret_cast<double *>(h->acc);
+  update_inverse(h, h->tmp, half);
+  r2c_plain(h, h->sig, h->work);
+  KOp lop;
+  lop.kind = K_MULREAL;
+  lop.real0 = half;
+  ROp sop;
+  sop.kind = R_SCALE;
+  sop.a = 1.0 / (double)h->n;
+  h->fft.c2r(h->work, h->work, h->tmp, lop, sop);
+  d2h(h, out, h->tmp, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+}  // extern "C"

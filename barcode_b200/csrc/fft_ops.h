@@ -1,0 +1,43 @@
+// barcode_b200/csrc/fft_ops.h -- functor descriptors fused into the FFT passes.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace bgpu {
+
+// ---------------------------------------------------------------------------
+// functor descriptors (plain structs: passed by value as kernel arguments)
+// ---------------------------------------------------------------------------
+enum KKind : int {
+  K_NONE = 0,
+  K_DISP = 1,        // a * (k_c/k^2) * (Im v, -Re v); 0 if k^2 <= 1e-14 or on a Nyquist plane (EqSolvers.cc:208-268)
+  K_GRAD = 2,        // k_c * (-Im v, Re v); 0 on a Nyquist plane (gradient.cpp:38-74)
+  K_MULREAL = 3,     // v * real0[off]  (HMC_help.cc:41-58 with the multiplier precomputed)
+  K_FINAL = 4,       // v * real0[off] + a * cplx0[off]   (prior + norm * h, HMC.cc:205)
+  K_INVLAP_SET = 5,  // store: out[off]  = (k_c/k^2)(Im v, -Re v); k^2 == 0 -> 0, Nyquist -> 0 (gradient.cpp:167-210)
+  K_INVLAP_ADD = 6   // store: out[off] += same
+};
+
+struct KOp {
+  int kind = K_NONE;
+  int comp = 0;                  // 0,1,2 -> k_x, k_y, k_z
+  double a = 1.0;
+  double kfac = 0.0;             // 2 pi / L
+  const double *real0 = nullptr;
+  const double2 *cplx0 = nullptr;
+};
+
+enum RKind : int {
+  R_SCALE = 0,      // out = a * v
+  R_SCALE_MUL = 1,  // out = a * v * aux[idx]
+  R_AXPY = 2,       // out += a * v
+  R_LOAD = 10,      // r2c load: in[idx]
+  R_LOAD_SCALE = 11 // r2c load: a * in[idx]
+};
+
+struct ROp {
+  int kind = R_SCALE;
+  double a = 1.0;
+  const double *aux = nullptr;
+};
+
+}  // namespace bgpu

@@ -1,0 +1,206 @@
+// barcode_b200/csrc/fft_plan.cu -- host side of the hand-written 3-D FFT:
+// twiddle tables, per-size tile shapes and the launch sequences for r2c / c2r.
+// Replaces plan_pkg / fftR2Cplanned / fftC2Rplanned
+// (/root/reference/barlib/src/fftwrapper.cc:88-125,281-324).
+#include "fft3d.h"
+
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fft.cuh"
+#include "util.h"
+
+namespace bgpu {
+
+// ---------------------------------------------------------------------------
+// tiny grids (N == 8): the eight-elements-per-thread z pass needs N/2 >= 8, so
+// rows are transformed by direct summation, one thread per row.  Only the
+// reference's smoke configuration (test/run/input.par, Nx = 8) lands here.
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void tiny_r2c_zpass(const double *__restrict__ in, double2 *__restrict__ out,
+                               const double2 *__restrict__ twN, ROp lop, size_t nrows) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  double x[N];
+  for (int j = 0; j < N; ++j) {
+    double v = in[row * N + j];
+    if (lop.kind == R_LOAD_SCALE) v *= lop.a;
+    else if (lop.kind == R_SCALE_MUL) v *= lop.a * lop.aux[row * N + j];
+    x[j] = v;
+  }
+  for (int k = 0; k <= N / 2; ++k) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int j = 0; j < N; ++j) {
+      const double2 w = twN[(j * k) % N];
+      acc.x += x[j] * w.x;
+      acc.y += x[j] * w.y;
+    }
+    if (k == 0 || k == N / 2) acc.y = 0.0;
+    out[row * (N / 2 + 1) + k] = acc;
+  }
+}
+
+template <int N>
+__global__ void tiny_c2r_zpass(const double2 *__restrict__ in, double *__restrict__ out,
+                               const double2 *__restrict__ twN, ROp sop, size_t nrows) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  double2 X[N / 2 + 1];
+  for (int k = 0; k <= N / 2; ++k) X[k] = in[row * (N / 2 + 1) + k];
+  X[0].y = 0.0;
+  X[N / 2].y = 0.0;
+  for (int j = 0; j < N; ++j) {
+    double acc = X[0].x + ((j & 1) ? -X[N / 2].x : X[N / 2].x);
+    for (int k = 1; k < N / 2; ++k) {
+      const double2 w = twN[(j * k) % N];  // exp(-i a); we need Re[X exp(+i a)] * 2
+      acc += 2.0 * (X[k].x * w.x + X[k].y * w.y);
+    }
+    double v = sop.a * acc;
+    const size_t idx = row * N + j;
+    if (sop.kind == R_SCALE_MUL) v *= sop.aux[idx];
+    else if (sop.kind == R_AXPY) v += out[idx];
+    out[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-size tile shapes
+// ---------------------------------------------------------------------------
+template <int N> struct Shape;
+template <> struct Shape<8>    { static constexpr int T = 4,  TR = 0;  };
+template <> struct Shape<16>   { static constexpr int T = 8,  TR = 16; };
+template <> struct Shape<32>   { static constexpr int T = 16, TR = 16; };
+template <> struct Shape<64>   { static constexpr int T = 16, TR = 16; };
+template <> struct Shape<128>  { static constexpr int T = 16, TR = 16; };
+template <> struct Shape<256>  { static constexpr int T = 8,  TR = 8;  };
+template <> struct Shape<512>  { static constexpr int T = 8,  TR = 8;  };
+template <> struct Shape<1024> { static constexpr int T = 4,  TR = 4;  };
+
+template <int N, int DIR, int AXIS>
+static void launch_strided(const double2 *in, double2 *out, const double2 *tw, KOp lop, KOp sop, cudaStream_t st) {
+  constexpr int T = Shape<N>::T;
+  constexpr int threads = T * N / 8;
+  constexpr int tiles = N * ((N / 2) / T) + N / T;
+  constexpr size_t smem = (size_t)N * T * sizeof(double2);
+  fft_strided_pass<N, T, DIR, AXIS><<<tiles, threads, smem, st>>>(in, out, tw, lop, sop);
+  BGPU_LAUNCHED(1);
+}
+
+template <int N>
+static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xout, ROp lop, KOp sop) {
+  const size_t nrows = (size_t)N * N;
+  if constexpr (N == 8) {
+    tiny_r2c_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(in, out, f.twN, lop, nrows);
+  } else {
+    constexpr int TR = Shape<N>::TR;
+    constexpr int M = N / 2;
+    constexpr size_t smem = (size_t)TR * (M + M / 8 + 1) * sizeof(double2);
+    fft_r2c_zpass<N, TR><<<(unsigned)(nrows / TR), TR * M / 8, smem, f.stream>>>(in, out, f.twN, f.twM, lop, nrows);
+  }
+  BGPU_LAUNCHED(1);
+  launch_strided<N, -1, 1>(out, out, f.twN, KOp{}, KOp{}, f.stream);
+  launch_strided<N, -1, 0>(out, xout ? xout : out, f.twN, KOp{}, sop, f.stream);
+}
+
+template <int N>
+static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *out, KOp lop, ROp sop) {
+  const size_t nrows = (size_t)N * N;
+  launch_strided<N, +1, 0>(in, work, f.twN, lop, KOp{}, f.stream);
+  launch_strided<N, +1, 1>(work, work, f.twN, KOp{}, KOp{}, f.stream);
+  if constexpr (N == 8) {
+    tiny_c2r_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(work, out, f.twN, sop, nrows);
+  } else {
+    constexpr int TR = Shape<N>::TR;
+    constexpr int M = N / 2;
+    constexpr size_t smem = (size_t)TR * (M + M / 8 + 1) * sizeof(double2);
+    fft_c2r_zpass<N, TR><<<(unsigned)(nrows / TR), TR * M / 8, smem, f.stream>>>(work, out, f.twN, f.twM, sop, nrows);
+  }
+  BGPU_LAUNCHED(1);
+}
+
+// opt in to > 48 KB dynamic shared memory; per device, so done at plan creation
+template <int N>
+static void configure_impl() {
+  constexpr int T = Shape<N>::T;
+  constexpr int smem_s = N * T * (int)sizeof(double2);
+  BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass<N, T, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
+  BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass<N, T, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
+  BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass<N, T, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
+  BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass<N, T, +1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
+  if constexpr (N > 8) {
+    constexpr int TR = Shape<N>::TR;
+    constexpr int M = N / 2;
+    constexpr int smem_z = TR * (M + M / 8 + 1) * (int)sizeof(double2);
+    BGPU_CUDA(cudaFuncSetAttribute(fft_r2c_zpass<N, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_z));
+    BGPU_CUDA(cudaFuncSetAttribute(fft_c2r_zpass<N, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_z));
+  }
+}
+
+static std::vector<double2> make_twiddles(int n) {
+  std::vector<double2> tw(n);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int k = 0; k < n; ++k) {
+    const long double a = two_pi * (long double)k / (long double)n;
+    tw[k] = make_double2((double)cosl(a), (double)-sinl(a));
+  }
+  // exact values on the axes and diagonals
+  for (int k = 0; k < n; ++k) {
+    if ((4 * k) % n == 0) {
+      const int q = (4 * k) / n;
+      tw[k] = make_double2(q == 0 ? 1.0 : (q == 2 ? -1.0 : 0.0), q == 1 ? -1.0 : (q == 3 ? 1.0 : 0.0));
+    }
+  }
+  return tw;
+}
+
+#define BGPU_DISPATCH_N(CALL)                     \
+  switch (N) {                                    \
+    case 8: CALL(8); break;                       \
+    case 16: CALL(16); break;                     \
+    case 32: CALL(32); break;                     \
+    case 64: CALL(64); break;                     \
+    case 128: CALL(128); break;                   \
+    case 256: CALL(256); break;                   \
+    case 512: CALL(512); break;                   \
+    case 1024: CALL(1024); break;                 \
+    default: throw std::runtime_error("bgpu: unsupported FFT size"); \
+  }
+
+void Fft3d::init(int n, cudaStream_t st) {
+  if (!supported(n)) throw std::runtime_error("bgpu: FFT size must be a power of two in [8, 1024], got " + std::to_string(n));
+  N = n;
+  stream = st;
+  auto a = make_twiddles(n), b = make_twiddles(n / 2);
+  BGPU_CUDA(cudaMalloc(&twN, sizeof(double2) * n));
+  BGPU_CUDA(cudaMalloc(&twM, sizeof(double2) * (n / 2)));
+  BGPU_CUDA(cudaMemcpy(twN, a.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
+  BGPU_CUDA(cudaMemcpy(twM, b.data(), sizeof(double2) * (n / 2), cudaMemcpyHostToDevice));
+#define CALL(n_) configure_impl<n_>()
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
+
+void Fft3d::destroy() {
+  if (twN) cudaFree(twN);
+  if (twM) cudaFree(twM);
+  twN = twM = nullptr;
+}
+
+bool Fft3d::supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 0; }
+
+void Fft3d::r2c(const double *in, double2 *out, double2 *xout, ROp lop, KOp sop) const {
+#define CALL(n) r2c_impl<n>(*this, in, out, xout, lop, sop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
+
+void Fft3d::c2r(const double2 *in, double2 *work, double *out, KOp lop, ROp sop) const {
+#define CALL(n) c2r_impl<n>(*this, in, work, out, lop, sop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
+
+}  // namespace bgpu

@@ -1,0 +1,587 @@
+// barcode_b200/csrc/kernels.cu -- the non-FFT kernels of the HMC hot path.
+//
+// Each kernel names the reference loop it replaces (paths under
+// /root/reference/barlib/src).  Integer cell indices and interpolation weights
+// follow the reference's arithmetic operation by operation (explicit
+// round-to-nearest intrinsics where nvcc would otherwise contract a*b+c into
+// an FMA, which the reference's x86-64 build never does), so positions, cell
+// indices and weights are bit-identical for identical displacement input.
+#include "kernels.h"
+
+#include <math.h>
+
+#include "util.h"
+
+namespace bgpu {
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+// pacman_coordinate, pacman.cpp:20-28
+__device__ __forceinline__ double pacman(double x, double L) {
+  if (x < 0.) {
+    x = fmod(x, L);
+    x = __dadd_rn(x, L);
+  }
+  if (x >= L) x = fmod(x, L);
+  return x;
+}
+
+// Lagrangian position + displacement (+ plane-parallel RSD), disp_part.cc:55-126, rsd.cc:30-64
+__device__ __forceinline__ void particle_position(const GridGeom &g, int i, int j, int k, double px, double py,
+                                                  double pz, double &x, double &y, double &z) {
+  const double r = __dmul_rn(0.5, g.d);
+  x = __dadd_rn(__dadd_rn(__dmul_rn(g.d, (double)i), r), px);
+  y = __dadd_rn(__dadd_rn(__dmul_rn(g.d, (double)j), r), py);
+  z = __dadd_rn(__dadd_rn(__dmul_rn(g.d, (double)k), r), pz);
+  x = pacman(x, g.L);
+  y = pacman(y, g.L);
+  z = pacman(z, g.L);
+  if (g.rsd) {
+    const double vez = __dmul_rn(g.cpecvel, pz);       // Lag2Eul.cc:378-381
+    const double ruxv = __dmul_rn(vez, g.v_norm);      // rsd.cc:52
+    z = pacman(__dadd_rn(z, ruxv), g.L);               // rsd.cc:55,63
+  }
+}
+
+// getCICcells + getCICweights for one coordinate, interpolate_grid.cpp:27-79
+__device__ __forceinline__ void cic_axis(double x, double d, double L, int N, int &i0, int &i1, double &t,
+                                         double &dx) {
+  double xpos = __dsub_rn(x, __dmul_rn(0.5, d));
+  xpos = pacman(xpos, L);
+  const double q = __ddiv_rn(xpos, d);
+  unsigned long long c = (unsigned long long)q;
+  c = (c + (unsigned long long)N) % (unsigned long long)N;
+  i0 = (int)c;
+  i1 = (int)((c + 1ull) % (unsigned long long)N);
+  dx = __dsub_rn(q, (double)c);
+  t = __dsub_rn(1.0, dx);
+}
+
+// NGP / TSC centre cell, massFunctions.cc:72-79,198-204
+__device__ __forceinline__ int ngp_axis(double x, double xmin, double d, int N) {
+  unsigned c = (unsigned)floor(__ddiv_rn(__dsub_rn(x, xmin), d));
+  return (int)(unsigned)fmod((double)c, (double)N);
+}
+
+// TSC cells and weights for one coordinate, massFunctions.cc:198-235
+__device__ __forceinline__ void tsc_axis(double x, double xmin, double d, int N, int (&c)[3], double (&w)[3],
+                                         double &dx) {
+  const unsigned i = (unsigned)ngp_axis(x, xmin, d, N);
+  c[1] = (int)i;
+  c[2] = (int)(unsigned)fmod((double)(i + 1u), (double)N);
+  c[0] = (int)(unsigned)fmod((double)(i - 1u + (unsigned)N), (double)N);
+  const double xc = (double)i + 0.5;
+  dx = __dsub_rn(__ddiv_rn(__dsub_rn(x, xmin), d), xc);
+  w[1] = __dsub_rn(0.75, __dmul_rn(dx, dx));
+  const double a = __dadd_rn(0.5, dx), b = __dsub_rn(0.5, dx);
+  w[2] = __dmul_rn(__dmul_rn(0.5, a), a);
+  w[0] = __dmul_rn(__dmul_rn(0.5, b), b);
+}
+
+__device__ __forceinline__ bool in_domain(const GridGeom &g, double x, double y, double z) {
+  if (g.masskernel == 2)  // massFunctions.cc:195 (closed upper bound)
+    return (x >= g.min1 && x <= g.min1 + g.L) && (y >= g.min2 && y <= g.min2 + g.L) &&
+           (z >= g.min3 && z <= g.min3 + g.L);
+  return (x >= g.min1 && x < g.min1 + g.L) && (y >= g.min2 && y < g.min2 + g.L) &&
+         (z >= g.min3 && z < g.min3 + g.L);
+}
+
+__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+
+// deposit one particle, getDensity_NGP / _CIC / _TSC (massFunctions.cc:49-364), unit mass
+__device__ __forceinline__ void deposit(const GridGeom &g, double x, double y, double z, double *__restrict__ rho) {
+  if (!in_domain(g, x, y, z)) return;
+  const int N = g.N;
+  if (g.masskernel == 1) {
+    int i0, i1, j0, j1, k0, k1;
+    double tx, dx, ty, dy, tz, dz;
+    cic_axis(x, g.d, g.L, N, i0, i1, tx, dx);
+    cic_axis(y, g.d, g.L, N, j0, j1, ty, dy);
+    cic_axis(z, g.d, g.L, N, k0, k1, tz, dz);
+    const size_t r00 = ((size_t)i0 * N + j0) * N, r01 = ((size_t)i0 * N + j1) * N;
+    const size_t r10 = ((size_t)i1 * N + j0) * N, r11 = ((size_t)i1 * N + j1) * N;
+    // mass*w_x*w_y*w_z evaluated left to right, massFunctions.cc:129-157
+    red_add(rho + r00 + k0, __dmul_rn(__dmul_rn(tx, ty), tz));
+    red_add(rho + r10 + k0, __dmul_rn(__dmul_rn(dx, ty), tz));
+    red_add(rho + r01 + k0, __dmul_rn(__dmul_rn(tx, dy), tz));
+    red_add(rho + r00 + k1, __dmul_rn(__dmul_rn(tx, ty), dz));
+    red_add(rho + r11 + k0, __dmul_rn(__dmul_rn(dx, dy), tz));
+    red_add(rho + r10 + k1, __dmul_rn(__dmul_rn(dx, ty), dz));
+    red_add(rho + r01 + k1, __dmul_rn(__dmul_rn(tx, dy), dz));
+    red_add(rho + r11 + k1, __dmul_rn(__dmul_rn(dx, dy), dz));
+  } else if (g.masskernel == 2) {
+    int ci[3], cj[3], ck[3];
+    double wi[3], wj[3], wk[3], u;
+    tsc_axis(x, g.min1, g.d, N, ci, wi, u);
+    tsc_axis(y, g.min2, g.d, N, cj, wj, u);
+    tsc_axis(z, g.min3, g.d, N, ck, wk, u);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const size_t row = ((size_t)ci[a] * N + cj[b]) * N;
+        const double wab = __dmul_rn(wi[a], wj[b]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) red_add(rho + row + ck[c], __dmul_rn(wab, wk[c]));
+      }
+  } else {
+    const int i = ngp_axis(x, g.min1, g.d, N), j = ngp_axis(y, g.min2, g.d, N), k = ngp_axis(z, g.min3, g.d, N);
+    red_add(rho + ((size_t)i * N + j) * N + k, 1.0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K7: scatter
+// ---------------------------------------------------------------------------
+__global__ void scatter_kernel(GridGeom g, const double *__restrict__ psix, const double *__restrict__ psiy,
+                               const double *__restrict__ psiz, double *__restrict__ rho, double *__restrict__ posx,
+                               double *__restrict__ posy, double *__restrict__ posz) {
+  const size_t n = (size_t)g.N * g.N * g.N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int k = (int)(idx % g.N);
+  const int j = (int)((idx / g.N) % g.N);
+  const int i = (int)(idx / ((size_t)g.N * g.N));
+  double x, y, z;
+  particle_position(g, i, j, k, psix[idx], psiy[idx], psiz[idx], x, y, z);
+  if (posx) {
+    posx[idx] = x;
+    posy[idx] = y;
+    posz[idx] = z;
+  }
+  deposit(g, x, y, z, rho);
+}
+
+__global__ void scatter_positions_kernel(GridGeom g, const double *__restrict__ x, const double *__restrict__ y,
+                                         const double *__restrict__ z, double *__restrict__ rho) {
+  const size_t n = (size_t)g.N * g.N * g.N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  deposit(g, x[idx], y[idx], z[idx], rho);
+}
+
+__global__ void cell_indices_kernel(GridGeom g, const double *__restrict__ x, const double *__restrict__ y,
+                                    const double *__restrict__ z, int *ci, int *cj, int *ck, size_t n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  if (g.masskernel == 1) {
+    int a, b;
+    double t, dx;
+    cic_axis(x[idx], g.d, g.L, g.N, a, b, t, dx);
+    ci[idx] = a;
+    cic_axis(y[idx], g.d, g.L, g.N, a, b, t, dx);
+    cj[idx] = a;
+    cic_axis(z[idx], g.d, g.L, g.N, a, b, t, dx);
+    ck[idx] = a;
+  } else {
+    ci[idx] = ngp_axis(x[idx], g.min1, g.d, g.N);
+    cj[idx] = ngp_axis(y[idx], g.min2, g.d, g.N);
+    ck[idx] = ngp_axis(z[idx], g.min3, g.d, g.N);
+  }
+}
+
+static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
+                    double *posx, double *posy, double *posz, cudaStream_t st) {
+  const size_t n = (size_t)g.N * g.N * g.N;
+  BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
+  scatter_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, psix, psiy, psiz, rho, posx, posy, posz);
+  BGPU_LAUNCHED(1);
+}
+
+void launch_scatter_positions(const GridGeom &g, const double *x, const double *y, const double *z, double *rho,
+                              cudaStream_t st) {
+  const size_t n = (size_t)g.N * g.N * g.N;
+  BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
+  scatter_positions_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, x, y, z, rho);
+  BGPU_LAUNCHED(1);
+}
+
+void launch_cell_indices(const GridGeom &g, const double *x, const double *y, const double *z, int *ci, int *cj,
+                         int *ck, size_t n, cudaStream_t st) {
+  cell_indices_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, x, y, z, ci, cj, ck, n);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// deterministic two-stage reductions (fixed grid, fixed tree)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double warp_part[kReduceThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < kReduceThreads / 32; ++w) r += warp_part[w];
+  }
+  __syncthreads();
+  return r;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kReduceThreads) final_sum_kernel(const double *__restrict__ part, int nparts,
+                                                                    double *__restrict__ out) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += kReduceThreads) v += part[i];
+  const double r = block_sum(v);
+  if (threadIdx.x == 0) *out = r;
+}
+
+template <class F>
+__global__ void __launch_bounds__(kReduceThreads) partial_sum_kernel(F f, size_t n, double *__restrict__ part) {
+  double v = 0.0;
+  const size_t stride = (size_t)gridDim.x * kReduceThreads;
+  for (size_t i = (size_t)blockIdx.x * kReduceThreads + threadIdx.x; i < n; i += stride) v += f(i);
+  const double r = block_sum(v);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+
+struct SumF {
+  const double *a;
+  __device__ double operator()(size_t i) const { return a[i]; }
+};
+struct HalfDotF {
+  const double *a, *b;
+  __device__ double operator()(size_t i) const { return 0.5 * a[i] * b[i]; }
+};
+struct KineticF {  // HMC.cc:88-110
+  const double *p, *conv, *mass_r;
+  __device__ double operator()(size_t i) const {
+    double dummy = conv ? conv[i] : 0.0;
+    if (mass_r) {
+      const double m = mass_r[i];
+      const double invM = m > 0.0 ? 1.0 / m : 0.0;
+      dummy += invM * p[i];
+    }
+    return 0.5 * p[i] * dummy;
+  }
+};
+
+template <class F>
+static void reduce(F f, size_t n, double *scratch, double *out, cudaStream_t st) {
+  const int blocks = (int)((n + kReduceThreads - 1) / kReduceThreads < (size_t)kReduceBlocks
+                               ? (n + kReduceThreads - 1) / kReduceThreads
+                               : (size_t)kReduceBlocks);
+  partial_sum_kernel<F><<<blocks, kReduceThreads, 0, st>>>(f, n, scratch);
+  final_sum_kernel<<<1, kReduceThreads, 0, st>>>(scratch, blocks, out);
+  BGPU_LAUNCHED(2);
+}
+
+void launch_sum(const double *a, size_t n, double *scratch, double *out, cudaStream_t st) {
+  reduce(SumF{a}, n, scratch, out, st);
+}
+void launch_half_dot(const double *a, const double *b, size_t n, double *scratch, double *out, cudaStream_t st) {
+  reduce(HalfDotF{a, b}, n, scratch, out, st);
+}
+void launch_kinetic(const double *p, const double *conv, const double *mass_r, size_t n, double *scratch,
+                    double *out, cudaStream_t st) {
+  reduce(KineticF{p, conv, mass_r}, n, scratch, out, st);
+}
+
+// ---------------------------------------------------------------------------
+// K8: overdensity + likelihood residual + -lnL
+//   overdens, massFunctions.cc:30-47
+//   Gaussian: gaussian_independent.cpp:24-42 (residual), :80-91 (value)
+//   Poisson:  poissonian.cpp:19-34 (residual), :60-73 (value)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double pow_bias(double x, double e) { return e == 1.0 ? x : pow(x, e); }
+
+struct ResidualF {
+  LikeParams lp;
+  double *rho_delta;
+  const double *sum_rho, *nobs, *noise, *window;
+  double *resid;
+  double inv_count;  // 1/N as the reference divides: nmean = sum / N
+  double count;
+  __device__ double operator()(size_t i) const {
+    const double nmean = __ddiv_rn(*sum_rho, count);
+    const double delta = __dsub_rn(__ddiv_rn(rho_delta[i], nmean), 1.0);
+    rho_delta[i] = delta;
+    const double w = window[i], n = nobs[i];
+    double r = 0.0, val = 0.0;
+    if (lp.likelihood == 1) {
+      const double base = __dadd_rn(1.0, __dmul_rn(lp.biasP, delta));
+      const double Lambda = __dmul_rn(__dmul_rn(w, lp.rho_c), pow_bias(base, lp.biasE));
+      if (w > 0. && Lambda > 0.0) {
+        const double sg = noise[i];
+        r = __ddiv_rn(__dsub_rn(n, Lambda), __dmul_rn(sg, sg));
+        const double q = __ddiv_rn(__dsub_rn(Lambda, n), sg);
+        val = __dmul_rn(0.5, __dmul_rn(q, q));
+      }
+    } else {
+      const double dens = __dadd_rn(1.0, __dmul_rn(lp.biasP, delta));
+      const double Lambda = __dmul_rn(__dmul_rn(w, lp.rho_c), pow_bias(dens, lp.biasE));
+      if (w > 0.0 && dens > 0.0) {
+        r = (1 - n / Lambda) * lp.rho_c * lp.biasE * lp.biasP * pow_bias(dens, lp.biasE - 1);
+        if (lp.exact_sign) r = -r;
+      }
+      if (w > 0. && Lambda > 0.0) val = __dsub_rn(Lambda, __dmul_rn(n, log(Lambda)));
+    }
+    if (resid) resid[i] = r;
+    return val;
+  }
+};
+
+void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const double *sum_rho, const double *nobs,
+                              const double *noise, const double *window, double *resid, size_t n, double *scratch,
+                              double *nll, cudaStream_t st) {
+  ResidualF f{lp, rho_delta, sum_rho, nobs, noise, window, resid, 1.0 / (double)n, (double)n};
+  reduce(f, n, scratch, nll, st);
+}
+
+// ---------------------------------------------------------------------------
+// K9: exact adjoint of the mass assignment (new).  One thread per
+// particle, pure gather: V_c = sum_cells r_cell * dW_cell/dx_c.  Deterministic.
+// The particle's own displacement is read and its V written in place.
+// ---------------------------------------------------------------------------
+__global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, double *__restrict__ ay,
+                                      double *__restrict__ az, const double *__restrict__ resid) {
+  const int N = g.N;
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int k = (int)(idx % N);
+  const int j = (int)((idx / N) % N);
+  const int i = (int)(idx / ((size_t)N * N));
+  double x, y, z;
+  particle_position(g, i, j, k, ax[idx], ay[idx], az[idx], x, y, z);
+  double vx = 0.0, vy = 0.0, vz = 0.0;
+  if (in_domain(g, x, y, z)) {
+    const double inv_d = 1.0 / g.d;
+    if (g.masskernel == 1) {
+      int ci[2], cj[2], ck[2];
+      double wi[2], wj[2], wk[2];
+      cic_axis(x, g.d, g.L, N, ci[0], ci[1], wi[0], wi[1]);
+      cic_axis(y, g.d, g.L, N, cj[0], cj[1], wj[0], wj[1]);
+      cic_axis(z, g.d, g.L, N, ck[0], ck[1], wk[0], wk[1]);
+      const double gsgn[2] = {-inv_d, inv_d};
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const size_t row = ((size_t)ci[a] * N + cj[b]) * N;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const double rc = __ldg(resid + row + ck[c]);
+            vx += rc * gsgn[a] * wj[b] * wk[c];
+            vy += rc * wi[a] * gsgn[b] * wk[c];
+            vz += rc * wi[a] * wj[b] * gsgn[c];
+          }
+        }
+    } else if (g.masskernel == 2) {
+      int ci[3], cj[3], ck[3];
+      double wi[3], wj[3], wk[3], dx, dy, dz;
+      tsc_axis(x, g.min1, g.d, N, ci, wi, dx);
+      tsc_axis(y, g.min2, g.d, N, cj, wj, dy);
+      tsc_axis(z, g.min3, g.d, N, ck, wk, dz);
+      // d/dx of (1/2 (1/2 - D)^2, 3/4 - D^2, 1/2 (1/2 + D)^2), D = x/d - (i + 1/2)
+      const double gi[3] = {-(0.5 - dx) * inv_d, -2.0 * dx * inv_d, (0.5 + dx) * inv_d};
+      const double gj[3] = {-(0.5 - dy) * inv_d, -2.0 * dy * inv_d, (0.5 + dy) * inv_d};
+      const double gk[3] = {-(0.5 - dz) * inv_d, -2.0 * dz * inv_d, (0.5 + dz) * inv_d};
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const size_t row = ((size_t)ci[a] * N + cj[b]) * N;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const double rc = __ldg(resid + row + ck[c]);
+            vx += rc * gi[a] * wj[b] * wk[c];
+            vy += rc * wi[a] * gj[b] * wk[c];
+            vz += rc * wi[a] * wj[b] * gk[c];
+          }
+        }
+    }  // NGP: piecewise-constant weights, derivative identically zero
+  }
+  if (g.rsd) vz += g.fgrow * vz;  // d z_s / d Psi_z = 1 + f (cf. HMC_models.cc:295-301)
+  ax[idx] = vx;
+  ay[idx] = vy;
+  az[idx] = vz;
+}
+
+void launch_gather_adjoint(const GridGeom &g, double *ax, double *ay, double *az, const double *resid,
+                           cudaStream_t st) {
+  const size_t n = (size_t)g.N * g.N * g.N;
+  gather_adjoint_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, ax, ay, az, resid);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// K5: r * d_c(delta), 4th-order central difference, gradient.cpp:81-153
+// ---------------------------------------------------------------------------
+__global__ void findif_product_kernel(const double *__restrict__ in, const double *__restrict__ resid,
+                                      double *__restrict__ out, int N, double fac, int comp) {
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  int c[3] = {(int)(idx / ((size_t)N * N)), (int)((idx / N) % N), (int)(idx % N)};
+  const size_t stride = comp == 0 ? (size_t)N * N : (comp == 1 ? (size_t)N : 1);
+  const int ii = c[comp];
+  const size_t base = idx - (size_t)ii * stride;
+  const int r = ii + 1 >= N ? ii + 1 - N : ii + 1, rr = ii + 2 >= N ? ii + 2 - N : ii + 2;
+  const int l = ii - 1 < 0 ? ii - 1 + N : ii - 1, ll = ii - 2 < 0 ? ii - 2 + N : ii - 2;
+  const double g = -(fac * ((4.0 / 3) * (in[base + l * stride] - in[base + r * stride]) -
+                            (1.0 / 6) * (in[base + ll * stride] - in[base + rr * stride])));
+  out[idx] = resid[idx] * g;
+}
+
+void launch_findif_product(const double *delta, const double *resid, double *out, int N, double L, int comp,
+                           cudaStream_t st) {
+  const size_t n = (size_t)N * N * N;
+  const double fac = (double)N / (2. * L);
+  findif_product_kernel<<<blocks_for(n, 256), 256, 0, st>>>(delta, resid, out, N, fac, comp);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// streaming helpers
+// ---------------------------------------------------------------------------
+__global__ void inverse_spectrum_kernel(const double *__restrict__ full, double *__restrict__ half, int N,
+                                        double normFS) {
+  const int nzh = N / 2 + 1;
+  const size_t n = (size_t)N * N * nzh;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int k = (int)(idx % nzh);
+  const size_t ij = idx / nzh;
+  const double c = full[ij * N + k];  // HMC_help.cc:44: corrFunc[k + N3*(j + N2*i)]
+  half[idx] = c > 0.0 ? normFS / c : 0.;
+}
+
+void launch_inverse_spectrum(const double *full, double *half, int N, double normFS, cudaStream_t st) {
+  const size_t n = (size_t)N * N * (N / 2 + 1);
+  inverse_spectrum_kernel<<<blocks_for(n, 256), 256, 0, st>>>(full, half, N, normFS);
+  BGPU_LAUNCHED(1);
+}
+
+__global__ void axpy_kernel(double *__restrict__ y, const double *__restrict__ x, double a, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));  // HMC.cc:294,339,352 (two roundings)
+}
+__global__ void scale_kernel(double *__restrict__ y, const double *__restrict__ x, double a, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i];
+}
+__global__ void axpy_div_kernel(double *__restrict__ y, const double *__restrict__ x, const double *__restrict__ m,
+                                double a, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double mm = m[i];
+    const double invM = mm > 0.0 ? 1.0 / mm : 0.0;  // HMC.cc:321-326
+    y[i] += a * (x[i] * invM);
+  }
+}
+__global__ void fill_kernel(double *__restrict__ y, double v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = v;
+}
+
+void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st) {
+  axpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n);
+  BGPU_LAUNCHED(1);
+}
+void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t st) {
+  scale_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n);
+  BGPU_LAUNCHED(1);
+}
+void launch_axpy_div(double *y, const double *x, const double *m, double a, size_t n, cudaStream_t st) {
+  axpy_div_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, m, a, n);
+  BGPU_LAUNCHED(1);
+}
+void launch_fill(double *y, double v, size_t n, cudaStream_t st) {
+  fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, v, n);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// A17: Hamiltonian mass types 0 / 1 / 4, HMC_mass.cc:117-124,163-172,315-368
+// ---------------------------------------------------------------------------
+__global__ void mass_kernel(const double *__restrict__ power, double *__restrict__ mass_f,
+                            double *__restrict__ mass_r, int type, double factor, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (type == 0) {
+    mass_r[i] = 1.0;
+  } else if (type == 1) {
+    const double P = power[i];
+    const double invP = P > 0.0 ? 1. / P : 0.;
+    mass_f[i] = factor * (1.0 * invP);
+  } else if (type == 4) {
+    mass_f[i] = factor * power[i];
+  }
+}
+
+void launch_mass(const double *power, double *mass_f, double *mass_r, int mass_type, double mass_factor, size_t n,
+                 cudaStream_t st) {
+  mass_kernel<<<blocks_for(n, 256), 256, 0, st>>>(power, mass_f, mass_r, mass_type, mass_factor, n);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// K13: create_GARFIELD's colouring and Hermitian symmetrisation, random.cpp:
+// 102-507.  The reference walks the folded octant (i,j,k <= N/2) serially
+// through 27 cases, but every half-array element (c <= N/2) is written exactly
+// once, so the loop is data parallel: one thread per half-array element picks
+// its source entry of the white-noise grid, conjugates it if it is the mirror
+// partner, and scales by sigma = sqrt(N^2/V * spec/2) read at the folded index.
+// ---------------------------------------------------------------------------
+__global__ void colour_momenta_kernel(const double2 *__restrict__ W, const double *__restrict__ spec,
+                                      double2 *__restrict__ half, int N, double amp) {
+  const int h = N / 2, nzh = h + 1;
+  const size_t n = (size_t)N * N * nzh;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int c = (int)(idx % nzh);
+  const int b = (int)((idx / nzh) % N);
+  const int a = (int)(idx / ((size_t)nzh * N));
+  const int fa = a > h ? N - a : a, fb = b > h ? N - b : b;
+  const double sigma = sqrt(amp * spec[((size_t)fa * N + fb) * N + c] / 2.0);
+  const bool a_fix = (a == 0 || a == h), b_fix = (b == 0 || b == h), c_fix = (c == 0 || c == h);
+  const int ma = (N - a) % N, mb = (N - b) % N;
+  double2 out;
+  if (a_fix && b_fix && c_fix) {
+    if (a == 0 && b == 0 && c == 0) {
+      out = make_double2(0.0, 0.0);                                 // random.cpp:347-351
+    } else {
+      const double2 w = W[((size_t)a * N + b) * N + c];
+      out = make_double2(w.x * (sqrt(2.0) * sigma), 0.0);           // :243-247, 439-483
+    }
+  } else {
+    bool mirror;
+    int sa = a, sb = b, sc = c;
+    if (!c_fix) {
+      mirror = (!a_fix && !b_fix && a > h && b > h);                // :136-140
+      if (mirror) { sa = ma; sb = mb; sc = N - c; }
+    } else {
+      mirror = (!b_fix && b > h) || (b_fix && !a_fix && a > h);     // :144-162, 251-268, 308-345, 355-409
+      if (mirror) { sa = ma; sb = mb; }
+    }
+    const double2 w = W[((size_t)sa * N + sb) * N + sc];
+    out = make_double2(w.x * sigma, mirror ? -(w.y * sigma) : w.y * sigma);
+  }
+  half[idx] = out;
+}
+
+void launch_colour_momenta(const double2 *white_full, const double *spec_full, double2 *half, int N, double amp,
+                           cudaStream_t st) {
+  const size_t n = (size_t)N * N * (N / 2 + 1);
+  colour_momenta_kernel<<<blocks_for(n, 256), 256, 0, st>>>(white_full, spec_full, half, N, amp);
+  BGPU_LAUNCHED(1);
+}
+
+__global__ void add_real_momenta_kernel(double *__restrict__ p, const double *__restrict__ mass_r,
+                                        const double *__restrict__ gauss, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += sqrt(mass_r[i]) * gauss[i];
+}
+
+void launch_add_real_momenta(double *p, const double *mass_r, const double *gauss, size_t n, cudaStream_t st) {
+  add_real_momenta_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, mass_r, gauss, n);
+  BGPU_LAUNCHED(1);
+}
+
+}  // namespace bgpu

@@ -1,0 +1,82 @@
+// barcode_b200/csrc/kernels.h -- launchers of the non-FFT hot-path kernels
+// (particles, likelihood, reductions, leapfrog, momentum colouring).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace bgpu {
+
+struct GridGeom {
+  int N;           // cells per axis (cubic)
+  double L;        // box length
+  double d;        // cell size L/N
+  double min1, min2, min3;
+  int masskernel;  // 0 NGP, 1 CIC, 2 TSC
+  int rsd;         // plane-parallel redshift-space shift of z
+  double cpecvel;  // f*100*E*a        (cosmo.cc:220-235)
+  double v_norm;   // 1/Hub/a          (rsd.cc:27,39)
+  double fgrow;    // f                (cosmo.cc:182-217)
+};
+
+struct LikeParams {
+  int likelihood;  // 0 Poisson, 1 Gaussian
+  double rho_c, biasP, biasE;
+  int exact_sign;  // Poisson residual in the Gaussian sign convention (exact adjoint only)
+};
+
+// number of partial sums the two-stage reductions use (fixed: deterministic order)
+constexpr int kReduceBlocks = 1024;
+constexpr int kReduceThreads = 256;
+
+// half-grid multiplier normFS / C(k) (0 where C <= 0), from a full real-indexed spectrum
+void launch_inverse_spectrum(const double *full, double *half, int N, double normFS, cudaStream_t st);
+
+// particle scatter: Psi -> rho (zeroed here); optional positions out
+void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
+                    double *posx, double *posy, double *posz, cudaStream_t st);
+// mass assignment on explicit positions (tests, bgpu_assign_density)
+void launch_scatter_positions(const GridGeom &g, const double *x, const double *y, const double *z, double *rho,
+                              cudaStream_t st);
+// integer cell indices (bit-exact parity tests): lower CIC cell or NGP/TSC centre cell per axis
+void launch_cell_indices(const GridGeom &g, const double *x, const double *y, const double *z, int *ci, int *cj,
+                         int *ck, size_t n, cudaStream_t st);
+
+// deterministic sum of an array -> *out (device scalar); scratch: kReduceBlocks doubles
+void launch_sum(const double *a, size_t n, double *scratch, double *out, cudaStream_t st);
+// deterministic 0.5 * sum a*b
+void launch_half_dot(const double *a, const double *b, size_t n, double *scratch, double *out, cudaStream_t st);
+// kinetic real-space part: 0.5 * sum p * (c + p/mass_r) with mass_r <= 0 -> 0; c may be null
+void launch_kinetic(const double *p, const double *conv, const double *mass_r, size_t n, double *scratch,
+                    double *out, cudaStream_t st);
+
+// delta = rho / mean - 1 (in place), residual r, and -lnL partial sum -> *nll (device scalar).
+// mean is read from the device scalar `sum_rho` (/N).  resid may be null (value only).
+void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const double *sum_rho, const double *nobs,
+                              const double *noise, const double *window, double *resid, size_t n, double *scratch,
+                              double *nll, cudaStream_t st);
+
+// exact adjoint of the mass assignment: V_c(p) = sum_cells r_c dW_c/dx_c, in place over Psi
+void launch_gather_adjoint(const GridGeom &g, double *psix_Vx, double *psiy_Vy, double *psiz_Vz,
+                           const double *resid, cudaStream_t st);
+
+// out = resid * d_c(delta) with the 4th-order finite difference of gradient.cpp:81-153
+void launch_findif_product(const double *delta, const double *resid, double *out, int N, double L, int comp,
+                           cudaStream_t st);
+
+// y += a * x ; y = a * x ; y += a * x / m (m <= 0 -> 0)
+void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st);
+void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t st);
+void launch_axpy_div(double *y, const double *x, const double *m, double a, size_t n, cudaStream_t st);
+void launch_fill(double *y, double v, size_t n, cudaStream_t st);
+
+// Hamiltonian mass types 0 / 1 / 4 (HMC_mass.cc:315-368)
+void launch_mass(const double *power, double *mass_f, double *mass_r, int mass_type, double mass_factor, size_t n,
+                 cudaStream_t st);
+
+// create_GARFIELD colouring + Hermitian symmetrisation into the half array (random.cpp:102-507)
+void launch_colour_momenta(const double2 *white_full, const double *spec_full, double2 *half, int N, double amp,
+                           cudaStream_t st);
+// p += sqrt(mass_r) * gauss (HMC_momenta.cc:76-92)
+void launch_add_real_momenta(double *p, const double *mass_r, const double *gauss, size_t n, cudaStream_t st);
+
+}  // namespace bgpu

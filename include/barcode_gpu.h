@@ -1,0 +1,128 @@
+/*
+ * include/barcode_gpu.h -- C ABI of the B200-native HMC gradient-and-leapfrog
+ * path for Barcode (libbarcode_b200.so).
+ *
+ * The reference (egpbos/barcode, /root/reference) has no plugin or FFI layer;
+ * the seam this library replaces is the set of free functions in
+ * barlib/src/HMC.cc, HMC_momenta.cc and HMC_mass.cc that the unchanged host
+ * driver (main.cc -> barcoderunner -> sample_maker -> call_hamil ->
+ * HamiltonianMC) calls once per candidate / leapfrog step.  Every entry point
+ * below cites the reference function it stands in for; INTEGRATION.md shows
+ * the glue a maintainer adds on the reference side
+ * (barcode_b200/csrc/barlib_gpu_glue.cc).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, PODs; no exceptions cross the boundary.  Every
+ *    call returns 0 on success, non-zero on failure; bgpu_last_error() returns
+ *    the message (the glue rethrows it as std::runtime_error, the reference's
+ *    only error channel, main.cc:195-197).
+ *  - arrays are caller-owned, double[N1*N2*N3], row-major with z fastest
+ *    (idx = k + N3*(j + N2*i), disp_part.cc:60), exactly the reference's
+ *    fftw_malloc'ed arrays.  Host-pointer calls copy in and out; the *_dev
+ *    calls take device pointers and run on the handle's stream.
+ *  - one host thread per handle (the reference is single-threaded and not
+ *    re-entrant either); use one handle per GPU / chain.
+ *  - there is no CPU fallback: creation fails loudly without a CUDA device.
+ */
+#ifndef BARCODE_GPU_H
+#define BARCODE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGPU_ABI_VERSION 1
+
+/* calc_h value for the exact mass-assignment adjoint (new; the reference only
+ * has exact adjoints for its SPH kernel, HMC_models.cc:200-372) */
+#define BGPU_CALC_H_EXACT 4
+
+typedef struct bgpu_handle bgpu_handle;
+
+/* The fields of DATA / HAMIL_DATA the path reads (struct_main.h:23-258,
+ * struct_hamil.h:51-212); names follow the reference / input.par. */
+typedef struct bgpu_params {
+  int N1, N2, N3;            /* cells per axis; cubic, power of two in [8, 1024] (init_par.cc:116-122) */
+  double L1, L2, L3;         /* box size [Mpc/h] */
+  double xllc, yllc, zllc;   /* origin -> min1..3 */
+  double xobs, yobs, zobs;   /* observer (only plane-parallel RSD is supported, as in rsd.cc:60-62) */
+  int planepar, periodic;
+  int masskernel;            /* mk: 0 NGP, 1 CIC, 2 TSC */
+  int likelihood;            /* 0 Poisson, 1 Gaussian */
+  int sfmodel;               /* 1 Zel'dovich; with rsd_model the reference runs Zel'dovich for any value */
+  int rsd_model;
+  int calc_h;                /* 0, 1 as the reference; BGPU_CALC_H_EXACT */
+  int mass_type;             /* 0 ones (R), 1 1/P (FS), 4 P (FS) */
+  double D1, D2, ascale, OM, OL;
+  double rho_c, biasP, biasE;
+  double deltaQ_factor;
+  int correct_delta;
+  double mass_factor;
+  int div_dH_by_N;
+  int device;                /* CUDA device ordinal */
+  int reserved[8];
+} bgpu_params;
+
+/* the reference's defaults (data/input.par, init_par.cc:574-578) */
+void bgpu_default_params(bgpu_params *p);
+int bgpu_abi_version(void);
+const char *bgpu_last_error(void);
+
+/* call_hamil.cc:38-44 (per-sample HAMIL_DATA) + INIT_FFTW (init_par.cc:418-428) */
+int bgpu_create(const bgpu_params *p, bgpu_handle **out);
+void bgpu_destroy(bgpu_handle *h);
+
+/* static inputs: data->observational->{Power, nobs, noise_sf, window} (main.cc:150-154).
+ * NULL leaves an array unchanged. */
+int bgpu_set_static(bgpu_handle *h, const double *Power, const double *nobs, const double *noise,
+                    const double *window);
+/* hd->mass_f / hd->mass_r as read back from auxmass_{f,r}.dat (HMC.cc:414-423) */
+int bgpu_set_mass(bgpu_handle *h, const double *mass_f, const double *mass_r);
+/* S6 Hamiltonian_mass (HMC_mass.cc:315-368), types 0/1/4; outputs may be NULL */
+int bgpu_hamiltonian_mass(bgpu_handle *h, double *mass_f_out, double *mass_r_out);
+
+/* S1 gradient_psi (HMC.cc:146-206): writes hd->gradpsi */
+int bgpu_gradient_psi(bgpu_handle *h, const double *signal, double *gradpsi);
+/* S2 psi (HMC.cc:124-143): n->psi_prior, n->psi_likeli and the hd->deltaX side effect (deltaX_out may be NULL) */
+int bgpu_psi(bgpu_handle *h, const double *signal, double *psi_prior, double *psi_likeli, double *deltaX_out);
+/* S3 kinetic_term (HMC.cc:64-121) */
+int bgpu_kinetic(bgpu_handle *h, const double *momenta, double *K);
+/* S4 Hamiltonian_EoM (HMC.cc:251-369) after its two RNG draws (Neps, epsilon stay with the host RNG) */
+int bgpu_leapfrog(bgpu_handle *h, const double *s_i, const double *p_i, uint64_t Neps, double epsilon,
+                  double *s_f, double *p_f);
+/* S5 draw_momenta (HMC_momenta.cc:42-92) after the RNG: white = the 2*N doubles of
+ * resolution_independent_random_grid_FS<double>(N1, rng, false) (random.hpp:36-120);
+ * real_gauss = the N gsl_ran_gaussian draws of draw_real_space_momenta, or NULL when !mass_rs */
+int bgpu_color_momenta(bgpu_handle *h, const double *white_complex_fullgrid, const double *real_gauss,
+                       double *momenta);
+/* Lag2Eul / Lag2Eul_rsd_zeldovich as likelihood_grad_log_like calls them (HMC_models.cc:383-406);
+ * pos* may be NULL */
+int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *posx, double *posy, double *posz);
+
+/* building blocks exposed for parity tests */
+int bgpu_assign_density(bgpu_handle *h, const double *x, const double *y, const double *z, double *rho);
+int bgpu_cell_indices(bgpu_handle *h, const double *x, const double *y, const double *z, size_t n, int *ci,
+                      int *cj, int *ck);
+int bgpu_fft_r2c(bgpu_handle *h, const double *in, double *out_complex);       /* fftR2C, fftwrapper.cc:56-84 */
+int bgpu_fft_c2r(bgpu_handle *h, const double *in_complex, double *out);       /* fftC2R, fftwrapper.cc:26-53 */
+int bgpu_convolve_inv_corr(bgpu_handle *h, const double *signal, const double *corr, double *out); /* HMC_help.cc:16-64 */
+
+/* device-pointer variants (fused on-device trajectory, PyTorch harness) */
+int bgpu_set_stream(bgpu_handle *h, void *cuda_stream);
+int bgpu_synchronize(bgpu_handle *h);
+int bgpu_gradient_psi_dev(bgpu_handle *h, const double *d_signal, double *d_gradpsi);
+int bgpu_psi_dev(bgpu_handle *h, const double *d_signal, double *psi_prior, double *psi_likeli, double *d_deltaX);
+int bgpu_kinetic_dev(bgpu_handle *h, const double *d_momenta, double *K);
+int bgpu_leapfrog_dev(bgpu_handle *h, double *d_signal, double *d_momenta, uint64_t Neps, double epsilon);
+
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t bgpu_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* BARCODE_GPU_H */

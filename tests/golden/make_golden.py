@@ -1,0 +1,117 @@
+"""Generate the golden fixtures in tests/golden/ from the compiled reference.
+
+Run in the build container (needs /root/reference and `make -C oracle`):
+
+    python tests/golden/make_golden.py
+
+Every output array below is produced by the UNMODIFIED reference sources
+(oracle/_ref/libbarcode_ref.so via oracle/ref.py); nothing comes from the numpy
+restatement or the CUDA path.  The reference's own tests hold no golden vector
+for the hot path, so these files are the pin.
+
+  pk_table.npz        the tabulated linear P(k) the reference reads (data/WMAP7_CAMB.dat),
+                      in the float32 precision of calc_power.cc:41-42
+  case_<name>.npz     inputs + reference outputs of one configuration at 16^3
+  garfield_n8.npz     white-noise stream, coloured field and momenta at 8^3
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref  # noqa: E402
+
+CAMB = "/root/reference/data/WMAP7_CAMB.dat"
+
+CASES = {
+    # BASELINE.json configs[0]: ZA + CIC, Gaussian, real space
+    "za_cic_gauss": dict(masskernel=1, likelihood=1, rsd_model=False, calc_h=0, mass_type=1),
+    # configs[1]: (2LPT requested ->) ZA + CIC, Gaussian, RSD (HMC_models.cc:395-400)
+    "za_cic_gauss_rsd": dict(masskernel=1, likelihood=1, rsd_model=True, calc_h=0, mass_type=1, sfmodel=2),
+    # configs[2]: ZA + TSC, Poisson
+    "za_tsc_poisson": dict(masskernel=2, likelihood=0, rsd_model=False, calc_h=0, mass_type=1),
+    "za_ngp_gauss_h1": dict(masskernel=0, likelihood=1, rsd_model=False, calc_h=1, mass_type=1),
+    "za_tsc_gauss_rsd_mass0": dict(masskernel=2, likelihood=1, rsd_model=True, calc_h=0, mass_type=0),
+    "za_cic_poisson_mass4_dq": dict(masskernel=1, likelihood=0, rsd_model=False, calc_h=0, mass_type=4,
+                                    deltaQ_factor=0.9, mass_factor=2.0),
+}
+
+N1, L1 = 16, 50.0
+NEPS_U, EPS_U = 0.3, 0.01   # N_eps_fac = 8 -> Neps = floor(8*0.3)+1 = 3 ; eps_fac = 1 -> eps = 0.01
+
+
+def main():
+    tab = np.loadtxt(CAMB)
+    np.savez_compressed(os.path.join(HERE, "pk_table.npz"), k=tab[:, 0].astype(np.float32),
+                        P=tab[:, 1].astype(np.float32))
+
+    for name, kw in CASES.items():
+        cfg = ref.Config(N1=N1, L1=L1, N_eps_fac=8.0, eps_fac=1.0, **kw)
+        R = ref.Reference(cfg)
+        P = R.readtab(CAMB)
+        truth = R.create_garfield(1, P)
+        one = np.ones(R.N)
+        R.set_inputs(window=one, noise=one)
+        dX_truth = R.forward(truth, want_pos=False)
+        rng = np.random.default_rng(11)
+        if cfg.likelihood == 1:
+            nobs = np.maximum(0.0, 1.0 + dX_truth + rng.standard_normal(R.N))
+        else:
+            nobs = rng.poisson(np.maximum(1.0 + dX_truth, 0.0)).astype(np.float64)
+        # a window with a masked corner exercises the w > 0 branches
+        window = one.copy().reshape(N1, N1, N1)
+        window[:3, :3, :3] = 0.0
+        window = window.ravel()
+        noise = 1.0 + 0.25 * rng.random(R.N)
+        R.set_inputs(nobs=nobs, window=window, noise=noise)
+        s = 0.5 * R.create_garfield(2, P)
+        R.set_inputs(signal=s)
+        mass_f, mass_r = R.hamiltonian_mass()
+        mom = R.draw_momenta(3)
+        out = dict(Power=P, nobs=nobs, noise=noise, window=window, signal=s, momenta=mom,
+                   mass_f=mass_f, mass_r=mass_r, truth=truth)
+        dX, x, y, z = R.forward(s)
+        out.update(deltaX_fwd=dX, posx=x, posy=y, posz=z)
+        out["grad_like"] = R.grad_log_like(s)
+        out["grad_prior"] = R.grad_log_prior(s)
+        out["gradpsi"] = R.gradient_psi(s)
+        pp, pl = R.psi(s)
+        out["psi_prior"], out["psi_like"] = pp, pl
+        out["deltaX_psi"] = R.array("deltaX").copy()
+        out["K"] = R.kinetic(mom)
+        sf, pf = R.EoM(s, mom, NEPS_U, EPS_U)
+        out["Neps"], out["epsilon"] = R.scalar("Neps"), R.scalar("epsilon")
+        out["s_f"], out["p_f"] = sf, pf
+        dH, sc = R.delta_hamiltonian(s, mom, sf, pf)
+        out["dH"] = dH
+        for k, v in sc.items():
+            out["dh_" + k] = v
+        out["D1"] = R.scalar("D1")
+        out["cfg"] = np.array(repr({**kw, "N1": N1, "L1": L1}))
+        np.savez_compressed(os.path.join(HERE, f"case_{name}.npz"), **out)
+        print(name, "gradpsi norm", np.linalg.norm(out["gradpsi"]), "dH", dH, "Neps", out["Neps"])
+        R.close()
+
+    # momentum draw at 8^3: the white-noise stream, its colouring with P and with 1/P
+    cfg = ref.Config(N1=8, L1=25.0)
+    R = ref.Reference(cfg)
+    P = R.readtab(CAMB)
+    white = ref.white_noise(8, 7)
+    field = R.create_garfield(7, P)
+    R.set_inputs(window=np.ones(R.N), noise=np.ones(R.N), nobs=np.ones(R.N))
+    mass_f, _ = R.hamiltonian_mass()
+    mom = R.draw_momenta(7)
+    raw, gauss = ref.rng_stream(7, 16, 16)
+    np.savez_compressed(os.path.join(HERE, "garfield_n8.npz"), Power=P, white=white, field=field, mass_f=mass_f,
+                        momenta=mom, raw=raw, gauss=gauss)
+    R.close()
+
+
+if __name__ == "__main__":
+    main()
