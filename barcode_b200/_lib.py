@@ -65,7 +65,11 @@ SIGNATURES = {
     "bgpu_kinetic_dev": (C.c_int, [_h, C.c_void_p, _dp]),
     "bgpu_leapfrog_dev": (C.c_int, [_h, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double]),
     "bgpu_kernel_launches": (C.c_uint64, []),
+    "bgpu_profile_begin": (C.c_int, []),
+    "bgpu_profile_end": (C.c_int, [_dp, C.POINTER(C.c_uint64), C.c_int]),
+    "bgpu_profile_kind_name": (C.c_char_p, [C.c_int]),
 }
+PROFILE_KINDS = 9
 
 _lib = None
 

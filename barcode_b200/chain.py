@@ -245,3 +245,18 @@ class Chain:
 
 def kernel_launches() -> int:
     return int(_lib.load().bgpu_kernel_launches())
+
+
+def profile_begin():
+    """Start recording CUDA events around every kernel-class launch (roofline leg of bench.py)."""
+    _lib.check(_lib.load().bgpu_profile_begin())
+
+
+def profile_end():
+    """Stop recording; returns {kernel class: (total ms, launches)}."""
+    L = _lib.load()
+    n = _lib.PROFILE_KINDS
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint64 * n)()
+    _lib.check(L.bgpu_profile_end(ms, cnt, n))
+    return {L.bgpu_profile_kind_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}

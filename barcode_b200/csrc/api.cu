@@ -17,7 +17,23 @@
 
 namespace bgpu {
 std::atomic<uint64_t> g_kernel_launches{0};
+Profiler g_prof;
+
+void Profiler::record_start(int k, cudaStream_t st) {
+  if (2 * used + 2 > ev.size()) {
+    const size_t old = ev.size();
+    ev.resize(old + 1024);
+    for (size_t i = old; i < ev.size(); ++i) BGPU_CUDA(cudaEventCreate(&ev[i]));
+  }
+  if (kind.size() <= used) kind.resize(used + 512);
+  kind[used] = k;
+  BGPU_CUDA(cudaEventRecord(ev[2 * used], st));
 }
+void Profiler::record_stop(cudaStream_t st) {
+  cudaEventRecord(ev[2 * used + 1], st);
+  ++used;
+}
+}  // namespace bgpu
 
 using namespace bgpu;
 
@@ -311,6 +327,39 @@ extern "C" {
 int bgpu_abi_version(void) { return BGPU_ABI_VERSION; }
 const char *bgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t bgpu_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int bgpu_profile_begin(void) {
+  g_prof.used = 0;
+  g_prof.on = true;
+  return 0;
+}
+
+int bgpu_profile_end(double *ms_per_kind, uint64_t *launches_per_kind, int nkinds) {
+  BGPU_TRY
+  g_prof.on = false;
+  for (int k = 0; k < nkinds; ++k) {
+    ms_per_kind[k] = 0.0;
+    launches_per_kind[k] = 0;
+  }
+  BGPU_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    float ms = 0.f;
+    BGPU_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    const int k = g_prof.kind[i];
+    if (k < nkinds) {
+      ms_per_kind[k] += ms;
+      launches_per_kind[k] += 1;
+    }
+  }
+  g_prof.used = 0;
+  BGPU_CATCH
+}
+
+const char *bgpu_profile_kind_name(int kind) {
+  static const char *names[KK_COUNT] = {"fft_strided_pass", "fft_r2c_zpass", "fft_c2r_zpass", "scatter",
+                                        "gather_adjoint", "overdens_residual", "reduce", "stream", "colour_momenta"};
+  return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "?";
+}
 
 void bgpu_default_params(bgpu_params *p) {
   std::memset(p, 0, sizeof(*p));

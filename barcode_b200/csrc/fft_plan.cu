@@ -85,6 +85,7 @@ static void launch_strided(const double2 *in, double2 *out, const double2 *tw, K
   constexpr int threads = T * N / 8;
   constexpr int tiles = N * ((N / 2) / T) + N / T;
   constexpr size_t smem = (size_t)N * T * sizeof(double2);
+  ProfScope prof(KK_FFT_STRIDED, st);
   fft_strided_pass<N, T, DIR, AXIS><<<tiles, threads, smem, st>>>(in, out, tw, lop, sop);
   BGPU_LAUNCHED(1);
 }
@@ -92,6 +93,8 @@ static void launch_strided(const double2 *in, double2 *out, const double2 *tw, K
 template <int N>
 static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xout, ROp lop, KOp sop) {
   const size_t nrows = (size_t)N * N;
+  {
+  ProfScope prof(KK_FFT_R2C_Z, f.stream);
   if constexpr (N == 8) {
     tiny_r2c_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(in, out, f.twN, lop, nrows);
   } else {
@@ -101,6 +104,7 @@ static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xo
     fft_r2c_zpass<N, TR><<<(unsigned)(nrows / TR), TR * M / 8, smem, f.stream>>>(in, out, f.twN, f.twM, lop, nrows);
   }
   BGPU_LAUNCHED(1);
+  }
   launch_strided<N, -1, 1>(out, out, f.twN, KOp{}, KOp{}, f.stream);
   launch_strided<N, -1, 0>(out, xout ? xout : out, f.twN, KOp{}, sop, f.stream);
 }
@@ -110,6 +114,7 @@ static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *o
   const size_t nrows = (size_t)N * N;
   launch_strided<N, +1, 0>(in, work, f.twN, lop, KOp{}, f.stream);
   launch_strided<N, +1, 1>(work, work, f.twN, KOp{}, KOp{}, f.stream);
+  ProfScope prof(KK_FFT_C2R_Z, f.stream);
   if constexpr (N == 8) {
     tiny_c2r_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(work, out, f.twN, sop, nrows);
   } else {

@@ -185,6 +185,7 @@ static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n 
 
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
                     double *posx, double *posy, double *posz, cudaStream_t st) {
+  ProfScope prof(KK_SCATTER, st);
   const size_t n = (size_t)g.N * g.N * g.N;
   BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
   scatter_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, psix, psiy, psiz, rho, posx, posy, posz);
@@ -193,6 +194,7 @@ void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, c
 
 void launch_scatter_positions(const GridGeom &g, const double *x, const double *y, const double *z, double *rho,
                               cudaStream_t st) {
+  ProfScope prof(KK_SCATTER, st);
   const size_t n = (size_t)g.N * g.N * g.N;
   BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
   scatter_positions_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, x, y, z, rho);
@@ -262,7 +264,8 @@ struct KineticF {  // HMC.cc:88-110
 };
 
 template <class F>
-static void reduce(F f, size_t n, double *scratch, double *out, cudaStream_t st) {
+static void reduce(F f, size_t n, double *scratch, double *out, cudaStream_t st, int kind = KK_REDUCE) {
+  ProfScope prof(kind, st);
   const int blocks = (int)((n + kReduceThreads - 1) / kReduceThreads < (size_t)kReduceBlocks
                                ? (n + kReduceThreads - 1) / kReduceThreads
                                : (size_t)kReduceBlocks);
@@ -330,7 +333,7 @@ void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const dou
                               const double *noise, const double *window, double *resid, size_t n, double *scratch,
                               double *nll, cudaStream_t st) {
   ResidualF f{lp, rho_delta, sum_rho, nobs, noise, window, resid, 1.0 / (double)n, (double)n};
-  reduce(f, n, scratch, nll, st);
+  reduce(f, n, scratch, nll, st, KK_RESIDUAL);
 }
 
 // ---------------------------------------------------------------------------
@@ -405,6 +408,7 @@ __global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, doubl
 
 void launch_gather_adjoint(const GridGeom &g, double *ax, double *ay, double *az, const double *resid,
                            cudaStream_t st) {
+  ProfScope prof(KK_GATHER, st);
   const size_t n = (size_t)g.N * g.N * g.N;
   gather_adjoint_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, ax, ay, az, resid);
   BGPU_LAUNCHED(1);
@@ -431,6 +435,7 @@ __global__ void findif_product_kernel(const double *__restrict__ in, const doubl
 
 void launch_findif_product(const double *delta, const double *resid, double *out, int N, double L, int comp,
                            cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
   const size_t n = (size_t)N * N * N;
   const double fac = (double)N / (2. * L);
   findif_product_kernel<<<blocks_for(n, 256), 256, 0, st>>>(delta, resid, out, N, fac, comp);
@@ -453,6 +458,7 @@ __global__ void inverse_spectrum_kernel(const double *__restrict__ full, double 
 }
 
 void launch_inverse_spectrum(const double *full, double *half, int N, double normFS, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
   const size_t n = (size_t)N * N * (N / 2 + 1);
   inverse_spectrum_kernel<<<blocks_for(n, 256), 256, 0, st>>>(full, half, N, normFS);
   BGPU_LAUNCHED(1);
@@ -481,18 +487,22 @@ __global__ void fill_kernel(double *__restrict__ y, double v, size_t n) {
 }
 
 void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
   axpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n);
   BGPU_LAUNCHED(1);
 }
 void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
   scale_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n);
   BGPU_LAUNCHED(1);
 }
 void launch_axpy_div(double *y, const double *x, const double *m, double a, size_t n, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
   axpy_div_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, m, a, n);
   BGPU_LAUNCHED(1);
 }
 void launch_fill(double *y, double v, size_t n, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
   fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, v, n);
   BGPU_LAUNCHED(1);
 }
@@ -517,6 +527,7 @@ __global__ void mass_kernel(const double *__restrict__ power, double *__restrict
 
 void launch_mass(const double *power, double *mass_f, double *mass_r, int mass_type, double mass_factor, size_t n,
                  cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
   mass_kernel<<<blocks_for(n, 256), 256, 0, st>>>(power, mass_f, mass_r, mass_type, mass_factor, n);
   BGPU_LAUNCHED(1);
 }
@@ -568,6 +579,7 @@ __global__ void colour_momenta_kernel(const double2 *__restrict__ W, const doubl
 
 void launch_colour_momenta(const double2 *white_full, const double *spec_full, double2 *half, int N, double amp,
                            cudaStream_t st) {
+  ProfScope prof(KK_COLOUR, st);
   const size_t n = (size_t)N * N * (N / 2 + 1);
   colour_momenta_kernel<<<blocks_for(n, 256), 256, 0, st>>>(white_full, spec_full, half, N, amp);
   BGPU_LAUNCHED(1);
@@ -580,6 +592,7 @@ __global__ void add_real_momenta_kernel(double *__restrict__ p, const double *__
 }
 
 void launch_add_real_momenta(double *p, const double *mass_r, const double *gauss, size_t n, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
   add_real_momenta_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, mass_r, gauss, n);
   BGPU_LAUNCHED(1);
 }

@@ -24,3 +24,45 @@ extern std::atomic<uint64_t> g_kernel_launches;
     BGPU_CUDA(cudaGetLastError());                             \
     ::bgpu::g_kernel_launches.fetch_add((n), std::memory_order_relaxed); \
   } while (0)
+
+// ---------------------------------------------------------------------------
+// optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on
+// the launching stream around every launch of a kernel class.  Off by default;
+// costs nothing when off.
+// ---------------------------------------------------------------------------
+#include <vector>
+namespace bgpu {
+enum KernelKind : int {
+  KK_FFT_STRIDED = 0,
+  KK_FFT_R2C_Z = 1,
+  KK_FFT_C2R_Z = 2,
+  KK_SCATTER = 3,
+  KK_GATHER = 4,
+  KK_RESIDUAL = 5,
+  KK_REDUCE = 6,
+  KK_STREAM = 7,
+  KK_COLOUR = 8,
+  KK_COUNT = 9
+};
+
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // start/stop pairs
+  std::vector<int> kind;
+  size_t used = 0;              // pairs in use
+  void record_start(int k, cudaStream_t st);
+  void record_stop(cudaStream_t st);
+};
+extern Profiler g_prof;
+
+struct ProfScope {
+  cudaStream_t st;
+  bool active;
+  ProfScope(int kind, cudaStream_t s) : st(s), active(g_prof.on) {
+    if (active) g_prof.record_start(kind, st);
+  }
+  ~ProfScope() {
+    if (active) g_prof.record_stop(st);
+  }
+};
+}  // namespace bgpu

@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- HMC gradient evaluations per second on Barcode's hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 256] [--calc-h 0|4] [--impl ours|reference]
+
+A "step" is one `gradient_psi` evaluation (HMC.cc:146-206) on one batch of
+synthetic Gaussian-random-field data.  The N=1 workload is BASELINE.json
+configs[1]: 256^3, CIC, Gaussian likelihood, plane-parallel RSD, `sfmodel = 2`
+requested -- for which the reference runs Zel'dovich (HMC_models.cc:395-400) --
+with the reference's own gradient for CIC (`calc_h = 0`, the only one it has).
+With N > 1 ranks (torchrun, one per GPU) every rank runs an independent chain
+with its own seed (BASELINE.json configs[2]'s sharding: no data-path
+collective), so scaling is weak and `value` is the sum over chains.
+
+Prints ONE JSON line on rank 0 (contract in the task statement; DESIGN.md
+section "Measurement" says what each key is).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hmc_gradient_evals_per_s"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--calc-h", type=int, default=0, choices=[0, 1, 4])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(grid: int, calc_h: int):
+    from barcode_b200 import inputs
+    L = inputs.box_length(grid)
+    cfg = dict(N1=grid, L1=L, masskernel=1, likelihood=1, rsd_model=True, sfmodel=2, calc_h=calc_h, mass_type=1)
+    name = (f"{grid}^3 ZA+CIC Gaussian likelihood, plane-parallel RSD, L={L:g} Mpc/h, calc_h={calc_h} "
+            "(BASELINE.json configs[1]; sfmodel=2 requested, the reference runs Zel'dovich under rsd_model)")
+    return cfg, name
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            hot = sorted(sm)[len(sm) // 2:]  # the upper half are the samples under load
+            out = {"sm_mhz": float(np.median(hot)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------- reference arm
+def reference_problem(R, grid, L, seed):
+    """Synthetic inputs for the reference arm, made by the reference itself
+    (create_GARFIELD / Lag2Eul, barcoderunner.cc:42-205) from the same P(k) table."""
+    from oracle import barcode_oracle as bo
+    from barcode_b200 import inputs
+    k_tab, p_tab = inputs.load_pk_table()
+    P = inputs.power_on_grid(k_tab, p_tab, grid, L).ravel()
+    one = np.ones(R.N)
+    R.set_inputs(Power=P, window=one, noise=one, nobs=one)
+    truth = R.create_garfield(seed, P)
+    dX = R.forward(truth, want_pos=False)
+    nobs = np.maximum(0.0, 1.0 + dX + np.random.default_rng(seed + 1000).standard_normal(R.N))
+    R.set_inputs(nobs=nobs)
+    s = 0.5 * R.create_garfield(seed + 1, P)
+    R.hamiltonian_mass()
+    return s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ref
+    cfg, name = workload(args.grid, 0)
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbarcode_ref.so was not built"}))
+        return 0
+    rc = ref.Config(N1=cfg["N1"], L1=cfg["L1"], masskernel=1, likelihood=1, rsd_model=True, sfmodel=2, calc_h=0,
+                    mass_type=1)
+    R = ref.Reference(rc)
+    s = reference_problem(R, args.grid, cfg["L1"], 1)
+    for _ in range(max(1, args.warmup)):
+        R.gradient_psi(s)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R.gradient_psi(s)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    cores = ref.num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "fft_backend": ref.fft_backend(),
+                   "note": "the reference's own gradient_psi (calc_h=0) on the host cores, OpenMP threads = cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": f"{args.steps} full gradient_psi calls at {args.grid}^3 after {max(1, args.warmup)} warm-up"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def cpu_baseline(args, cfg):
+    """The compiled reference (oracle/_ref) timed on this box's host cores: a bounded sample of
+    the same workload (full-size gradient_psi calls, about 10-30 s of CPU work)."""
+    from oracle import ref
+    if not ref.available():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    rc = ref.Config(N1=cfg["N1"], L1=cfg["L1"], masskernel=1, likelihood=1, rsd_model=True, sfmodel=2, calc_h=0,
+                    mass_type=1)
+    R = ref.Reference(rc)
+    s = reference_problem(R, cfg["N1"], cfg["L1"], 1)
+    t0 = time.perf_counter()
+    R.gradient_psi(s)
+    t1 = time.perf_counter() - t0
+    reps = int(min(5, max(1, 15.0 / max(t1, 1e-3))))
+    sec = R.time_gradient_psi(s, reps)   # one more warm-up call inside, then `reps` timed (omp_get_wtime)
+    R.close()
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": ref.num_threads(), "kind": "reference",
+            "sample": f"{reps} full gradient_psi calls at {cfg['N1']}^3 (calc_h=0) after 2 warm-up calls; "
+                      f"FFT backend: {ref.fft_backend()}"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from barcode_b200 import chain as bc
+    from barcode_b200 import inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg, name = workload(args.grid, args.calc_h)
+    n = args.grid ** 3
+    launches0 = bc.kernel_launches()
+    ch = bc.Chain(bc.Params(device=local_rank, **cfg))
+    prob = inputs.synthetic_problem(ch, seed=1 + 17 * rank)
+    stream = torch.cuda.current_stream()
+    ch.set_stream(stream.cuda_stream)
+    d_s = torch.from_numpy(np.ascontiguousarray(prob["signal"]).reshape(-1)).cuda()
+    d_g = torch.empty_like(d_s)
+    d_p = torch.from_numpy(np.ascontiguousarray(prob["momenta"]).reshape(-1)).cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    counted = {}
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l_before = bc.kernel_launches()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        counted["launches"] = bc.kernel_launches() - l_before
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def grad_step():
+        ch.gradient_psi_dev(d_s.data_ptr(), d_g.data_ptr())
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms = timed(grad_step, args.steps, args.warmup)
+    launches_timed = counted["launches"]
+    clock_info = clocks.stop() if rank == 0 else {}
+    value = world * args.steps / (ms * 1e-3)
+
+    # the other gradient (exact adjoint when the headline is calc_h=0 and vice versa), same steps
+    other_h = 4 if args.calc_h != 4 else 0
+    ch2 = bc.Chain(bc.Params(device=local_rank, **{**cfg, "calc_h": other_h}))
+    ch2.set_static(Power=prob["Power"], nobs=prob["nobs"], noise=prob["noise"], window=prob["window"])
+    ch2.set_stream(stream.cuda_stream)
+    ms_other = timed(lambda: ch2.gradient_psi_dev(d_s.data_ptr(), d_g.data_ptr()), args.steps, args.warmup)
+    ch2.close()
+
+    # one leapfrog step = kick, M^-1 p, drift, gradient, kick (HMC.cc:289-352)
+    ch.hamiltonian_mass()
+    d_s2, d_p2 = d_s.clone(), d_p.clone()
+    ms_leap = timed(lambda: ch.leapfrog_dev(d_s2.data_ptr(), d_p2.data_ptr(), 1, 1e-3), max(2, args.steps // 2), 1)
+    leap_steps = max(2, args.steps // 2)
+
+    # roofline leg: the same K steps again with CUDA events around every kernel launch
+    bc.profile_begin()
+    for _ in range(args.steps):
+        grad_step()
+    prof = bc.profile_end()
+    total_prof = sum(v[0] for v in prof.values())
+    dom = max(prof.items(), key=lambda kv: kv[1][0])
+    nh = args.grid * args.grid * (args.grid // 2 + 1)
+    alg_bytes = {  # algorithmic bytes per launch of each kernel class ("Kernels")
+        "fft_strided_pass": 2 * nh * 16,            # read + write the half-complex array once
+        "fft_r2c_zpass": n * 8 + nh * 16,
+        "fft_c2r_zpass": n * 8 + nh * 16,
+        "scatter": 4 * n * 8,                       # Psi_x,y,z in, rho out
+        "gather_adjoint": 7 * n * 8,
+        "overdens_residual": 5 * n * 8,
+        "reduce": n * 8,
+        "stream": 3 * n * 8,
+        "colour_momenta": n * 16 + nh * 16,
+    }
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom_name, (dom_ms, dom_cnt) = dom
+    achieved = alg_bytes[dom_name] / (dom_ms * 1e-3 / dom_cnt) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "launches_per_step": dom_cnt / args.steps, "avg_launch_ms": dom_ms / dom_cnt,
+        "share_of_step": dom_ms / total_prof,
+        "per_kernel": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                           "GBps": (alg_bytes[k] / (v[0] * 1e-3 / v[1]) / 1e9) if v[1] else None}
+                       for k, v in prof.items() if v[1]},
+        "whole_path": {"algorithmic_bytes_per_eval": 260 * n, "achieved_GBps": 260 * n * value / world / 1e9,
+                       "frac": 260 * n * value / world / 1e9 / peak_gbs,
+                       "note": "SURVEY 8(d): 260 N bytes per exact-adjoint evaluation; calc_h=0 does 12 FFTs instead of 8"},
+    }
+
+    # end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
+    h_s = torch.from_numpy(np.ascontiguousarray(prob["signal"]).reshape(-1)).pin_memory()
+    h_g = torch.empty(n, dtype=torch.float64).pin_memory()
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+
+    def e2e_step():
+        rc = ch.L.bgpu_gradient_psi(ch._h, C.cast(h_s.data_ptr(), dp), C.cast(h_g.data_ptr(), dp))
+        if rc != 0:
+            raise RuntimeError(ch.L.bgpu_last_error().decode())
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * args.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 8,
+           "d2h_bytes_per_step": n * 8, "ms_per_step": 1e3 * float(dt.item()) / args.steps,
+           "api": "bgpu_gradient_psi(host signal -> host gradpsi), pinned host buffers"}
+
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base = cpu_baseline(args, cfg)
+    ch.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "grid": args.grid, "calc_h": args.calc_h,
+                       "parallelism": f"{world} independent chain(s), one per GPU, no data-path collective",
+                       "l2": f"inputs larger than L2: {12 * n * 8 / 2**20:.0f} MiB of FP64 arrays are streamed per "
+                             "evaluation against 126 MB of L2; no explicit flush"},
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches_timed),
+            "clocks": clock_info,
+            "also": {
+                f"gradient_evals_per_s_calc_h_{other_h}": world * args.steps / (ms_other * 1e-3),
+                "leapfrog_steps_per_s": world * leap_steps / (ms_leap * 1e-3),
+                "kernel_launches_total": int(bc.kernel_launches() - launches0),
+            },
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
