@@ -192,7 +192,7 @@ __device__ __forceinline__ double2 kop_load(const KOp &op, double2 v, size_t off
       const double ksq = kx * kx + ky * ky + kz * kz;
       if (!(ksq > 1.e-14)) return make_double2(0.0, 0.0);
       const double kc = op.comp == 0 ? kx : (op.comp == 1 ? ky : kz);
-      const double f = op.a * ((1.0 / ksq) * kc);
+      const double f = op.a * (__drcp_rn(ksq) * kc);
       return make_double2(f * v.y, f * -v.x);
     }
     case K_GRAD: {
@@ -217,7 +217,7 @@ __device__ __forceinline__ void kop_store(const KOp &op, double2 *__restrict__ o
         const double ksq = kx * kx + ky * ky + kz * kz;
         if (ksq > 0.0) {
           const double kc = op.comp == 0 ? kx : (op.comp == 1 ? ky : kz);
-          const double f = kc * (1.0 / ksq);
+          const double f = kc * __drcp_rn(ksq);
           r = make_double2(f * v.y, -f * v.x);
         }
       }
@@ -272,18 +272,39 @@ __global__ void __launch_bounds__(T *N / 8)
   const size_t stride = (AXIS == 0) ? (size_t)N * NZH : (size_t)NZH;
   const size_t base = ((AXIS == 0) ? (size_t)other * NZH : (size_t)other * N * NZH) + iz;
 
+  // all eight loads are issued before anything consumes them (one round trip, not eight)
   double2 v[8];
 #pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    const int r = t + m * (N / 8);
-    const size_t off = base + (size_t)r * stride;
-    double2 x = in[off];
-    if (lop.kind != K_NONE) {
+  for (int m = 0; m < 8; ++m) v[m] = in[base + (size_t)(t + m * (N / 8)) * stride];
+  if (lop.kind == K_MULREAL || lop.kind == K_FINAL) {
+    double f[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) f[m] = __ldg(lop.real0 + base + (size_t)(t + m * (N / 8)) * stride);
+    if (lop.kind == K_FINAL) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        double2 hh[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          hh[m] = __ldg(lop.cplx0 + base + (size_t)(t + (4 * half + m) * (N / 8)) * stride);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int mm = 4 * half + m;
+          v[mm] = make_double2(v[mm].x * f[mm] + lop.a * hh[m].x, v[mm].y * f[mm] + lop.a * hh[m].y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) v[m] = make_double2(v[m].x * f[m], v[m].y * f[m]);
+    }
+  } else if (lop.kind != K_NONE) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int r = t + m * (N / 8);
       const int ix = (AXIS == 0) ? r : other;
       const int iy = (AXIS == 0) ? other : r;
-      x = kop_load<N>(lop, x, off, ix, iy, iz);
+      v[m] = kop_load<N>(lop, v[m], 0, ix, iy, iz);
     }
-    v[m] = x;
   }
 
   SmStrided sm{smem, T, p};
@@ -300,6 +321,139 @@ __global__ void __launch_bounds__(T *N / 8)
     } else {
       out[off] = v[m];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// persistent, software-pipelined variant of the strided pass (used for N >= 128).
+//
+// The plain kernel above serialises load -> stages -> store inside a CTA, and
+// with the register file limiting it to ~32 warps per SM the memory pipe idles
+// while warps compute (ncu, round 1: long_scoreboard 63 % of stall samples, 36 %
+// of DRAM peak).  Here a CTA walks tiles blockIdx.x, +gridDim.x, ... and, before
+// it transforms tile i, every thread issues cp.async (LDGSTS) copies of the
+// eight elements IT will own in tile i+1 into a second shared-memory buffer.
+// The slots are thread-private, so no barrier guards them: a thread waits on
+// its own copy group, lifts its eight values into registers and immediately
+// re-arms the buffer with the tile after.  HBM reads therefore overlap the
+// whole butterfly / exchange / store phase of the previous tile.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int N, int T, int AXIS>
+__device__ __forceinline__ void strided_tile_coords(int tile, int p, int &other, int &iz, size_t &base) {
+  constexpr int NZH = N / 2 + 1;
+  constexpr int NTZ = (N / 2) / T;
+  constexpr int NMAIN = N * NTZ;
+  if (tile < NMAIN) {
+    other = tile / NTZ;
+    iz = (tile % NTZ) * T + p;
+  } else {
+    other = (tile - NMAIN) * T + p;
+    iz = N / 2;
+  }
+  base = ((AXIS == 0) ? (size_t)other * NZH : (size_t)other * N * NZH) + iz;
+}
+
+template <int N, int T, int DIR, int AXIS>
+__global__ void __launch_bounds__(T *N / 8, (T * N / 8 <= 256) ? 3 : 1)
+    fft_strided_pass_pipelined(const double2 *__restrict__ in, double2 *__restrict__ out,
+                               const double2 *__restrict__ tw, KOp lop, KOp sop) {
+  extern __shared__ double2 smem[];
+  constexpr int NZH = N / 2 + 1;
+  constexpr int NTILES = N * ((N / 2) / T) + N / T;
+  double2 *xch = smem;           // stage exchanges of the current tile
+  double2 *pre = smem + N * T;   // thread-private landing slots of the next tile
+  const int p = threadIdx.x % T;
+  const int t = threadIdx.x / T;
+  constexpr size_t stride = (AXIS == 0) ? (size_t)N * NZH : (size_t)NZH;
+
+  int tile = blockIdx.x;
+  int other, iz;
+  size_t base;
+  if (tile < NTILES) {
+    strided_tile_coords<N, T, AXIS>(tile, p, other, iz, base);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int r = t + m * (N / 8);
+      cp_async16(pre + r * T + p, in + base + (size_t)r * stride);
+    }
+  }
+  cp_async_commit();
+
+  while (tile < NTILES) {
+    cp_async_wait_all();
+    double2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = pre[(t + m * (N / 8)) * T + p];
+
+    // re-arm the landing slots with the tile after this one
+    const int next = tile + gridDim.x;
+    if (next < NTILES) {
+      int o2, z2;
+      size_t b2;
+      strided_tile_coords<N, T, AXIS>(next, p, o2, z2, b2);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int r = t + m * (N / 8);
+        cp_async16(pre + r * T + p, in + b2 + (size_t)r * stride);
+      }
+    }
+    cp_async_commit();
+
+    if (lop.kind == K_MULREAL || lop.kind == K_FINAL) {
+      double f[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) f[m] = __ldg(lop.real0 + base + (size_t)(t + m * (N / 8)) * stride);
+      if (lop.kind == K_FINAL) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          double2 hh[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            hh[m] = __ldg(lop.cplx0 + base + (size_t)(t + (4 * half + m) * (N / 8)) * stride);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int mm = 4 * half + m;
+            v[mm] = make_double2(v[mm].x * f[mm] + lop.a * hh[m].x, v[mm].y * f[mm] + lop.a * hh[m].y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = make_double2(v[m].x * f[m], v[m].y * f[m]);
+      }
+    } else if (lop.kind != K_NONE) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int r = t + m * (N / 8);
+        const int ix = (AXIS == 0) ? r : other;
+        const int iy = (AXIS == 0) ? other : r;
+        v[m] = kop_load<N>(lop, v[m], 0, ix, iy, iz);
+      }
+    }
+
+    SmStrided sm{xch, T, p};
+    fft_stages<N, 1, DIR, SmStrided>(v, t, tw, sm);
+
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int r = t + m * (N / 8);
+      const size_t off = base + (size_t)r * stride;
+      if (sop.kind != K_NONE) {
+        const int ix = (AXIS == 0) ? r : other;
+        const int iy = (AXIS == 0) ? other : r;
+        kop_store<N>(sop, out, v[m], off, ix, iy, iz);
+      } else {
+        out[off] = v[m];
+      }
+    }
+    tile = next;
+    if (tile < NTILES) strided_tile_coords<N, T, AXIS>(tile, p, other, iz, base);
   }
 }
 

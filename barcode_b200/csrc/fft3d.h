@@ -12,6 +12,7 @@ struct Fft3d {
   double2 *twN = nullptr;  // exp(-2 pi i k / N)
   double2 *twM = nullptr;  // exp(-2 pi i k / (N/2))
   cudaStream_t stream = nullptr;
+  int strided_blocks = 0;  // persistent grid of the pipelined strided pass: SMs x resident CTAs
 
   void init(int n, cudaStream_t st);
   void destroy();

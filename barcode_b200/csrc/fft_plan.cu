@@ -80,13 +80,20 @@ template <> struct Shape<512>  { static constexpr int T = 8,  TR = 8;  };
 template <> struct Shape<1024> { static constexpr int T = 4,  TR = 4;  };
 
 template <int N, int DIR, int AXIS>
-static void launch_strided(const double2 *in, double2 *out, const double2 *tw, KOp lop, KOp sop, cudaStream_t st) {
+static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, const double2 *tw, KOp lop, KOp sop,
+                           cudaStream_t st) {
   constexpr int T = Shape<N>::T;
   constexpr int threads = T * N / 8;
   constexpr int tiles = N * ((N / 2) / T) + N / T;
   constexpr size_t smem = (size_t)N * T * sizeof(double2);
-  ProfScope prof(KK_FFT_STRIDED, st);
-  fft_strided_pass<N, T, DIR, AXIS><<<tiles, threads, smem, st>>>(in, out, tw, lop, sop);
+  ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
+  if constexpr (N >= 128) {
+    // persistent + cp.async prefetch: one wave of CTAs walks all tiles
+    const int blocks = f.strided_blocks < tiles ? f.strided_blocks : tiles;
+    fft_strided_pass_pipelined<N, T, DIR, AXIS><<<blocks, threads, 2 * smem, st>>>(in, out, tw, lop, sop);
+  } else {
+    fft_strided_pass<N, T, DIR, AXIS><<<tiles, threads, smem, st>>>(in, out, tw, lop, sop);
+  }
   BGPU_LAUNCHED(1);
 }
 
@@ -105,15 +112,15 @@ static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xo
   }
   BGPU_LAUNCHED(1);
   }
-  launch_strided<N, -1, 1>(out, out, f.twN, KOp{}, KOp{}, f.stream);
-  launch_strided<N, -1, 0>(out, xout ? xout : out, f.twN, KOp{}, sop, f.stream);
+  launch_strided<N, -1, 1>(f, out, out, f.twN, KOp{}, KOp{}, f.stream);
+  launch_strided<N, -1, 0>(f, out, xout ? xout : out, f.twN, KOp{}, sop, f.stream);
 }
 
 template <int N>
 static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *out, KOp lop, ROp sop) {
   const size_t nrows = (size_t)N * N;
-  launch_strided<N, +1, 0>(in, work, f.twN, lop, KOp{}, f.stream);
-  launch_strided<N, +1, 1>(work, work, f.twN, KOp{}, KOp{}, f.stream);
+  launch_strided<N, +1, 0>(f, in, work, f.twN, lop, KOp{}, f.stream);
+  launch_strided<N, +1, 1>(f, work, work, f.twN, KOp{}, KOp{}, f.stream);
   ProfScope prof(KK_FFT_C2R_Z, f.stream);
   if constexpr (N == 8) {
     tiny_c2r_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(work, out, f.twN, sop, nrows);
@@ -128,9 +135,26 @@ static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *o
 
 // opt in to > 48 KB dynamic shared memory; per device, so done at plan creation
 template <int N>
-static void configure_impl() {
+static void configure_impl(Fft3d &f) {
   constexpr int T = Shape<N>::T;
   constexpr int smem_s = N * T * (int)sizeof(double2);
+  if constexpr (N >= 128) {
+    constexpr int smem_p = 2 * smem_s;
+    BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass_pipelined<N, T, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+    BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass_pipelined<N, T, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+    BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass_pipelined<N, T, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+    BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass_pipelined<N, T, +1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+    int dev = 0, sms = 0, occ = 0, occ_min = 1 << 30;
+    BGPU_CUDA(cudaGetDevice(&dev));
+    BGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_strided_pass_pipelined<N, T, +1, 0>, T * N / 8, smem_p));
+    occ_min = occ < occ_min ? occ : occ_min;
+    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_strided_pass_pipelined<N, T, -1, 0>, T * N / 8, smem_p));
+    occ_min = occ < occ_min ? occ : occ_min;
+    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_strided_pass_pipelined<N, T, +1, 1>, T * N / 8, smem_p));
+    occ_min = occ < occ_min ? occ : occ_min;
+    f.strided_blocks = sms * (occ_min > 0 ? occ_min : 1);
+  }
   BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass<N, T, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
   BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass<N, T, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
   BGPU_CUDA(cudaFuncSetAttribute(fft_strided_pass<N, T, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
@@ -183,7 +207,7 @@ void Fft3d::init(int n, cudaStream_t st) {
   BGPU_CUDA(cudaMalloc(&twM, sizeof(double2) * (n / 2)));
   BGPU_CUDA(cudaMemcpy(twN, a.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
   BGPU_CUDA(cudaMemcpy(twM, b.data(), sizeof(double2) * (n / 2), cudaMemcpyHostToDevice));
-#define CALL(n_) configure_impl<n_>()
+#define CALL(n_) configure_impl<n_>(*this)
   BGPU_DISPATCH_N(CALL)
 #undef CALL
 }

@@ -237,7 +237,15 @@ template <class F>
 __global__ void __launch_bounds__(kReduceThreads) partial_sum_kernel(F f, size_t n, double *__restrict__ part) {
   double v = 0.0;
   const size_t stride = (size_t)gridDim.x * kReduceThreads;
-  for (size_t i = (size_t)blockIdx.x * kReduceThreads + threadIdx.x; i < n; i += stride) v += f(i);
+  size_t i = (size_t)blockIdx.x * kReduceThreads + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const double a = f(i), b = f(i + stride), c = f(i + 2 * stride), d = f(i + 3 * stride);
+    v += a;
+    v += b;
+    v += c;
+    v += d;
+  }
+  for (; i < n; i += stride) v += f(i);
   const double r = block_sum(v);
   if (threadIdx.x == 0) part[blockIdx.x] = r;
 }
@@ -293,24 +301,19 @@ void launch_kinetic(const double *p, const double *conv, const double *mass_r, s
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double pow_bias(double x, double e) { return e == 1.0 ? x : pow(x, e); }
 
-struct ResidualF {
+struct ResidualEval {
   LikeParams lp;
-  double *rho_delta;
-  const double *sum_rho, *nobs, *noise, *window;
-  double *resid;
-  double inv_count;  // 1/N as the reference divides: nmean = sum / N
-  double count;
-  __device__ double operator()(size_t i) const {
-    const double nmean = __ddiv_rn(*sum_rho, count);
-    const double delta = __dsub_rn(__ddiv_rn(rho_delta[i], nmean), 1.0);
-    rho_delta[i] = delta;
-    const double w = window[i], n = nobs[i];
-    double r = 0.0, val = 0.0;
+  double nmean;
+  // returns the -lnL term; writes delta and r
+  __device__ __forceinline__ double operator()(double rho, double n, double sg, double w, double &delta,
+                                               double &r) const {
+    delta = __dsub_rn(__ddiv_rn(rho, nmean), 1.0);
+    r = 0.0;
+    double val = 0.0;
     if (lp.likelihood == 1) {
       const double base = __dadd_rn(1.0, __dmul_rn(lp.biasP, delta));
       const double Lambda = __dmul_rn(__dmul_rn(w, lp.rho_c), pow_bias(base, lp.biasE));
       if (w > 0. && Lambda > 0.0) {
-        const double sg = noise[i];
         r = __ddiv_rn(__dsub_rn(n, Lambda), __dmul_rn(sg, sg));
         const double q = __ddiv_rn(__dsub_rn(Lambda, n), sg);
         val = __dmul_rn(0.5, __dmul_rn(q, q));
@@ -324,16 +327,64 @@ struct ResidualF {
       }
       if (w > 0. && Lambda > 0.0) val = __dsub_rn(Lambda, __dmul_rn(n, log(Lambda)));
     }
-    if (resid) resid[i] = r;
     return val;
   }
 };
 
+// two elements per thread per trip (16-byte loads), two trips in flight
+__global__ void __launch_bounds__(kReduceThreads)
+    overdens_residual_kernel(LikeParams lp, double2 *__restrict__ rho_delta, const double *__restrict__ sum_rho,
+                             const double2 *__restrict__ nobs, const double2 *__restrict__ noise,
+                             const double2 *__restrict__ window, double2 *__restrict__ resid, size_t n2, double count,
+                             double *__restrict__ part) {
+  ResidualEval ev{lp, __ddiv_rn(*sum_rho, count)};
+  double acc = 0.0;
+  const size_t stride = (size_t)gridDim.x * kReduceThreads;
+  size_t i = (size_t)blockIdx.x * kReduceThreads + threadIdx.x;
+  for (; i + stride < n2; i += 2 * stride) {
+    const size_t j = i + stride;
+    const double2 ra = rho_delta[i], rb = rho_delta[j];
+    const double2 na = nobs[i], nb = nobs[j];
+    const double2 sa = noise[i], sb = noise[j];
+    const double2 wa = window[i], wb = window[j];
+    double2 da, db, qa, qb;
+    acc += ev(ra.x, na.x, sa.x, wa.x, da.x, qa.x);
+    acc += ev(ra.y, na.y, sa.y, wa.y, da.y, qa.y);
+    acc += ev(rb.x, nb.x, sb.x, wb.x, db.x, qb.x);
+    acc += ev(rb.y, nb.y, sb.y, wb.y, db.y, qb.y);
+    rho_delta[i] = da;
+    rho_delta[j] = db;
+    if (resid) {
+      resid[i] = qa;
+      resid[j] = qb;
+    }
+  }
+  for (; i < n2; i += stride) {
+    const double2 ra = rho_delta[i], na = nobs[i], sa = noise[i], wa = window[i];
+    double2 da, qa;
+    acc += ev(ra.x, na.x, sa.x, wa.x, da.x, qa.x);
+    acc += ev(ra.y, na.y, sa.y, wa.y, da.y, qa.y);
+    rho_delta[i] = da;
+    if (resid) resid[i] = qa;
+  }
+  const double r = block_sum(acc);
+  if (threadIdx.x == 0) part[blockIdx.x] = r;
+}
+
 void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const double *sum_rho, const double *nobs,
                               const double *noise, const double *window, double *resid, size_t n, double *scratch,
                               double *nll, cudaStream_t st) {
-  ResidualF f{lp, rho_delta, sum_rho, nobs, noise, window, resid, 1.0 / (double)n, (double)n};
-  reduce(f, n, scratch, nll, st, KK_RESIDUAL);
+  ProfScope prof(KK_RESIDUAL, st);
+  const size_t n2 = n / 2;  // n = N^3 with N a power of two >= 8
+  const int blocks = (int)((n2 + kReduceThreads - 1) / kReduceThreads < (size_t)kReduceBlocks
+                               ? (n2 + kReduceThreads - 1) / kReduceThreads
+                               : (size_t)kReduceBlocks);
+  overdens_residual_kernel<<<blocks, kReduceThreads, 0, st>>>(
+      lp, reinterpret_cast<double2 *>(rho_delta), sum_rho, reinterpret_cast<const double2 *>(nobs),
+      reinterpret_cast<const double2 *>(noise), reinterpret_cast<const double2 *>(window),
+      reinterpret_cast<double2 *>(resid), n2, (double)n, scratch);
+  final_sum_kernel<<<1, kReduceThreads, 0, st>>>(scratch, blocks, nll);
+  BGPU_LAUNCHED(2);
 }
 
 // ---------------------------------------------------------------------------

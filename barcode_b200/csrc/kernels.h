@@ -25,7 +25,7 @@ struct LikeParams {
 };
 
 // number of partial sums the two-stage reductions use (fixed: deterministic order)
-constexpr int kReduceBlocks = 1024;
+constexpr int kReduceBlocks = 1184;  // 148 SMs x 8 resident CTAs
 constexpr int kReduceThreads = 256;
 
 // half-grid multiplier normFS / C(k) (0 where C <= 0), from a full real-indexed spectrum

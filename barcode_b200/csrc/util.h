@@ -42,7 +42,8 @@ enum KernelKind : int {
   KK_REDUCE = 6,
   KK_STREAM = 7,
   KK_COLOUR = 8,
-  KK_COUNT = 9
+  KK_FFT_STRIDED_X = 9,
+  KK_COUNT = 10
 };
 
 struct Profiler {

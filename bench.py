@@ -272,7 +272,7 @@ def run_ours(args):
     dom = max(prof.items(), key=lambda kv: kv[1][0])
     nh = args.grid * args.grid * (args.grid // 2 + 1)
     alg_bytes = {  # algorithmic bytes per launch of each kernel class ("Kernels")
-        "fft_strided_pass": 2 * nh * 16,            # read + write the half-complex array once
+        "fft_strided_pass_y": 2 * nh * 16, "fft_strided_pass_x": 2 * nh * 16,            # read + write the half-complex array once
         "fft_r2c_zpass": n * 8 + nh * 16,
         "fft_c2r_zpass": n * 8 + nh * 16,
         "scatter": 4 * n * 8,                       # Psi_x,y,z in, rho out
