@@ -36,7 +36,6 @@ def power_on_grid(k_tab, p_tab, N: int, L: float, chunk: int = 32) -> np.ndarray
     kt = np.asarray(k_tab, dtype=np.float32).astype(np.float64)
     pt = np.asarray(p_tab, dtype=np.float32).astype(np.float64)
     k = calc_ki(N, L)
-    k2yz = (k[:, None] ** 2 + k[None, :] ** 2)
     out = np.empty((N, N, N))
     for i0 in range(0, N, chunk):
         i1 = min(N, i0 + chunk)
@@ -47,7 +46,6 @@ def power_on_grid(k_tab, p_tab, N: int, L: float, chunk: int = 32) -> np.ndarray
         x_lo, x_hi = kt[idx], kt[idx + 1]
         y_lo, y_hi = pt[idx], pt[idx + 1]
         out[i0:i1] = (y_lo + (ktot - x_lo) / (x_hi - x_lo) * (y_hi - y_lo)).reshape(i1 - i0, N, N)
-    del k2yz
     out[0, 0, 0] = 0.0
     return out
 

@@ -109,7 +109,7 @@ def rfft(a):
 
 def irfft(c, N):
     """fftC2R: inverse including 1/N (fftwrapper.cc:26-53)."""
-    return np.fft.irfftn(c, s=(N, N, N))
+    return np.fft.irfftn(c, s=(N, N, N), axes=(0, 1, 2))
 
 
 def power_on_grid(k_tab, p_tab, N: int, L: float) -> np.ndarray:
@@ -188,9 +188,9 @@ def pacman(x, L):
 
 
 def E_hubble(a, OM, OL):
-    """cosmo.cc E_Hubble_a: sqrt(OM/a^3 + OL + OC/a^2)."""
-    OC = 1.0 - OM - OL
-    return np.sqrt(OM / a / a / a + OL + OC / a / a)
+    """E_Hubble_a, cosmo.cc:26-31: sqrt(OM/(a*a*a) + OK/(a*a) + OL)."""
+    OK = 1.0 - OM - OL
+    return np.sqrt(OM / (a * a * a) + OK / (a * a) + OL)
 
 
 def fgrow(a, OM, OL):
