@@ -130,6 +130,15 @@ def reference_problem(R, grid, L, seed):
     return s
 
 
+def use_all_host_threads(ref):
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    ref.lib().ref_set_num_threads(max(1, n))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,6 +150,7 @@ def run_reference(args):
         return 0
     rc = ref.Config(N1=cfg["N1"], L1=cfg["L1"], masskernel=1, likelihood=1, rsd_model=True, sfmodel=2, calc_h=0,
                     mass_type=1)
+    use_all_host_threads(ref)
     R = ref.Reference(rc)
     s = reference_problem(R, args.grid, cfg["L1"], 1)
     for _ in range(max(1, args.warmup)):
@@ -175,6 +185,7 @@ def cpu_baseline(args, cfg):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     rc = ref.Config(N1=cfg["N1"], L1=cfg["L1"], masskernel=1, likelihood=1, rsd_model=True, sfmodel=2, calc_h=0,
                     mass_type=1)
+    use_all_host_threads(ref)
     R = ref.Reference(rc)
     s = reference_problem(R, cfg["N1"], cfg["L1"], 1)
     t0 = time.perf_counter()
@@ -190,24 +201,21 @@ def cpu_baseline(args, cfg):
 
 def run_ours(args):
     import torch
-    import torch.distributed as dist
     from barcode_b200 import chain as bc
-    from barcode_b200 import inputs
+    from barcode_b200 import inputs, multi
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    info = multi.rank_info()
+    world, rank, local_rank = info.world, info.rank, info.local_rank
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    multi.init("nccl", info, torch.device("cuda", local_rank))
 
     cfg, name = workload(args.grid, args.calc_h)
     n = args.grid ** 3
     launches0 = bc.kernel_launches()
     ch = bc.Chain(bc.Params(device=local_rank, **cfg))
-    prob = inputs.synthetic_problem(ch, seed=1 + 17 * rank)
+    prob = inputs.synthetic_problem(ch, seed=multi.chain_seed(1, rank))
     stream = torch.cuda.current_stream()
     ch.set_stream(stream.cuda_stream)
     d_s = torch.from_numpy(np.ascontiguousarray(prob["signal"]).reshape(-1)).cuda()
@@ -215,8 +223,7 @@ def run_ours(args):
     d_p = torch.from_numpy(np.ascontiguousarray(prob["momenta"]).reshape(-1)).cuda()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        multi.barrier(info)
         torch.cuda.synchronize()
 
     counted = {}
@@ -233,10 +240,7 @@ def run_ours(args):
         e1.record(stream)
         counted["launches"] = bc.kernel_launches() - l_before
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return multi.max_over_ranks(e0.elapsed_time(e1), info, "cuda")
 
     def grad_step():
         ch.gradient_psi_dev(d_s.data_ptr(), d_g.data_ptr())
@@ -323,11 +327,9 @@ def run_ours(args):
     for _ in range(args.steps):
         e2e_step()
     torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * args.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 8,
-           "d2h_bytes_per_step": n * 8, "ms_per_step": 1e3 * float(dt.item()) / args.steps,
+    dt = multi.max_over_ranks(time.perf_counter() - t0, info, "cuda")
+    e2e = {"value": world * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 8,
+           "d2h_bytes_per_step": n * 8, "ms_per_step": 1e3 * dt / args.steps,
            "api": "bgpu_gradient_psi(host signal -> host gradpsi), pinned host buffers"}
 
     base = None
@@ -353,8 +355,7 @@ def run_ours(args):
             },
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    multi.finalize()
     return 0
 
 
