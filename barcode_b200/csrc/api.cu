@@ -44,6 +44,7 @@ struct bgpu_handle {
   int N = 0;
   size_t n = 0;    // N^3
   size_t nh = 0;   // N^2 (N/2+1)
+  size_t nhp = 0;  // N^2 (N/2+2): padded row pitch of the real half-grid multipliers
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   Fft3d fft;
@@ -406,6 +407,7 @@ int bgpu_create(const bgpu_params *p, bgpu_handle **out) {
   h->N = p->N1;
   h->n = (size_t)h->N * h->N * h->N;
   h->nh = (size_t)h->N * h->N * (h->N / 2 + 1);
+  h->nhp = (size_t)h->N * h->N * (h->N / 2 + 2);
   BGPU_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   h->fft.init(h->N, h->stream);
@@ -435,8 +437,8 @@ int bgpu_create(const bgpu_params *p, bgpu_handle **out) {
   h->like.exact_sign = 0;
 
   dalloc(h->power, h->n); dalloc(h->nobs, h->n); dalloc(h->noise, h->n); dalloc(h->window, h->n);
-  dalloc(h->inv_power, h->nh);
-  dalloc(h->mass_f, h->n); dalloc(h->mass_r, h->n); dalloc(h->inv_mass, h->nh);
+  dalloc(h->inv_power, h->nhp);
+  dalloc(h->mass_f, h->n); dalloc(h->mass_r, h->n); dalloc(h->inv_mass, h->nhp);
   dalloc(h->sig, h->n); dalloc(h->mom, h->n); dalloc(h->grad, h->n);
   for (int c = 0; c < 3; ++c) dalloc(h->psi[c], h->n);
   dalloc(h->delta, h->n); dalloc(h->resid, h->n); dalloc(h->tmp, h->n);

@@ -177,15 +177,7 @@ __device__ __forceinline__ double2 kop_load(const KOp &op, double2 v, size_t off
   switch (op.kind) {
     case K_NONE:
       return v;
-    case K_MULREAL: {
-      const double f = __ldg(op.real0 + off);
-      return make_double2(v.x * f, v.y * f);
-    }
-    case K_FINAL: {
-      const double f = __ldg(op.real0 + off);
-      const double2 h = __ldg(op.cplx0 + off);
-      return make_double2(v.x * f + op.a * h.x, v.y * f + op.a * h.y);
-    }
+    // K_MULREAL / K_FINAL read operand arrays and are handled by the pass kernels themselves
     case K_DISP: {
       if (ix == N / 2 || iy == N / 2 || iz == N / 2) return make_double2(0.0, 0.0);
       const double kx = kval(ix, N, op.kfac), ky = kval(iy, N, op.kfac), kz = kval(iz, N, op.kfac);
@@ -227,11 +219,6 @@ __device__ __forceinline__ void kop_store(const KOp &op, double2 *__restrict__ o
         r.y += o.y;
       }
       out[off] = r;
-      return;
-    }
-    case K_MULREAL: {
-      const double f = __ldg(op.real0 + off);
-      out[off] = make_double2(v.x * f, v.y * f);
       return;
     }
     default:
@@ -278,8 +265,11 @@ __global__ void __launch_bounds__(T *N / 8)
   for (int m = 0; m < 8; ++m) v[m] = in[base + (size_t)(t + m * (N / 8)) * stride];
   if (lop.kind == K_MULREAL || lop.kind == K_FINAL) {
     double f[8];
+    // the real multiplier array has row pitch N/2+2 (16-byte rows, see RealPitch)
+    const size_t rstride = (AXIS == 0) ? (size_t)N * (NZH + 1) : (size_t)(NZH + 1);
+    const size_t rbase = ((AXIS == 0) ? (size_t)other * (NZH + 1) : (size_t)other * N * (NZH + 1)) + iz;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) f[m] = __ldg(lop.real0 + base + (size_t)(t + m * (N / 8)) * stride);
+    for (int m = 0; m < 8; ++m) f[m] = __ldg(lop.real0 + rbase + (size_t)(t + m * (N / 8)) * rstride);
     if (lop.kind == K_FINAL) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -408,8 +398,10 @@ __global__ void __launch_bounds__(T *N / 8, (T * N / 8 <= 256) ? 3 : 1)
 
     if (lop.kind == K_MULREAL || lop.kind == K_FINAL) {
       double f[8];
+      const size_t rstride = (AXIS == 0) ? (size_t)N * (NZH + 1) : (size_t)(NZH + 1);
+      const size_t rbase = ((AXIS == 0) ? (size_t)other * (NZH + 1) : (size_t)other * N * (NZH + 1)) + iz;
 #pragma unroll
-      for (int m = 0; m < 8; ++m) f[m] = __ldg(lop.real0 + base + (size_t)(t + m * (N / 8)) * stride);
+      for (int m = 0; m < 8; ++m) f[m] = __ldg(lop.real0 + rbase + (size_t)(t + m * (N / 8)) * rstride);
       if (lop.kind == K_FINAL) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {

@@ -1,7 +1,10 @@
 // barcode_b200/csrc/fft3d.h -- host interface of the hand-written 3-D real FFT
 // (kernels in fft.cuh, launch sequences in fft_plan.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <vector>
 
 #include "fft_ops.h"
 
@@ -13,6 +16,18 @@ struct Fft3d {
   double2 *twM = nullptr;  // exp(-2 pi i k / (N/2))
   cudaStream_t stream = nullptr;
   int strided_blocks = 0;  // persistent grid of the pipelined strided pass: SMs x resident CTAs
+  int sm_count = 0;
+  bool use_tma = true;     // TMA-staged strided pass (fft_tma.cuh); BGPU_FFT_TMA=0 selects the cp.async one
+
+  // tensor maps of the half-grid arrays the TMA pass has touched (keyed by base pointer)
+  struct MapEntry {
+    const void *base;
+    int axis;
+    bool cplx;
+    CUtensorMap map;
+  };
+  mutable std::vector<MapEntry> maps_;
+  const CUtensorMap &tensor_map(const void *base, int axis, bool cplx) const;
 
   void init(int n, cudaStream_t st);
   void destroy();

@@ -9,7 +9,11 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "fft.cuh"
+#include "fft_tma.cuh"
 #include "util.h"
 
 namespace bgpu {
@@ -79,6 +83,133 @@ template <> struct Shape<256>  { static constexpr int T = 8,  TR = 8;  };
 template <> struct Shape<512>  { static constexpr int T = 8,  TR = 8;  };
 template <> struct Shape<1024> { static constexpr int T = 4,  TR = 4;  };
 
+// ---------------------------------------------------------------------------
+// TMA-staged strided pass (fft_tma.cuh): tensor maps and launch
+// ---------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    BGPU_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("bgpu: cuTensorMapEncodeTiled is not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// tensor map over a half-grid array seen as doubles: dims (fastest first) [row doubles][y][x];
+// the box is 8 pencils wide (cplx: 16 doubles = 128 B, real: 8 doubles = 64 B) and `rows` long
+// along the transformed axis.
+static CUtensorMap make_half_grid_map(const void *base, int N, int axis, bool cplx) {
+  CUtensorMap m;
+  const cuuint64_t nzh = (cuuint64_t)N / 2 + 1;
+  const cuuint64_t row_doubles = cplx ? 2 * nzh : nzh;                 // valid extent
+  const cuuint64_t pitch = cplx ? nzh * 16 : (nzh + 1) * 8;            // bytes, multiple of 16
+  const cuuint64_t dims[3] = {row_doubles, (cuuint64_t)N, (cuuint64_t)N};
+  const cuuint64_t strides[2] = {pitch, pitch * (cuuint64_t)N};
+  const cuuint32_t rows = N > 256 ? 256 : N;
+  const cuuint32_t box[3] = {cplx ? 16u : 8u, axis == 1 ? rows : 1u, axis == 0 ? rows : 1u};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 cplx ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("bgpu: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return m;
+}
+
+const CUtensorMap &Fft3d::tensor_map(const void *base, int axis, bool cplx) const {
+  for (auto &e : maps_)
+    if (e.base == base && e.axis == axis && e.cplx == cplx) return e.map;
+  if (maps_.size() >= 64) maps_.clear();
+  maps_.push_back(MapEntry{base, axis, cplx, make_half_grid_map(base, N, axis, cplx)});
+  return maps_.back().map;
+}
+
+template <int N> struct TmaShape;
+template <> struct TmaShape<128> { static constexpr int E = 8,  MINB = 4; };
+template <> struct TmaShape<256> { static constexpr int E = 8,  MINB = 2; };
+template <> struct TmaShape<512> { static constexpr int E = 16, MINB = 1; };
+
+// ring depth: as many stages (at most 3) as fit beside the co-resident CTAs
+template <int N, int AUX>
+struct TmaStages {
+  static constexpr int per_cta = (227 * 1024 - 2048) / (AUX == 0 ? TmaShape<N>::MINB : 1);
+  static constexpr int fit = per_cta / TmaTile<N, AUX>::stage_bytes;
+  static constexpr int value = fit >= 3 ? 3 : fit;
+};
+
+template <int N> constexpr bool tma_has_size() { return N == 128 || N == 256 || N == 512; }
+
+template <int N, int AUX>
+constexpr bool tma_supported() {
+  if constexpr (!tma_has_size<N>()) return false;
+  else return TmaStages<N, AUX>::value >= 2;
+}
+
+template <int N, int DIR, int AXIS, int AUX>
+static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp lop, KOp sop, cudaStream_t st) {
+  constexpr int E = TmaShape<N>::E;
+  constexpr int MINB = AUX == 0 ? TmaShape<N>::MINB : 1;
+  constexpr int NSTAGE = TmaStages<N, AUX>::value;
+  constexpr int threads = 8 * (N / E);
+  constexpr int smem = NSTAGE * TmaTile<N, AUX>::stage_bytes + 1024 + 64;
+  constexpr int tiles = N * ((N / 2 + 1 + 7) / 8);
+  auto kern = fft_strided_tma<N, E, NSTAGE, DIR, AXIS, AUX, MINB>;
+  static int blocks_per_sm = 0;  // per instantiation; attribute set once per process and device 0..n share the value
+  if (!blocks_per_sm) {
+    BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    blocks_per_sm = occ > 0 ? occ : 1;
+  }
+  TmaMaps maps;
+  maps.in = f.tensor_map(in, AXIS, true);
+  maps.out = f.tensor_map(out, AXIS, true);
+  maps.auxr = AUX >= 1 ? f.tensor_map(lop.real0, AXIS, false) : maps.in;
+  maps.auxc = AUX >= 2 ? f.tensor_map(lop.cplx0, AXIS, true) : maps.in;
+  int blocks = f.sm_count * blocks_per_sm;
+  if (blocks > tiles) blocks = tiles;
+  ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
+  kern<<<blocks, threads, smem, st>>>(maps, f.twN, lop, sop);
+  BGPU_LAUNCHED(1);
+}
+
+// returns true if the TMA kernel took the launch
+template <int N, int DIR, int AXIS>
+static bool try_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp lop, KOp sop, cudaStream_t st) {
+  if (!f.use_tma) return false;
+  if constexpr (!tma_has_size<N>()) {
+    return false;
+  } else {
+    const bool sop_ok = sop.kind == K_NONE || sop.kind == K_INVLAP_SET || sop.kind == K_INVLAP_ADD;
+    if (!sop_ok) return false;
+    if (lop.kind == K_MULREAL || lop.kind == K_FINAL) {
+      if constexpr (DIR == +1 && AXIS == 0) {
+        if (lop.kind == K_MULREAL) {
+          if constexpr (tma_supported<N, 1>()) {
+            launch_strided_tma<N, DIR, AXIS, 1>(f, in, out, lop, sop, st);
+            return true;
+          }
+        } else {
+          if constexpr (tma_supported<N, 2>()) {
+            launch_strided_tma<N, DIR, AXIS, 2>(f, in, out, lop, sop, st);
+            return true;
+          }
+        }
+      }
+      return false;
+    }
+    launch_strided_tma<N, DIR, AXIS, 0>(f, in, out, lop, sop, st);
+    return true;
+  }
+}
+
 template <int N, int DIR, int AXIS>
 static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, const double2 *tw, KOp lop, KOp sop,
                            cudaStream_t st) {
@@ -86,6 +217,7 @@ static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, cons
   constexpr int threads = T * N / 8;
   constexpr int tiles = N * ((N / 2) / T) + N / T;
   constexpr size_t smem = (size_t)N * T * sizeof(double2);
+  if (try_strided_tma<N, DIR, AXIS>(f, in, out, lop, sop, st)) return;
   ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
   if constexpr (N >= 128) {
     // persistent + cp.async prefetch: one wave of CTAs walks all tiles
@@ -202,6 +334,14 @@ void Fft3d::init(int n, cudaStream_t st) {
   if (!supported(n)) throw std::runtime_error("bgpu: FFT size must be a power of two in [8, 1024], got " + std::to_string(n));
   N = n;
   stream = st;
+  {
+    int dev = 0;
+    BGPU_CUDA(cudaGetDevice(&dev));
+    BGPU_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    const char *e = std::getenv("BGPU_FFT_TMA");
+    use_tma = !(e && e[0] == '0');
+    maps_.clear();
+  }
   auto a = make_twiddles(n), b = make_twiddles(n / 2);
   BGPU_CUDA(cudaMalloc(&twN, sizeof(double2) * n));
   BGPU_CUDA(cudaMalloc(&twM, sizeof(double2) * (n / 2)));

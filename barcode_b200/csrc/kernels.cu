@@ -498,19 +498,25 @@ void launch_findif_product(const double *delta, const double *resid, double *out
 // ---------------------------------------------------------------------------
 __global__ void inverse_spectrum_kernel(const double *__restrict__ full, double *__restrict__ half, int N,
                                         double normFS) {
-  const int nzh = N / 2 + 1;
-  const size_t n = (size_t)N * N * nzh;
+  // rows of the half-grid multiplier are padded to N/2+2 doubles so that the row pitch is a
+  // multiple of 16 bytes (a TMA tensor-map requirement, fft_tma.cuh); the pad element is 0
+  const int nzp = N / 2 + 2;
+  const size_t n = (size_t)N * N * nzp;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  const int k = (int)(idx % nzh);
-  const size_t ij = idx / nzh;
+  const int k = (int)(idx % nzp);
+  const size_t ij = idx / nzp;
+  if (k > N / 2) {
+    half[idx] = 0.;
+    return;
+  }
   const double c = full[ij * N + k];  // HMC_help.cc:44: corrFunc[k + N3*(j + N2*i)]
   half[idx] = c > 0.0 ? normFS / c : 0.;
 }
 
 void launch_inverse_spectrum(const double *full, double *half, int N, double normFS, cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);
-  const size_t n = (size_t)N * N * (N / 2 + 1);
+  const size_t n = (size_t)N * N * (N / 2 + 2);
   inverse_spectrum_kernel<<<blocks_for(n, 256), 256, 0, st>>>(full, half, N, normFS);
   BGPU_LAUNCHED(1);
 }

@@ -43,7 +43,7 @@ def loaded_chain(c, **over):
 
 
 # ---------------------------------------------------------------- FFT
-@pytest.mark.parametrize("N", [8, 16, 32, 64, 128])
+@pytest.mark.parametrize("N", [8, 16, 32, 64, 128, 256])
 def test_fft_matches_numpy(N):
     from barcode_b200.chain import Chain, Params
     rng = np.random.default_rng(N)
@@ -271,3 +271,60 @@ def test_large_grid_properties(N):
         assert errs[1] < errs[0]
         sb, pb = ch.leapfrog(sf, -pf, 2, 1e-3)
         assert rel_l2(sb, s) < 1e-9 and rel_l2(pb, -p0) < 1e-9
+
+
+# ---------------------------------------------------------------- the TMA-staged FFT pass (N >= 128)
+def _problem_128(seed=11):
+    from barcode_b200 import inputs
+    N = 128
+    L = inputs.box_length(N)
+    rng = np.random.default_rng(seed)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L)
+    n = N ** 3
+    nobs = np.maximum(0.0, 1.0 + 0.3 * rng.standard_normal(n))
+    noise = np.ones(n)
+    window = np.ones(n)
+    s = 0.4 * rng.standard_normal((N, N, N))
+    return N, L, P, nobs, noise, window, s
+
+
+@pytest.mark.parametrize("calc_h,masskernel,rsd", [(0, 1, True), (4, 1, False), (0, 2, False)])
+def test_gradient_128_matches_oracle(calc_h, masskernel, rsd):
+    """128^3 runs through the TMA-staged strided pass (fft_tma.cuh); the oracle is the numpy restatement."""
+    from barcode_b200.chain import Chain, Params
+    from oracle import barcode_oracle as bo
+    N, L, P, nobs, noise, window, s = _problem_128()
+    kw = dict(N1=N, L1=L, masskernel=masskernel, likelihood=1, rsd_model=rsd, calc_h=calc_h, mass_type=1)
+    with Chain(Params(**kw)) as ch:
+        ch.set_static(Power=P, nobs=nobs, noise=noise, window=window)
+        g = ch.gradient_psi(s)
+        pp, pl, dX = ch.psi(s)
+    p = bo.Params(**kw)
+    go = bo.gradient_psi(p, s, P, nobs, noise, window)
+    assert rel_l2(g, go) < TOL
+    po, lo, dXo = bo.psi(p, s, P, nobs, noise, window)
+    assert abs(pp - po) <= TOL * abs(po) and abs(pl - lo) <= TOL * abs(lo)
+    assert rel_l2(dX, dXo) < TOL
+
+
+@pytest.mark.parametrize("N", [128, 256])
+def test_tma_pass_matches_cp_async_pass(N, monkeypatch):
+    """Two independent implementations of the strided pass (TMA ring vs cp.async) agree to rounding."""
+    from barcode_b200.chain import Chain, Params
+    from barcode_b200 import inputs
+    L = inputs.box_length(N)
+    rng = np.random.default_rng(5)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L)
+    n = N ** 3
+    s = 0.3 * rng.standard_normal(n)
+    nobs = 1.0 + 0.1 * rng.standard_normal(n)
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("BGPU_FFT_TMA", tma)
+        with Chain(Params(N1=N, L1=L, masskernel=1, likelihood=1, rsd_model=True, calc_h=0)) as ch:
+            ch.set_static(Power=P, nobs=nobs, noise=np.ones(n), window=np.ones(n))
+            ch.hamiltonian_mass()
+            out[tma] = (ch.gradient_psi(s), ch.convolve_inv_corr(s, P), ch.kinetic_term(s))
+    assert rel_l2(out["1"][0], out["0"][0]) < 1e-13
+    assert rel_l2(out["1"][1], out["0"][1]) < 1e-14
+    assert abs(out["1"][2] - out["0"][2]) <= 1e-13 * abs(out["0"][2])
