@@ -86,11 +86,8 @@ template <> struct Shape<1024> { static constexpr int T = 4,  TR = 4;  };
 // ---------------------------------------------------------------------------
 // TMA-staged strided pass (fft_tma.cuh): tensor maps and launch
 // ---------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_tiled_fn() {
+EncodeTiledFn encode_tiled_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -229,10 +226,73 @@ static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, cons
   BGPU_LAUNCHED(1);
 }
 
+// ---------------------------------------------------------------------------
+// bulk-copy-staged z pass (fft_tma.cuh)
+// ---------------------------------------------------------------------------
+template <int N> struct ZShape;
+template <> struct ZShape<128>  { static constexpr int E = 8,  TR = 32, MINB = 2; };
+template <> struct ZShape<256>  { static constexpr int E = 8,  TR = 16, MINB = 2; };
+template <> struct ZShape<512>  { static constexpr int E = 8,  TR = 8,  MINB = 2; };
+template <> struct ZShape<1024> { static constexpr int E = 16, TR = 4,  MINB = 1; };
+
+template <int N> constexpr bool ztma_has_size() { return N == 128 || N == 256 || N == 512 || N == 1024; }
+
+template <int N, bool C2R, bool AUX>
+static void launch_zpass_tma(const Fft3d &f, const void *in, void *out, ROp op, cudaStream_t st) {
+  constexpr int E = ZShape<N>::E, TR = ZShape<N>::TR;
+  constexpr int MINB = AUX ? 1 : ZShape<N>::MINB;
+  constexpr int NSTAGE = 3;
+  constexpr int threads = TR * (N / 2 / E);
+  using Z = ZTile<N, TR, NSTAGE, AUX>;
+  constexpr int smem = Z::smem_bytes;
+  static_assert(smem <= 227 * 1024, "z-pass ring does not fit");
+  auto kern = fft_zpass_tma<N, E, TR, NSTAGE, C2R, AUX, MINB>;
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    blocks_per_sm = occ > 0 ? occ : 1;
+  }
+  const int ntiles = (N * N) / TR;
+  int blocks = f.sm_count * blocks_per_sm;
+  if (blocks > ntiles) blocks = ntiles;
+  ProfScope prof(C2R ? KK_FFT_C2R_Z : KK_FFT_R2C_Z, st);
+  kern<<<blocks, threads, smem, st>>>(in, out, f.twN, f.twM, op, ntiles);
+  BGPU_LAUNCHED(1);
+}
+
+template <int N>
+static bool try_r2c_zpass_tma(const Fft3d &f, const double *in, double2 *out, ROp lop) {
+  if constexpr (!ztma_has_size<N>()) {
+    return false;
+  } else {
+    if (!f.use_tma || !(lop.kind == R_LOAD || lop.kind == R_LOAD_SCALE)) return false;
+    launch_zpass_tma<N, false, false>(f, in, out, lop, f.stream);
+    return true;
+  }
+}
+
+template <int N>
+static bool try_c2r_zpass_tma(const Fft3d &f, const double2 *in, double *out, ROp sop) {
+  if constexpr (!ztma_has_size<N>()) {
+    return false;
+  } else {
+    if (!f.use_tma) return false;
+    if (sop.kind == R_SCALE_MUL)
+      launch_zpass_tma<N, true, true>(f, in, out, sop, f.stream);
+    else if (sop.kind == R_SCALE || sop.kind == R_AXPY)
+      launch_zpass_tma<N, true, false>(f, in, out, sop, f.stream);
+    else
+      return false;
+    return true;
+  }
+}
+
 template <int N>
 static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xout, ROp lop, KOp sop) {
   const size_t nrows = (size_t)N * N;
-  {
+  if (!try_r2c_zpass_tma<N>(f, in, out, lop)) {
   ProfScope prof(KK_FFT_R2C_Z, f.stream);
   if constexpr (N == 8) {
     tiny_r2c_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(in, out, f.twN, lop, nrows);
@@ -253,6 +313,7 @@ static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *o
   const size_t nrows = (size_t)N * N;
   launch_strided<N, +1, 0>(f, in, work, f.twN, lop, KOp{}, f.stream);
   launch_strided<N, +1, 1>(f, work, work, f.twN, KOp{}, KOp{}, f.stream);
+  if (try_c2r_zpass_tma<N>(f, work, out, sop)) return;
   ProfScope prof(KK_FFT_C2R_Z, f.stream);
   if constexpr (N == 8) {
     tiny_c2r_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(work, out, f.twN, sop, nrows);

@@ -157,8 +157,19 @@ __device__ __forceinline__ void wp_load_twiddles(double2 (*twr)[E], int t, const
   }
 }
 
-template <int N, int E, int S, int DIR, int STG>
-__device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, int p, uint32_t tile, const double2 (*twr)[E]) {
+// where a pencil's elements live in shared memory
+struct ColAccess {  // column p of a 128-byte-swizzled tile (strided pass)
+  uint32_t tile;
+  int p;
+  __device__ __forceinline__ uint32_t at(int e) const { return tile_addr(tile, e, p); }
+};
+struct RowAccess {  // a contiguous row of double2 (z pass)
+  uint32_t row;
+  __device__ __forceinline__ uint32_t at(int e) const { return row + (uint32_t)e * 16u; }
+};
+
+template <int N, int E, int S, int DIR, int STG, class Acc>
+__device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc, const double2 (*twr)[E]) {
   constexpr int LP = N / E;
   constexpr int R = StageRadix<N, S>::value;
   constexpr int NB = E / R;
@@ -175,7 +186,7 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, int p, uint32_
       bf2<DIR>(v[j], v[j + NB]);
   }
   if constexpr (!last) {
-    __syncwarp();  // every lane has lifted its inputs out of the column
+    __syncwarp();  // every lane has lifted its inputs out of the pencil's storage
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const int b = t + j * LP;
@@ -187,7 +198,7 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, int p, uint32_
         if (k > 0) x = cmul(x, twr[STG][j + k * NB]);
         int e = q + R * base + k * S;
         if constexpr (S == 1) e ^= (e >> 3) & 7;  // conflict-free stride-8 scatter
-        sts128(tile_addr(tile, e, p), x);
+        sts128(acc.at(e), x);
       }
     }
     __syncwarp();
@@ -195,9 +206,9 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, int p, uint32_
     for (int m = 0; m < E; ++m) {
       int e = t + m * LP;
       if constexpr (S == 1) e ^= (e >> 3) & 7;
-      v[m] = lds128(tile_addr(tile, e, p));
+      v[m] = lds128(acc.at(e));
     }
-    wp_stages<N, E, S * R, DIR, STG + 1>(v, t, p, tile, twr);
+    wp_stages<N, E, S * R, DIR, STG + 1, Acc>(v, t, acc, twr);
   }
 }
 
@@ -358,7 +369,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
       for (int m = 0; m < E; ++m) v[m] = rc.apply(v[m], t + m * LP);
     }
 
-    wp_stages<N, E, 1, DIR, 0>(v, t, p, tbase, twr);
+    wp_stages<N, E, 1, DIR, 0>(v, t, ColAccess{tbase, p}, twr);
 
     if (sop.kind == K_INVLAP_SET || sop.kind == K_INVLAP_ADD) {
       RotCtx<N, AXIS> rc;
@@ -390,6 +401,206 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
     }
   }
   if (tid == 0) bulk_wait<0>();
+}
+
+
+// ---------------------------------------------------------------------------
+// z pass (contiguous axis) with bulk-copy staging.
+//
+// Rows are contiguous in global memory on both sides (N doubles / N/2+1 double2), so a tile of
+// TR rows moves with one cp.async.bulk (UBLKCP) per row -- issued by the lanes of warp 0, each
+// lane owning "its" row of every stage, store and reload included (bulk groups are per thread).
+// A row is transformed in place by the N/(2E) lanes of one warp as an N/2-point complex FFT of
+// z[j] = x[2j] + i x[2j+1] plus the Hermitian split / merge; the row pitch in shared memory is
+// N*8 + 32 bytes so the N/2+1 outputs fit over the N/2 inputs.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f64_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;\n" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+
+// exp(-2 pi i m / 16), m = 0..7: with LP = M/E lanes per row and E = 8, w_N^(t + m LP) = w_N^t * this
+__device__ __forceinline__ double2 root16(int m) {
+  constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+  switch (m & 7) {
+    case 0: return make_double2(1.0, 0.0);
+    case 1: return make_double2(c1, -s1);
+    case 2: return make_double2(h, -h);
+    case 3: return make_double2(s1, -c1);
+    case 4: return make_double2(0.0, -1.0);
+    case 5: return make_double2(-s1, -c1);
+    case 6: return make_double2(-h, -h);
+    default: return make_double2(-c1, -s1);
+  }
+}
+
+template <int N, int TR, int NSTAGE, bool AUX>
+struct ZTile {
+  static constexpr int pitch = N * 8 + 32;
+  static constexpr int main_bytes = TR * pitch;
+  static constexpr int aux_bytes = AUX ? TR * N * 8 : 0;
+  static constexpr int stage_bytes = main_bytes + aux_bytes;
+  static constexpr int smem_bytes = NSTAGE * stage_bytes + 1024 + 64;
+};
+
+// C2R = false: real rows -> half-complex rows (forward);  C2R = true: half-complex -> real (inverse).
+// AUX (C2R only): multiply the real result by a second real array (R_SCALE_MUL).
+template <int N, int E, int TR, int NSTAGE, bool C2R, bool AUX, int MINB>
+__global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
+    fft_zpass_tma(const void *__restrict__ in, void *__restrict__ out, const double2 *__restrict__ twN,
+                  const double2 *__restrict__ twM, ROp op, int ntiles) {
+  constexpr int M = N / 2;
+  constexpr int LP = M / E;
+  constexpr int DIR = C2R ? +1 : -1;
+  constexpr int NSTG = StageCount<M>::value;
+  using Z = ZTile<N, TR, NSTAGE, AUX>;
+  constexpr uint32_t in_row_bytes = C2R ? (M + 1) * 16 : N * 8;
+  constexpr uint32_t out_row_bytes = C2R ? N * 8 : (M + 1) * 16;
+  static_assert(LP >= 8 && LP <= 32 && TR <= 32, "row must live inside one warp; warp 0 issues one copy per row");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t *smem_al = smem_raw + (smem0 - smem_u32(smem_raw));
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_al + NSTAGE * Z::stage_bytes);
+
+  const int tid = threadIdx.x;
+  const int row = tid / LP;
+  const int t = tid % LP;
+  const int my_count = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const char *gin = static_cast<const char *>(in);
+  char *gout = static_cast<char *>(out);
+
+  // warp 0, lane r: load row r of my i-th tile
+  auto issue_load = [&](int i) {
+    const int s = i % NSTAGE;
+    const size_t grow = (size_t)(blockIdx.x + (size_t)i * gridDim.x) * TR + tid;
+    if (tid == 0) mbar_expect_tx(&full[s], TR * (in_row_bytes + (AUX ? N * 8 : 0)));
+    __syncwarp();
+    if (tid < TR) {
+      bulk_load_1d(smem_al + s * Z::stage_bytes + tid * Z::pitch, gin + grow * in_row_bytes, in_row_bytes, &full[s]);
+      if constexpr (AUX)
+        bulk_load_1d(smem_al + s * Z::stage_bytes + Z::main_bytes + tid * (N * 8),
+                     reinterpret_cast<const char *>(op.aux) + grow * (N * 8), N * 8, &full[s]);
+    }
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid < 32) {
+#pragma unroll
+    for (int i = 0; i < NSTAGE - 1; ++i)
+      if (i < my_count) issue_load(i);
+  }
+
+  double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
+  wp_load_twiddles<M, E, 1, DIR, 0>(twr, t, twM);
+  // split / merge twiddle w_N^k, k = t + m LP: for E == 8, LP = N/16 and w_N^(m LP) is a 16th root of unity
+  const double2 wt = __ldg(twN + t);
+  auto split_twiddle = [&](int m) -> double2 {
+    if constexpr (E == 8) return m == 0 ? wt : cmul(wt, root16(m));
+    else return __ldg(twN + t + m * LP);
+  };
+
+  for (int i = 0; i < my_count; ++i) {
+    const int s = i % NSTAGE;
+    const uint32_t rbase = smem0 + s * Z::stage_bytes + row * Z::pitch;
+    const RowAccess acc{rbase};
+    mbar_wait(&full[s], (i / NSTAGE) & 1);
+
+    double2 v[E];
+    if constexpr (!C2R) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[m] = lds128(acc.at(t + m * LP));
+      if (op.kind == R_LOAD_SCALE) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = make_double2(v[m].x * op.a, v[m].y * op.a);
+      }
+      wp_stages<M, E, 1, DIR, 0>(v, t, acc, twr);
+      // Hermitian split: X[k] = E + w^k O, E = (Z[k] + conj Z[M-k])/2, O = (Z[k] - conj Z[M-k])/(2i)
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < E; ++m) sts128(acc.at(t + m * LP), v[m]);
+      __syncwarp();
+      double2 zm[E];
+#pragma unroll
+      for (int m = 0; m < E; ++m) zm[m] = lds128(acc.at((M - (t + m * LP)) & (M - 1)));
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        const int k = t + m * LP;
+        const double2 zk = v[m];
+        const double2 e = make_double2(0.5 * (zk.x + zm[m].x), 0.5 * (zk.y - zm[m].y));
+        const double2 o = make_double2(0.5 * (zk.y + zm[m].y), -0.5 * (zk.x - zm[m].x));
+        const double2 w = split_twiddle(m);
+        sts128(acc.at(k), cadd(e, cmul(w, o)));
+        if (k == 0) sts128(acc.at(M), make_double2(e.x - o.x, 0.0));  // w_N^M = -1; E[0], O[0] real
+      }
+    } else {
+      // Hermitian merge: Z[k] = E' + i O', E' = X[k] + conj X[M-k], O' = (X[k] - conj X[M-k]) conj(w^k)
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        const int k = t + m * LP;
+        double2 xk = lds128(acc.at(k));
+        double2 xm = lds128(acc.at(M - k));
+        if (k == 0) {  // FFTW's c2r ignores the imaginary parts of the self-conjugate bins
+          xk.y = 0.0;
+          xm.y = 0.0;
+        }
+        const double2 e = make_double2(xk.x + xm.x, xk.y - xm.y);
+        const double2 d = make_double2(xk.x - xm.x, xk.y + xm.y);
+        const double2 o = cmul(d, cconj(split_twiddle(m)));
+        v[m] = make_double2(e.x - o.y, e.y + o.x);
+      }
+      wp_stages<M, E, 1, DIR, 0>(v, t, acc, twr);
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        const int j = t + m * LP;
+        double2 x = make_double2(op.a * v[m].x, op.a * v[m].y);
+        if constexpr (AUX) {
+          const double2 y = lds128(smem0 + s * Z::stage_bytes + Z::main_bytes + row * (N * 8) + j * 16);
+          x.x *= y.x;
+          x.y *= y.y;
+        }
+        sts128(acc.at(j), x);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid < 32) {
+      if (tid < TR) {
+        const size_t grow = (size_t)(blockIdx.x + (size_t)i * gridDim.x) * TR + tid;
+        const void *src = smem_al + s * Z::stage_bytes + tid * Z::pitch;
+        if (C2R && op.kind == R_AXPY)
+          bulk_reduce_add_f64_1d(gout + grow * out_row_bytes, src, out_row_bytes);
+        else
+          bulk_store_1d(gout + grow * out_row_bytes, src, out_row_bytes);
+      }
+      bulk_commit();
+      const int j = i + NSTAGE - 1;
+      if (j < my_count) {
+        bulk_wait_read<1>();  // my row of the stage used one iteration ago has drained
+        issue_load(j);
+      }
+    }
+  }
+  if (tid < 32) bulk_wait<0>();
 }
 
 }  // namespace bgpu
