@@ -44,6 +44,9 @@ SIGNATURES = {
     "bgpu_last_error": (C.c_char_p, []),
     "bgpu_create": (C.c_int, [C.POINTER(BgpuParams), C.POINTER(_h)]),
     "bgpu_destroy": (None, [_h]),
+    "bgpu_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "bgpu_slab_create": (C.c_int, [C.POINTER(BgpuParams), C.c_int, C.c_int, C.c_void_p, C.POINTER(_h)]),
+    "bgpu_slab_info": (C.c_int, [_h, _ip, _ip, _ip, _ip]),
     "bgpu_set_static": (C.c_int, [_h, _dp, _dp, _dp, _dp]),
     "bgpu_set_mass": (C.c_int, [_h, _dp, _dp]),
     "bgpu_hamiltonian_mass": (C.c_int, [_h, _dp, _dp]),
@@ -69,7 +72,7 @@ SIGNATURES = {
     "bgpu_profile_end": (C.c_int, [_dp, C.POINTER(C.c_uint64), C.c_int]),
     "bgpu_profile_kind_name": (C.c_char_p, [C.c_int]),
 }
-PROFILE_KINDS = 10
+PROFILE_KINDS = 12
 
 _lib = None
 

@@ -104,6 +104,11 @@ class Chain:
     def shape(self):
         return (self.N1, self.N1, self.N1)
 
+    @property
+    def kshape(self):
+        """Shape of a k-space (half-complex) array: [x][y][z <= N/2]."""
+        return (self.N1, self.N1, self.N1 // 2 + 1)
+
     # -- inputs -----------------------------------------------------------
     def set_static(self, Power=None, nobs=None, noise=None, window=None):
         arrs = [None if a is None else _f64(a, self.N) for a in (Power, nobs, noise, window)]
@@ -201,7 +206,7 @@ class Chain:
         a = _f64(a, self.N)
         out = np.empty(2 * self.Nhalf)
         _lib.check(self.L.bgpu_fft_r2c(self._h, _dp(a), _dp(out)))
-        return out.view(np.complex128).reshape(self.N1, self.N1, self.N1 // 2 + 1)
+        return out.view(np.complex128).reshape(self.kshape)
 
     def fft_c2r(self, c):
         c = np.ascontiguousarray(c, dtype=np.complex128).reshape(-1)

@@ -13,6 +13,7 @@
 
 #include "fft3d.h"
 #include "kernels.h"
+#include "nccl_comm.h"
 #include "util.h"
 
 namespace bgpu {
@@ -68,11 +69,23 @@ struct bgpu_handle {
   // reductions
   double *partials = nullptr, *dscal = nullptr;
   double *hscal = nullptr;  // pinned
+
+  // x-slab decomposition.  A cube handle has G = 1, Ns = N, x0 = 0 and no halo;
+  // n / nh / nhp are always the LOCAL element counts.
+  int G = 1, rank = 0, Ns = 0, x0 = 0;
+  double ncells = 0.0;          // N^3, the global cell count (FFT normalisation, mean density)
+  NcclComm *comm = nullptr;
+  int Hmax = 0;                 // halo planes allocated each side of rho_ext
+  double *rho_ext = nullptr;    // [(Ns + 2 Hmax)][N][N]; delta points at the owned planes inside it
+  double *halo_recv = nullptr;  // 2 * Hmax * N^2
+  double2 *sendbuf = nullptr, *recvbuf = nullptr;
+  int *dflag = nullptr;         // device flag: a particle left the halo
+  int *hflag = nullptr;         // pinned copy
 };
 
 namespace {
 
-enum Scal { S_SUMRHO = 0, S_NLL = 1, S_PRIOR = 2, S_KIN = 3, S_P0 = 4, S_COUNT = 8 };
+enum Scal { S_SUMRHO = 0, S_NLL = 1, S_PRIOR = 2, S_KIN = 3, S_P0 = 4, S_MAXPSI = 5, S_COUNT = 8 };
 
 template <class T>
 void dalloc(T *&ptr, size_t count) {
@@ -85,7 +98,22 @@ void h2d(bgpu_handle *h, double *dst, const double *src, size_t count) {
 void d2h(bgpu_handle *h, double *dst, const double *src, size_t count) {
   BGPU_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 }
-void sync(bgpu_handle *h) { BGPU_CUDA(cudaStreamSynchronize(h->stream)); }
+void sync(bgpu_handle *h) {
+  if (h->dflag)
+    BGPU_CUDA(cudaMemcpyAsync(h->hflag, h->dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  BGPU_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->dflag && *h->hflag) {
+    *h->hflag = 0;
+    cudaMemsetAsync(h->dflag, 0, sizeof(int), h->stream);
+    throw std::runtime_error("bgpu: a particle moved beyond the mass-assignment halo of its slab (displacement > " +
+                             std::to_string(h->Hmax) + " cells along x); use fewer ranks for this field");
+  }
+}
+
+// sum a device scalar over the ranks of a slab-decomposed chain (no-op on a cube)
+void allreduce_scalar(bgpu_handle *h, int which) {
+  if (h->G > 1) h->comm->all_reduce_sum(h->dscal + which, 1, h->stream);
+}
 
 void require(bool ok, const char *msg) {
   if (!ok) throw std::runtime_error(msg);
@@ -130,7 +158,7 @@ void validate(const bgpu_params &p) {
 // Lag2Eul_zeldovich / _rsd_zeldovich from s^ (already in h->shat): Psi -> rho -> sum(rho).
 // dQ / rsd are arguments because the Poisson log-likelihood ignores both (poissonian.cpp:54-56).
 void forward_from_shat(bgpu_handle *h, double dQ, bool rsd, double *px, double *py, double *pz) {
-  const double inv_n = 1.0 / (double)h->n;
+  const double inv_n = 1.0 / h->ncells;
   // in = dQ * s ; phi = -D1 * in (Lag2Eul.cc:88) ; Psi^_c = (k_c/k^2)(Im phi^, -Re phi^)
   const double a = -h->p.D1 * dQ;
   for (int c = 2; c >= 0; --c) {
@@ -146,8 +174,36 @@ void forward_from_shat(bgpu_handle *h, double dQ, bool rsd, double *px, double *
   }
   GridGeom g = h->geom;
   g.rsd = rsd ? 1 : 0;
-  launch_scatter(g, h->psi[0], h->psi[1], h->psi[2], h->delta, px, py, pz, h->stream);
+  const size_t plane = (size_t)h->N * h->N;
+  if (h->G > 1) {
+    // halo width from the largest x displacement on any rank (+1 plane for the upper CIC / TSC
+    // neighbour, +1 for the lower TSC neighbour and rounding)
+    launch_max_abs(h->psi[0], h->n, h->partials, h->dscal + S_MAXPSI, h->stream);
+    h->comm->all_reduce_max(h->dscal + S_MAXPSI, 1, h->stream);
+    BGPU_CUDA(cudaMemcpyAsync(h->hscal + S_MAXPSI, h->dscal + S_MAXPSI, sizeof(double), cudaMemcpyDeviceToHost,
+                              h->stream));
+    BGPU_CUDA(cudaStreamSynchronize(h->stream));
+    int H = (int)std::ceil(h->hscal[S_MAXPSI] / g.d) + 2;
+    if (!(h->hscal[S_MAXPSI] == h->hscal[S_MAXPSI]) || H > h->Hmax)
+      throw std::runtime_error("bgpu: displacement of " + std::to_string(h->hscal[S_MAXPSI] / g.d) +
+                               " cells along x exceeds the slab halo (" + std::to_string(h->Hmax) + " planes)");
+    g.H = H;
+    h->delta = h->rho_ext + (size_t)H * plane;
+  }
+  launch_scatter(g, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, px, py, pz, h->stream);
+  if (h->G > 1) {
+    // my lower halo belongs to rank-1's last planes, my upper halo to rank+1's first planes
+    ProfScope prof(KK_HALO, h->stream);
+    const int H = g.H, lo = (h->rank + h->G - 1) % h->G, hi = (h->rank + 1) % h->G;
+    const size_t cnt = (size_t)H * plane;
+    double *ext = h->rho_ext;
+    h->comm->exchange2(ext, lo, ext + (size_t)(h->Ns + H) * plane, hi, h->halo_recv, hi, h->halo_recv + cnt, lo, cnt,
+                       h->stream);
+    launch_add(ext + (size_t)h->Ns * plane, h->halo_recv, cnt, h->stream);        // from rank+1 -> my last H planes
+    launch_add(ext + (size_t)H * plane, h->halo_recv + cnt, cnt, h->stream);      // from rank-1 -> my first H planes
+  }
   launch_sum(h->delta, h->n, h->partials, h->dscal + S_SUMRHO, h->stream);
+  allreduce_scalar(h, S_SUMRHO);
 }
 
 void r2c_plain(bgpu_handle *h, const double *in, double2 *out) {
@@ -161,13 +217,13 @@ void r2c_plain(bgpu_handle *h, const double *in, double2 *out) {
 void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   require(h->have_power && h->have_obs, "bgpu: bgpu_set_static (Power, nobs, noise, window) must be called first");
   const bgpu_params &p = h->p;
-  const double inv_n = 1.0 / (double)h->n;
+  const double inv_n = 1.0 / h->ncells;
   r2c_plain(h, d_s, h->shat);
   forward_from_shat(h, p.deltaQ_factor, p.rsd_model != 0, nullptr, nullptr, nullptr);
   LikeParams lp = h->like;
   lp.exact_sign = (p.calc_h == BGPU_CALC_H_EXACT) ? 1 : 0;
   launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->nobs, h->noise, h->window, h->resid, h->n,
-                           h->partials, h->dscal + S_NLL, h->stream);
+                           h->ncells, h->partials, h->dscal + S_NLL, h->stream);
 
   // norm = -1 * deltaQ_factor * (D1 if correct_delta)   (HMC_models.cc:460-469)
   double norm = -1.0;
@@ -242,7 +298,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
 void psi_device(bgpu_handle *h, const double *d_s) {
   require(h->have_power && h->have_obs, "bgpu: bgpu_set_static (Power, nobs, noise, window) must be called first");
   const bgpu_params &p = h->p;
-  const double inv_n = 1.0 / (double)h->n;
+  const double inv_n = 1.0 / h->ncells;
   r2c_plain(h, d_s, h->shat);
   KOp lop;
   lop.kind = K_MULREAL;
@@ -252,19 +308,21 @@ void psi_device(bgpu_handle *h, const double *d_s) {
   sop.a = inv_n;
   h->fft.c2r(h->shat, h->work, h->tmp, lop, sop);
   launch_half_dot(d_s, h->tmp, h->n, h->partials, h->dscal + S_PRIOR, h->stream);
+  allreduce_scalar(h, S_PRIOR);
 
   const bool gauss = p.likelihood == 1;
   forward_from_shat(h, gauss ? p.deltaQ_factor : 1.0, gauss ? (p.rsd_model != 0) : false, nullptr, nullptr, nullptr);
   LikeParams lp = h->like;
   lp.exact_sign = 0;
   launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->nobs, h->noise, h->window, nullptr, h->n,
-                           h->partials, h->dscal + S_NLL, h->stream);
+                           h->ncells, h->partials, h->dscal + S_NLL, h->stream);
+  allreduce_scalar(h, S_NLL);
 }
 
 // M^-1 p (HMC.cc:298-327, :69-99) -> h->tmp ; returns false if there is no Fourier part
 void apply_inv_mass_fs(bgpu_handle *h, const double *d_p) {
   require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
-  const double inv_n = 1.0 / (double)h->n;
+  const double inv_n = 1.0 / h->ncells;
   r2c_plain(h, d_p, h->work);
   KOp lop;
   lop.kind = K_MULREAL;
@@ -280,6 +338,7 @@ void kinetic_device(bgpu_handle *h, const double *d_p) {
   if (h->mass_fs) apply_inv_mass_fs(h, d_p);
   launch_kinetic(d_p, h->mass_fs ? h->tmp : nullptr, h->mass_rs ? h->mass_r : nullptr, h->n, h->partials,
                  h->dscal + S_KIN, h->stream);
+  allreduce_scalar(h, S_KIN);
 }
 
 // Hamiltonian_EoM (HMC.cc:251-369) after the RNG draws, in place on device
@@ -295,14 +354,28 @@ void leapfrog_device(bgpu_handle *h, double *d_s, double *d_p, uint64_t Neps, do
     gradient_device(h, d_s, h->grad);                            // :343-344
     launch_axpy(d_p, h->grad, -(0.5 * eps), h->n, h->stream);   // :351-352
     // :360-364 -- stop a trajectory whose momentum has run away
-    BGPU_CUDA(cudaMemcpyAsync(h->hscal + S_P0, d_p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->G > 1) {  // every rank must take the same decision: rank 0 owns momenta[0]
+      launch_max_abs(d_p, 1, h->partials, h->dscal + S_P0, h->stream);
+      if (h->rank != 0) BGPU_CUDA(cudaMemsetAsync(h->dscal + S_P0, 0, sizeof(double), h->stream));
+      h->comm->all_reduce_max(h->dscal + S_P0, 1, h->stream);
+      BGPU_CUDA(cudaMemcpyAsync(h->hscal + S_P0, h->dscal + S_P0, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      BGPU_CUDA(cudaMemcpyAsync(h->hscal + S_P0, d_p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
     sync(h);
     if (std::fabs(h->hscal[S_P0]) > 1e50) break;
   }
 }
 
 void update_inverse(bgpu_handle *h, const double *full, double *half) {
-  launch_inverse_spectrum(full, half, h->N, h->normFS, h->stream);
+  if (h->G == 1) {
+    launch_inverse_spectrum(full, half, h->N, h->normFS, h->stream);
+    return;
+  }
+  // the multiplier is needed at (all x, my y rows): transpose it like a k-space array
+  launch_inverse_spectrum_pack(full, h->sendbuf, h->N, h->Ns, h->normFS, h->stream);
+  h->comm->all_to_all(h->sendbuf, h->recvbuf, (size_t)h->Ns * h->Ns * (h->N / 2 + 1) * 2, h->stream);
+  launch_inverse_spectrum_unpack(h->recvbuf, half, h->N, h->Ns, h->stream);
 }
 
 }  // namespace
@@ -359,7 +432,7 @@ int bgpu_profile_end(double *ms_per_kind, uint64_t *launches_per_kind, int nkind
 const char *bgpu_profile_kind_name(int kind) {
   static const char *names[KK_COUNT] = {"fft_strided_pass_y", "fft_r2c_zpass", "fft_c2r_zpass", "scatter",
                                         "gather_adjoint", "overdens_residual", "reduce", "stream", "colour_momenta",
-                                        "fft_strided_pass_x"};
+                                        "fft_strided_pass_x", "all_to_all", "halo_exchange"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "?";
 }
 
@@ -389,12 +462,25 @@ void bgpu_default_params(bgpu_params *p) {
   p->device = 0;
 }
 
-int bgpu_create(const bgpu_params *p, bgpu_handle **out) {
+static int create_impl(const bgpu_params *p, int rank, int nranks, const void *nccl_id, bgpu_handle **out) {
   bgpu_handle *h = nullptr;
   BGPU_TRY
   require(p && out, "bgpu_create: null argument");
   *out = nullptr;
   validate(*p);
+  if (nranks > 1) {
+    // the slab path runs on the TMA-staged FFT passes and covers what needs no particle
+    // data across slabs beyond the density halo
+    require(p->N1 == 128 || p->N1 == 256 || p->N1 == 512,
+            "bgpu_slab_create: the slab-decomposed transform supports N = 128, 256, 512");
+    require(rank >= 0 && rank < nranks && p->N1 % nranks == 0 && p->N1 / nranks >= 8,
+            "bgpu_slab_create: N1 must be a multiple of the number of ranks, at least 8 planes per rank");
+    require(p->calc_h == 0 || p->calc_h == 1,
+            "bgpu_slab_create: calc_h must be 0 or 1 (the exact adjoint's residual halo is not built yet)");
+    require(!(p->calc_h == 0 && p->likelihood == 0),
+            "bgpu_slab_create: Poisson + calc_h = 0 differentiates by finite differences across slabs; not built yet");
+    require(nccl_id != nullptr, "bgpu_slab_create: a NCCL unique id is required");
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -405,14 +491,36 @@ int bgpu_create(const bgpu_params *p, bgpu_handle **out) {
   h = new bgpu_handle;
   h->p = *p;
   h->N = p->N1;
-  h->n = (size_t)h->N * h->N * h->N;
-  h->nh = (size_t)h->N * h->N * (h->N / 2 + 1);
-  h->nhp = (size_t)h->N * h->N * (h->N / 2 + 2);
+  h->G = nranks;
+  h->rank = rank;
+  h->Ns = h->N / nranks;
+  h->x0 = rank * h->Ns;
+  h->ncells = (double)h->N * h->N * h->N;
+  h->n = (size_t)h->Ns * h->N * h->N;
+  h->nh = (size_t)h->Ns * h->N * (h->N / 2 + 1);
+  h->nhp = (size_t)h->Ns * h->N * (h->N / 2 + 2);
   BGPU_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
+  if (nranks > 1) {
+    h->comm = new NcclComm(nccl_id, rank, nranks);
+    dalloc(h->sendbuf, h->nh);
+    dalloc(h->recvbuf, h->nh);
+    h->Hmax = h->Ns < 24 ? h->Ns : 24;
+    dalloc(h->halo_recv, (size_t)2 * h->Hmax * h->N * h->N);
+    BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->dflag), sizeof(int)));
+    BGPU_CUDA(cudaMemsetAsync(h->dflag, 0, sizeof(int), h->stream));
+    BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hflag), sizeof(int)));
+    *h->hflag = 0;
+    h->fft.G = nranks;
+    h->fft.rank = rank;
+    h->fft.Ns = h->Ns;
+    h->fft.comm = h->comm;
+    h->fft.sendbuf = h->sendbuf;
+    h->fft.recvbuf = h->recvbuf;
+  }
   h->fft.init(h->N, h->stream);
   h->kfac = 2. * M_PI / p->L1;                                      // scale_space.cpp:42
-  h->normFS = (p->L1 * p->L2 * p->L3) / (double)h->n;               // HMC_help.cc:26
+  h->normFS = (p->L1 * p->L2 * p->L3) / h->ncells;                  // HMC_help.cc:26
   h->mass_fs = (p->mass_type == 1 || p->mass_type == 4);            // struct_hamil.h:276-296
   h->mass_rs = (p->mass_type == 0);
 
@@ -430,6 +538,10 @@ int bgpu_create(const bgpu_params *p, bgpu_handle **out) {
     const double Hub = 100. * std::sqrt(p->OM / p->ascale / p->ascale / p->ascale + p->OL + OC / p->ascale / p->ascale);
     g.v_norm = 1. / Hub / p->ascale;                                 // rsd.cc:39
   }
+  g.x0 = h->x0;
+  g.Ns = h->Ns;
+  g.H = 0;
+  g.flag = h->dflag;
   h->like.likelihood = p->likelihood;
   h->like.rho_c = p->rho_c;
   h->like.biasP = p->biasP;
@@ -441,7 +553,9 @@ int bgpu_create(const bgpu_params *p, bgpu_handle **out) {
   dalloc(h->mass_f, h->n); dalloc(h->mass_r, h->n); dalloc(h->inv_mass, h->nhp);
   dalloc(h->sig, h->n); dalloc(h->mom, h->n); dalloc(h->grad, h->n);
   for (int c = 0; c < 3; ++c) dalloc(h->psi[c], h->n);
-  dalloc(h->delta, h->n); dalloc(h->resid, h->n); dalloc(h->tmp, h->n);
+  dalloc(h->rho_ext, (size_t)(h->Ns + 2 * h->Hmax) * h->N * h->N);
+  h->delta = h->rho_ext;   // a cube has no halo; a slab moves delta to its owned planes per evaluation
+  dalloc(h->resid, h->n); dalloc(h->tmp, h->n);
   dalloc(h->shat, h->nh); dalloc(h->dhat, h->nh); dalloc(h->work, h->nh); dalloc(h->acc, h->nh);
   dalloc(h->partials, (size_t)kReduceBlocks); dalloc(h->dscal, (size_t)S_COUNT);
   BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hscal), S_COUNT * sizeof(double)));
@@ -458,20 +572,45 @@ int bgpu_create(const bgpu_params *p, bgpu_handle **out) {
   return 0;
 }
 
+int bgpu_create(const bgpu_params *p, bgpu_handle **out) { return create_impl(p, 0, 1, nullptr, out); }
+
+int bgpu_nccl_unique_id(void *out128) {
+  BGPU_TRY
+  require(out128 != nullptr, "bgpu_nccl_unique_id: null argument");
+  NcclComm::unique_id(out128);
+  BGPU_CATCH
+}
+
+int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out) {
+  return create_impl(p, rank, nranks, nccl_id128, out);
+}
+
+int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *nx_local) {
+  if (!h) return 1;
+  if (rank) *rank = h->rank;
+  if (nranks) *nranks = h->G;
+  if (x0) *x0 = h->x0;
+  if (nx_local) *nx_local = h->Ns;
+  return 0;
+}
+
 void bgpu_destroy(bgpu_handle *h) {
   if (!h) return;
   cudaSetDevice(h->p.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->mass_f, h->mass_r, h->inv_mass,
-                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->delta, h->resid, h->tmp,
-                     h->partials, h->dscal};
+                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->tmp,
+                     h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
     if (q) cudaFree(q);
-  double2 *cplx[] = {h->shat, h->dhat, h->work, h->acc};
+  double2 *cplx[] = {h->shat, h->dhat, h->work, h->acc, h->sendbuf, h->recvbuf};
   for (double2 *q : cplx)
     if (q) cudaFree(q);
+  if (h->dflag) cudaFree(h->dflag);
+  if (h->hflag) cudaFreeHost(h->hflag);
   if (h->hscal) cudaFreeHost(h->hscal);
   h->fft.destroy();
+  delete h->comm;
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -627,6 +766,7 @@ int bgpu_color_momenta(bgpu_handle *h, const double *white, const double *real_g
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
   require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
+  require(h->G == 1, "bgpu_color_momenta: not available on a slab-decomposed chain yet (colour on the host or a cube handle)");
   if (h->mass_fs) {
     require(white != nullptr, "bgpu_color_momenta: white noise is required for a Fourier-space mass");
     // the full complex grid (2N doubles) is staged through dhat+acc's storage? no: own temporary
@@ -634,11 +774,11 @@ int bgpu_color_momenta(bgpu_handle *h, const double *white, const double *real_g
     dalloc(d_white, h->n);
     try {
       BGPU_CUDA(cudaMemcpyAsync(d_white, white, h->n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-      const double amp = (double)h->n * (double)h->n / (h->p.L1 * h->p.L2 * h->p.L3);  // random.cpp:81-83
+      const double amp = h->ncells * h->ncells / (h->p.L1 * h->p.L2 * h->p.L3);  // random.cpp:81-83
       launch_colour_momenta(d_white, h->mass_f, h->work, h->N, amp, h->stream);
       ROp sop;
       sop.kind = R_SCALE;
-      sop.a = 1.0 / (double)h->n;
+      sop.a = 1.0 / h->ncells;
       h->fft.c2r(h->work, h->work, h->mom, KOp{}, sop);
       sync(h);
     } catch (...) {
@@ -677,8 +817,8 @@ int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *p
   LikeParams lp = h->like;
   lp.exact_sign = 0;
   launch_fill(h->mom, 1.0, h->n, h->stream);
-  launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->mom, h->mom, h->mom, nullptr, h->n, h->partials,
-                           h->dscal + S_NLL, h->stream);
+  launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->mom, h->mom, h->mom, nullptr, h->n, h->ncells,
+                           h->partials, h->dscal + S_NLL, h->stream);
   d2h(h, deltaX, h->delta, h->n);
   sync(h);
   BGPU_CATCH
@@ -730,7 +870,7 @@ int bgpu_fft_c2r(bgpu_handle *h, const double *in_complex, double *out) {
   h2d(h, reinterpret_cast<double *>(h->work), in_complex, 2 * h->nh);
   ROp sop;
   sop.kind = R_SCALE;
-  sop.a = 1.0 / (double)h->n;   // fftwrapper.cc:43-45
+  sop.a = 1.0 / h->ncells;   // fftwrapper.cc:43-45
   h->fft.c2r(h->work, h->work, h->tmp, KOp{}, sop);
   d2h(h, out, h->tmp, h->n);
   sync(h);
@@ -751,7 +891,7 @@ int bgpu_convolve_inv_corr(bgpu_handle *h, const double *signal, const double *c
   lop.real0 = half;
   ROp sop;
   sop.kind = R_SCALE;
-  sop.a = 1.0 / (double)h->n;
+  sop.a = 1.0 / h->ncells;
   h->fft.c2r(h->work, h->work, h->tmp, lop, sop);
   d2h(h, out, h->tmp, h->n);
   sync(h);

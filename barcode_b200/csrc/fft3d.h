@@ -16,6 +16,13 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();
 
+// what the slab transform needs from the communication layer (nccl_comm.cu)
+struct SlabComm {
+  virtual ~SlabComm() {}
+  // peer h receives doubles [h*count, (h+1)*count) of `send` into block `my rank` of its `recv`
+  virtual void all_to_all(const void *send, void *recv, size_t count_doubles, cudaStream_t st) = 0;
+};
+
 struct Fft3d {
   int N = 0;
   double2 *twN = nullptr;  // exp(-2 pi i k / N)
@@ -25,15 +32,23 @@ struct Fft3d {
   int sm_count = 0;
   bool use_tma = true;     // TMA-staged strided pass (fft_tma.cuh); BGPU_FFT_TMA=0 selects the cp.async one
 
-  // tensor maps of the half-grid arrays the TMA pass has touched (keyed by base pointer)
+  // tensor maps of the half-grid arrays the TMA pass has touched (keyed by base pointer and layout)
   struct MapEntry {
     const void *base;
     int axis;
     bool cplx;
+    int layout, n_slow, n_mid;
     CUtensorMap map;
   };
   mutable std::vector<MapEntry> maps_;
-  const CUtensorMap &tensor_map(const void *base, int axis, bool cplx) const;
+  const CUtensorMap &tensor_map(const void *base, int axis, bool cplx, int layout, int n_slow, int n_mid) const;
+
+  // x-slab decomposition over G ranks: this rank holds x planes [rank*Ns, (rank+1)*Ns) of
+  // every real array, [Ns][N][N], and y rows [rank*Ns, ...) of every k-space array, [N][Ns][N/2+1]
+  // ("transposed" layout).  Set before init(); G == 1 is the plain cube.
+  int G = 1, rank = 0, Ns = 0;
+  SlabComm *comm = nullptr;                  // all-to-all provider (NCCL), owned by the caller
+  double2 *sendbuf = nullptr, *recvbuf = nullptr;  // packed [peer][Ns][Ns][N/2+1], owned by the caller
 
   void init(int n, cudaStream_t st);
   void destroy();

@@ -99,32 +99,50 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// tensor map over a half-grid array seen as doubles: dims (fastest first) [row doubles][y][x];
-// the box is 8 pencils wide (cplx: 16 doubles = 128 B, real: 8 doubles = 64 B) and `rows` long
-// along the transformed axis.
-static CUtensorMap make_half_grid_map(const void *base, int N, int axis, bool cplx) {
+// Tensor maps over half-grid arrays seen as doubles.
+//   layout 0: [n_slow][n_mid][row]     rank 3; the box is 8 pencils wide (cplx: 16 doubles = 128 B,
+//             real: 8 doubles = 64 B) and `rows` long along the transformed axis (axis 1 = mid,
+//             axis 0 = slow).  Cube: n_slow = n_mid = N.  x-slab [Ns][N][.]: the y pass.
+//             Transposed slab [N][Ns][.]: the x pass.
+//   layout 1: [G][Ns][Ns][row]         rank 4, the packed all-to-all buffer [peer][x_l][y_l][z]; the
+//             box is min(Ns, 256) rows of one (peer, x_l).
+static CUtensorMap make_half_grid_map(const void *base, int N, int axis, bool cplx, int layout, int n_slow,
+                                      int n_mid) {
   CUtensorMap m;
   const cuuint64_t nzh = (cuuint64_t)N / 2 + 1;
   const cuuint64_t row_doubles = cplx ? 2 * nzh : nzh;                 // valid extent
   const cuuint64_t pitch = cplx ? nzh * 16 : (nzh + 1) * 8;            // bytes, multiple of 16
-  const cuuint64_t dims[3] = {row_doubles, (cuuint64_t)N, (cuuint64_t)N};
-  const cuuint64_t strides[2] = {pitch, pitch * (cuuint64_t)N};
-  const cuuint32_t rows = N > 256 ? 256 : N;
-  const cuuint32_t box[3] = {cplx ? 16u : 8u, axis == 1 ? rows : 1u, axis == 0 ? rows : 1u};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box,
-                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 cplx ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r;
+  if (layout == 0) {
+    const cuuint64_t dims[3] = {row_doubles, (cuuint64_t)n_mid, (cuuint64_t)n_slow};
+    const cuuint64_t strides[2] = {pitch, pitch * (cuuint64_t)n_mid};
+    const cuuint32_t rows = N > 256 ? 256 : N;
+    const cuuint32_t box[3] = {cplx ? 16u : 8u, axis == 1 ? rows : 1u, axis == 0 ? rows : 1u};
+    r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, cplx ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t ns = (cuuint64_t)n_mid, g = (cuuint64_t)n_slow;  // n_mid = Ns, n_slow = G
+    const cuuint64_t dims[4] = {row_doubles, ns, ns, g};
+    const cuuint64_t strides[3] = {pitch, pitch * ns, pitch * ns * ns};
+    const cuuint32_t box[4] = {16u, (cuuint32_t)(ns < 256 ? ns : 256), 1u, 1u};
+    r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) throw std::runtime_error("bgpu: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return m;
 }
 
-const CUtensorMap &Fft3d::tensor_map(const void *base, int axis, bool cplx) const {
+const CUtensorMap &Fft3d::tensor_map(const void *base, int axis, bool cplx, int layout, int n_slow, int n_mid) const {
   for (auto &e : maps_)
-    if (e.base == base && e.axis == axis && e.cplx == cplx) return e.map;
-  if (maps_.size() >= 64) maps_.clear();
-  maps_.push_back(MapEntry{base, axis, cplx, make_half_grid_map(base, N, axis, cplx)});
+    if (e.base == base && e.axis == axis && e.cplx == cplx && e.layout == layout && e.n_slow == n_slow &&
+        e.n_mid == n_mid)
+      return e.map;
+  if (maps_.size() >= 96) maps_.clear();
+  maps_.push_back(MapEntry{base, axis, cplx, layout, n_slow, n_mid,
+                           make_half_grid_map(base, N, axis, cplx, layout, n_slow, n_mid)});
   return maps_.back().map;
 }
 
@@ -149,14 +167,22 @@ constexpr bool tma_supported() {
   else return TmaStages<N, AUX>::value >= 2;
 }
 
+// how one strided pass sees its input and output arrays (see make_half_grid_map)
+struct PassIo {
+  int n_other = 0;      // pencils' "other" extent; 0 = N (cube)
+  int other0 = 0;       // global index of other == 0
+  bool in_packed = false, out_packed = false;
+  int G = 1, Ns = 0;
+};
+
 template <int N, int DIR, int AXIS, int AUX>
-static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp lop, KOp sop, cudaStream_t st) {
+static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp lop, KOp sop, const PassIo &io,
+                               cudaStream_t st) {
   constexpr int E = TmaShape<N>::E;
   constexpr int MINB = AUX == 0 ? TmaShape<N>::MINB : 1;
   constexpr int NSTAGE = TmaStages<N, AUX>::value;
   constexpr int threads = 8 * (N / E);
   constexpr int smem = NSTAGE * TmaTile<N, AUX>::stage_bytes + 1024 + 64;
-  constexpr int tiles = N * ((N / 2 + 1 + 7) / 8);
   auto kern = fft_strided_tma<N, E, NSTAGE, DIR, AXIS, AUX, MINB>;
   static int blocks_per_sm = 0;  // per instantiation; attribute set once per process and device 0..n share the value
   if (!blocks_per_sm) {
@@ -165,21 +191,27 @@ static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, 
     BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     blocks_per_sm = occ > 0 ? occ : 1;
   }
+  const int n_other = io.n_other ? io.n_other : N;
+  // extents of the rank-3 layout: the pass axis has N entries, the other strided axis n_other
+  const int n_slow = AXIS == 0 ? N : n_other, n_mid = AXIS == 0 ? n_other : N;
   TmaMaps maps;
-  maps.in = f.tensor_map(in, AXIS, true);
-  maps.out = f.tensor_map(out, AXIS, true);
-  maps.auxr = AUX >= 1 ? f.tensor_map(lop.real0, AXIS, false) : maps.in;
-  maps.auxc = AUX >= 2 ? f.tensor_map(lop.cplx0, AXIS, true) : maps.in;
+  maps.in = io.in_packed ? f.tensor_map(in, AXIS, true, 1, io.G, io.Ns) : f.tensor_map(in, AXIS, true, 0, n_slow, n_mid);
+  maps.out = io.out_packed ? f.tensor_map(out, AXIS, true, 1, io.G, io.Ns) : f.tensor_map(out, AXIS, true, 0, n_slow, n_mid);
+  maps.auxr = AUX >= 1 ? f.tensor_map(lop.real0, AXIS, false, 0, n_slow, n_mid) : maps.in;
+  maps.auxc = AUX >= 2 ? f.tensor_map(lop.cplx0, AXIS, true, 0, n_slow, n_mid) : maps.in;
+  PassGeom geo{n_other, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0};
+  const int tiles = n_other * ((N / 2 + 1 + 7) / 8);
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > tiles) blocks = tiles;
   ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
-  kern<<<blocks, threads, smem, st>>>(maps, f.twN, lop, sop);
+  kern<<<blocks, threads, smem, st>>>(maps, f.twN, lop, sop, geo);
   BGPU_LAUNCHED(1);
 }
 
 // returns true if the TMA kernel took the launch
 template <int N, int DIR, int AXIS>
-static bool try_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp lop, KOp sop, cudaStream_t st) {
+static bool try_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp lop, KOp sop, const PassIo &io,
+                            cudaStream_t st) {
   if (!f.use_tma) return false;
   if constexpr (!tma_has_size<N>()) {
     return false;
@@ -190,31 +222,33 @@ static bool try_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp
       if constexpr (DIR == +1 && AXIS == 0) {
         if (lop.kind == K_MULREAL) {
           if constexpr (tma_supported<N, 1>()) {
-            launch_strided_tma<N, DIR, AXIS, 1>(f, in, out, lop, sop, st);
+            launch_strided_tma<N, DIR, AXIS, 1>(f, in, out, lop, sop, io, st);
             return true;
           }
         } else {
           if constexpr (tma_supported<N, 2>()) {
-            launch_strided_tma<N, DIR, AXIS, 2>(f, in, out, lop, sop, st);
+            launch_strided_tma<N, DIR, AXIS, 2>(f, in, out, lop, sop, io, st);
             return true;
           }
         }
       }
       return false;
     }
-    launch_strided_tma<N, DIR, AXIS, 0>(f, in, out, lop, sop, st);
+    launch_strided_tma<N, DIR, AXIS, 0>(f, in, out, lop, sop, io, st);
     return true;
   }
 }
 
 template <int N, int DIR, int AXIS>
 static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, const double2 *tw, KOp lop, KOp sop,
-                           cudaStream_t st) {
+                           cudaStream_t st, const PassIo &io = PassIo{}) {
   constexpr int T = Shape<N>::T;
   constexpr int threads = T * N / 8;
   constexpr int tiles = N * ((N / 2) / T) + N / T;
   constexpr size_t smem = (size_t)N * T * sizeof(double2);
-  if (try_strided_tma<N, DIR, AXIS>(f, in, out, lop, sop, st)) return;
+  if (try_strided_tma<N, DIR, AXIS>(f, in, out, lop, sop, io, st)) return;
+  if (f.G > 1 || io.n_other)
+    throw std::runtime_error("bgpu: the slab-decomposed transform needs the TMA-staged pass (N = 128, 256 or 512)");
   ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
   if constexpr (N >= 128) {
     // persistent + cp.async prefetch: one wave of CTAs walks all tiles
@@ -254,7 +288,7 @@ static void launch_zpass_tma(const Fft3d &f, const void *in, void *out, ROp op, 
     BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     blocks_per_sm = occ > 0 ? occ : 1;
   }
-  const int ntiles = (N * N) / TR;
+  const int ntiles = (f.Ns * N) / TR;
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > ntiles) blocks = ntiles;
   ProfScope prof(C2R ? KK_FFT_C2R_Z : KK_FFT_R2C_Z, st);
@@ -289,10 +323,18 @@ static bool try_c2r_zpass_tma(const Fft3d &f, const double2 *in, double *out, RO
   }
 }
 
+// all-to-all of the packed buffers: peer h gets / gives block h (Ns*Ns*(N/2+1) complex numbers)
+static void slab_all_to_all(const Fft3d &f, const double2 *send, double2 *recv) {
+  const size_t blk = (size_t)f.Ns * f.Ns * (f.N / 2 + 1);
+  ProfScope prof(KK_ALLTOALL, f.stream);
+  f.comm->all_to_all(send, recv, blk * 2, f.stream);
+}
+
 template <int N>
 static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xout, ROp lop, KOp sop) {
-  const size_t nrows = (size_t)N * N;
+  const size_t nrows = (size_t)f.Ns * N;
   if (!try_r2c_zpass_tma<N>(f, in, out, lop)) {
+  if (f.G > 1) throw std::runtime_error("bgpu: the slab-decomposed transform needs the bulk-copy z pass (N >= 128)");
   ProfScope prof(KK_FFT_R2C_Z, f.stream);
   if constexpr (N == 8) {
     tiny_r2c_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(in, out, f.twN, lop, nrows);
@@ -304,16 +346,49 @@ static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xo
   }
   BGPU_LAUNCHED(1);
   }
-  launch_strided<N, -1, 1>(f, out, out, f.twN, KOp{}, KOp{}, f.stream);
-  launch_strided<N, -1, 0>(f, out, xout ? xout : out, f.twN, KOp{}, sop, f.stream);
+  if (f.G == 1) {
+    launch_strided<N, -1, 1>(f, out, out, f.twN, KOp{}, KOp{}, f.stream);
+    launch_strided<N, -1, 0>(f, out, xout ? xout : out, f.twN, KOp{}, sop, f.stream);
+    return;
+  }
+  // slab: y pass on my x planes, stored straight into the packed send buffer; all-to-all; x pass on
+  // the transposed layout [x][y_local][z] (= the receive buffer, block h holding the x planes of rank h)
+  PassIo y_io;
+  y_io.n_other = f.Ns;
+  y_io.out_packed = true;
+  y_io.G = f.G;
+  y_io.Ns = f.Ns;
+  launch_strided<N, -1, 1>(f, out, f.sendbuf, f.twN, KOp{}, KOp{}, f.stream, y_io);
+  slab_all_to_all(f, f.sendbuf, f.recvbuf);
+  PassIo x_io;
+  x_io.n_other = f.Ns;
+  x_io.other0 = f.rank * f.Ns;
+  launch_strided<N, -1, 0>(f, f.recvbuf, xout ? xout : out, f.twN, KOp{}, sop, f.stream, x_io);
 }
 
 template <int N>
 static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *out, KOp lop, ROp sop) {
-  const size_t nrows = (size_t)N * N;
-  launch_strided<N, +1, 0>(f, in, work, f.twN, lop, KOp{}, f.stream);
-  launch_strided<N, +1, 1>(f, work, work, f.twN, KOp{}, KOp{}, f.stream);
+  const size_t nrows = (size_t)f.Ns * N;
+  if (f.G == 1) {
+    launch_strided<N, +1, 0>(f, in, work, f.twN, lop, KOp{}, f.stream);
+    launch_strided<N, +1, 1>(f, work, work, f.twN, KOp{}, KOp{}, f.stream);
+  } else {
+    // slab: x pass on the transposed layout into the send buffer (block h = the x planes of rank h,
+    // contiguous); all-to-all; y pass reads the packed receive buffer and writes my x planes
+    PassIo x_io;
+    x_io.n_other = f.Ns;
+    x_io.other0 = f.rank * f.Ns;
+    launch_strided<N, +1, 0>(f, in, f.sendbuf, f.twN, lop, KOp{}, f.stream, x_io);
+    slab_all_to_all(f, f.sendbuf, f.recvbuf);
+    PassIo y_io;
+    y_io.n_other = f.Ns;
+    y_io.in_packed = true;
+    y_io.G = f.G;
+    y_io.Ns = f.Ns;
+    launch_strided<N, +1, 1>(f, f.recvbuf, work, f.twN, KOp{}, KOp{}, f.stream, y_io);
+  }
   if (try_c2r_zpass_tma<N>(f, work, out, sop)) return;
+  if (f.G > 1) throw std::runtime_error("bgpu: the slab-decomposed transform needs the bulk-copy z pass (N >= 128)");
   ProfScope prof(KK_FFT_C2R_Z, f.stream);
   if constexpr (N == 8) {
     tiny_c2r_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(work, out, f.twN, sop, nrows);
@@ -394,6 +469,7 @@ static std::vector<double2> make_twiddles(int n) {
 void Fft3d::init(int n, cudaStream_t st) {
   if (!supported(n)) throw std::runtime_error("bgpu: FFT size must be a power of two in [8, 1024], got " + std::to_string(n));
   N = n;
+  if (G == 1) Ns = n;
   stream = st;
   {
     int dev = 0;

@@ -87,6 +87,21 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, int c0
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                             const void *smem_src) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 template <int K>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -228,6 +243,19 @@ struct TmaMaps {
   CUtensorMap in, out, auxr, auxc;
 };
 
+// Shape of one strided pass.  A full cube has n_other = N pencils' worth of "other" index
+// (x planes for the y pass, y rows for the x pass) and no packing.  In the slab-decomposed
+// transform (fft_slab.cu) a rank holds n_other = N/G of them, `other0` is the global index of the
+// first (the k-space functors need global wave numbers), and the y pass reads / writes the
+// all-to-all buffers directly: `*_packed` = rows per peer block of the rank-4 tensor map
+// [z][y_local][x_local][peer], 0 for the plain rank-3 map.
+struct PassGeom {
+  int n_other;
+  int other0;
+  int in_packed;
+  int out_packed;
+};
+
 // shared-memory address of (row, pencil p) in a 64-byte-swizzled tile of doubles (T = 8 per row)
 __device__ __forceinline__ uint32_t tile_addr_r(uint32_t tile, int row, int p) {
   return tile + (uint32_t)row * 64u + (uint32_t)((((p >> 1) ^ ((row >> 1) & 3)) << 4) | ((p & 1) << 3));
@@ -282,12 +310,13 @@ struct RotCtx {
 
 template <int N, int E, int NSTAGE, int DIR, int AXIS, int AUX, int MINB>
 __global__ void __launch_bounds__(8 * (N / E), MINB)
-    fft_strided_tma(const __grid_constant__ TmaMaps maps, const double2 *__restrict__ tw, KOp lop, KOp sop) {
+    fft_strided_tma(const __grid_constant__ TmaMaps maps, const double2 *__restrict__ tw, KOp lop, KOp sop,
+                    PassGeom geo) {
   constexpr int T = 8;
   constexpr int LP = N / E;
   constexpr int NZH = N / 2 + 1;
   constexpr int ZT = (NZH + T - 1) / T;
-  constexpr int NTILES = N * ZT;
+  const int NTILES = geo.n_other * ZT;
   constexpr int NSTG = StageCount<N>::value;
   constexpr int ROWS_PER_BOX = N > 256 ? 256 : N;
   using Tile = TmaTile<N, AUX>;
@@ -310,6 +339,12 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
     const int other = tile / ZT, zt = tile % ZT;
     uint8_t *dst = smem_al + s * Tile::stage_bytes;
     mbar_expect_tx(&full[s], Tile::stage_bytes);
+    if (AXIS == 1 && geo.in_packed) {  // rows arrive grouped by the peer that sent them
+      const int rb = geo.in_packed < 256 ? geo.in_packed : 256;
+      for (int r0 = 0; r0 < N; r0 += rb)
+        tma_load_4d(dst + r0 * 128, &maps.in, zt * 2 * T, r0 % geo.in_packed, other, r0 / geo.in_packed, &full[s]);
+      return;
+    }
 #pragma unroll
     for (int r0 = 0; r0 < N; r0 += ROWS_PER_BOX) {
       const int c1 = AXIS == 0 ? other : r0, c2 = AXIS == 0 ? r0 : other;
@@ -326,9 +361,15 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
     fence_barrier_init();
   }
   __syncthreads();
+  // With three stages the tile two iterations ahead is requested after this iteration's store
+  // (its stage drained an iteration ago).  With two stages (the variants whose operand tiles eat
+  // the shared memory) the next tile is requested at the TOP of the iteration instead, as soon
+  // as the store issued a moment ago has finished reading its stage, so the load still overlaps
+  // the whole transform.
+  constexpr bool EARLY = (NSTAGE == 2);
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < NSTAGE - 1; ++i)
+    for (int i = 0; i < (EARLY ? 1 : NSTAGE - 1); ++i)
       if (i < my_count) issue_load(i);
   }
 
@@ -342,6 +383,12 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
     const int other = tile / ZT, zt = tile % ZT;
     const int iz = zt * T + p;
     const uint32_t tbase = smem0 + s * Tile::stage_bytes;
+    if constexpr (EARLY) {
+      if (tid == 0 && i + 1 < my_count) {
+        bulk_wait_read<0>();
+        issue_load(i + 1);
+      }
+    }
     mbar_wait(&full[s], (i / NSTAGE) & 1);
 
     double2 v[E];
@@ -364,7 +411,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
       }
     } else if (lop.kind != K_NONE) {
       RotCtx<N, AXIS> rc;
-      rc.setup(lop, other, iz);
+      rc.setup(lop, other + geo.other0, iz);
 #pragma unroll
       for (int m = 0; m < E; ++m) v[m] = rc.apply(v[m], t + m * LP);
     }
@@ -373,7 +420,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
 
     if (sop.kind == K_INVLAP_SET || sop.kind == K_INVLAP_ADD) {
       RotCtx<N, AXIS> rc;
-      rc.setup(sop, other, iz);
+      rc.setup(sop, other + geo.other0, iz);
 #pragma unroll
       for (int m = 0; m < E; ++m) v[m] = rc.apply(v[m], t + m * LP);
     }
@@ -383,6 +430,12 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
+      if (AXIS == 1 && geo.out_packed) {  // rows leave grouped by the peer they go to
+        const int rb = geo.out_packed < 256 ? geo.out_packed : 256;
+        for (int r0 = 0; r0 < N; r0 += rb)
+          tma_store_4d(&maps.out, zt * 2 * T, r0 % geo.out_packed, other, r0 / geo.out_packed,
+                       smem_al + s * Tile::stage_bytes + r0 * 128);
+      } else
 #pragma unroll
       for (int r0 = 0; r0 < N; r0 += ROWS_PER_BOX) {
         const int c1 = AXIS == 0 ? other : r0, c2 = AXIS == 0 ? r0 : other;
@@ -393,10 +446,12 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
           tma_store_3d(&maps.out, zt * 2 * T, c1, c2, src);
       }
       bulk_commit();
-      const int j = i + NSTAGE - 1;
-      if (j < my_count) {
-        bulk_wait_read<1>();  // the store issued one iteration ago has drained its stage
-        issue_load(j);
+      if constexpr (!EARLY) {
+        const int j = i + NSTAGE - 1;
+        if (j < my_count) {
+          bulk_wait_read<1>();  // the store issued one iteration ago has drained its stage
+          issue_load(j);
+        }
       }
     }
   }

@@ -37,6 +37,19 @@ __device__ __forceinline__ void deposit(const GridGeom &g, bool valid, double x,
   const int lane = threadIdx.x & 31;
   valid = valid && in_domain(g, x, y, z);
   const int N = g.N;
+  // plane of the (possibly halo-extended, slab-local) density tile that global cell plane c maps to
+  const int lo = g.x0 - g.H, np = g.Ns + 2 * g.H;
+  auto plane = [&](int c) -> unsigned {
+    int l = c - lo;
+    if (l < 0) l += N;
+    if (l >= N) l -= N;
+    if (l >= np) {  // beyond the halo: drop the deposit and raise the flag (the host turns it into an error)
+      if (g.flag) *g.flag = 1;
+      l = 0;
+      valid = false;
+    }
+    return (unsigned)l;
+  };
   if (g.masskernel == 1) {
     int ci[2] = {0, 0}, cj[2] = {0, 0}, ck[2] = {0, 0};
     double wi[2] = {0, 0}, wj[2] = {0, 0}, wk[2] = {0, 0};
@@ -44,6 +57,8 @@ __device__ __forceinline__ void deposit(const GridGeom &g, bool valid, double x,
       cic_axis(x, g.d, g.L, N, ci[0], ci[1], wi[0], wi[1]);
       cic_axis(y, g.d, g.L, N, cj[0], cj[1], wj[0], wj[1]);
       cic_axis(z, g.d, g.L, N, ck[0], ck[1], wk[0], wk[1]);
+      ci[0] = (int)plane(ci[0]);
+      ci[1] = (int)plane(ci[1]);
     }
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -71,6 +86,8 @@ __device__ __forceinline__ void deposit(const GridGeom &g, bool valid, double x,
       tsc_axis(x, g.min1, g.d, N, ci, wi, u);
       tsc_axis(y, g.min2, g.d, N, cj, wj, u);
       tsc_axis(z, g.min3, g.d, N, ck, wk, u);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) ci[a] = (int)plane(ci[a]);
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -97,8 +114,9 @@ __device__ __forceinline__ void deposit(const GridGeom &g, bool valid, double x,
         }
       }
   } else if (valid) {
-    const int i = ngp_axis(x, g.min1, g.d, N), j = ngp_axis(y, g.min2, g.d, N), k = ngp_axis(z, g.min3, g.d, N);
-    red_add(rho + ((size_t)i * N + j) * N + k, 1.0);
+    const int i = (int)plane(ngp_axis(x, g.min1, g.d, N)), j = ngp_axis(y, g.min2, g.d, N),
+              k = ngp_axis(z, g.min3, g.d, N);
+    if (valid) red_add(rho + ((size_t)i * N + j) * N + k, 1.0);
   }
 }
 
@@ -108,14 +126,14 @@ __device__ __forceinline__ void deposit(const GridGeom &g, bool valid, double x,
 __global__ void scatter_kernel(GridGeom g, const double *__restrict__ psix, const double *__restrict__ psiy,
                                const double *__restrict__ psiz, double *__restrict__ rho, double *__restrict__ posx,
                                double *__restrict__ posy, double *__restrict__ posz) {
-  const size_t n = (size_t)g.N * g.N * g.N;
+  const size_t n = (size_t)g.Ns * g.N * g.N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = idx < n;  // no early return: deposit() shuffles across the whole warp
   double x = 0., y = 0., z = 0.;
   if (valid) {
     const int k = (int)(idx % g.N);
     const int j = (int)((idx / g.N) % g.N);
-    const int i = (int)(idx / ((size_t)g.N * g.N));
+    const int i = g.x0 + (int)(idx / ((size_t)g.N * g.N));
     particle_position(g, i, j, k, psix[idx], psiy[idx], psiz[idx], x, y, z);
     if (posx) {
       posx[idx] = x;
@@ -159,8 +177,8 @@ static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n 
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
                     double *posx, double *posy, double *posz, cudaStream_t st) {
   ProfScope prof(KK_SCATTER, st);
-  const size_t n = (size_t)g.N * g.N * g.N;
-  BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
+  const size_t n = (size_t)g.Ns * g.N * g.N;
+  BGPU_CUDA(cudaMemsetAsync(rho, 0, (size_t)(g.Ns + 2 * g.H) * g.N * g.N * sizeof(double), st));
   scatter_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, psix, psiy, psiz, rho, posx, posy, posz);
   BGPU_LAUNCHED(1);
 }
@@ -351,8 +369,8 @@ __global__ void __launch_bounds__(kReduceThreads, 4)
 }
 
 void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const double *sum_rho, const double *nobs,
-                              const double *noise, const double *window, double *resid, size_t n, double *scratch,
-                              double *nll, cudaStream_t st) {
+                              const double *noise, const double *window, double *resid, size_t n,
+                              double ncells_global, double *scratch, double *nll, cudaStream_t st) {
   ProfScope prof(KK_RESIDUAL, st);
   const size_t n2 = n / 2;  // n = N^3 with N a power of two >= 8
   const int blocks = (int)((n2 + kReduceThreads - 1) / kReduceThreads < (size_t)kReduceBlocks
@@ -362,7 +380,7 @@ void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const dou
   kern<<<blocks, kReduceThreads, 0, st>>>(
       lp, reinterpret_cast<double2 *>(rho_delta), sum_rho, reinterpret_cast<const double2 *>(nobs),
       reinterpret_cast<const double2 *>(noise), reinterpret_cast<const double2 *>(window),
-      reinterpret_cast<double2 *>(resid), n2, (double)n, scratch);
+      reinterpret_cast<double2 *>(resid), n2, ncells_global, scratch);
   final_sum_kernel<<<1, kReduceThreads, 0, st>>>(scratch, blocks, nll);
   BGPU_LAUNCHED(2);
 }
@@ -631,6 +649,87 @@ __global__ void add_real_momenta_kernel(double *__restrict__ p, const double *__
 void launch_add_real_momenta(double *p, const double *mass_r, const double *gauss, size_t n, cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);
   add_real_momenta_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, mass_r, gauss, n);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// slab helpers: halo sizing (max |Psi_x|), halo accumulation, transposed inverse spectrum
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kReduceThreads) partial_max_abs_kernel(const double *__restrict__ a, size_t n,
+                                                                         double *__restrict__ part) {
+  __shared__ double wp[kReduceThreads / 32];
+  double v = 0.0;
+  for (size_t i = (size_t)blockIdx.x * kReduceThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kReduceThreads)
+    v = fmax(v, fabs(a[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) wp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kReduceThreads / 32; ++w) v = fmax(v, wp[w]);
+    part[blockIdx.x] = v;
+  }
+}
+__global__ void final_max_kernel(const double *__restrict__ part, int nparts, double *__restrict__ out) {
+  double v = 0.0;
+  for (int i = 0; i < nparts; ++i) v = fmax(v, part[i]);
+  *out = v;
+}
+
+void launch_max_abs(const double *a, size_t n, double *scratch, double *out, cudaStream_t st) {
+  ProfScope prof(KK_REDUCE, st);
+  const int blocks = (int)((n + kReduceThreads - 1) / kReduceThreads < (size_t)kReduceBlocks
+                               ? (n + kReduceThreads - 1) / kReduceThreads
+                               : (size_t)kReduceBlocks);
+  partial_max_abs_kernel<<<blocks, kReduceThreads, 0, st>>>(a, n, scratch);
+  final_max_kernel<<<1, 1, 0, st>>>(scratch, blocks, out);
+  BGPU_LAUNCHED(2);
+}
+
+__global__ void add_kernel(double *__restrict__ dst, const double *__restrict__ src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+void launch_add(double *dst, const double *src, size_t n, cudaStream_t st) {
+  ProfScope prof(KK_HALO, st);
+  add_kernel<<<blocks_for(n, 256), 256, 0, st>>>(dst, src, n);
+  BGPU_LAUNCHED(1);
+}
+
+__global__ void inverse_spectrum_pack_kernel(const double *__restrict__ full, double2 *__restrict__ packed, int N,
+                                             int Ns, double normFS) {
+  const int nzh = N / 2 + 1;
+  const size_t n = (size_t)Ns * N * nzh;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int z = (int)(idx % nzh);
+  const int y = (int)((idx / nzh) % N);
+  const int xl = (int)(idx / ((size_t)nzh * N));
+  const double c = full[((size_t)xl * N + y) * N + z];  // HMC_help.cc:44
+  const int peer = y / Ns, yl = y % Ns;
+  packed[(((size_t)peer * Ns + xl) * Ns + yl) * nzh + z] = make_double2(c > 0.0 ? normFS / c : 0., 0.);
+}
+__global__ void inverse_spectrum_unpack_kernel(const double2 *__restrict__ tr, double *__restrict__ half, int N,
+                                               int Ns) {
+  const int nzh = N / 2 + 1, nzp = N / 2 + 2;
+  const size_t n = (size_t)N * Ns * nzp;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int z = (int)(idx % nzp);
+  const size_t row = idx / nzp;  // x * Ns + y_l
+  half[idx] = z < nzh ? tr[row * nzh + z].x : 0.;
+}
+void launch_inverse_spectrum_pack(const double *full_xslab, double2 *packed, int N, int Ns, double normFS,
+                                  cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  const size_t n = (size_t)Ns * N * (N / 2 + 1);
+  inverse_spectrum_pack_kernel<<<blocks_for(n, 256), 256, 0, st>>>(full_xslab, packed, N, Ns, normFS);
+  BGPU_LAUNCHED(1);
+}
+void launch_inverse_spectrum_unpack(const double2 *transposed, double *half, int N, int Ns, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  const size_t n = (size_t)N * Ns * (N / 2 + 2);
+  inverse_spectrum_unpack_kernel<<<blocks_for(n, 256), 256, 0, st>>>(transposed, half, N, Ns);
   BGPU_LAUNCHED(1);
 }
 

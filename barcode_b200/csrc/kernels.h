@@ -16,6 +16,11 @@ struct GridGeom {
   double cpecvel;  // f*100*E*a        (cosmo.cc:220-235)
   double v_norm;   // 1/Hub/a          (rsd.cc:27,39)
   double fgrow;    // f                (cosmo.cc:182-217)
+  // x-slab decomposition; a full cube has x0 = 0, Ns = N, H = 0.
+  int x0;          // global x index of the first Lagrangian plane this rank owns
+  int Ns;          // planes owned
+  int H;           // halo planes each side of the density tile: rho is [(Ns + 2H)][N][N], plane 0 = global x0 - H
+  int *flag;       // set to 1 if a particle left the halo (device int), may be null when H == 0 and Ns == N
 };
 
 struct LikeParams {
@@ -41,6 +46,17 @@ void launch_scatter_positions(const GridGeom &g, const double *x, const double *
 void launch_cell_indices(const GridGeom &g, const double *x, const double *y, const double *z, int *ci, int *cj,
                          int *ck, size_t n, cudaStream_t st);
 
+// max |a[i]| -> *out (device scalar); scratch: kReduceBlocks doubles
+void launch_max_abs(const double *a, size_t n, double *scratch, double *out, cudaStream_t st);
+// dst[i] += src[i]
+void launch_add(double *dst, const double *src, size_t n, cudaStream_t st);
+// slab variant of launch_inverse_spectrum, stage 1: the multiplier of my x planes as complex numbers in
+// the packed all-to-all layout [peer][x_l][y_l][z <= N/2]; stage 2 (after the all-to-all): real parts
+// into the transposed half grid [x][y_l][N/2+2]
+void launch_inverse_spectrum_pack(const double *full_xslab, double2 *packed, int N, int Ns, double normFS,
+                                  cudaStream_t st);
+void launch_inverse_spectrum_unpack(const double2 *transposed, double *half, int N, int Ns, cudaStream_t st);
+
 // deterministic sum of an array -> *out (device scalar); scratch: kReduceBlocks doubles
 void launch_sum(const double *a, size_t n, double *scratch, double *out, cudaStream_t st);
 // deterministic 0.5 * sum a*b
@@ -52,8 +68,8 @@ void launch_kinetic(const double *p, const double *conv, const double *mass_r, s
 // delta = rho / mean - 1 (in place), residual r, and -lnL partial sum -> *nll (device scalar).
 // mean is read from the device scalar `sum_rho` (/N).  resid may be null (value only).
 void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const double *sum_rho, const double *nobs,
-                              const double *noise, const double *window, double *resid, size_t n, double *scratch,
-                              double *nll, cudaStream_t st);
+                              const double *noise, const double *window, double *resid, size_t n, double ncells_global,
+                              double *scratch, double *nll, cudaStream_t st);
 
 // exact adjoint of the mass assignment: V_c(p) = sum_cells r_c dW_c/dx_c, in place over Psi
 void launch_gather_adjoint(const GridGeom &g, double *psix_Vx, double *psiy_Vy, double *psiz_Vz,

@@ -43,7 +43,9 @@ enum KernelKind : int {
   KK_STREAM = 7,
   KK_COLOUR = 8,
   KK_FFT_STRIDED_X = 9,
-  KK_COUNT = 10
+  KK_ALLTOALL = 10,
+  KK_HALO = 11,
+  KK_COUNT = 12
 };
 
 struct Profiler {

@@ -296,9 +296,16 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dom_name, (dom_ms, dom_cnt) = dom
     achieved = alg_bytes[dom_name] / (dom_ms * 1e-3 / dom_cnt) / 1e9
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture, if one exists
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            traffic = json.load(f).get(str(args.grid), {}).get(dom_name)
+    except (OSError, ValueError):
+        pass
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-        "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak_gbs, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes[dom_name],
+        "peak_source": peak_src,
         "launches_per_step": dom_cnt / args.steps, "avg_launch_ms": dom_ms / dom_cnt,
         "share_of_step": dom_ms / total_prof,
         "per_kernel": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,

@@ -75,6 +75,18 @@ const char *bgpu_last_error(void);
 int bgpu_create(const bgpu_params *p, bgpu_handle **out);
 void bgpu_destroy(bgpu_handle *h);
 
+/* One chain across G GPUs of a box, x-slab decomposition: rank r owns planes
+ * i in [r*N1/G, (r+1)*N1/G) of EVERY array argument below, i.e. the contiguous sub-array
+ * double[N1/G][N2][N3] of the reference's layout (and of its output files).  One process per GPU;
+ * rank 0 calls bgpu_nccl_unique_id and the host program hands the 128 bytes to the other ranks
+ * (MPI_Bcast, a file, torch.distributed ...).  The distributed FFT transposes with NCCL
+ * all-to-all, the mass-assignment halo goes to the two x neighbours, scalars are all-reduced; every
+ * rank must make the same sequence of calls.  Supported: N1 in {128, 256, 512}, calc_h 0 / 1
+ * (Gaussian likelihood for calc_h 0), NGP / CIC / TSC, RSD; bgpu_color_momenta is not. */
+int bgpu_nccl_unique_id(void *out128);
+int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out);
+int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *nx_local);
+
 /* static inputs: data->observational->{Power, nobs, noise_sf, window} (main.cc:150-154).
  * NULL leaves an array unchanged. */
 int bgpu_set_static(bgpu_handle *h, const double *Power, const double *nobs, const double *noise,
@@ -124,7 +136,7 @@ uint64_t bgpu_kernel_launches(void);
 /* per-kernel-class device timing (bench.py's roofline leg): CUDA events on the launching
  * stream around every launch between begin and end; a launch of the reduce / residual class
  * is a pair of kernels.  nkinds <= BGPU_PROFILE_KINDS. */
-#define BGPU_PROFILE_KINDS 10
+#define BGPU_PROFILE_KINDS 12
 int bgpu_profile_begin(void);
 int bgpu_profile_end(double *ms_per_kind, uint64_t *launches_per_kind, int nkinds);
 const char *bgpu_profile_kind_name(int kind);
