@@ -7,7 +7,9 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -81,6 +83,7 @@ struct bgpu_handle {
   double2 *sendbuf = nullptr, *recvbuf = nullptr;
   int *dflag = nullptr;         // device flag: a particle left the halo
   int *hflag = nullptr;         // pinned copy
+  void *peer_base[8] = {};      // other ranks' receive buffers, opened through CUDA IPC
 };
 
 namespace {
@@ -193,12 +196,14 @@ void forward_from_shat(bgpu_handle *h, double dQ, bool rsd, double *px, double *
   launch_scatter(g, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, px, py, pz, h->stream);
   if (h->G > 1) {
     // my lower halo belongs to rank-1's last planes, my upper halo to rank+1's first planes
-    ProfScope prof(KK_HALO, h->stream);
     const int H = g.H, lo = (h->rank + h->G - 1) % h->G, hi = (h->rank + 1) % h->G;
     const size_t cnt = (size_t)H * plane;
     double *ext = h->rho_ext;
-    h->comm->exchange2(ext, lo, ext + (size_t)(h->Ns + H) * plane, hi, h->halo_recv, hi, h->halo_recv + cnt, lo, cnt,
-                       h->stream);
+    {
+      ProfScope prof(KK_HALO, h->stream);
+      h->comm->exchange2(ext, lo, ext + (size_t)(h->Ns + H) * plane, hi, h->halo_recv, hi, h->halo_recv + cnt, lo, cnt,
+                         h->stream);
+    }
     launch_add(ext + (size_t)h->Ns * plane, h->halo_recv, cnt, h->stream);        // from rank+1 -> my last H planes
     launch_add(ext + (size_t)H * plane, h->halo_recv + cnt, cnt, h->stream);      // from rank-1 -> my first H planes
   }
@@ -282,14 +287,20 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     }
   }
   // gradpsi = IFFT[(V/N)/P s^ + norm * h^]
+  ROp sop;
+  sop.kind = R_SCALE;
+  sop.a = inv_n;
+  if (h->G > 1 && h->N >= 512) {
+    // the TMA-staged x pass cannot hold both operand tiles at this size: combine in a pass of its own
+    launch_kfinal_combine(h->shat, h->inv_power, h->acc, h->acc, norm, h->N, h->nh, h->stream);
+    h->fft.c2r(h->acc, h->work, d_out, KOp{}, sop);
+    return;
+  }
   KOp lop;
   lop.kind = K_FINAL;
   lop.a = norm;
   lop.real0 = h->inv_power;
   lop.cplx0 = h->acc;
-  ROp sop;
-  sop.kind = R_SCALE;
-  sop.a = inv_n;
   h->fft.c2r(h->shat, h->work, d_out, lop, sop);
 }
 
@@ -376,6 +387,7 @@ void update_inverse(bgpu_handle *h, const double *full, double *half) {
   launch_inverse_spectrum_pack(full, h->sendbuf, h->N, h->Ns, h->normFS, h->stream);
   h->comm->all_to_all(h->sendbuf, h->recvbuf, (size_t)h->Ns * h->Ns * (h->N / 2 + 1) * 2, h->stream);
   launch_inverse_spectrum_unpack(h->recvbuf, half, h->N, h->Ns, h->stream);
+  h->comm->barrier(h->stream);  // the receive buffer is free again before any peer's next transform writes it
 }
 
 }  // namespace
@@ -504,7 +516,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   if (nranks > 1) {
     h->comm = new NcclComm(nccl_id, rank, nranks);
     dalloc(h->sendbuf, h->nh);
-    dalloc(h->recvbuf, h->nh);
+    dalloc(h->recvbuf, 2 * h->nh);   // two receive buffers, alternating between transforms
     h->Hmax = h->Ns < 24 ? h->Ns : 24;
     dalloc(h->halo_recv, (size_t)2 * h->Hmax * h->N * h->N);
     BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->dflag), sizeof(int)));
@@ -517,6 +529,34 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     h->fft.comm = h->comm;
     h->fft.sendbuf = h->sendbuf;
     h->fft.recvbuf = h->recvbuf;
+    const char *e2 = std::getenv("BGPU_SLAB_P2P");
+    if (!(e2 && e2[0] == '0')) {
+      // fused transpose: map every rank's receive buffers into this process (CUDA IPC over NVLink peer
+      // access); the 64-byte handles travel through the NCCL communicator itself
+      static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+      require(nranks <= 8, "bgpu_slab_create: at most 8 ranks (one box)");
+      cudaIpcMemHandle_t mine;
+      BGPU_CUDA(cudaIpcGetMemHandle(&mine, h->recvbuf));
+      std::vector<cudaIpcMemHandle_t> out_h(nranks, mine), in_h(nranks);
+      double *d_x = nullptr;
+      dalloc(d_x, (size_t)2 * nranks * 8);
+      BGPU_CUDA(cudaMemcpyAsync(d_x, out_h.data(), (size_t)nranks * 64, cudaMemcpyHostToDevice, h->stream));
+      h->comm->all_to_all(d_x, d_x + (size_t)nranks * 8, 8, h->stream);
+      BGPU_CUDA(cudaMemcpyAsync(in_h.data(), d_x + (size_t)nranks * 8, (size_t)nranks * 64, cudaMemcpyDeviceToHost,
+                                h->stream));
+      BGPU_CUDA(cudaStreamSynchronize(h->stream));
+      cudaFree(d_x);
+      for (int r = 0; r < nranks; ++r) {
+        void *base = h->recvbuf;
+        if (r != rank) {
+          BGPU_CUDA(cudaIpcOpenMemHandle(&base, in_h[r], cudaIpcMemLazyEnablePeerAccess));
+          h->peer_base[r] = base;
+        }
+        h->fft.peer_recv[0][r] = static_cast<double2 *>(base);
+        h->fft.peer_recv[1][r] = static_cast<double2 *>(base) + h->nh;
+      }
+      h->fft.p2p = true;
+    }
   }
   h->fft.init(h->N, h->stream);
   h->kfac = 2. * M_PI / p->L1;                                      // scale_space.cpp:42
@@ -597,7 +637,23 @@ int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *n
 void bgpu_destroy(bgpu_handle *h) {
   if (!h) return;
   cudaSetDevice(h->p.device);
+  if (h->comm && h->stream) {
+    // collective: nobody unmaps or frees a receive buffer a peer may still be writing to
+    try {
+      h->comm->barrier(h->stream);
+    } catch (...) {
+    }
+  }
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void *q : h->peer_base)
+    if (q) cudaIpcCloseMemHandle(q);
+  if (h->comm && h->stream) {
+    try {
+      h->comm->barrier(h->stream);
+      cudaStreamSynchronize(h->stream);
+    } catch (...) {
+    }
+  }
   double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->mass_f, h->mass_r, h->inv_mass,
                      h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->tmp,
                      h->partials, h->dscal, h->halo_recv};

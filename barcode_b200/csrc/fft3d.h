@@ -21,6 +21,8 @@ struct SlabComm {
   virtual ~SlabComm() {}
   // peer h receives doubles [h*count, (h+1)*count) of `send` into block `my rank` of its `recv`
   virtual void all_to_all(const void *send, void *recv, size_t count_doubles, cudaStream_t st) = 0;
+  // every rank's work enqueued before this call is complete before any rank's work enqueued after it starts
+  virtual void barrier(cudaStream_t st) = 0;
 };
 
 struct Fft3d {
@@ -49,6 +51,12 @@ struct Fft3d {
   int G = 1, rank = 0, Ns = 0;
   SlabComm *comm = nullptr;                  // all-to-all provider (NCCL), owned by the caller
   double2 *sendbuf = nullptr, *recvbuf = nullptr;  // packed [peer][Ns][Ns][N/2+1], owned by the caller
+  // fused transpose over peer memory: peer_recv[b][h] = receive buffer b of rank h as mapped into this
+  // process (own rank: the local pointer); two buffers alternate (`parity`)
+  bool p2p = false;
+  double2 *peer_recv[2][8] = {};
+  mutable int parity = 0;
+  void barrier() const;  // cross-rank, stream-ordered
 
   void init(int n, cudaStream_t st);
   void destroy();

@@ -126,7 +126,8 @@ static CUtensorMap make_half_grid_map(const void *base, int N, int axis, bool cp
     const cuuint64_t ns = (cuuint64_t)n_mid, g = (cuuint64_t)n_slow;  // n_mid = Ns, n_slow = G
     const cuuint64_t dims[4] = {row_doubles, ns, ns, g};
     const cuuint64_t strides[3] = {pitch, pitch * ns, pitch * ns * ns};
-    const cuuint32_t box[4] = {16u, (cuuint32_t)(ns < 256 ? ns : 256), 1u, 1u};
+    const cuuint32_t rb = (cuuint32_t)(ns < 256 ? ns : 256);
+    const cuuint32_t box[4] = {16u, axis == 1 ? rb : 1u, axis == 1 ? 1u : rb, 1u};  // rows along y_l or x_l
     r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -173,6 +174,8 @@ struct PassIo {
   int other0 = 0;       // global index of other == 0
   bool in_packed = false, out_packed = false;
   int G = 1, Ns = 0;
+  double2 *const *peer_out = nullptr;  // fused transpose: receive buffer of every rank, as mapped here
+  int my_rank = 0;
 };
 
 template <int N, int DIR, int AXIS, int AUX>
@@ -196,10 +199,15 @@ static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, 
   const int n_slow = AXIS == 0 ? N : n_other, n_mid = AXIS == 0 ? n_other : N;
   TmaMaps maps;
   maps.in = io.in_packed ? f.tensor_map(in, AXIS, true, 1, io.G, io.Ns) : f.tensor_map(in, AXIS, true, 0, n_slow, n_mid);
-  maps.out = io.out_packed ? f.tensor_map(out, AXIS, true, 1, io.G, io.Ns) : f.tensor_map(out, AXIS, true, 0, n_slow, n_mid);
+  maps.out = io.peer_out ? maps.in
+             : io.out_packed ? f.tensor_map(out, AXIS, true, 1, io.G, io.Ns)
+                             : f.tensor_map(out, AXIS, true, 0, n_slow, n_mid);
   maps.auxr = AUX >= 1 ? f.tensor_map(lop.real0, AXIS, false, 0, n_slow, n_mid) : maps.in;
   maps.auxc = AUX >= 2 ? f.tensor_map(lop.cplx0, AXIS, true, 0, n_slow, n_mid) : maps.in;
-  PassGeom geo{n_other, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0};
+  if (io.peer_out)
+    for (int h = 0; h < io.G; ++h) maps.peer[h] = f.tensor_map(io.peer_out[h], AXIS, true, 1, io.G, io.Ns);
+  PassGeom geo{n_other, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0, io.peer_out ? io.Ns : 0,
+               io.my_rank};
   const int tiles = n_other * ((N / 2 + 1 + 7) / 8);
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > tiles) blocks = tiles;
@@ -355,14 +363,28 @@ static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xo
   // the transposed layout [x][y_local][z] (= the receive buffer, block h holding the x planes of rank h)
   PassIo y_io;
   y_io.n_other = f.Ns;
-  y_io.out_packed = true;
   y_io.G = f.G;
   y_io.Ns = f.Ns;
-  launch_strided<N, -1, 1>(f, out, f.sendbuf, f.twN, KOp{}, KOp{}, f.stream, y_io);
-  slab_all_to_all(f, f.sendbuf, f.recvbuf);
   PassIo x_io;
   x_io.n_other = f.Ns;
   x_io.other0 = f.rank * f.Ns;
+  if (f.p2p) {
+    // fused transpose: the y pass stores every tile straight into the peers' receive buffers (TMA over
+    // NVLink); one cross-rank barrier, then the x pass reads what the peers wrote here.  Receive
+    // buffers alternate between transforms, so the barrier of this transform also orders the next
+    // transform's writes after every rank's reads of that buffer.
+    double2 *const *peers = f.peer_recv[f.parity];
+    y_io.peer_out = peers;
+    y_io.my_rank = f.rank;
+    launch_strided<N, -1, 1>(f, out, nullptr, f.twN, KOp{}, KOp{}, f.stream, y_io);
+    f.barrier();
+    launch_strided<N, -1, 0>(f, peers[f.rank], xout ? xout : out, f.twN, KOp{}, sop, f.stream, x_io);
+    f.parity ^= 1;
+    return;
+  }
+  y_io.out_packed = true;
+  launch_strided<N, -1, 1>(f, out, f.sendbuf, f.twN, KOp{}, KOp{}, f.stream, y_io);
+  slab_all_to_all(f, f.sendbuf, f.recvbuf);
   launch_strided<N, -1, 0>(f, f.recvbuf, xout ? xout : out, f.twN, KOp{}, sop, f.stream, x_io);
 }
 
@@ -378,14 +400,26 @@ static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *o
     PassIo x_io;
     x_io.n_other = f.Ns;
     x_io.other0 = f.rank * f.Ns;
-    launch_strided<N, +1, 0>(f, in, f.sendbuf, f.twN, lop, KOp{}, f.stream, x_io);
-    slab_all_to_all(f, f.sendbuf, f.recvbuf);
+    x_io.G = f.G;
+    x_io.Ns = f.Ns;
     PassIo y_io;
     y_io.n_other = f.Ns;
     y_io.in_packed = true;
     y_io.G = f.G;
     y_io.Ns = f.Ns;
-    launch_strided<N, +1, 1>(f, f.recvbuf, work, f.twN, KOp{}, KOp{}, f.stream, y_io);
+    if (f.p2p) {
+      double2 *const *peers = f.peer_recv[f.parity];
+      x_io.peer_out = peers;
+      x_io.my_rank = f.rank;
+      launch_strided<N, +1, 0>(f, in, nullptr, f.twN, lop, KOp{}, f.stream, x_io);
+      f.barrier();
+      launch_strided<N, +1, 1>(f, peers[f.rank], work, f.twN, KOp{}, KOp{}, f.stream, y_io);
+      f.parity ^= 1;
+    } else {
+      launch_strided<N, +1, 0>(f, in, f.sendbuf, f.twN, lop, KOp{}, f.stream, x_io);
+      slab_all_to_all(f, f.sendbuf, f.recvbuf);
+      launch_strided<N, +1, 1>(f, f.recvbuf, work, f.twN, KOp{}, KOp{}, f.stream, y_io);
+    }
   }
   if (try_c2r_zpass_tma<N>(f, work, out, sop)) return;
   if (f.G > 1) throw std::runtime_error("bgpu: the slab-decomposed transform needs the bulk-copy z pass (N >= 128)");
@@ -493,6 +527,11 @@ void Fft3d::destroy() {
   if (twN) cudaFree(twN);
   if (twM) cudaFree(twM);
   twN = twM = nullptr;
+}
+
+void Fft3d::barrier() const {
+  ProfScope prof(KK_ALLTOALL, stream);
+  comm->barrier(stream);
 }
 
 bool Fft3d::supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 0; }

@@ -239,8 +239,11 @@ struct TmaTile {
   static constexpr int stage_bytes = main_bytes + auxr_bytes + auxc_bytes;
 };
 
+constexpr int kMaxPeers = 8;  // GPUs of one box
+
 struct TmaMaps {
   CUtensorMap in, out, auxr, auxc;
+  CUtensorMap peer[kMaxPeers];  // receive buffers of the slab ranks (peer-mapped over NVLink), rank-4
 };
 
 // Shape of one strided pass.  A full cube has n_other = N pencils' worth of "other" index
@@ -254,6 +257,11 @@ struct PassGeom {
   int other0;
   int in_packed;
   int out_packed;
+  // fused transpose: > 0 = rows per peer (Ns); the tile's rows [h*Ns, (h+1)*Ns) are stored straight into
+  // block `my_rank` of rank h's receive buffer [src][x_l][y_l][z] over NVLink (maps.peer[h]), for both
+  // pass axes -- the all-to-all of the distributed transform happens inside the pass kernel
+  int out_peers;
+  int my_rank;
 };
 
 // shared-memory address of (row, pencil p) in a 64-byte-swizzled tile of doubles (T = 8 per row)
@@ -430,7 +438,15 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
-      if (AXIS == 1 && geo.out_packed) {  // rows leave grouped by the peer they go to
+      if (geo.out_peers) {
+        const int ns = geo.out_peers, rb = ns < 256 ? ns : 256;
+        for (int r0 = 0; r0 < N; r0 += rb) {
+          const int h = r0 / ns, rl = r0 % ns;
+          // [z][y_l][x_l][src]: the y pass (AXIS 1) scatters its y rows, the x pass its x rows
+          tma_store_4d(&maps.peer[h], zt * 2 * T, AXIS == 1 ? rl : other, AXIS == 1 ? other : rl, geo.my_rank,
+                       smem_al + s * Tile::stage_bytes + r0 * 128);
+        }
+      } else if (AXIS == 1 && geo.out_packed) {  // rows leave grouped by the peer they go to
         const int rb = geo.out_packed < 256 ? geo.out_packed : 256;
         for (int r0 = 0; r0 < N; r0 += rb)
           tma_store_4d(&maps.out, zt * 2 * T, r0 % geo.out_packed, other, r0 / geo.out_packed,

@@ -733,4 +733,24 @@ void launch_inverse_spectrum_unpack(const double2 *transposed, double *half, int
   BGPU_LAUNCHED(1);
 }
 
+// out = a_real * s + norm * h on the (transposed) half grid: the K_FINAL combination as its own pass,
+// for the configurations whose strided pass cannot stage both operand tiles (N = 512 on a slab)
+__global__ void kfinal_combine_kernel(const double2 *__restrict__ s, const double *__restrict__ mult,
+                                      const double2 *__restrict__ hh, double2 *__restrict__ out, double norm, int nzh,
+                                      size_t n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const size_t row = idx / nzh;
+  const int z = (int)(idx - row * nzh);
+  const double f = mult[row * (nzh + 1) + z];
+  const double2 a = s[idx], b = hh[idx];
+  out[idx] = make_double2(a.x * f + norm * b.x, a.y * f + norm * b.y);
+}
+void launch_kfinal_combine(const double2 *s, const double *mult, const double2 *h, double2 *out, double norm, int N,
+                           size_t n_half, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  kfinal_combine_kernel<<<blocks_for(n_half, 256), 256, 0, st>>>(s, mult, h, out, norm, N / 2 + 1, n_half);
+  BGPU_LAUNCHED(1);
+}
+
 }  // namespace bgpu

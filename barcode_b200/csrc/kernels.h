@@ -57,6 +57,10 @@ void launch_inverse_spectrum_pack(const double *full_xslab, double2 *packed, int
                                   cudaStream_t st);
 void launch_inverse_spectrum_unpack(const double2 *transposed, double *half, int N, int Ns, cudaStream_t st);
 
+// out = mult * s + norm * h on a half grid (mult has the padded row pitch N/2+2)
+void launch_kfinal_combine(const double2 *s, const double *mult, const double2 *h, double2 *out, double norm, int N,
+                           size_t n_half, cudaStream_t st);
+
 // deterministic sum of an array -> *out (device scalar); scratch: kReduceBlocks doubles
 void launch_sum(const double *a, size_t n, double *scratch, double *out, cudaStream_t st);
 // deterministic 0.5 * sum a*b

@@ -70,10 +70,17 @@ NcclComm::NcclComm(const void *id128, int rank_, int nranks_) : rank(rank_), nra
   ncclComm_t c = nullptr;
   check(api().CommInitRank(&c, nranks, id, rank), "ncclCommInitRank");
   comm = c;
+  cudaMalloc(reinterpret_cast<void **>(&token), sizeof(double));
+  cudaMemset(token, 0, sizeof(double));
 }
 
 NcclComm::~NcclComm() {
   if (comm) api().CommDestroy(static_cast<ncclComm_t>(comm));
+  if (token) cudaFree(token);
+}
+
+void NcclComm::barrier(cudaStream_t st) {
+  check(api().AllReduce(token, token, 1, ncclDouble, ncclSum, static_cast<ncclComm_t>(comm), st), "ncclAllReduce");
 }
 
 void NcclComm::all_to_all(const void *send, void *recv, size_t count, cudaStream_t st) {

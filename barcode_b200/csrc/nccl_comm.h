@@ -14,6 +14,7 @@ namespace bgpu {
 struct NcclComm : SlabComm {
   int rank = 0, nranks = 1;
   void *comm = nullptr;  // ncclComm_t
+  double *token = nullptr;  // device scalar the barrier reduces
 
   // 128-byte ncclUniqueId; call on one rank and distribute (MPI, a file, torch.distributed ...)
   static void unique_id(void *out128);
@@ -21,6 +22,7 @@ struct NcclComm : SlabComm {
   ~NcclComm() override;
 
   void all_to_all(const void *send, void *recv, size_t count_doubles, cudaStream_t st) override;
+  void barrier(cudaStream_t st) override;  // a one-element all-reduce on `st`
   void all_reduce_sum(double *buf, size_t count, cudaStream_t st);  // in place
   void all_reduce_max(double *buf, size_t count, cudaStream_t st);  // in place
   // one grouped neighbour exchange: send a -> rank `to_a`, b -> `to_b`; receive ra <- `from_a`, rb <- `from_b`

@@ -50,6 +50,70 @@ def power_on_grid(k_tab, p_tab, N: int, L: float, chunk: int = 32) -> np.ndarray
     return out
 
 
+def power_on_planes(k_tab, p_tab, N: int, L: float, x0: int, nx: int) -> np.ndarray:
+    """The planes [x0, x0 + nx) of power_on_grid: what one rank of a slab-decomposed chain holds."""
+    kt = np.asarray(k_tab, dtype=np.float32).astype(np.float64)
+    pt = np.asarray(p_tab, dtype=np.float32).astype(np.float64)
+    k = calc_ki(N, L)
+    out = np.empty((nx, N, N))
+    for c0 in range(0, nx, 16):
+        c1 = min(nx, c0 + 16)
+        k2 = (k[x0 + c0:x0 + c1, None, None] ** 2 + k[None, :, None] ** 2) + k[None, None, :] ** 2
+        ktot = np.sqrt(k2).ravel()
+        idx = np.clip(np.searchsorted(kt, ktot, side="right") - 1, 0, len(kt) - 2)
+        x_lo, x_hi = kt[idx], kt[idx + 1]
+        y_lo, y_hi = pt[idx], pt[idx + 1]
+        out[c0:c1] = (y_lo + (ktot - x_lo) / (x_hi - x_lo) * (y_hi - y_lo)).reshape(c1 - c0, N, N)
+    if x0 == 0:
+        out[0, 0, 0] = 0.0
+    return out
+
+
+def power_on_kslab(k_tab, p_tab, N: int, L: float, y0: int, ny: int) -> np.ndarray:
+    """P(|k|) on the transposed k-space slab [x][y0 <= y < y0 + ny][z <= N/2] (slab.SlabChain.kshape)."""
+    kt = np.asarray(k_tab, dtype=np.float32).astype(np.float64)
+    pt = np.asarray(p_tab, dtype=np.float32).astype(np.float64)
+    k = calc_ki(N, L)
+    nzh = N // 2 + 1
+    out = np.empty((N, ny, nzh))
+    for c0 in range(0, N, 16):
+        c1 = min(N, c0 + 16)
+        k2 = (k[c0:c1, None, None] ** 2 + k[None, y0:y0 + ny, None] ** 2) + k[None, None, :nzh] ** 2
+        ktot = np.sqrt(k2).ravel()
+        idx = np.clip(np.searchsorted(kt, ktot, side="right") - 1, 0, len(kt) - 2)
+        x_lo, x_hi = kt[idx], kt[idx + 1]
+        y_lo, y_hi = pt[idx], pt[idx + 1]
+        out[c0:c1] = (y_lo + (ktot - x_lo) / (x_hi - x_lo) * (y_hi - y_lo)).reshape(c1 - c0, ny, nzh)
+    if y0 == 0:
+        out[0, 0, 0] = 0.0
+    return out
+
+
+def slab_problem(sc, seed: int = 1, signal_scale: float = 0.5):
+    """`synthetic_problem` for a slab-decomposed chain, every array a local slab: Gaussian random
+    fields are made with the chain's own distributed FFT (white noise -> r2c -> * sqrt(P n / V) ->
+    c2r), nobs = max(0, 1 + forward(truth) + N(0, 1)), window = noise = 1."""
+    N, L = sc.N1, sc.params.L1
+    k_tab, p_tab = load_pk_table()
+    P = power_on_planes(k_tab, p_tab, N, L, sc.x0, sc.Ns)
+    Pk = power_on_kslab(k_tab, p_tab, N, L, sc.x0, sc.Ns)
+    amp = np.sqrt(np.maximum(Pk, 0.0) * float(N) ** 3 / L ** 3)
+    ones = np.ones(sc.shape)
+    sc.set_static(Power=P, nobs=ones, noise=ones, window=ones)
+
+    def grf(sd):
+        w = np.random.default_rng(1000003 * sd + sc.rank).standard_normal(sc.shape)
+        return sc.fft_c2r(sc.fft_r2c(w) * amp)
+
+    truth = grf(seed)
+    d_eul = sc.forward(truth)
+    nobs = np.maximum(0.0, 1.0 + d_eul + np.random.default_rng(7 * seed + 1000 + sc.rank).standard_normal(sc.shape))
+    sc.set_static(nobs=nobs)
+    signal = signal_scale * grf(seed + 1)
+    sc.hamiltonian_mass()
+    return dict(Power=P, nobs=nobs, signal=signal)
+
+
 def box_length(N: int) -> float:
     """The shipped cell size: 200 Mpc/h over 64 cells (data/input.par:123-125)."""
     return N * (200.0 / 64.0)

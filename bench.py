@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--calc-h", type=int, default=0, choices=[0, 1, 4])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="chains", choices=["chains", "slab"],
+                    help="N > 1 GPUs: independent chains (weak scaling, default) or ONE chain, x-slab decomposed "
+                         "(strong scaling; BASELINE.json configs[3], [4])")
     return ap.parse_args()
 
 
@@ -366,10 +369,87 @@ def run_ours(args):
     return 0
 
 
+def run_slab(args):
+    """ONE chain across all ranks (x-slab decomposition, barcode_b200/slab.py): strong scaling.
+    value = gradient evaluations of that one chain per second, device-timed, max over ranks."""
+    import torch
+    from barcode_b200 import chain as bc
+    from barcode_b200 import inputs, multi, slab
+
+    info = multi.rank_info()
+    world, rank, local_rank = info.world, info.rank, info.local_rank
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    multi.init("nccl", info, torch.device("cuda", local_rank))
+    cfg, name = workload(args.grid, args.calc_h)
+    sc = slab.SlabChain.create(bc.Params(device=local_rank, **cfg), rank, world)
+    prob = inputs.slab_problem(sc, seed=1)
+    stream = torch.cuda.current_stream()
+    sc.set_stream(stream.cuda_stream)
+    d_s = torch.from_numpy(np.ascontiguousarray(prob["signal"]).reshape(-1)).cuda()
+    d_g = torch.empty_like(d_s)
+
+    def barrier():
+        multi.barrier(info)
+        torch.cuda.synchronize()
+
+    def step():
+        sc.gradient_psi_dev(d_s.data_ptr(), d_g.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = bc.kernel_launches()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    launches = bc.kernel_launches() - l0
+    barrier()
+    ms = multi.max_over_ranks(e0.elapsed_time(e1), info, "cuda")
+    clock_info = clocks.stop() if rank == 0 else {}
+    bc.profile_begin()
+    for _ in range(args.steps):
+        step()
+    prof = bc.profile_end()
+    n_loc = sc.N
+    nh_loc = sc.Nhalf
+    # bytes each rank sends per all-to-all (its whole k-space slab minus the block it keeps)
+    a2a_bytes = nh_loc * 16 * (world - 1) / max(world, 1)
+    per_kernel = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                  for k, v in prof.items() if v[1]}
+    if "all_to_all" in per_kernel and world > 1:
+        t = prof["all_to_all"][0] * 1e-3 / prof["all_to_all"][1]
+        per_kernel["all_to_all"]["GBps_sent_per_gpu"] = a2a_bytes / t / 1e9
+        per_kernel["all_to_all"]["frac_of_nvlink_770GBps"] = a2a_bytes / t / 1e9 / 770.0
+    sc.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "grid": args.grid, "calc_h": args.calc_h,
+                       "parallelism": f"one chain, x-slab decomposed over {world} GPU(s): distributed FFT with NCCL "
+                                      "all-to-all, halo-exchanged mass assignment",
+                       "l2": "inputs larger than L2; no explicit flush"},
+            "per_kernel": per_kernel, "local_cells": n_loc, "gpu_launches": int(launches), "clocks": clock_info,
+        }
+        print(json.dumps(line))
+    multi.finalize()
+    return 0
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "slab":
+        return run_slab(args)
     return run_ours(args)
 
 

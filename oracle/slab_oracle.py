@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE -- numpy restatement of the slab-decomposed chain's data movement.
+
+The product (barcode_b200/csrc: fft_plan.cu r2c_impl / c2r_impl, api.cu forward_from_shat,
+kernels.cu deposit) distributes the reference's 3-D FFT (fftwrapper.cc:26-125) and mass
+assignment (massFunctions.cc:49-364) over x slabs; the reference itself has no distributed mode,
+so the check is self-consistency: the distributed algorithm, run with numpy per rank and
+torch.distributed for the exchanges (gloo on CPU), must reproduce the single-process oracle
+(oracle/barcode_oracle.py).  The partition arithmetic is imported from the product
+(barcode_b200/slab.py) -- that is the piece under test.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from barcode_b200 import slab
+from oracle import barcode_oracle as bo
+
+
+def _all_to_all(blocks, rank, world, dist):
+    """blocks[h] goes to rank h; returns the list of blocks received, indexed by source rank."""
+    import torch
+    mine = torch.from_numpy(np.ascontiguousarray(np.stack(blocks)).view(np.float64))
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)   # gloo has no all_to_all: gather everything, keep what is addressed to me
+    cplx = blocks[0].dtype == np.complex128
+    res = []
+    for src in range(world):
+        a = out[src].numpy()[rank]
+        res.append(a.view(np.complex128) if cplx else a)
+    return res
+
+
+def slab_rfftn(local, N, rank, world, dist):
+    """Real x-slab [Ns][N][N] -> transposed k-space slab [x][y_local][z <= N/2]."""
+    x0, Ns = slab.slab_range(N, rank, world)
+    nzh = N // 2 + 1
+    zy = np.fft.fft(np.fft.rfft(local, axis=2), axis=1)                      # local z and y passes
+    packed = np.empty(world * Ns * Ns * nzh, dtype=np.complex128)            # the y pass stores packed
+    xl, y, z = np.meshgrid(np.arange(Ns), np.arange(N), np.arange(nzh), indexing="ij")
+    packed[slab.packed_index(N, Ns, xl, y, z)] = zy
+    blocks = list(packed.reshape(world, Ns, Ns, nzh))
+    recv = _all_to_all(blocks, rank, world, dist)                            # block src = x planes of rank src
+    tr = np.concatenate(recv, axis=0)                                        # [x][y_local][z]
+    return np.fft.fft(tr, axis=0)                                            # local x pass
+
+
+def slab_irfftn(kslab, N, rank, world, dist):
+    """Transposed k-space slab -> real x-slab (1/N^3 included, fftwrapper.cc:43-45)."""
+    x0, Ns = slab.slab_range(N, rank, world)
+    nzh = N // 2 + 1
+    tr = np.fft.ifft(kslab, axis=0)                                          # x pass on [x][y_local][z]
+    blocks = [np.ascontiguousarray(tr[h * Ns:(h + 1) * Ns]) for h in range(world)]
+    recv = _all_to_all(blocks, rank, world, dist)                            # from rank src: [x_l][y_l of src][z]
+    zy = np.concatenate(recv, axis=1)                                        # [x_l][y][z], y = src*Ns + y_l
+    return np.fft.irfft(np.fft.ifft(zy, axis=1), n=N, axis=2)
+
+
+def slab_density(p: bo.Params, psi_local, rank, world, dist):
+    """Mass assignment of this rank's particles into a halo-extended tile, halos added into the
+    neighbours; returns (rho of the owned planes [Ns][N][N], halo width H)."""
+    import torch
+    N, d, L = p.N1, p.d, p.L1
+    x0, Ns = slab.slab_range(N, rank, world)
+    # positions of my Lagrangian planes (bo.positions on the slab: global lattice coordinate of plane i)
+    g = d * np.arange(N, dtype=np.float64) + 0.5 * d
+    x = bo.pacman(g[x0:x0 + Ns, None, None] + psi_local[0], L)
+    y = bo.pacman(g[None, :, None] + psi_local[1], L)
+    z = bo.pacman(g[None, None, :] + psi_local[2], L)
+    if p.rsd_model:
+        vez = bo.c_pecvel(p.ascale, p.OM, p.OL) * psi_local[2]
+        OC = 1.0 - p.OM - p.OL
+        Hub = 100.0 * np.sqrt(p.OM / p.ascale / p.ascale / p.ascale + p.OL + OC / p.ascale / p.ascale)
+        z = bo.pacman(z + vez * (1.0 / Hub / p.ascale), L)
+    # halo width from the largest x displacement on any rank
+    m = torch.tensor([float(np.abs(psi_local[0]).max())], dtype=torch.float64)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    H = slab.halo_planes(float(m.item()), d)
+    assert H <= Ns, "halo wider than a slab"
+    ext = np.zeros((Ns + 2 * H) * N * N)
+    xs, ys, zs = x.ravel(), np.broadcast_to(y, x.shape).ravel(), np.broadcast_to(z, x.shape).ravel()
+    assert p.masskernel == 1, "the slab oracle restates the CIC deposit"
+    ok = bo._in_domain(p, xs, ys, zs, False)
+    i0, i1, tx, dx = bo.cic_cells_weights(p, xs[ok])
+    j0, j1, ty, dy = bo.cic_cells_weights(p, ys[ok])
+    k0, k1, tz, dz = bo.cic_cells_weights(p, zs[ok])
+    for ii, wx in ((i0, tx), (i1, dx)):
+        li = slab.ext_plane(ii, x0, H, N)
+        assert (li < Ns + 2 * H).all(), "a particle left the halo"
+        for jj, wy in ((j0, ty), (j1, dy)):
+            for kk, wz in ((k0, tz), (k1, dz)):
+                np.add.at(ext, kk + N * (jj + N * li), (1.0 * wx) * wy * wz)
+    ext = ext.reshape(Ns + 2 * H, N, N)
+    # lower halo -> last planes of rank-1, upper halo -> first planes of rank+1
+    halos = torch.from_numpy(np.stack([ext[:H], ext[Ns + H:]]))
+    allh = [torch.empty_like(halos) for _ in range(world)]
+    dist.all_gather(allh, halos)
+    lo, hi = (rank - 1) % world, (rank + 1) % world
+    own = ext[H:H + Ns].copy()
+    own[Ns - H:] += allh[hi][0].numpy()   # rank+1's lower halo are my last planes
+    own[:H] += allh[lo][1].numpy()        # rank-1's upper halo are my first planes
+    return own, H

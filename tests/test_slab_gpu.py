@@ -1,0 +1,30 @@
+"""The slab-decomposed chain on real GPUs (needs >= 2): tools/slab_check.py under torchrun compares it,
+quantity by quantity, with the single-GPU chain (which the parity tests pin to the reference)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_slab_chain_matches_single_gpu_chain(p2p):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    world = 4 if n >= 4 else 2
+    env = dict(os.environ, BGPU_SLAB_P2P=p2p)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29655",
+                        os.path.join(ROOT, "tools", "slab_check.py"), "--grid", "128"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "OK" in r.stdout
