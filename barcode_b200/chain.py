@@ -35,7 +35,8 @@ class Params:
     calc_h: int = 0
     mass_type: int = 1
     D1: float = 1.0
-    D2: float = -3.0 / 7.0
+    D2: float = -3.0 / 7.0 * 0.272 ** (-1.0 / 143.0)   # init_par.cc:526-528 at z = 0
+    slength: float = 4.0
     ascale: float = 1.0
     OM: float = 0.272
     OL: float = 0.728

@@ -145,8 +145,12 @@ void validate(const bgpu_params &p) {
           "bgpu: calc_h must be 0, 1 or 4 (exact adjoint); 2/3 need the SPH kernel (HMC_models.cc:316-319)");
   require(p.mass_type == 0 || p.mass_type == 1 || p.mass_type == 4,
           "bgpu: mass_type must be 0, 1 or 4 on the GPU path (2/3/5/6/60 are cold set-up paths)");
-  require(p.sfmodel == 1 || p.rsd_model,
-          "bgpu: sfmodel != 1 (2LPT/ALPT, Lag2Eul_non_zeldovich) is not implemented on the GPU path yet");
+  if (p.sfmodel != 1 && !p.rsd_model) {
+    // Lag2Eul_non_zeldovich (2LPT + spherical collapse split at slength).  The reference has no adjoint
+    // for it (HMC_models.cc:458): its gradients are calc_h 0 / 1 on the forward density.
+    require(p.calc_h == 0 || p.calc_h == 1, "bgpu: sfmodel != 1 supports calc_h 0 and 1 (no exact adjoint of the 2LPT/ALPT model yet)");
+    require(p.slength > 0., "bgpu: sfmodel != 1 needs slength > 0 (the ALPT smoothing radius, input.par slength)");
+  }
   if (p.rsd_model) {
     require(p.planepar != 0, "Non-plane-parallel RSD model is not yet implemented in calc_V! Use planepar = true.");
     require(p.periodic != 0, "bgpu: RSD needs periodic boundary conditions (rsd.cc:59-64)");
@@ -158,25 +162,48 @@ void validate(const bgpu_params &p) {
 // device pipelines
 // ---------------------------------------------------------------------------
 
-// Lag2Eul_zeldovich / _rsd_zeldovich from s^ (already in h->shat): Psi -> rho -> sum(rho).
+void r2c_plain(bgpu_handle *h, const double *in, double2 *out);
+
+// Lag2Eul_zeldovich / _rsd_zeldovich / _non_zeldovich from s (d_s) and s^ (already in h->shat): Psi -> rho -> sum(rho).
 // dQ / rsd are arguments because the Poisson log-likelihood ignores both (poissonian.cpp:54-56).
-void forward_from_shat(bgpu_handle *h, double dQ, bool rsd, double *px, double *py, double *pz) {
+void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, double *px, double *py, double *pz) {
   const double inv_n = 1.0 / h->ncells;
-  // in = dQ * s ; phi = -D1 * in (Lag2Eul.cc:88) ; Psi^_c = (k_c/k^2)(Im phi^, -Re phi^)
-  const double a = -h->p.D1 * dQ;
+  const bool zeldovich = (h->p.sfmodel == 1 || h->p.rsd_model);  // HMC_models.cc:395-406
+  ROp scale_n;
+  scale_n.kind = R_SCALE;
+  scale_n.a = inv_n;
+  const double2 *disp_src = h->shat;
+  double disp_a = -h->p.D1 * dQ;  // in = dQ * s ; phi = -D1 * in (Lag2Eul.cc:88)
+  if (!zeldovich) {
+    // Lag2Eul_non_zeldovich (Lag2Eul.cc:138-268) in 7 transforms instead of the reference's 22:
+    //   phi1 = IFFT[-s^/k^2]; d2 = D1 in - D2 delta2(phi1); sc = spherical collapse(in);
+    //   C^ = K FFT[d2] + (1 - K) FFT[sc]; Psi_c = IFFT[-i k_c/k^2 C^] -- the projection and the smoothing
+    //   are linear, so K o Psi^LPT + Psi^SC - K o Psi^SC is formed once in k-space
+    KOp pois;
+    pois.kind = K_NEGINVK2;
+    pois.a = dQ;
+    pois.kfac = h->kfac;
+    h->fft.c2r(h->shat, h->work, h->psi[0], pois, scale_n);
+    launch_lpt2_source(h->psi[0], d_s, h->psi[1], h->N, h->p.L1, dQ, h->p.D1, h->p.D2, h->stream);
+    r2c_plain(h, h->psi[1], h->dhat);
+    launch_sc_divergence(d_s, h->psi[2], h->n, dQ, h->p.D1, h->stream);
+    r2c_plain(h, h->psi[2], h->acc);
+    launch_alpt_combine(h->dhat, h->acc, h->N, h->kfac, h->p.slength, h->stream);
+    disp_src = h->dhat;
+    disp_a = 1.0;  // theta2velcomp on +theta (Lag2Eul.cc:238): the sign differs from the Zel'dovich branch
+  }
+  // Psi^_c = a (k_c/k^2)(Im f^, -Re f^)
   for (int c = 2; c >= 0; --c) {
     KOp lop;
     lop.kind = K_DISP;
     lop.comp = c;
-    lop.a = a;
+    lop.a = disp_a;
     lop.kfac = h->kfac;
-    ROp sop;
-    sop.kind = R_SCALE;
-    sop.a = inv_n;
-    h->fft.c2r(h->shat, h->work, h->psi[c], lop, sop);
+    h->fft.c2r(disp_src, h->work, h->psi[c], lop, scale_n);
   }
   GridGeom g = h->geom;
   g.rsd = rsd ? 1 : 0;
+  g.cellbound = zeldovich ? 0 : 1;
   const size_t plane = (size_t)h->N * h->N;
   if (h->G > 1) {
     // halo width from the largest x displacement on any rank (+1 plane for the upper CIC / TSC
@@ -224,7 +251,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   const bgpu_params &p = h->p;
   const double inv_n = 1.0 / h->ncells;
   r2c_plain(h, d_s, h->shat);
-  forward_from_shat(h, p.deltaQ_factor, p.rsd_model != 0, nullptr, nullptr, nullptr);
+  forward_from_shat(h, d_s, p.deltaQ_factor, p.rsd_model != 0, nullptr, nullptr, nullptr);
   LikeParams lp = h->like;
   lp.exact_sign = (p.calc_h == BGPU_CALC_H_EXACT) ? 1 : 0;
   launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->nobs, h->noise, h->window, h->resid, h->n,
@@ -322,7 +349,7 @@ void psi_device(bgpu_handle *h, const double *d_s) {
   allreduce_scalar(h, S_PRIOR);
 
   const bool gauss = p.likelihood == 1;
-  forward_from_shat(h, gauss ? p.deltaQ_factor : 1.0, gauss ? (p.rsd_model != 0) : false, nullptr, nullptr, nullptr);
+  forward_from_shat(h, d_s, gauss ? p.deltaQ_factor : 1.0, gauss ? (p.rsd_model != 0) : false, nullptr, nullptr, nullptr);
   LikeParams lp = h->like;
   lp.exact_sign = 0;
   launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->nobs, h->noise, h->window, nullptr, h->n,
@@ -462,7 +489,8 @@ void bgpu_default_params(bgpu_params *p) {
   p->calc_h = 0;
   p->mass_type = 1;
   p->D1 = 1.0;
-  p->D2 = -3. / 7.;
+  p->D2 = -3. / 7. * std::pow(0.272, -1. / 143.);  // init_par.cc:526-528 at z = 0
+  p->slength = 4.0;                          // data/input.par:121
   p->ascale = 1.0;
   p->OM = 0.272;                            // init_par.cc:38,480-483 (cmbcosm = 3)
   p->OL = 0.728;
@@ -489,6 +517,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
             "bgpu_slab_create: N1 must be a multiple of the number of ranks, at least 8 planes per rank");
     require(p->calc_h == 0 || p->calc_h == 1,
             "bgpu_slab_create: calc_h must be 0 or 1 (the exact adjoint's residual halo is not built yet)");
+    require(p->sfmodel == 1 || p->rsd_model,
+            "bgpu_slab_create: the 2LPT/ALPT model differentiates by finite differences across slabs; not built yet");
     require(!(p->calc_h == 0 && p->likelihood == 0),
             "bgpu_slab_create: Poisson + calc_h = 0 differentiates by finite differences across slabs; not built yet");
     require(nccl_id != nullptr, "bgpu_slab_create: a NCCL unique id is required");
@@ -582,6 +612,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   g.Ns = h->Ns;
   g.H = 0;
   g.flag = h->dflag;
+  g.cellbound = 0;
   h->like.likelihood = p->likelihood;
   h->like.rho_c = p->rho_c;
   h->like.biasP = p->biasP;
@@ -862,7 +893,7 @@ int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *p
   r2c_plain(h, h->sig, h->shat);
   const bool want_pos = posx && posy && posz;
   // positions are staged in grad / resid / tmp (free during the forward model)
-  forward_from_shat(h, h->p.deltaQ_factor, h->p.rsd_model != 0, want_pos ? h->grad : nullptr,
+  forward_from_shat(h, h->sig, h->p.deltaQ_factor, h->p.rsd_model != 0, want_pos ? h->grad : nullptr,
                     want_pos ? h->resid : nullptr, want_pos ? h->tmp : nullptr);
   if (want_pos) {
     d2h(h, posx, h->grad, h->n);

@@ -192,6 +192,12 @@ __device__ __forceinline__ double2 kop_load(const KOp &op, double2 v, size_t off
       const double kc = kval(op.comp == 0 ? ix : (op.comp == 1 ? iy : iz), N, op.kfac);
       return make_double2(-kc * v.y, kc * v.x);
     }
+    case K_NEGINVK2: {
+      const double kx = kval(ix, N, op.kfac), ky = kval(iy, N, op.kfac), kz = kval(iz, N, op.kfac);
+      const double ksq = kx * kx + ky * ky + kz * kz;
+      const double f = ksq > 0.0 ? -op.a * __drcp_rn(ksq) : 0.0;
+      return make_double2(f * v.x, f * v.y);
+    }
     default:
       return v;
   }

@@ -14,7 +14,8 @@ enum KKind : int {
   K_MULREAL = 3,     // v * real0[off]  (HMC_help.cc:41-58 with the multiplier precomputed)
   K_FINAL = 4,       // v * real0[off] + a * cplx0[off]   (prior + norm * h, HMC.cc:205)
   K_INVLAP_SET = 5,  // store: out[off]  = (k_c/k^2)(Im v, -Re v); k^2 == 0 -> 0, Nyquist -> 0 (gradient.cpp:167-210)
-  K_INVLAP_ADD = 6   // store: out[off] += same
+  K_INVLAP_ADD = 6,  // store: out[off] += same
+  K_NEGINVK2 = 7     // a * v * (-1/k^2), 0 at k^2 == 0, no Nyquist zeroing (PoissonSolver, EqSolvers.cc:29-64)
 };
 
 struct KOp {

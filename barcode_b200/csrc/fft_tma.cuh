@@ -277,6 +277,7 @@ __device__ __forceinline__ uint32_t tile_addr_r(uint32_t tile, int row, int p) {
 //   K_DISP    f = a k_c / k^2, 0 if k^2 <= 1e-14 or on a Nyquist plane   (EqSolvers.cc:208-268)
 //   K_GRAD    f = -k_c,        0 on a Nyquist plane                       (gradient.cpp:38-74)
 //   K_INVLAP  f = k_c / k^2,   0 if k^2 == 0 or on a Nyquist plane        (gradient.cpp:167-210)
+// K_NEGINVK2 (PoissonSolver, EqSolvers.cc:29-64) is the scalar -a / k^2 (0 at k = 0) on both parts.
 // ---------------------------------------------------------------------------
 template <int N, int AXIS>
 struct RotCtx {
@@ -297,6 +298,11 @@ struct RotCtx {
   }
   __device__ __forceinline__ double2 apply(double2 v, int r) const {
     const double kr = kval(r, N, kfac);
+    if (kind == K_NEGINVK2) {  // a scalar multiplier, not a rotation: PoissonSolver's -1/k^2
+      const double ksq = kr * kr + c2;
+      const double g = ksq > 0.0 ? -a * __drcp_rn(ksq) : 0.0;
+      return make_double2(g * v.x, g * v.y);
+    }
     const double kc = sel == 0 ? kr : (sel == 1 ? k_oth : k_z);
     double f;
     if (kind == K_GRAD) {

@@ -133,8 +133,19 @@ __global__ void scatter_kernel(GridGeom g, const double *__restrict__ psix, cons
   if (valid) {
     const int k = (int)(idx % g.N);
     const int j = (int)((idx / g.N) % g.N);
-    const int i = g.x0 + (int)(idx / ((size_t)g.N * g.N));
-    particle_position(g, i, j, k, psix[idx], psiy[idx], psiz[idx], x, y, z);
+    const int il = (int)(idx / ((size_t)g.N * g.N));
+    const int i = g.x0 + il;
+    double px = psix[idx], py = psiy[idx], pz = psiz[idx];
+    if (g.cellbound) {
+      // cellboundcomp (massFunctions.cc:588-660): every displacement averaged with its (i-1, j-1, k-1)
+      // neighbour, periodically -- folded into the read instead of a pass over three arrays
+      const int N = g.N;
+      const size_t m = ((size_t)(il == 0 ? N - 1 : il - 1) * N + (j == 0 ? N - 1 : j - 1)) * N + (k == 0 ? N - 1 : k - 1);
+      px = 0.5 * (psix[m] + px);
+      py = 0.5 * (psiy[m] + py);
+      pz = 0.5 * (psiz[m] + pz);
+    }
+    particle_position(g, i, j, k, px, py, pz, x, y, z);
     if (posx) {
       posx[idx] = x;
       posy[idx] = y;
@@ -750,6 +761,99 @@ void launch_kfinal_combine(const double2 *s, const double *mult, const double2 *
                            size_t n_half, cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);
   kfinal_combine_kernel<<<blocks_for(n_half, 256), 256, 0, st>>>(s, mult, h, out, norm, N / 2 + 1, n_half);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// A9: Lag2Eul_non_zeldovich (Lag2Eul.cc:138-312), the pieces that are not FFTs
+// ---------------------------------------------------------------------------
+// 4th-order central difference of gradient.cpp:81-153 along one axis at cell (c0, c1, c2), evaluated
+// with periodic wrap: -fac * ((4/3)(f[-1] - f[+1]) - (1/6)(f[-2] - f[+2]))
+__device__ __forceinline__ int wrap_idx(int i, int N) { return i < 0 ? i + N : (i >= N ? i - N : i); }
+
+template <int AX>
+__device__ __forceinline__ double findif_at(const double *__restrict__ f, int N, int i, int j, int k, double fac) {
+  auto at = [&](int o) {
+    const int ii = AX == 0 ? wrap_idx(i + o, N) : i, jj = AX == 1 ? wrap_idx(j + o, N) : j,
+              kk = AX == 2 ? wrap_idx(k + o, N) : k;
+    return f[((size_t)ii * N + jj) * N + kk];
+  };
+  return -(fac * ((4.0 / 3) * (at(-1) - at(1)) - (1.0 / 6) * (at(-2) - at(2))));
+}
+
+// second derivative d_B d_A phi at (i, j, k): the same stencil applied twice, as calc_m2v_mem does with
+// GFINDIFF (EqSolvers.cc:396-407)
+template <int A, int B>
+__device__ __forceinline__ double findif2_at(const double *__restrict__ f, int N, int i, int j, int k, double fac) {
+  auto g = [&](int o) {  // d_A phi at the point shifted by o along B
+    const int ii = B == 0 ? wrap_idx(i + o, N) : i, jj = B == 1 ? wrap_idx(j + o, N) : j,
+              kk = B == 2 ? wrap_idx(k + o, N) : k;
+    return findif_at<A>(f, N, ii, jj, kk, fac);
+  };
+  return -(fac * ((4.0 / 3) * (g(-1) - g(1)) - (1.0 / 6) * (g(-2) - g(2))));
+}
+
+// out = D1 * (dQ s) - D2 * delta2, delta2 = sum of the 2x2 minors of the Hessian of phi
+// (calc_m2v_mem, EqSolvers.cc:373-422; Lag2Eul.cc:196-198)
+__global__ void lpt2_source_kernel(const double *__restrict__ phi, const double *__restrict__ s, double *__restrict__ out,
+                                   int N, double fac, double dQ, double D1, double D2) {
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int k = (int)(idx % N), j = (int)((idx / N) % N), i = (int)(idx / ((size_t)N * N));
+  const double xx = findif2_at<0, 0>(phi, N, i, j, k, fac), yy = findif2_at<1, 1>(phi, N, i, j, k, fac),
+               zz = findif2_at<2, 2>(phi, N, i, j, k, fac);
+  const double xy = findif2_at<0, 1>(phi, N, i, j, k, fac), xz = findif2_at<0, 2>(phi, N, i, j, k, fac),
+               yz = findif2_at<1, 2>(phi, N, i, j, k, fac);
+  const double m2v = xx * yy - xy * xy + xx * zz - xz * xz + yy * zz - yz * yz;
+  out[idx] = D1 * (dQ * s[idx]) - D2 * m2v;
+}
+
+// spherical-collapse divergence (Lag2Eul.cc:206-223): -3 (sqrt(1 + 2/3 psilin) - 1), psilin = -D1 in,
+// and +3 where the root's argument is not positive
+__global__ void sc_divergence_kernel(const double *__restrict__ s, double *__restrict__ out, size_t n, double dQ,
+                                     double D1) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const double psilin = -D1 * (dQ * s[idx]);
+  const double arg = 1. + 2. / 3. * psilin;
+  double psisc = arg > 0. ? 3. * (sqrt(arg) - 1.) : -3.;
+  out[idx] = -psisc;
+}
+
+// C^ = K D2^ + (1 - K) D4^ on the half grid, K = exp(-k^2 rS^2 / 2) (kernelcomp filtertype 1,
+// convolution.cpp:224-322; its normalisation, the k = 0 value, is 1): Psi_c = K o Psi^LPT_c +
+// Psi^SC_c - K o Psi^SC_c (Lag2Eul.cc:238-268) before the -i k_c / k^2 projection, which is linear
+__global__ void alpt_combine_kernel(double2 *__restrict__ d2, const double2 *__restrict__ d4, int N, double kfac,
+                                    double rS) {
+  const int nzh = N / 2 + 1;
+  const size_t n = (size_t)N * N * nzh;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int z = (int)(idx % nzh), y = (int)((idx / nzh) % N), x = (int)(idx / ((size_t)nzh * N));
+  auto kv = [&](int i) { return (i <= N / 2) ? kfac * (double)i : -kfac * (double)(N - i); };
+  const double kx = kv(x), ky = kv(y), kz = kv(z);
+  const double K = exp(-(kx * kx + ky * ky + kz * kz) * (rS * rS) / 2.);
+  const double2 a = d2[idx], b = d4[idx];
+  d2[idx] = make_double2(K * a.x + (b.x - K * b.x), K * a.y + (b.y - K * b.y));
+}
+
+void launch_lpt2_source(const double *phi, const double *s, double *out, int N, double L, double dQ, double D1,
+                        double D2, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  const size_t n = (size_t)N * N * N;
+  lpt2_source_kernel<<<blocks_for(n, 256), 256, 0, st>>>(phi, s, out, N, (double)N / (2. * L), dQ, D1, D2);
+  BGPU_LAUNCHED(1);
+}
+void launch_sc_divergence(const double *s, double *out, size_t n, double dQ, double D1, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  sc_divergence_kernel<<<blocks_for(n, 256), 256, 0, st>>>(s, out, n, dQ, D1);
+  BGPU_LAUNCHED(1);
+}
+void launch_alpt_combine(double2 *d2, const double2 *d4, int N, double kfac, double rS, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  const size_t n = (size_t)N * N * (N / 2 + 1);
+  alpt_combine_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d2, d4, N, kfac, rS);
   BGPU_LAUNCHED(1);
 }
 

@@ -21,6 +21,7 @@ struct GridGeom {
   int Ns;          // planes owned
   int H;           // halo planes each side of the density tile: rho is [(Ns + 2H)][N][N], plane 0 = global x0 - H
   int *flag;       // set to 1 if a particle left the halo (device int), may be null when H == 0 and Ns == N
+  int cellbound;   // displacements are cell-boundary averaged on read (cellboundcomp; non-Zel'dovich model)
 };
 
 struct LikeParams {
@@ -60,6 +61,13 @@ void launch_inverse_spectrum_unpack(const double2 *transposed, double *half, int
 // out = mult * s + norm * h on a half grid (mult has the padded row pitch N/2+2)
 void launch_kfinal_combine(const double2 *s, const double *mult, const double2 *h, double2 *out, double norm, int N,
                            size_t n_half, cudaStream_t st);
+
+// Lag2Eul_non_zeldovich's real-space pieces (Lag2Eul.cc:138-268): 2LPT source D1 dQ s - D2 delta2(phi),
+// spherical-collapse divergence, and the ALPT combination K D2^ + (1 - K) D4^ (in place over d2)
+void launch_lpt2_source(const double *phi, const double *s, double *out, int N, double L, double dQ, double D1,
+                        double D2, cudaStream_t st);
+void launch_sc_divergence(const double *s, double *out, size_t n, double dQ, double D1, cudaStream_t st);
+void launch_alpt_combine(double2 *d2, const double2 *d4, int N, double kfac, double rS, cudaStream_t st);
 
 // deterministic sum of an array -> *out (device scalar); scratch: kReduceBlocks doubles
 void launch_sum(const double *a, size_t n, double *scratch, double *out, cudaStream_t st);

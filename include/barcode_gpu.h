@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BGPU_ABI_VERSION 1
+#define BGPU_ABI_VERSION 2
 
 /* calc_h value for the exact mass-assignment adjoint (new; the reference only
  * has exact adjoints for its SPH kernel, HMC_models.cc:200-372) */
@@ -52,11 +52,13 @@ typedef struct bgpu_params {
   int planepar, periodic;
   int masskernel;            /* mk: 0 NGP, 1 CIC, 2 TSC */
   int likelihood;            /* 0 Poisson, 1 Gaussian */
-  int sfmodel;               /* 1 Zel'dovich; with rsd_model the reference runs Zel'dovich for any value */
+  int sfmodel;               /* 1 Zel'dovich; else Lag2Eul_non_zeldovich (2LPT + spherical collapse, ALPT);
+                              * with rsd_model the reference runs Zel'dovich for any value */
   int rsd_model;
   int calc_h;                /* 0, 1 as the reference; BGPU_CALC_H_EXACT */
   int mass_type;             /* 0 ones (R), 1 1/P (FS), 4 P (FS) */
   double D1, D2, ascale, OM, OL;
+  double slength;            /* ALPT smoothing radius [Mpc/h] (input.par slength -> n->kth, struct_hamil.h:259); sfmodel != 1 */
   double rho_c, biasP, biasE;
   double deltaQ_factor;
   int correct_delta;

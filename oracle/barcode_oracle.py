@@ -39,6 +39,9 @@ class Params:
     calc_h: int = 0            # 0, 1 reference; 4 = exact mass-assignment adjoint (new)
     mass_type: int = 1         # 0 ones (R), 1 1/P (FS), 4 P (FS)  (HMC_mass.cc:315-368)
     D1: float = 1.0
+    D2: float = -3.0 / 7.0 * 0.272 ** (-1.0 / 143.0)  # init_par.cc:526-528 at z = 0: -3/7 D1^2 Omega^(-1/143)
+    sfmodel: int = 1           # 1 Zel'dovich; anything else -> Lag2Eul_non_zeldovich (Lag2Eul.cc:329-331)
+    slength: float = 4.0       # n->kth = data->numerical->slength (struct_hamil.h:259): ALPT smoothing radius
     ascale: float = 1.0
     OM: float = 0.272          # init_par.cc:38,482 (cmbcosm = 3)
     OL: float = 0.728
@@ -309,6 +312,64 @@ def overdens(rho) -> np.ndarray:
     return rho / mean - 1.0
 
 
+def poisson_solver(p: Params, delta):
+    """PoissonSolver (EqSolvers.cc:29-64): IFFT[-1/k^2 FFT[delta]], 0 at k^2 == 0; NO Nyquist zeroing."""
+    N = p.N1
+    dh = rfft(delta.reshape(N, N, N))
+    kx, ky, kz = k_grids(N, p.L1)
+    ksq = kx * kx + ky * ky + kz * kz
+    fac = np.where(ksq > 0, -1.0 / np.where(ksq > 0, ksq, 1.0), 0.0)
+    return irfft(dh * fac, N)
+
+
+def calc_m2v(p: Params, phi):
+    """calc_m2v_mem with GFINDIFF (EqSolvers.cc:373-422): second derivatives by applying the 4th-order
+    finite difference twice, then the sum of the three 2x2 minors of the Hessian."""
+    dx = gradfindif(p, phi, 1)
+    Lxx, Lxy, Lxz = gradfindif(p, dx, 1), gradfindif(p, dx, 2), gradfindif(p, dx, 3)
+    dy = gradfindif(p, phi, 2)
+    Lyy, Lyz = gradfindif(p, dy, 2), gradfindif(p, dy, 3)
+    Lzz = gradfindif(p, gradfindif(p, phi, 3), 3)
+    return Lxx * Lyy - Lxy * Lxy + Lxx * Lzz - Lxz * Lxz + Lyy * Lzz - Lyz * Lyz
+
+
+def alpt_kernel(p: Params):
+    """kernelcomp with filtertype 1 (convolution.cpp:224-322): exp(-k^2 rS^2 / 2) on the grid, divided by
+    the sum of its inverse transform (= its k = 0 value, 1, up to rounding)."""
+    N = p.N1
+    kx, ky, kz = k_grids(N, p.L1)
+    return np.exp(-(kx * kx + ky * ky + kz * kz) * (p.slength * p.slength) / 2.0)
+
+
+def convcomp(p: Params, a, kern):
+    """convcomp (convolution.cpp:327-377): IFFT[kernel * FFT[a]] (the reference does it with full c2c
+    transforms and the kernel re-read from `auxkernelr<int(slength)>.dat`)."""
+    N = p.N1
+    return irfft(rfft(a.reshape(N, N, N)) * kern, N)
+
+
+def displacement_non_zeldovich(p: Params, s):
+    """Lag2Eul_non_zeldovich up to Psi (Lag2Eul.cc:138-268): theta = D1 s - D2 delta2 smoothed by K,
+    spherical-collapse divergence on the small scales, then cellboundcomp (massFunctions.cc:588-660):
+    every Psi averaged with its (i-1, j-1, k-1) neighbour, periodically."""
+    N = p.N1
+    s = s.reshape(N, N, N)
+    phi1 = poisson_solver(p, s)
+    d2 = calc_m2v(p, phi1)
+    kern = alpt_kernel(p)
+    lpt = convcomp(p, p.D1 * s - p.D2 * d2, kern)
+    psilin = -p.D1 * s
+    arg = 1.0 + 2.0 / 3.0 * psilin
+    sc = -np.where(arg > 0.0, 3.0 * (np.sqrt(np.where(arg > 0.0, arg, 0.0)) - 1.0), -3.0)
+    A = theta2vel(p, lpt)
+    B = theta2vel(p, sc)
+    out = []
+    for a, b in zip(A, B):
+        tot = (a + b) - convcomp(p, b, kern)
+        out.append(0.5 * (np.roll(tot, (1, 1, 1), (0, 1, 2)) + tot))
+    return out
+
+
 def forward(p: Params, signal):
     """likelihood_grad_log_like's forward half (HMC_models.cc:383-406) ->
     Lag2Eul_zeldovich / _rsd_zeldovich (Lag2Eul.cc:69-132, 338-424).
@@ -317,7 +378,10 @@ def forward(p: Params, signal):
     s = signal.reshape(N, N, N)
     if p.deltaQ_factor != 1.0:
         s = p.deltaQ_factor * s
-    psi = theta2vel(p, -p.D1 * s)
+    if p.sfmodel == 1 or p.rsd_model:   # the reference runs Zel'dovich under rsd_model for any sfmodel
+        psi = theta2vel(p, -p.D1 * s)
+    else:
+        psi = displacement_non_zeldovich(p, s)
     x, y, z = positions(p, psi)
     rho = density(p, x, y, z)
     return overdens(rho), (x, y, z), psi

@@ -186,6 +186,10 @@ class Reference:
         _chk(lib().ref_readtab(self.h, fname.encode()))
         return self.array("Power").copy()
 
+    def kernelcomp(self):
+        """Write <cwd>/auxkernelr<int(slength)>.dat, which the non-Zel'dovich forward model re-reads."""
+        _chk(lib().ref_kernelcomp(self.h))
+
     def hamiltonian_mass(self):
         _chk(lib().ref_hamiltonian_mass(self.h))
         return self.array("mass_f").copy(), self.array("mass_r").copy()

@@ -28,6 +28,7 @@
 #include "init_par.h"
 #include "calc_power.h"
 #include "HMC.h"
+#include "convolution.hpp"
 #include "HMC_momenta.h"
 #include "HMC_mass.h"
 #include "HMC_help.h"
@@ -447,6 +448,22 @@ int ref_forward(void *hv, const double *signal, double *deltaX, double *posx, do
   if (posx) std::memcpy(posx, hd->posx, n->N * sizeof(double));
   if (posy) std::memcpy(posy, hd->posy, n->N * sizeof(double));
   if (posz) std::memcpy(posz, hd->posz, n->N * sizeof(double));
+  REF_CATCH
+}
+
+/* kernelcomp as barcoderunner calls it before sampling (barcoderunner.cc:371-374): writes
+ * <dir>auxkernelr<int(slength)>.dat, which convcomp re-reads on every call (convolution.cpp:354-359) */
+int ref_kernelcomp(void *hv) {
+  auto *h = static_cast<ref_handle *>(hv);
+  REF_TRY
+  NUMERICAL *n = h->data->numerical;
+  /* the HMC call sites read the kernel with dir = "" (HMC_models.cc:405), i.e. from the working directory
+   * as "auxkernelr<r>.dat"; write it there (with dir = "./" add_extension_if_missing sees the dot of "./"
+   * and drops the ".dat", IOfunctionsGen.cc:185-191) */
+  const std::string saved = n->dir;
+  n->dir = "";
+  kernelcomp(n->L1, n->L2, n->L3, n->N1, n->N2, n->N3, n->slength, 1, h->data);
+  n->dir = saved;
   REF_CATCH
 }
 

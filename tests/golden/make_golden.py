@@ -40,6 +40,12 @@ CASES = {
     "za_tsc_gauss_rsd_mass0": dict(masskernel=2, likelihood=1, rsd_model=True, calc_h=0, mass_type=0),
     "za_cic_poisson_mass4_dq": dict(masskernel=1, likelihood=0, rsd_model=False, calc_h=0, mass_type=4,
                                     deltaQ_factor=0.9, mass_factor=2.0),
+    # Lag2Eul_non_zeldovich (2LPT + spherical collapse, ALPT split at slength; Lag2Eul.cc:138-312): every
+    # sfmodel != 1 without rsd_model.  configs[3]'s forward model.
+    "alpt_cic_gauss": dict(masskernel=1, likelihood=1, rsd_model=False, calc_h=0, mass_type=1, sfmodel=2,
+                           slength=4.0),
+    "alpt_tsc_poisson_h1": dict(masskernel=2, likelihood=0, rsd_model=False, calc_h=1, mass_type=1, sfmodel=3,
+                                slength=6.0, deltaQ_factor=0.95),
 }
 
 N1, L1 = 16, 50.0
@@ -51,10 +57,18 @@ def main():
     np.savez_compressed(os.path.join(HERE, "pk_table.npz"), k=tab[:, 0].astype(np.float32),
                         P=tab[:, 1].astype(np.float32))
 
+    only = set(sys.argv[1:])
     for name, kw in CASES.items():
+        if only and name not in only:
+            continue
         cfg = ref.Config(N1=N1, L1=L1, N_eps_fac=8.0, eps_fac=1.0, **kw)
         R = ref.Reference(cfg)
         P = R.readtab(CAMB)
+        if kw.get("sfmodel", 1) != 1 and not kw.get("rsd_model", False):
+            # the ALPT kernel file is re-read from the working directory on every forward evaluation
+            import tempfile
+            os.chdir(tempfile.mkdtemp(prefix="barcode_golden_"))
+            R.kernelcomp()
         truth = R.create_garfield(1, P)
         one = np.ones(R.N)
         R.set_inputs(window=one, noise=one)
@@ -93,11 +107,14 @@ def main():
         for k, v in sc.items():
             out["dh_" + k] = v
         out["D1"] = R.scalar("D1")
+        out["D2"] = R.scalar("D2")
         out["cfg"] = np.array(repr({**kw, "N1": N1, "L1": L1}))
         np.savez_compressed(os.path.join(HERE, f"case_{name}.npz"), **out)
         print(name, "gradpsi norm", np.linalg.norm(out["gradpsi"]), "dH", dH, "Neps", out["Neps"])
         R.close()
 
+    if only:
+        return
     # momentum draw at 8^3: the white-noise stream, its colouring with P and with 1/P
     cfg = ref.Config(N1=8, L1=25.0)
     R = ref.Reference(cfg)

@@ -37,7 +37,7 @@ def test_header_symbols_are_exported_and_typed(lib):
 
 def test_abi_version_and_defaults(lib):
     from barcode_b200._lib import BgpuParams
-    assert lib.bgpu_abi_version() == 1
+    assert lib.bgpu_abi_version() == 2
     p = BgpuParams()
     lib.bgpu_default_params(C.byref(p))
     assert (p.N1, p.N2, p.N3) == (64, 64, 64) and p.L1 == 200.0          # data/input.par:117-125

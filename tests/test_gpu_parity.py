@@ -21,7 +21,7 @@ def make_chain(cfg, **over):
     kw = dict(N1=cfg["N1"], L1=cfg["L1"], masskernel=cfg["masskernel"], likelihood=cfg["likelihood"],
               rsd_model=cfg["rsd_model"], calc_h=cfg["calc_h"], mass_type=cfg["mass_type"],
               sfmodel=cfg.get("sfmodel", 1), deltaQ_factor=cfg.get("deltaQ_factor", 1.0),
-              mass_factor=cfg.get("mass_factor", 1.0))
+              mass_factor=cfg.get("mass_factor", 1.0), slength=cfg.get("slength", 4.0))
     kw.update(over)
     return Chain(Params(**kw))
 
@@ -30,7 +30,8 @@ def oracle_params(cfg, **over):
     from oracle import barcode_oracle as bo
     kw = dict(N1=cfg["N1"], L1=cfg["L1"], masskernel=cfg["masskernel"], likelihood=cfg["likelihood"],
               rsd_model=cfg["rsd_model"], calc_h=cfg["calc_h"], mass_type=cfg["mass_type"],
-              deltaQ_factor=cfg.get("deltaQ_factor", 1.0), mass_factor=cfg.get("mass_factor", 1.0))
+              deltaQ_factor=cfg.get("deltaQ_factor", 1.0), mass_factor=cfg.get("mass_factor", 1.0),
+              sfmodel=cfg.get("sfmodel", 1), slength=cfg.get("slength", 4.0))
     kw.update(over)
     return bo.Params(**kw)
 
@@ -288,13 +289,16 @@ def _problem_128(seed=11):
     return N, L, P, nobs, noise, window, s
 
 
-@pytest.mark.parametrize("calc_h,masskernel,rsd", [(0, 1, True), (4, 1, False), (0, 2, False)])
-def test_gradient_128_matches_oracle(calc_h, masskernel, rsd):
-    """128^3 runs through the TMA-staged strided pass (fft_tma.cuh); the oracle is the numpy restatement."""
+@pytest.mark.parametrize("calc_h,masskernel,rsd,sfmodel", [(0, 1, True, 1), (4, 1, False, 1), (0, 2, False, 1),
+                                                            (0, 1, False, 2)])
+def test_gradient_128_matches_oracle(calc_h, masskernel, rsd, sfmodel):
+    """128^3 runs through the TMA-staged strided pass (fft_tma.cuh); the oracle is the numpy restatement.
+    sfmodel = 2 is Lag2Eul_non_zeldovich (2LPT + spherical collapse, ALPT split at slength = 8 Mpc/h)."""
     from barcode_b200.chain import Chain, Params
     from oracle import barcode_oracle as bo
     N, L, P, nobs, noise, window, s = _problem_128()
-    kw = dict(N1=N, L1=L, masskernel=masskernel, likelihood=1, rsd_model=rsd, calc_h=calc_h, mass_type=1)
+    kw = dict(N1=N, L1=L, masskernel=masskernel, likelihood=1, rsd_model=rsd, calc_h=calc_h, mass_type=1,
+              sfmodel=sfmodel, slength=8.0)
     with Chain(Params(**kw)) as ch:
         ch.set_static(Power=P, nobs=nobs, noise=noise, window=window)
         g = ch.gradient_psi(s)
