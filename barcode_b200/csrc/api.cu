@@ -84,6 +84,12 @@ struct bgpu_handle {
   int *dflag = nullptr;         // device flag: a particle left the halo
   int *hflag = nullptr;         // pinned copy
   void *peer_base[8] = {};      // other ranks' receive buffers, opened through CUDA IPC
+
+  // host-pointer API: input rows stream in under the first z pass, result rows stream out under the last
+  cudaStream_t copy_stream = nullptr;
+  static constexpr int kChunks = 8;
+  cudaEvent_t ev_up[kChunks] = {}, ev_dn[kChunks] = {};
+  const ChunkHooks *in_hooks = nullptr, *out_hooks = nullptr;
 };
 
 namespace {
@@ -250,7 +256,9 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   require(h->have_power && h->have_obs, "bgpu: bgpu_set_static (Power, nobs, noise, window) must be called first");
   const bgpu_params &p = h->p;
   const double inv_n = 1.0 / h->ncells;
+  h->fft.hooks = h->in_hooks;   // rows of the signal may still be arriving from the host
   r2c_plain(h, d_s, h->shat);
+  h->fft.hooks = nullptr;
   forward_from_shat(h, d_s, p.deltaQ_factor, p.rsd_model != 0, nullptr, nullptr, nullptr);
   LikeParams lp = h->like;
   lp.exact_sign = (p.calc_h == BGPU_CALC_H_EXACT) ? 1 : 0;
@@ -272,6 +280,8 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     sop.a = inv_n;
     h->fft.c2r(h->shat, h->work, d_out, lop, sop);
     launch_axpy(d_out, h->resid, norm, h->n, h->stream);
+    if (h->out_hooks && h->out_hooks->after)
+      for (int c = 0; c < h->out_hooks->chunks; ++c) h->out_hooks->after(h->out_hooks->ctx, c);
     return;
   }
 
@@ -320,7 +330,9 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   if (h->G > 1 && h->N >= 512) {
     // the TMA-staged x pass cannot hold both operand tiles at this size: combine in a pass of its own
     launch_kfinal_combine(h->shat, h->inv_power, h->acc, h->acc, norm, h->N, h->nh, h->stream);
+    h->fft.hooks = h->out_hooks;
     h->fft.c2r(h->acc, h->work, d_out, KOp{}, sop);
+    h->fft.hooks = nullptr;
     return;
   }
   KOp lop;
@@ -328,7 +340,9 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   lop.a = norm;
   lop.real0 = h->inv_power;
   lop.cplx0 = h->acc;
+  h->fft.hooks = h->out_hooks;  // rows of the gradient leave for the host as the last z pass produces them
   h->fft.c2r(h->shat, h->work, d_out, lop, sop);
+  h->fft.hooks = nullptr;
 }
 
 // psi (HMC.cc:124-143): prior 1/2 s.S^-1 s (gaussian.cpp:20-35) and -lnL
@@ -543,6 +557,11 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   h->nhp = (size_t)h->Ns * h->N * (h->N / 2 + 2);
   BGPU_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
+  BGPU_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < bgpu_handle::kChunks; ++c) {
+    BGPU_CUDA(cudaEventCreateWithFlags(&h->ev_up[c], cudaEventDisableTiming));
+    BGPU_CUDA(cudaEventCreateWithFlags(&h->ev_dn[c], cudaEventDisableTiming));
+  }
   if (nranks > 1) {
     h->comm = new NcclComm(nccl_id, rank, nranks);
     dalloc(h->sendbuf, h->nh);
@@ -693,6 +712,14 @@ void bgpu_destroy(bgpu_handle *h) {
   double2 *cplx[] = {h->shat, h->dhat, h->work, h->acc, h->sendbuf, h->recvbuf};
   for (double2 *q : cplx)
     if (q) cudaFree(q);
+  if (h->copy_stream) {
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamDestroy(h->copy_stream);
+  }
+  for (int c = 0; c < bgpu_handle::kChunks; ++c) {
+    if (h->ev_up[c]) cudaEventDestroy(h->ev_up[c]);
+    if (h->ev_dn[c]) cudaEventDestroy(h->ev_dn[c]);
+  }
   if (h->dflag) cudaFree(h->dflag);
   if (h->hflag) cudaFreeHost(h->hflag);
   if (h->hscal) cudaFreeHost(h->hscal);
@@ -772,12 +799,60 @@ int bgpu_gradient_psi_dev(bgpu_handle *h, const double *d_signal, double *d_grad
   BGPU_CATCH
 }
 
+namespace {
+struct StreamIo {
+  bgpu_handle *h;
+  double *host_out;
+};
+void wait_upload(void *ctx, int c) {
+  auto *io = static_cast<StreamIo *>(ctx);
+  cudaStreamWaitEvent(io->h->stream, io->h->ev_up[c], 0);
+}
+void start_download(void *ctx, int c) {
+  auto *io = static_cast<StreamIo *>(ctx);
+  bgpu_handle *h = io->h;
+  const size_t per = h->n / bgpu_handle::kChunks;
+  cudaEventRecord(h->ev_dn[c], h->stream);
+  cudaStreamWaitEvent(h->copy_stream, h->ev_dn[c], 0);
+  cudaMemcpyAsync(io->host_out + c * per, h->grad + c * per, per * sizeof(double), cudaMemcpyDeviceToHost,
+                  h->copy_stream);
+}
+}  // namespace
+
 int bgpu_gradient_psi(bgpu_handle *h, const double *signal, double *gradpsi) {
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
-  h2d(h, h->sig, signal, h->n);
-  gradient_device(h, h->sig, h->grad);
-  d2h(h, gradpsi, h->grad, h->n);
+  // The signal goes up in kChunks slabs of x planes on a copy stream; the first z pass starts on a slab
+  // as soon as it has landed, and the last z pass hands each slab of the gradient to the copy stream
+  // while it transforms the next -- the two PCIe transfers hide under the transforms at either end.
+  constexpr int C = bgpu_handle::kChunks;
+  const size_t per = h->n / C;
+  cudaStreamSynchronize(h->copy_stream);  // nothing of a previous call is in flight
+  cudaEventRecord(h->ev_dn[0], h->stream);
+  cudaStreamWaitEvent(h->copy_stream, h->ev_dn[0], 0);  // h->sig is free once earlier work on the chain is done
+  for (int c = 0; c < C; ++c) {
+    BGPU_CUDA(cudaMemcpyAsync(h->sig + c * per, signal + c * per, per * sizeof(double), cudaMemcpyHostToDevice,
+                              h->copy_stream));
+    BGPU_CUDA(cudaEventRecord(h->ev_up[c], h->copy_stream));
+  }
+  StreamIo io{h, gradpsi};
+  ChunkHooks in_h, out_h;
+  in_h.chunks = out_h.chunks = C;
+  in_h.before = wait_upload;
+  out_h.after = start_download;
+  in_h.ctx = out_h.ctx = &io;
+  h->in_hooks = &in_h;
+  h->out_hooks = &out_h;
+  try {
+    gradient_device(h, h->sig, h->grad);
+  } catch (...) {
+    h->in_hooks = h->out_hooks = nullptr;
+    h->fft.hooks = nullptr;
+    cudaStreamSynchronize(h->copy_stream);
+    throw;
+  }
+  h->in_hooks = h->out_hooks = nullptr;
+  BGPU_CUDA(cudaStreamSynchronize(h->copy_stream));
   sync(h);
   BGPU_CATCH
 }

@@ -25,6 +25,17 @@ struct SlabComm {
   virtual void barrier(cudaStream_t st) = 0;
 };
 
+// Streaming hooks for the host-pointer API: the first transform of an evaluation can start on the rows
+// that have already arrived from the host, the last one can hand rows back while later rows are still
+// being transformed.  `before(ctx, c)` is called ahead of the z pass over row chunk c of an r2c,
+// `after(ctx, c)` behind the z pass over chunk c of a c2r; chunk c = rows [c, c+1) * Ns*N/chunks.
+struct ChunkHooks {
+  int chunks = 1;
+  void (*before)(void *ctx, int chunk) = nullptr;
+  void (*after)(void *ctx, int chunk) = nullptr;
+  void *ctx = nullptr;
+};
+
 struct Fft3d {
   int N = 0;
   double2 *twN = nullptr;  // exp(-2 pi i k / N)
@@ -33,6 +44,7 @@ struct Fft3d {
   int strided_blocks = 0;  // persistent grid of the pipelined strided pass: SMs x resident CTAs
   int sm_count = 0;
   bool use_tma = true;     // TMA-staged strided pass (fft_tma.cuh); BGPU_FFT_TMA=0 selects the cp.async one
+  mutable const ChunkHooks *hooks = nullptr;  // set around ONE transform by the caller, consumed by its z pass
 
   // tensor maps of the half-grid arrays the TMA pass has touched (keyed by base pointer and layout)
   struct MapEntry {

@@ -280,7 +280,8 @@ template <> struct ZShape<1024> { static constexpr int E = 16, TR = 4,  MINB = 1
 template <int N> constexpr bool ztma_has_size() { return N == 128 || N == 256 || N == 512 || N == 1024; }
 
 template <int N, bool C2R, bool AUX>
-static void launch_zpass_tma(const Fft3d &f, const void *in, void *out, ROp op, cudaStream_t st) {
+static void launch_zpass_tma(const Fft3d &f, const void *in, void *out, ROp op, cudaStream_t st, size_t row0 = 0,
+                             size_t nrows = 0) {
   constexpr int E = ZShape<N>::E, TR = ZShape<N>::TR;
   constexpr int MINB = AUX ? 1 : ZShape<N>::MINB;
   constexpr int NSTAGE = 3;
@@ -296,11 +297,17 @@ static void launch_zpass_tma(const Fft3d &f, const void *in, void *out, ROp op, 
     BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     blocks_per_sm = occ > 0 ? occ : 1;
   }
-  const int ntiles = (f.Ns * N) / TR;
+  // rows [row0, row0 + nrows) of the (x, y) row set; all of them by default
+  if (!nrows) nrows = (size_t)f.Ns * N;
+  const size_t real_off = row0 * N * sizeof(double), cplx_off = row0 * (N / 2 + 1) * sizeof(double2);
+  const char *pin = static_cast<const char *>(in) + (C2R ? cplx_off : real_off);
+  char *pout = static_cast<char *>(out) + (C2R ? real_off : cplx_off);
+  if (op.aux) op.aux += row0 * N;
+  const int ntiles = (int)(nrows / TR);
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > ntiles) blocks = ntiles;
   ProfScope prof(C2R ? KK_FFT_C2R_Z : KK_FFT_R2C_Z, st);
-  kern<<<blocks, threads, smem, st>>>(in, out, f.twN, f.twM, op, ntiles);
+  kern<<<blocks, threads, smem, st>>>(pin, pout, f.twN, f.twM, op, ntiles);
   BGPU_LAUNCHED(1);
 }
 
@@ -310,6 +317,18 @@ static bool try_r2c_zpass_tma(const Fft3d &f, const double *in, double2 *out, RO
     return false;
   } else {
     if (!f.use_tma || !(lop.kind == R_LOAD || lop.kind == R_LOAD_SCALE)) return false;
+    const ChunkHooks *hk = f.hooks;
+    if (hk && hk->before && hk->chunks > 1 && ((size_t)f.Ns * N) % ((size_t)hk->chunks * ZShape<N>::TR) == 0) {
+      // the caller streams the input in: wait for each slab of rows just before its z pass
+      const size_t per = (size_t)f.Ns * N / hk->chunks;
+      for (int c = 0; c < hk->chunks; ++c) {
+        hk->before(hk->ctx, c);
+        launch_zpass_tma<N, false, false>(f, in, out, lop, f.stream, c * per, per);
+      }
+      return true;
+    }
+    if (hk && hk->before)
+      for (int c = 0; c < hk->chunks; ++c) hk->before(hk->ctx, c);
     launch_zpass_tma<N, false, false>(f, in, out, lop, f.stream);
     return true;
   }
@@ -321,12 +340,25 @@ static bool try_c2r_zpass_tma(const Fft3d &f, const double2 *in, double *out, RO
     return false;
   } else {
     if (!f.use_tma) return false;
-    if (sop.kind == R_SCALE_MUL)
+    const ChunkHooks *hk = f.hooks;
+    if (sop.kind == R_SCALE_MUL) {
       launch_zpass_tma<N, true, true>(f, in, out, sop, f.stream);
-    else if (sop.kind == R_SCALE || sop.kind == R_AXPY)
+    } else if (sop.kind == R_SCALE || sop.kind == R_AXPY) {
+      if (hk && hk->after && hk->chunks > 1 && ((size_t)f.Ns * N) % ((size_t)hk->chunks * ZShape<N>::TR) == 0) {
+        // the caller streams the result out: hand over each slab of rows as soon as its z pass is queued
+        const size_t per = (size_t)f.Ns * N / hk->chunks;
+        for (int c = 0; c < hk->chunks; ++c) {
+          launch_zpass_tma<N, true, false>(f, in, out, sop, f.stream, c * per, per);
+          hk->after(hk->ctx, c);
+        }
+        return true;
+      }
       launch_zpass_tma<N, true, false>(f, in, out, sop, f.stream);
-    else
+    } else {
       return false;
+    }
+    if (hk && hk->after)
+      for (int c = 0; c < hk->chunks; ++c) hk->after(hk->ctx, c);
     return true;
   }
 }
@@ -343,6 +375,8 @@ static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xo
   const size_t nrows = (size_t)f.Ns * N;
   if (!try_r2c_zpass_tma<N>(f, in, out, lop)) {
   if (f.G > 1) throw std::runtime_error("bgpu: the slab-decomposed transform needs the bulk-copy z pass (N >= 128)");
+  if (f.hooks && f.hooks->before)
+    for (int c = 0; c < f.hooks->chunks; ++c) f.hooks->before(f.hooks->ctx, c);
   ProfScope prof(KK_FFT_R2C_Z, f.stream);
   if constexpr (N == 8) {
     tiny_r2c_zpass<N><<<(unsigned)((nrows + 63) / 64), 64, 0, f.stream>>>(in, out, f.twN, lop, nrows);
@@ -433,6 +467,8 @@ static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *o
     fft_c2r_zpass<N, TR><<<(unsigned)(nrows / TR), TR * M / 8, smem, f.stream>>>(work, out, f.twN, f.twM, sop, nrows);
   }
   BGPU_LAUNCHED(1);
+  if (f.hooks && f.hooks->after)
+    for (int c = 0; c < f.hooks->chunks; ++c) f.hooks->after(f.hooks->ctx, c);
 }
 
 // opt in to > 48 KB dynamic shared memory; per device, so done at plan creation

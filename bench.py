@@ -342,6 +342,31 @@ def run_ours(args):
            "d2h_bytes_per_step": n * 8, "ms_per_step": 1e3 * dt / args.steps,
            "api": "bgpu_gradient_psi(host signal -> host gradpsi), pinned host buffers"}
 
+    # the call the reference's driver makes once per HMC candidate: Hamiltonian_EoM -> bgpu_leapfrog with host
+    # s_i, p_i in and s_f, p_f out (Neps = 8); Neps + 1 gradient evaluations per call
+    neps = 8
+    h_p = torch.from_numpy(np.ascontiguousarray(prob["momenta"]).reshape(-1)).pin_memory()
+    h_sf = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_pf = torch.empty(n, dtype=torch.float64).pin_memory()
+
+    def traj():
+        rc = ch.L.bgpu_leapfrog(ch._h, C.cast(h_s.data_ptr(), dp), C.cast(h_p.data_ptr(), dp), neps, 1e-3,
+                                C.cast(h_sf.data_ptr(), dp), C.cast(h_pf.data_ptr(), dp))
+        if rc != 0:
+            raise RuntimeError(ch.L.bgpu_last_error().decode())
+
+    traj()
+    barrier()
+    t0 = time.perf_counter()
+    ntraj = max(1, args.steps // 5)
+    for _ in range(ntraj):
+        traj()
+    torch.cuda.synchronize()
+    dt_traj = multi.max_over_ranks(time.perf_counter() - t0, info, "cuda")
+    e2e["trajectory"] = {"api": "bgpu_leapfrog(host s_i, p_i -> host s_f, p_f), Neps = 8", "gradient_evals_per_s":
+                         world * ntraj * (neps + 1) / dt_traj, "leapfrog_steps_per_s": world * ntraj * neps / dt_traj,
+                         "h2d_bytes_per_call": 2 * n * 8, "d2h_bytes_per_call": 2 * n * 8}
+
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = cpu_baseline(args, cfg)
