@@ -25,7 +25,7 @@ class BgpuParams(C.Structure):
         ("masskernel", C.c_int), ("likelihood", C.c_int), ("sfmodel", C.c_int), ("rsd_model", C.c_int),
         ("calc_h", C.c_int), ("mass_type", C.c_int),
         ("D1", C.c_double), ("D2", C.c_double), ("ascale", C.c_double), ("OM", C.c_double), ("OL", C.c_double),
-        ("slength", C.c_double),
+        ("particle_kernel_h_rel", C.c_double), ("slength", C.c_double),
         ("rho_c", C.c_double), ("biasP", C.c_double), ("biasE", C.c_double),
         ("deltaQ_factor", C.c_double), ("correct_delta", C.c_int),
         ("mass_factor", C.c_double),

@@ -37,6 +37,7 @@ class Params:
     D1: float = 1.0
     D2: float = -3.0 / 7.0 * 0.272 ** (-1.0 / 143.0)   # init_par.cc:526-528 at z = 0
     slength: float = 4.0
+    particle_kernel_h_rel: float = 1.0
     ascale: float = 1.0
     OM: float = 0.272
     OL: float = 0.728

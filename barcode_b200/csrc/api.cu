@@ -90,6 +90,10 @@ struct bgpu_handle {
   static constexpr int kChunks = 8;
   cudaEvent_t ev_up[kChunks] = {}, ev_dn[kChunks] = {};
   const ChunkHooks *in_hooks = nullptr, *out_hooks = nullptr;
+
+  // SPH kernel hull (SPH_kernel_3D_cells_hull_1): k half-range per (i, j) column, on the device
+  int *sph_kmax = nullptr;
+  int sph_R = 0;
 };
 
 namespace {
@@ -143,12 +147,18 @@ void validate(const bgpu_params &p) {
   require(p.N1 == p.N2 && p.N2 == p.N3, "bgpu: only cubic grids are supported (the reference sets N2=N3=N1, init_par.cc:116-122)");
   require(Fft3d::supported(p.N1), "bgpu: N1 must be a power of two in [8, 1024]");
   require(p.L1 == p.L2 && p.L2 == p.L3 && p.L1 > 0, "bgpu: only cubic boxes are supported");
-  require(p.masskernel >= 0 && p.masskernel <= 2,
-          "bgpu: masskernel must be 0 (NGP), 1 (CIC) or 2 (TSC); the SPH kernel (3) is not implemented on the GPU path yet");
+  require(p.masskernel >= 0 && p.masskernel <= 3, "bgpu: masskernel must be 0 (NGP), 1 (CIC), 2 (TSC) or 3 (SPH)");
+  if (p.masskernel == 3)
+    require(p.particle_kernel_h_rel > 0. && p.particle_kernel_h_rel <= p.N1 / 4.,
+            "bgpu: particle_kernel_h_rel must be in (0, N1/4] for the SPH kernel (init_par.cc:373-375)");
   require(p.likelihood == 0 || p.likelihood == 1,
           "bgpu: likelihood must be 0 (Poisson) or 1 (Gaussian); lognormal / GRF are not implemented on the GPU path yet");
-  require(p.calc_h == 0 || p.calc_h == 1 || p.calc_h == BGPU_CALC_H_EXACT,
-          "bgpu: calc_h must be 0, 1 or 4 (exact adjoint); 2/3 need the SPH kernel (HMC_models.cc:316-319)");
+  require(p.calc_h == 0 || p.calc_h == 1 || p.calc_h == 2 || p.calc_h == BGPU_CALC_H_EXACT,
+          "bgpu: calc_h must be 0, 1, 2 (SPH adjoint) or 4 (NGP/CIC/TSC adjoint); 3 is not implemented");
+  require(p.calc_h == 0 || p.calc_h == 1 || (p.calc_h == 2 && p.masskernel == 3) ||
+              (p.calc_h == BGPU_CALC_H_EXACT && p.masskernel != 3),
+          "Must use SPH mass kernel (masskernel = 3) when using likelihood_calc_h_SPH (calc_h = 2); the exact "
+          "adjoint of the SPH kernel is calc_h = 2, of NGP/CIC/TSC calc_h = 4");
   require(p.mass_type == 0 || p.mass_type == 1 || p.mass_type == 4,
           "bgpu: mass_type must be 0, 1 or 4 on the GPU path (2/3/5/6/60 are cold set-up paths)");
   if (p.sfmodel != 1 && !p.rsd_model) {
@@ -226,7 +236,10 @@ void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, d
     g.H = H;
     h->delta = h->rho_ext + (size_t)H * plane;
   }
-  launch_scatter(g, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, px, py, pz, h->stream);
+  if (g.masskernel == 3)
+    launch_scatter_sph(g, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, px, py, pz, h->stream);
+  else
+    launch_scatter(g, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, px, py, pz, h->stream);
   if (h->G > 1) {
     // my lower halo belongs to rank-1's last planes, my upper halo to rank+1's first planes
     const int H = g.H, lo = (h->rank + h->G - 1) % h->G, hi = (h->rank + 1) % h->G;
@@ -312,7 +325,11 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     }
   } else {
     // exact adjoint: V = gather(r) in place over Psi, then the same back-projection
-    launch_gather_adjoint(h->geom, h->psi[0], h->psi[1], h->psi[2], h->resid, h->stream);
+    if (p.calc_h == 2)
+      launch_gather_sph(h->geom, h->psi[0], h->psi[1], h->psi[2], h->resid, h->sph_kmax, h->sph_R,
+                        p.rho_c * (p.L1 * p.L2 * p.L3) / h->ncells, h->stream);
+    else
+      launch_gather_adjoint(h->geom, h->psi[0], h->psi[1], h->psi[2], h->resid, h->stream);
     for (int c = 0; c < 3; ++c) {
       ROp lop2;
       lop2.kind = R_LOAD;
@@ -505,6 +522,7 @@ void bgpu_default_params(bgpu_params *p) {
   p->D1 = 1.0;
   p->D2 = -3. / 7. * std::pow(0.272, -1. / 143.);  // init_par.cc:526-528 at z = 0
   p->slength = 4.0;                          // data/input.par:121
+  p->particle_kernel_h_rel = 1.0;            // data/input.par:134
   p->ascale = 1.0;
   p->OM = 0.272;                            // init_par.cc:38,480-483 (cmbcosm = 3)
   p->OL = 0.728;
@@ -531,6 +549,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
             "bgpu_slab_create: N1 must be a multiple of the number of ranks, at least 8 planes per rank");
     require(p->calc_h == 0 || p->calc_h == 1,
             "bgpu_slab_create: calc_h must be 0 or 1 (the exact adjoint's residual halo is not built yet)");
+    require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
     require(p->sfmodel == 1 || p->rsd_model,
             "bgpu_slab_create: the 2LPT/ALPT model differentiates by finite differences across slabs; not built yet");
     require(!(p->calc_h == 0 && p->likelihood == 0),
@@ -632,6 +651,26 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   g.H = 0;
   g.flag = h->dflag;
   g.cellbound = 0;
+  g.sph_h = p->particle_kernel_h_rel * g.d;
+  if (p->masskernel == 3) {
+    // SPH_kernel_3D_cells + _hull_1 (SPH_kernel.cpp:62-139)
+    const double d = g.d, reach_len = 2. * g.sph_h;
+    const int R = (int)(reach_len / d) + 1, W = 2 * R + 1;
+    std::vector<int> kmax((size_t)W * W, -1);
+    for (int i1 = -R; i1 <= R; ++i1)
+      for (int i2 = -R; i2 <= R; ++i2)
+        for (int i3 = -R; i3 <= R; ++i3) {
+          const double dx = (std::abs((double)i1) - 0.5) * d, dy = (std::abs((double)i2) - 0.5) * d,
+                       dz = (std::abs((double)i3) - 0.5) * d;
+          if (dx * dx + dy * dy + dz * dz <= reach_len * reach_len) {
+            int &km = kmax[(size_t)(i1 + R) * W + (i2 + R)];
+            if (std::abs(i3) > km) km = std::abs(i3);
+          }
+        }
+    h->sph_R = R;
+    BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->sph_kmax), kmax.size() * sizeof(int)));
+    BGPU_CUDA(cudaMemcpy(h->sph_kmax, kmax.data(), kmax.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   h->like.likelihood = p->likelihood;
   h->like.rho_c = p->rho_c;
   h->like.biasP = p->biasP;
@@ -720,6 +759,7 @@ void bgpu_destroy(bgpu_handle *h) {
     if (h->ev_up[c]) cudaEventDestroy(h->ev_up[c]);
     if (h->ev_dn[c]) cudaEventDestroy(h->ev_dn[c]);
   }
+  if (h->sph_kmax) cudaFree(h->sph_kmax);
   if (h->dflag) cudaFree(h->dflag);
   if (h->hflag) cudaFreeHost(h->hflag);
   if (h->hscal) cudaFreeHost(h->hscal);

@@ -76,7 +76,7 @@ bool same_params(const bgpu_params &a, const bgpu_params &b) {
          a.planepar == b.planepar && a.periodic == b.periodic && a.masskernel == b.masskernel &&
          a.likelihood == b.likelihood && a.sfmodel == b.sfmodel && a.rsd_model == b.rsd_model &&
          a.calc_h == b.calc_h && a.mass_type == b.mass_type && a.D1 == b.D1 && a.D2 == b.D2 &&
-         a.slength == b.slength && a.ascale == b.ascale &&
+         a.slength == b.slength && a.particle_kernel_h_rel == b.particle_kernel_h_rel && a.ascale == b.ascale &&
          a.OM == b.OM && a.OL == b.OL && a.rho_c == b.rho_c && a.biasP == b.biasP && a.biasE == b.biasE &&
          a.deltaQ_factor == b.deltaQ_factor && a.correct_delta == b.correct_delta &&
          a.mass_factor == b.mass_factor;
@@ -102,6 +102,7 @@ bgpu_params params_from(struct HAMIL_DATA *hd, struct DATA *data) {
   p.mass_type = n->mass_type;
   p.D1 = hd->D1; p.D2 = hd->D2; p.ascale = hd->ascale; p.OM = hd->OM; p.OL = hd->OL;
   p.slength = n->kth;
+  p.particle_kernel_h_rel = n->particle_kernel_h / ((n->d1 + n->d2 + n->d3) / 3.);
   p.rho_c = hd->rho_c; p.biasP = hd->biasP; p.biasE = hd->biasE;
   p.deltaQ_factor = n->deltaQ_factor;
   p.correct_delta = n->correct_delta;

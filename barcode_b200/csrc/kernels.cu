@@ -194,12 +194,18 @@ void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, c
   BGPU_LAUNCHED(1);
 }
 
+__global__ void scatter_sph_positions_kernel(GridGeom g, const double *__restrict__ x, const double *__restrict__ y,
+                                             const double *__restrict__ z, double *__restrict__ rho);
+
 void launch_scatter_positions(const GridGeom &g, const double *x, const double *y, const double *z, double *rho,
                               cudaStream_t st) {
   ProfScope prof(KK_SCATTER, st);
   const size_t n = (size_t)g.N * g.N * g.N;
   BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
-  scatter_positions_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, x, y, z, rho);
+  if (g.masskernel == 3)
+    scatter_sph_positions_kernel<<<blocks_for(n, 128), 128, 0, st>>>(g, x, y, z, rho);
+  else
+    scatter_positions_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, x, y, z, rho);
   BGPU_LAUNCHED(1);
 }
 
@@ -854,6 +860,150 @@ void launch_alpt_combine(double2 *d2, const double2 *d4, int N, double kfac, dou
   ProfScope prof(KK_STREAM, st);
   const size_t n = (size_t)N * N * (N / 2 + 1);
   alpt_combine_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d2, d4, N, kfac, rS);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// SPH spline mass assignment and its exact adjoint (the reference's shipped default,
+// data/input.par:11-13,134): getDensity_SPH (massFunctions.cc:392-495) and
+// likelihood_calc_V_SPH (HMC_models.cc:200-303, SPH_kernel.cpp:62-208)
+// ---------------------------------------------------------------------------
+// Monaghan W_4 spline, SPH_kernel_3D (massFunctions.cc:366-384)
+__device__ __forceinline__ double sph_kernel(double r, double h) {
+  const double q = r / h;
+  const double a = 1. / M_PI / (h * h * h);
+  if (q <= 1.) return a * (1 - 3. / 2 * q * q + 3. / 4 * q * q * q);
+  if (q <= 2.) {
+    const double t = 2. - q;
+    return a * (1. / 4 * (t * t * t));
+  }
+  return 0.;
+}
+
+__device__ void deposit_sph(const GridGeom &g, double x, double y, double z, double *__restrict__ rho);
+
+// one thread per particle; every cell within `reach` of the particle's own cell whose centre is
+// within 2h receives W(r, h) (unit mass, no normalisation: overdens divides by the mean afterwards)
+__global__ void scatter_sph_kernel(GridGeom g, const double *__restrict__ psix, const double *__restrict__ psiy,
+                                   const double *__restrict__ psiz, double *__restrict__ rho, double *__restrict__ posx,
+                                   double *__restrict__ posy, double *__restrict__ posz) {
+  const int N = g.N;
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int k = (int)(idx % N), j = (int)((idx / N) % N), i = (int)(idx / ((size_t)N * N));
+  double x, y, z;
+  particle_position(g, i, j, k, psix[idx], psiy[idx], psiz[idx], x, y, z);
+  if (posx) {
+    posx[idx] = x;
+    posy[idx] = y;
+    posz[idx] = z;
+  }
+  deposit_sph(g, x, y, z, rho);
+}
+
+__device__ void deposit_sph(const GridGeom &g, double x, double y, double z, double *__restrict__ rho) {
+  const int N = g.N;
+  if (!in_domain(g, x, y, z)) return;
+  const double d = g.d, h = g.sph_h;
+  const int reach = (int)(2 * h / d) + 1;
+  const int ix = (int)(unsigned long long)(x / d), iy = (int)(unsigned long long)(y / d),
+            iz = (int)(unsigned long long)(z / d);
+  const double ccx = ((double)ix + 0.5) * d, ccy = ((double)iy + 0.5) * d, ccz = ((double)iz + 0.5) * d;
+  for (int i1 = -reach; i1 <= reach; ++i1) {
+    const double dx = x - (ccx + (double)i1 * d);
+    const int kx = (N + i1 + ix) % N;
+    for (int i2 = -reach; i2 <= reach; ++i2) {
+      const double dy = y - (ccy + (double)i2 * d);
+      const int ky = (N + i2 + iy) % N;
+      const double rxy = dx * dx + dy * dy;
+      double *row = rho + ((size_t)kx * N + ky) * N;
+      for (int i3 = -reach; i3 <= reach; ++i3) {
+        const double dz = z - (ccz + (double)i3 * d);
+        const double r = sqrt(rxy + dz * dz);
+        if (r / h <= 2.) red_add(row + (N + i3 + iz) % N, sph_kernel(r, h));
+      }
+    }
+  }
+}
+
+__global__ void scatter_sph_positions_kernel(GridGeom g, const double *__restrict__ x, const double *__restrict__ y,
+                                             const double *__restrict__ z, double *__restrict__ rho) {
+  const size_t n = (size_t)g.N * g.N * g.N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) deposit_sph(g, x[idx], y[idx], z[idx], rho);
+}
+
+void launch_scatter_sph(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
+                        double *posx, double *posy, double *posz, cudaStream_t st) {
+  ProfScope prof(KK_SCATTER, st);
+  const size_t n = (size_t)g.N * g.N * g.N;
+  BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
+  scatter_sph_kernel<<<blocks_for(n, 128), 128, 0, st>>>(g, psix, psiy, psiz, rho, posx, posy, posz);
+  BGPU_LAUNCHED(1);
+}
+
+// V_p = (rho_c V/N) sum_{hull cells} r_c gradW((x_p - x_c)/h); the hull is every (i, j) column with the
+// inclusive k range that can reach the central cell (kmax[(i+R)(2R+1) + (j+R)], -1 = column not in the hull);
+// gradW = partial(q) * (x_p - x_c)/h / (pi h^4).  In place over Psi.  Deterministic (pure gather).
+__global__ void gather_sph_kernel(GridGeom g, double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az,
+                                  const double *__restrict__ resid, const int *__restrict__ kmax, int R,
+                                  double normalize) {
+  const int N = g.N;
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int k = (int)(idx % N), j = (int)((idx / N) % N), i = (int)(idx / ((size_t)N * N));
+  double px, py, pz;
+  particle_position(g, i, j, k, ax[idx], ay[idx], az[idx], px, py, pz);
+  const double d = g.d, h = g.sph_h, h_inv = 1. / h, d_h = d * h_inv;
+  const double norm = 1. / (M_PI * (h * h) * (h * h));
+  const int ix = (int)(px / d), iy = (int)(py / d), iz = (int)(pz / d);
+  const double dpcx = px * h_inv - ((double)ix + 0.5) * d_h, dpcy = py * h_inv - ((double)iy + 0.5) * d_h,
+               dpcz = pz * h_inv - ((double)iz + 0.5) * d_h;
+  double vx = 0., vy = 0., vz = 0.;
+  for (int i1 = -R; i1 <= R; ++i1) {
+    const double dxh = dpcx - (double)i1 * d_h;
+    const int kx = (ix + i1 + N) % N;
+    for (int i2 = -R; i2 <= R; ++i2) {
+      const int K = kmax[(i1 + R) * (2 * R + 1) + (i2 + R)];
+      if (K < 0) continue;
+      const double dyh = dpcy - (double)i2 * d_h;
+      const double qxy = dxh * dxh + dyh * dyh;
+      const double *row = resid + ((size_t)kx * N + (iy + i2 + N) % N) * N;
+      for (int i3 = -K; i3 <= K; ++i3) {
+        const double dzh = dpcz - (double)i3 * d_h;
+        const double q_sq = qxy + dzh * dzh;
+        if (q_sq > 4.) continue;
+        const double q = sqrt(q_sq);
+        double partial;
+        if (q_sq > 1.) {
+          const double qm = q - 2.;
+          partial = -0.75 * qm * qm * norm / q;
+        } else {
+          partial = (2.25 * q - 3.) * norm;
+        }
+        const double c = __ldg(row + (iz + i3 + N) % N) * partial;
+        vx += c * dxh;
+        vy += c * dyh;
+        vz += c * dzh;
+      }
+    }
+  }
+  vx *= normalize;
+  vy *= normalize;
+  vz *= normalize;
+  if (g.rsd) vz += g.fgrow * vz;  // HMC_models.cc:295-301
+  ax[idx] = vx;
+  ay[idx] = vy;
+  az[idx] = vz;
+}
+
+void launch_gather_sph(const GridGeom &g, double *ax, double *ay, double *az, const double *resid, const int *kmax,
+                       int R, double normalize, cudaStream_t st) {
+  ProfScope prof(KK_GATHER, st);
+  const size_t n = (size_t)g.N * g.N * g.N;
+  gather_sph_kernel<<<blocks_for(n, 128), 128, 0, st>>>(g, ax, ay, az, resid, kmax, R, normalize);
   BGPU_LAUNCHED(1);
 }
 

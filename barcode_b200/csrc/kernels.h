@@ -22,6 +22,7 @@ struct GridGeom {
   int H;           // halo planes each side of the density tile: rho is [(Ns + 2H)][N][N], plane 0 = global x0 - H
   int *flag;       // set to 1 if a particle left the halo (device int), may be null when H == 0 and Ns == N
   int cellbound;   // displacements are cell-boundary averaged on read (cellboundcomp; non-Zel'dovich model)
+  double sph_h;    // SPH scale length particle_kernel_h = h_rel * d (init_par.cc:379), masskernel 3
 };
 
 struct LikeParams {
@@ -40,6 +41,12 @@ void launch_inverse_spectrum(const double *full, double *half, int N, double nor
 // particle scatter: Psi -> rho (zeroed here); optional positions out
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
                     double *posx, double *posy, double *posz, cudaStream_t st);
+// SPH spline mass assignment (masskernel 3, getDensity_SPH) and its exact adjoint (calc_h = 2,
+// likelihood_calc_V_SPH): kmax[(i+R)(2R+1) + (j+R)] is the hull's k half-range of column (i, j), -1 = none
+void launch_scatter_sph(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
+                        double *posx, double *posy, double *posz, cudaStream_t st);
+void launch_gather_sph(const GridGeom &g, double *psix_Vx, double *psiy_Vy, double *psiz_Vz, const double *resid,
+                       const int *kmax, int R, double normalize, cudaStream_t st);
 // mass assignment on explicit positions (tests, bgpu_assign_density)
 void launch_scatter_positions(const GridGeom &g, const double *x, const double *y, const double *z, double *rho,
                               cudaStream_t st);

@@ -50,14 +50,15 @@ typedef struct bgpu_params {
   double xllc, yllc, zllc;   /* origin -> min1..3 */
   double xobs, yobs, zobs;   /* observer (only plane-parallel RSD is supported, as in rsd.cc:60-62) */
   int planepar, periodic;
-  int masskernel;            /* mk: 0 NGP, 1 CIC, 2 TSC */
+  int masskernel;            /* mk: 0 NGP, 1 CIC, 2 TSC, 3 SPH spline */
   int likelihood;            /* 0 Poisson, 1 Gaussian */
   int sfmodel;               /* 1 Zel'dovich; else Lag2Eul_non_zeldovich (2LPT + spherical collapse, ALPT);
                               * with rsd_model the reference runs Zel'dovich for any value */
   int rsd_model;
-  int calc_h;                /* 0, 1 as the reference; BGPU_CALC_H_EXACT */
+  int calc_h;                /* 0, 1, 2 (SPH adjoint, needs masskernel 3) as the reference; BGPU_CALC_H_EXACT */
   int mass_type;             /* 0 ones (R), 1 1/P (FS), 4 P (FS) */
   double D1, D2, ascale, OM, OL;
+  double particle_kernel_h_rel; /* SPH scale length in cells (input.par particle_kernel_h_rel); masskernel 3 */
   double slength;            /* ALPT smoothing radius [Mpc/h] (input.par slength -> n->kth, struct_hamil.h:259); sfmodel != 1 */
   double rho_c, biasP, biasE;
   double deltaQ_factor;

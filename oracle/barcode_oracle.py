@@ -42,6 +42,7 @@ class Params:
     D2: float = -3.0 / 7.0 * 0.272 ** (-1.0 / 143.0)  # init_par.cc:526-528 at z = 0: -3/7 D1^2 Omega^(-1/143)
     sfmodel: int = 1           # 1 Zel'dovich; anything else -> Lag2Eul_non_zeldovich (Lag2Eul.cc:329-331)
     slength: float = 4.0       # n->kth = data->numerical->slength (struct_hamil.h:259): ALPT smoothing radius
+    particle_kernel_h_rel: float = 1.0   # SPH scale length in cells (init_par.cc:379; masskernel 3)
     ascale: float = 1.0
     OM: float = 0.272          # init_par.cc:38,482 (cmbcosm = 3)
     OL: float = 0.728
@@ -67,6 +68,10 @@ class Params:
     @property
     def vol(self):
         return self.L1 * self.L1 * self.L1
+
+    @property
+    def kernel_h(self):  # init_par.cc:377-379 (cubic cells)
+        return self.particle_kernel_h_rel * self.d
 
     @property
     def mass_fs(self):  # struct_hamil.h:276-313
@@ -301,9 +306,97 @@ def density(p: Params, x, y, z) -> np.ndarray:
             for b in range(3):
                 for c in range(3):
                     np.add.at(rho, ck[c] + N * (cj[b] + N * ci[a]), (1.0 * wi[a]) * wj[b] * wk[c])
+    elif p.masskernel == 3:
+        rho = density_sph(p, x, y, z).ravel()
     else:
-        raise NotImplementedError("masskernel %d (SPH is SURVEY section 8f row F1)" % p.masskernel)
+        raise NotImplementedError("masskernel %d" % p.masskernel)
     return rho.reshape(N, N, N)
+
+
+def sph_kernel(r, h):
+    """SPH_kernel_3D (massFunctions.cc:366-384): Monaghan W_4 spline."""
+    q = r / h
+    a = 1.0 / np.pi / (h * h * h)
+    return np.where(q <= 1.0, a * (1 - 3.0 / 2 * q * q + 3.0 / 4 * q * q * q),
+                    np.where(q <= 2.0, a * (1.0 / 4 * (2.0 - q) ** 3), 0.0))
+
+
+def density_sph(p: Params, x, y, z):
+    """getDensity_SPH (massFunctions.cc:392-495): every particle adds W(r, h) to the cells within
+    reach = int(2h/d)+1 of its own cell whose centre is within 2h; unit masses, no normalisation."""
+    N, d, h = p.N1, p.d, p.kernel_h
+    ok = _in_domain(p, x, y, z, False)
+    x, y, z = x[ok], y[ok], z[ok]
+    reach = int(2 * h / d) + 1
+    ix, iy, iz = (x / d).astype(np.int64), (y / d).astype(np.int64), (z / d).astype(np.int64)
+    ccx, ccy, ccz = (ix + 0.5) * d, (iy + 0.5) * d, (iz + 0.5) * d
+    rho = np.zeros(N * N * N)
+    for i1 in range(-reach, reach + 1):
+        dx = x - (ccx + i1 * d)
+        kx = (N + i1 + ix) % N
+        for i2 in range(-reach, reach + 1):
+            dy = y - (ccy + i2 * d)
+            ky = (N + i2 + iy) % N
+            for i3 in range(-reach, reach + 1):
+                dz = z - (ccz + i3 * d)
+                kz = (N + i3 + iz) % N
+                r = np.sqrt(dx * dx + dy * dy + dz * dz)
+                m = r / h <= 2.0
+                np.add.at(rho, (kz + N * (ky + N * kx))[m], sph_kernel(r[m], h))
+    return rho.reshape(N, N, N)
+
+
+def sph_hull(p: Params):
+    """SPH_kernel_3D_cells + SPH_kernel_3D_cells_hull_1 (SPH_kernel.cpp:62-139): the (i, j) columns
+    and their inclusive k range that can hold a cell centre within 2h of any point of the central cell."""
+    d, h = p.d, p.kernel_h
+    reach = int(2 * h / d) + 1
+    hull = {}
+    for i1 in range(-reach, reach + 1):
+        for i2 in range(-reach, reach + 1):
+            for i3 in range(-reach, reach + 1):
+                r_sq = ((abs(i1) - 0.5) * d) ** 2 + ((abs(i2) - 0.5) * d) ** 2 + ((abs(i3) - 0.5) * d) ** 2
+                if r_sq <= (2 * h) ** 2:
+                    lo, hi = hull.get((i1, i2), (i3, i3))
+                    hull[(i1, i2)] = (min(lo, i3), max(hi, i3))
+    return hull
+
+
+def calc_V_sph(p: Params, r, x, y, z):
+    """likelihood_calc_V_SPH (HMC_models.cc:200-303): V_p = (rho_c V/N) sum_cells r_c gradW((x_p - x_c)/h)
+    with gradW = partial * (x_p - x_c)/h / (pi h^4) (grad_SPH_kernel_3D_h_units, SPH_kernel.cpp:148-208);
+    z component times (1 + f) under plane-parallel RSD."""
+    N, d, h = p.N1, p.d, p.kernel_h
+    x, y, z = (np.asarray(a, dtype=np.float64).ravel() for a in (x, y, z))
+    r = np.asarray(r, dtype=np.float64).reshape(N, N, N)
+    norm = 1.0 / (np.pi * h ** 4)
+    ix, iy, iz = (x / d).astype(np.int64), (y / d).astype(np.int64), (z / d).astype(np.int64)
+    h_inv = 1.0 / h
+    d_h = d * h_inv
+    dpc = [x * h_inv - (ix + 0.5) * d_h, y * h_inv - (iy + 0.5) * d_h, z * h_inv - (iz + 0.5) * d_h]
+    V = [np.zeros_like(x) for _ in range(3)]
+    for (i1, i2), (k0, k1) in sph_hull(p).items():
+        dxh = dpc[0] - i1 * d_h
+        dyh = dpc[1] - i2 * d_h
+        kx, ky = (ix + i1) % N, (iy + i2) % N
+        for i3 in range(k0, k1 + 1):
+            dzh = dpc[2] - i3 * d_h
+            kz = (iz + i3) % N
+            q_sq = dxh * dxh + dyh * dyh + dzh * dzh
+            q = np.sqrt(q_sq)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                partial = np.where(q_sq > 4, 0.0, np.where(q_sq > 1, -0.75 * (q - 2) * (q - 2) * norm / q,
+                                                           (2.25 * q - 3) * norm))
+            c = r[kx, ky, kz] * partial
+            V[0] += c * dxh
+            V[1] += c * dyh
+            V[2] += c * dzh
+    normalize = p.rho_c * p.vol / float(p.N)
+    V = [normalize * v for v in V]
+    if p.rsd_model:
+        V[2] = V[2] + fgrow(p.ascale, p.OM, p.OL) * V[2]
+    shp = (N, N, N)
+    return [v.reshape(shp) for v in V]
 
 
 def overdens(rho) -> np.ndarray:
@@ -547,6 +640,10 @@ def grad_log_like(p: Params, signal, nobs, noise, window):
         h = calc_h0(p, dX, nobs, noise, window)
     elif p.calc_h == 1:
         h = partial_f(p, dX, nobs, noise, window)
+    elif p.calc_h == 2:
+        # likelihood_calc_h_SPH (HMC_models.cc:312-372): the reference's exact adjoint, SPH kernel only
+        r = partial_f(p, dX, nobs, noise, window)
+        h = grad_inv_lap_sum(p, calc_V_sph(p, r, x, y, z))
     elif p.calc_h == 4:
         r = partial_f(p, dX, nobs, noise, window, exact_sign=True)
         mean = 1.0  # rho/mean: mean == 1 analytically for NGP/CIC/TSC

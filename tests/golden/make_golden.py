@@ -44,6 +44,12 @@ CASES = {
     # sfmodel != 1 without rsd_model.  configs[3]'s forward model.
     "alpt_cic_gauss": dict(masskernel=1, likelihood=1, rsd_model=False, calc_h=0, mass_type=1, sfmodel=2,
                            slength=4.0),
+    # the reference's shipped default (data/input.par:11-13,134): SPH spline mass assignment with its exact
+    # adjoint, calc_h = 2 (likelihood_calc_h_SPH, HMC_models.cc:312-372)
+    "za_sph_gauss_h2": dict(masskernel=3, likelihood=1, rsd_model=False, calc_h=2, mass_type=1),
+    "za_sph_gauss_rsd_h2": dict(masskernel=3, likelihood=1, rsd_model=True, calc_h=2, mass_type=1,
+                                particle_kernel_h_rel=1.3),
+    "za_sph_poisson_h2": dict(masskernel=3, likelihood=0, rsd_model=False, calc_h=2, mass_type=4),
     "alpt_tsc_poisson_h1": dict(masskernel=2, likelihood=0, rsd_model=False, calc_h=1, mass_type=1, sfmodel=3,
                                 slength=6.0, deltaQ_factor=0.95),
 }

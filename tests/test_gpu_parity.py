@@ -21,7 +21,8 @@ def make_chain(cfg, **over):
     kw = dict(N1=cfg["N1"], L1=cfg["L1"], masskernel=cfg["masskernel"], likelihood=cfg["likelihood"],
               rsd_model=cfg["rsd_model"], calc_h=cfg["calc_h"], mass_type=cfg["mass_type"],
               sfmodel=cfg.get("sfmodel", 1), deltaQ_factor=cfg.get("deltaQ_factor", 1.0),
-              mass_factor=cfg.get("mass_factor", 1.0), slength=cfg.get("slength", 4.0))
+              mass_factor=cfg.get("mass_factor", 1.0), slength=cfg.get("slength", 4.0),
+              particle_kernel_h_rel=cfg.get("particle_kernel_h_rel", 1.0))
     kw.update(over)
     return Chain(Params(**kw))
 
@@ -31,7 +32,8 @@ def oracle_params(cfg, **over):
     kw = dict(N1=cfg["N1"], L1=cfg["L1"], masskernel=cfg["masskernel"], likelihood=cfg["likelihood"],
               rsd_model=cfg["rsd_model"], calc_h=cfg["calc_h"], mass_type=cfg["mass_type"],
               deltaQ_factor=cfg.get("deltaQ_factor", 1.0), mass_factor=cfg.get("mass_factor", 1.0),
-              sfmodel=cfg.get("sfmodel", 1), slength=cfg.get("slength", 4.0))
+              sfmodel=cfg.get("sfmodel", 1), slength=cfg.get("slength", 4.0),
+              particle_kernel_h_rel=cfg.get("particle_kernel_h_rel", 1.0))
     kw.update(over)
     return bo.Params(**kw)
 
@@ -108,7 +110,8 @@ def test_density_same_positions(case):
         rho = ch.assign_density(case["posx"], case["posy"], case["posz"])
     ref = bo.density(oracle_params(cfg), case["posx"], case["posy"], case["posz"])
     assert rel_l2(rho, ref) < 1e-13
-    assert abs(rho.sum() - rho.size) < 1e-8 * rho.size  # unit masses, partition of unity
+    if cfg["masskernel"] != 3:  # the SPH kernel is not normalised on the grid (massFunctions.cc:476-494)
+        assert abs(rho.sum() - rho.size) < 1e-8 * rho.size  # unit masses, partition of unity
 
 
 def test_forward_density_and_positions(case):

@@ -15,7 +15,8 @@ def params(cfg, **over):
     kw = dict(N1=cfg["N1"], L1=cfg["L1"], masskernel=cfg["masskernel"], likelihood=cfg["likelihood"],
               rsd_model=cfg["rsd_model"], calc_h=cfg["calc_h"], mass_type=cfg["mass_type"],
               deltaQ_factor=cfg.get("deltaQ_factor", 1.0), mass_factor=cfg.get("mass_factor", 1.0),
-              D1=1.0, sfmodel=cfg.get("sfmodel", 1), slength=cfg.get("slength", 4.0))
+              D1=1.0, sfmodel=cfg.get("sfmodel", 1), slength=cfg.get("slength", 4.0),
+              particle_kernel_h_rel=cfg.get("particle_kernel_h_rel", 1.0))
     kw.update(over)
     return bo.Params(**kw)
 
