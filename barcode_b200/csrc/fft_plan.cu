@@ -172,6 +172,7 @@ constexpr bool tma_supported() {
 struct PassIo {
   int n_other = 0;      // pencils' "other" extent; 0 = N (cube)
   int other0 = 0;       // global index of other == 0
+  int other_begin = 0, other_count = 0;  // this launch walks others [begin, begin + count); count 0 = all
   bool in_packed = false, out_packed = false;
   int G = 1, Ns = 0;
   double2 *const *peer_out = nullptr;  // fused transpose: receive buffer of every rank, as mapped here
@@ -206,9 +207,10 @@ static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, 
   maps.auxc = AUX >= 2 ? f.tensor_map(lop.cplx0, AXIS, true, 0, n_slow, n_mid) : maps.in;
   if (io.peer_out)
     for (int h = 0; h < io.G; ++h) maps.peer[h] = f.tensor_map(io.peer_out[h], AXIS, true, 1, io.G, io.Ns);
-  PassGeom geo{n_other, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0, io.peer_out ? io.Ns : 0,
-               io.my_rank};
-  const int tiles = n_other * ((N / 2 + 1 + 7) / 8);
+  const int count = io.other_count ? io.other_count : n_other;
+  PassGeom geo{count, io.other_begin, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0,
+               io.peer_out ? io.Ns : 0, io.my_rank};
+  const int tiles = count * ((N / 2 + 1 + 7) / 8);
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > tiles) blocks = tiles;
   ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
@@ -255,7 +257,7 @@ static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, cons
   constexpr int tiles = N * ((N / 2) / T) + N / T;
   constexpr size_t smem = (size_t)N * T * sizeof(double2);
   if (try_strided_tma<N, DIR, AXIS>(f, in, out, lop, sop, io, st)) return;
-  if (f.G > 1 || io.n_other)
+  if (f.G > 1 || io.n_other || io.other_count)
     throw std::runtime_error("bgpu: the slab-decomposed transform needs the TMA-staged pass (N = 128, 256 or 512)");
   ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
   if constexpr (N >= 128) {
@@ -363,6 +365,92 @@ static bool try_c2r_zpass_tma(const Fft3d &f, const double2 *in, double *out, RO
   }
 }
 
+// ---------------------------------------------------------------------------
+// L2-resident z+y sweep.  The z and y passes both work inside one x plane, so instead of sweeping
+// the whole array twice (z pass writes N^2(N/2+1) complex numbers to HBM, y pass reads them back)
+// the planes are walked in chunks small enough to stay in the 126 MB L2: the z pass of a chunk is
+// followed at once by the y pass of the same planes, which finds its input in L2 and overwrites it
+// in place, so each element crosses the HBM interface once on the way in (real) and once on the way
+// out (after the y pass).  Chunks alternate between two streams so that the tail of one chunk's
+// kernels overlaps the head of the next chunk's.
+// ---------------------------------------------------------------------------
+template <int N>
+static int l2_chunk_planes(const Fft3d &f) {
+  if constexpr (!tma_has_size<N>()) {
+    return 0;
+  } else {
+    if (!f.use_tma || f.G != 1 || f.hooks || !f.l2_chunk_bytes) return 0;
+    const size_t plane = (size_t)N * (N / 2 + 1) * sizeof(double2);
+    int P = 1;
+    while ((size_t)(2 * P) * plane <= f.l2_chunk_bytes && 2 * P < N) P *= 2;
+    if ((size_t)N * plane <= f.l2_chunk_bytes) return 0;  // the whole array is L2-resident anyway
+    return P;
+  }
+}
+
+struct ChunkStreams {
+  const Fft3d &f;
+  bool two;
+  ChunkStreams(const Fft3d &f_, int nch) : f(f_), two(f_.side && !g_prof.on && nch > 1) {
+    if (two) {
+      BGPU_CUDA(cudaEventRecord(f.ev_fork, f.stream));
+      BGPU_CUDA(cudaStreamWaitEvent(f.side, f.ev_fork, 0));
+    }
+  }
+  cudaStream_t of(int c) const { return (two && (c & 1)) ? f.side : f.stream; }
+  void join() {
+    if (two) {
+      BGPU_CUDA(cudaEventRecord(f.ev_join, f.side));
+      BGPU_CUDA(cudaStreamWaitEvent(f.stream, f.ev_join, 0));
+    }
+  }
+};
+
+template <int N>
+static bool r2c_zy_chunked(const Fft3d &f, const double *in, double2 *out, ROp lop) {
+  if (!(lop.kind == R_LOAD || lop.kind == R_LOAD_SCALE)) return false;
+  const int P = l2_chunk_planes<N>(f);
+  if (!P) return false;
+  if constexpr (tma_has_size<N>()) {
+    const int nch = N / P;
+    ChunkStreams cs(f, nch);
+    for (int c = 0; c < nch; ++c) {
+      cudaStream_t st = cs.of(c);
+      launch_zpass_tma<N, false, false>(f, in, out, lop, st, (size_t)c * P * N, (size_t)P * N);
+      PassIo io;
+      io.other_begin = c * P;
+      io.other_count = P;
+      launch_strided<N, -1, 1>(f, out, out, f.twN, KOp{}, KOp{}, st, io);
+    }
+    cs.join();
+  }
+  return true;
+}
+
+template <int N>
+static bool c2r_yz_chunked(const Fft3d &f, double2 *work, double *out, ROp sop) {
+  if (!(sop.kind == R_SCALE_MUL || sop.kind == R_SCALE || sop.kind == R_AXPY)) return false;
+  const int P = l2_chunk_planes<N>(f);
+  if (!P) return false;
+  if constexpr (tma_has_size<N>()) {
+    const int nch = N / P;
+    ChunkStreams cs(f, nch);
+    for (int c = 0; c < nch; ++c) {
+      cudaStream_t st = cs.of(c);
+      PassIo io;
+      io.other_begin = c * P;
+      io.other_count = P;
+      launch_strided<N, +1, 1>(f, work, work, f.twN, KOp{}, KOp{}, st, io);
+      if (sop.kind == R_SCALE_MUL)
+        launch_zpass_tma<N, true, true>(f, work, out, sop, st, (size_t)c * P * N, (size_t)P * N);
+      else
+        launch_zpass_tma<N, true, false>(f, work, out, sop, st, (size_t)c * P * N, (size_t)P * N);
+    }
+    cs.join();
+  }
+  return true;
+}
+
 // all-to-all of the packed buffers: peer h gets / gives block h (Ns*Ns*(N/2+1) complex numbers)
 static void slab_all_to_all(const Fft3d &f, const double2 *send, double2 *recv) {
   const size_t blk = (size_t)f.Ns * f.Ns * (f.N / 2 + 1);
@@ -373,6 +461,10 @@ static void slab_all_to_all(const Fft3d &f, const double2 *send, double2 *recv) 
 template <int N>
 static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xout, ROp lop, KOp sop) {
   const size_t nrows = (size_t)f.Ns * N;
+  if (r2c_zy_chunked<N>(f, in, out, lop)) {
+    launch_strided<N, -1, 0>(f, out, xout ? xout : out, f.twN, KOp{}, sop, f.stream);
+    return;
+  }
   if (!try_r2c_zpass_tma<N>(f, in, out, lop)) {
   if (f.G > 1) throw std::runtime_error("bgpu: the slab-decomposed transform needs the bulk-copy z pass (N >= 128)");
   if (f.hooks && f.hooks->before)
@@ -427,6 +519,7 @@ static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *o
   const size_t nrows = (size_t)f.Ns * N;
   if (f.G == 1) {
     launch_strided<N, +1, 0>(f, in, work, f.twN, lop, KOp{}, f.stream);
+    if (c2r_yz_chunked<N>(f, work, out, sop)) return;
     launch_strided<N, +1, 1>(f, work, work, f.twN, KOp{}, KOp{}, f.stream);
   } else {
     // slab: x pass on the transposed layout into the send buffer (block h = the x planes of rank h,
@@ -548,6 +641,15 @@ void Fft3d::init(int n, cudaStream_t st) {
     const char *e = std::getenv("BGPU_FFT_TMA");
     use_tma = !(e && e[0] == '0');
     maps_.clear();
+    // L2-resident z+y sweep: chunk size in MiB (0 = off) and one or two streams
+    const char *mb = std::getenv("BGPU_FFT_L2CHUNK_MB");
+    l2_chunk_bytes = (size_t)(mb ? std::atoi(mb) : 32) << 20;
+    const char *ns = std::getenv("BGPU_FFT_L2STREAMS");
+    if (!(ns && ns[0] == '1')) {
+      BGPU_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      BGPU_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      BGPU_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
   }
   auto a = make_twiddles(n), b = make_twiddles(n / 2);
   BGPU_CUDA(cudaMalloc(&twN, sizeof(double2) * n));
@@ -563,6 +665,12 @@ void Fft3d::destroy() {
   if (twN) cudaFree(twN);
   if (twM) cudaFree(twM);
   twN = twM = nullptr;
+  if (side) {
+    cudaStreamDestroy(side);
+    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_join);
+    side = nullptr;
+  }
 }
 
 void Fft3d::barrier() const {
