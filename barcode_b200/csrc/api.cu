@@ -502,7 +502,8 @@ int bgpu_profile_end(double *ms_per_kind, uint64_t *launches_per_kind, int nkind
 const char *bgpu_profile_kind_name(int kind) {
   static const char *names[KK_COUNT] = {"fft_strided_pass_y", "fft_r2c_zpass", "fft_c2r_zpass", "scatter",
                                         "gather_adjoint", "overdens_residual", "reduce", "stream", "colour_momenta",
-                                        "fft_strided_pass_x", "all_to_all", "halo_exchange"};
+                                        "fft_strided_pass_x", "all_to_all", "halo_exchange", "fft_zy_fused_r2c",
+                                        "fft_zy_fused_c2r"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "?";
 }
 

@@ -45,11 +45,11 @@ struct Fft3d {
   int sm_count = 0;
   bool use_tma = true;     // TMA-staged strided pass (fft_tma.cuh); BGPU_FFT_TMA=0 selects the cp.async one
   mutable const ChunkHooks *hooks = nullptr;  // set around ONE transform by the caller, consumed by its z pass
-  // L2-resident z+y sweep (fft_plan.cu): bytes of half-complex planes per chunk (0 = off), and the second
-  // stream + fork/join events the chunks alternate on
-  size_t l2_chunk_bytes = 0;
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // fused z+y kernel (fft_fused.cuh): per-plane completion counters, their running target, producer lead
+  bool use_fused = false;  // BGPU_FFT_FUSED=1
+  unsigned long long *zy_ready = nullptr;
+  mutable unsigned long long zy_epoch = 0;
+  int zy_lead = 0;
 
   // tensor maps of the half-grid arrays the TMA pass has touched (keyed by base pointer and layout)
   struct MapEntry {

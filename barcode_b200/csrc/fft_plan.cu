@@ -14,6 +14,7 @@
 
 #include "fft.cuh"
 #include "fft_tma.cuh"
+#include "fft_fused.cuh"
 #include "util.h"
 
 namespace bgpu {
@@ -366,88 +367,55 @@ static bool try_c2r_zpass_tma(const Fft3d &f, const double2 *in, double *out, RO
 }
 
 // ---------------------------------------------------------------------------
-// L2-resident z+y sweep.  The z and y passes both work inside one x plane, so instead of sweeping
-// the whole array twice (z pass writes N^2(N/2+1) complex numbers to HBM, y pass reads them back)
-// the planes are walked in chunks small enough to stay in the 126 MB L2: the z pass of a chunk is
-// followed at once by the y pass of the same planes, which finds its input in L2 and overwrites it
-// in place, so each element crosses the HBM interface once on the way in (real) and once on the way
-// out (after the y pass).  Chunks alternate between two streams so that the tail of one chunk's
-// kernels overlaps the head of the next chunk's.
+// fused z+y passes (fft_fused.cuh): one persistent kernel, intermediate kept in L2
 // ---------------------------------------------------------------------------
+template <int N> struct ZyShape { static constexpr bool ok = false; static constexpr int EZ = 8, TR = 8, EY = 8; };
+template <> struct ZyShape<256> { static constexpr bool ok = true; static constexpr int EZ = 8, TR = 16, EY = 8; };
+
 template <int N>
-static int l2_chunk_planes(const Fft3d &f) {
-  if constexpr (!tma_has_size<N>()) {
-    return 0;
-  } else {
-    if (!f.use_tma || f.G != 1 || f.hooks || !f.l2_chunk_bytes) return 0;
-    const size_t plane = (size_t)N * (N / 2 + 1) * sizeof(double2);
-    int P = 1;
-    while ((size_t)(2 * P) * plane <= f.l2_chunk_bytes && 2 * P < N) P *= 2;
-    if ((size_t)N * plane <= f.l2_chunk_bytes) return 0;  // the whole array is L2-resident anyway
-    return P;
+static bool zy_fused_ok(const Fft3d &f) {
+  return ZyShape<N>::ok && f.use_tma && f.use_fused && f.G == 1 && !f.hooks && f.zy_ready;
+}
+
+template <int N, bool C2R, bool AUX>
+static void launch_zy_fused(const Fft3d &f, const void *zsrc, void *zdst, const double2 *cplx, ROp op) {
+  if constexpr (ZyShape<N>::ok) {
+    using S = ZyShape<N>;
+    constexpr int NS = AUX ? 2 : 3;
+    using L = ZySmem<N, S::TR, NS, NS, AUX>;
+    auto kern = fft_zy_fused<N, S::EZ, S::TR, S::EY, NS, NS, C2R, AUX>;
+    static bool configured = false;
+    if (!configured) {
+      BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::bytes));
+      int occ = 0;
+      BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 512, L::bytes));
+      if (occ < 1) throw std::runtime_error("bgpu: the fused z+y kernel does not fit on this device");
+      configured = true;
+    }
+    const CUtensorMap &ymap = f.tensor_map(cplx, 1, true, 0, N, N);
+    constexpr int per_plane = C2R ? (N / 2 + 1 + 7) / 8 : N / S::TR;  // producer tiles per plane
+    f.zy_epoch += per_plane;
+    ZyCtl ctl{f.zy_ready, f.zy_epoch, f.zy_lead};
+    ProfScope prof(C2R ? KK_FFT_ZY_C2R : KK_FFT_ZY_R2C, f.stream);
+    // every CTA must be resident (the roles wait on each other across CTAs): one per SM
+    kern<<<f.sm_count, 512, L::bytes, f.stream>>>(ymap, zsrc, zdst, f.twN, f.twM, op, ctl);
+    BGPU_LAUNCHED(1);
   }
 }
 
-struct ChunkStreams {
-  const Fft3d &f;
-  bool two;
-  ChunkStreams(const Fft3d &f_, int nch) : f(f_), two(f_.side && !g_prof.on && nch > 1) {
-    if (two) {
-      BGPU_CUDA(cudaEventRecord(f.ev_fork, f.stream));
-      BGPU_CUDA(cudaStreamWaitEvent(f.side, f.ev_fork, 0));
-    }
-  }
-  cudaStream_t of(int c) const { return (two && (c & 1)) ? f.side : f.stream; }
-  void join() {
-    if (two) {
-      BGPU_CUDA(cudaEventRecord(f.ev_join, f.side));
-      BGPU_CUDA(cudaStreamWaitEvent(f.stream, f.ev_join, 0));
-    }
-  }
-};
-
 template <int N>
-static bool r2c_zy_chunked(const Fft3d &f, const double *in, double2 *out, ROp lop) {
-  if (!(lop.kind == R_LOAD || lop.kind == R_LOAD_SCALE)) return false;
-  const int P = l2_chunk_planes<N>(f);
-  if (!P) return false;
-  if constexpr (tma_has_size<N>()) {
-    const int nch = N / P;
-    ChunkStreams cs(f, nch);
-    for (int c = 0; c < nch; ++c) {
-      cudaStream_t st = cs.of(c);
-      launch_zpass_tma<N, false, false>(f, in, out, lop, st, (size_t)c * P * N, (size_t)P * N);
-      PassIo io;
-      io.other_begin = c * P;
-      io.other_count = P;
-      launch_strided<N, -1, 1>(f, out, out, f.twN, KOp{}, KOp{}, st, io);
-    }
-    cs.join();
-  }
+static bool r2c_zy_fused(const Fft3d &f, const double *in, double2 *out, ROp lop) {
+  if (!zy_fused_ok<N>(f) || !(lop.kind == R_LOAD || lop.kind == R_LOAD_SCALE)) return false;
+  launch_zy_fused<N, false, false>(f, in, out, out, lop);
   return true;
 }
 
 template <int N>
-static bool c2r_yz_chunked(const Fft3d &f, double2 *work, double *out, ROp sop) {
-  if (!(sop.kind == R_SCALE_MUL || sop.kind == R_SCALE || sop.kind == R_AXPY)) return false;
-  const int P = l2_chunk_planes<N>(f);
-  if (!P) return false;
-  if constexpr (tma_has_size<N>()) {
-    const int nch = N / P;
-    ChunkStreams cs(f, nch);
-    for (int c = 0; c < nch; ++c) {
-      cudaStream_t st = cs.of(c);
-      PassIo io;
-      io.other_begin = c * P;
-      io.other_count = P;
-      launch_strided<N, +1, 1>(f, work, work, f.twN, KOp{}, KOp{}, st, io);
-      if (sop.kind == R_SCALE_MUL)
-        launch_zpass_tma<N, true, true>(f, work, out, sop, st, (size_t)c * P * N, (size_t)P * N);
-      else
-        launch_zpass_tma<N, true, false>(f, work, out, sop, st, (size_t)c * P * N, (size_t)P * N);
-    }
-    cs.join();
-  }
+static bool c2r_yz_fused(const Fft3d &f, double2 *work, double *out, ROp sop) {
+  if (!zy_fused_ok<N>(f)) return false;
+  if (sop.kind == R_SCALE_MUL) launch_zy_fused<N, true, true>(f, work, out, work, sop);
+  else if (sop.kind == R_SCALE || sop.kind == R_AXPY) launch_zy_fused<N, true, false>(f, work, out, work, sop);
+  else return false;
   return true;
 }
 
@@ -461,7 +429,7 @@ static void slab_all_to_all(const Fft3d &f, const double2 *send, double2 *recv) 
 template <int N>
 static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xout, ROp lop, KOp sop) {
   const size_t nrows = (size_t)f.Ns * N;
-  if (r2c_zy_chunked<N>(f, in, out, lop)) {
+  if (r2c_zy_fused<N>(f, in, out, lop)) {
     launch_strided<N, -1, 0>(f, out, xout ? xout : out, f.twN, KOp{}, sop, f.stream);
     return;
   }
@@ -519,7 +487,7 @@ static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *o
   const size_t nrows = (size_t)f.Ns * N;
   if (f.G == 1) {
     launch_strided<N, +1, 0>(f, in, work, f.twN, lop, KOp{}, f.stream);
-    if (c2r_yz_chunked<N>(f, work, out, sop)) return;
+    if (c2r_yz_fused<N>(f, work, out, sop)) return;
     launch_strided<N, +1, 1>(f, work, work, f.twN, KOp{}, KOp{}, f.stream);
   } else {
     // slab: x pass on the transposed layout into the send buffer (block h = the x planes of rank h,
@@ -641,15 +609,17 @@ void Fft3d::init(int n, cudaStream_t st) {
     const char *e = std::getenv("BGPU_FFT_TMA");
     use_tma = !(e && e[0] == '0');
     maps_.clear();
-    // L2-resident z+y sweep: chunk size in MiB (0 = off) and one or two streams
-    const char *mb = std::getenv("BGPU_FFT_L2CHUNK_MB");
-    l2_chunk_bytes = (size_t)(mb ? std::atoi(mb) : 32) << 20;
-    const char *ns = std::getenv("BGPU_FFT_L2STREAMS");
-    if (!(ns && ns[0] == '1')) {
-      BGPU_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-      BGPU_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-      BGPU_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
+    // fused z+y kernel (fft_fused.cuh).  Opt-in: measured on B200 at 256^3 it is correct but ~25 % slower than
+    // the two separate passes -- the passes are bound by shared-memory bandwidth and
+    // latency on the SM, not by HBM, so halving the HBM traffic does not pay by itself.
+    const char *fu = std::getenv("BGPU_FFT_FUSED");
+    use_fused = fu && fu[0] == '1';
+    const char *ld = std::getenv("BGPU_FFT_LEAD");
+    zy_lead = ld ? std::atoi(ld) : 96;
+    if (zy_lead < 48) zy_lead = 48;  // must exceed the planes spanned by a role's ring (3 tiles of stride SMs/tiles-per-plane)
+    BGPU_CUDA(cudaMalloc(&zy_ready, sizeof(unsigned long long) * n));
+    BGPU_CUDA(cudaMemset(zy_ready, 0, sizeof(unsigned long long) * n));
+    zy_epoch = 0;
   }
   auto a = make_twiddles(n), b = make_twiddles(n / 2);
   BGPU_CUDA(cudaMalloc(&twN, sizeof(double2) * n));
@@ -665,12 +635,8 @@ void Fft3d::destroy() {
   if (twN) cudaFree(twN);
   if (twM) cudaFree(twM);
   twN = twM = nullptr;
-  if (side) {
-    cudaStreamDestroy(side);
-    cudaEventDestroy(ev_fork);
-    cudaEventDestroy(ev_join);
-    side = nullptr;
-  }
+  if (zy_ready) cudaFree(zy_ready);
+  zy_ready = nullptr;
 }
 
 void Fft3d::barrier() const {

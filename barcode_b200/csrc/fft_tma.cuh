@@ -524,6 +524,81 @@ __device__ __forceinline__ double2 root16(int m) {
   }
 }
 
+// One row of the z pass, in place in shared memory (rbase = the row, N/2 + 1 double2 of room): forward =
+// N/2-point complex FFT of z[j] = x[2j] + i x[2j+1] + Hermitian split; inverse = Hermitian merge + FFT.
+// Lane t of the LP = N/(2E) lanes that own the row; `auxrow` (AUX) = the row of the real multiplier.
+template <int N, int E, bool C2R, bool AUX>
+__device__ __forceinline__ void zrow_transform(uint32_t rbase, uint32_t auxrow, int t,
+                                               const double2 (*twr)[E], double2 wt,
+                                               const double2 *__restrict__ twN, const ROp &op) {
+  constexpr int M = N / 2;
+  constexpr int LP = M / E;
+  constexpr int DIR = C2R ? +1 : -1;
+  const RowAccess acc{rbase};
+  auto split_twiddle = [&](int m) -> double2 {
+    if constexpr (E == 8) return m == 0 ? wt : cmul(wt, root16(m));
+    else return __ldg(twN + t + m * LP);
+  };
+  double2 v[E];
+  if constexpr (!C2R) {
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = lds128(acc.at(t + m * LP));
+    if (op.kind == R_LOAD_SCALE) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[m] = make_double2(v[m].x * op.a, v[m].y * op.a);
+    }
+    wp_stages<M, E, 1, DIR, 0>(v, t, acc, twr);
+    // Hermitian split: X[k] = E + w^k O, E = (Z[k] + conj Z[M-k])/2, O = (Z[k] - conj Z[M-k])/(2i)
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < E; ++m) sts128(acc.at(t + m * LP), v[m]);
+    __syncwarp();
+    double2 zm[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) zm[m] = lds128(acc.at((M - (t + m * LP)) & (M - 1)));
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+      const int k = t + m * LP;
+      const double2 zk = v[m];
+      const double2 e = make_double2(0.5 * (zk.x + zm[m].x), 0.5 * (zk.y - zm[m].y));
+      const double2 o = make_double2(0.5 * (zk.y + zm[m].y), -0.5 * (zk.x - zm[m].x));
+      const double2 w = split_twiddle(m);
+      sts128(acc.at(k), cadd(e, cmul(w, o)));
+      if (k == 0) sts128(acc.at(M), make_double2(e.x - o.x, 0.0));  // w_N^M = -1; E[0], O[0] real
+    }
+  } else {
+    // Hermitian merge: Z[k] = E' + i O', E' = X[k] + conj X[M-k], O' = (X[k] - conj X[M-k]) conj(w^k)
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+      const int k = t + m * LP;
+      double2 xk = lds128(acc.at(k));
+      double2 xm = lds128(acc.at(M - k));
+      if (k == 0) {  // FFTW's c2r ignores the imaginary parts of the self-conjugate bins
+        xk.y = 0.0;
+        xm.y = 0.0;
+      }
+      const double2 e = make_double2(xk.x + xm.x, xk.y - xm.y);
+      const double2 d = make_double2(xk.x - xm.x, xk.y + xm.y);
+      const double2 o = cmul(d, cconj(split_twiddle(m)));
+      v[m] = make_double2(e.x - o.y, e.y + o.x);
+    }
+    wp_stages<M, E, 1, DIR, 0>(v, t, acc, twr);
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+      const int j = t + m * LP;
+      double2 x = make_double2(op.a * v[m].x, op.a * v[m].y);
+      if constexpr (AUX) {
+        const double2 y = lds128(auxrow + j * 16);
+        x.x *= y.x;
+        x.y *= y.y;
+      }
+      sts128(acc.at(j), x);
+    }
+  }
+}
+
 template <int N, int TR, int NSTAGE, bool AUX>
 struct ZTile {
   static constexpr int pitch = N * 8 + 32;
@@ -590,75 +665,13 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
   wp_load_twiddles<M, E, 1, DIR, 0>(twr, t, twM);
   // split / merge twiddle w_N^k, k = t + m LP: for E == 8, LP = N/16 and w_N^(m LP) is a 16th root of unity
   const double2 wt = __ldg(twN + t);
-  auto split_twiddle = [&](int m) -> double2 {
-    if constexpr (E == 8) return m == 0 ? wt : cmul(wt, root16(m));
-    else return __ldg(twN + t + m * LP);
-  };
 
   for (int i = 0; i < my_count; ++i) {
     const int s = i % NSTAGE;
     const uint32_t rbase = smem0 + s * Z::stage_bytes + row * Z::pitch;
-    const RowAccess acc{rbase};
     mbar_wait(&full[s], (i / NSTAGE) & 1);
 
-    double2 v[E];
-    if constexpr (!C2R) {
-#pragma unroll
-      for (int m = 0; m < E; ++m) v[m] = lds128(acc.at(t + m * LP));
-      if (op.kind == R_LOAD_SCALE) {
-#pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = make_double2(v[m].x * op.a, v[m].y * op.a);
-      }
-      wp_stages<M, E, 1, DIR, 0>(v, t, acc, twr);
-      // Hermitian split: X[k] = E + w^k O, E = (Z[k] + conj Z[M-k])/2, O = (Z[k] - conj Z[M-k])/(2i)
-      __syncwarp();
-#pragma unroll
-      for (int m = 0; m < E; ++m) sts128(acc.at(t + m * LP), v[m]);
-      __syncwarp();
-      double2 zm[E];
-#pragma unroll
-      for (int m = 0; m < E; ++m) zm[m] = lds128(acc.at((M - (t + m * LP)) & (M - 1)));
-      __syncwarp();
-#pragma unroll
-      for (int m = 0; m < E; ++m) {
-        const int k = t + m * LP;
-        const double2 zk = v[m];
-        const double2 e = make_double2(0.5 * (zk.x + zm[m].x), 0.5 * (zk.y - zm[m].y));
-        const double2 o = make_double2(0.5 * (zk.y + zm[m].y), -0.5 * (zk.x - zm[m].x));
-        const double2 w = split_twiddle(m);
-        sts128(acc.at(k), cadd(e, cmul(w, o)));
-        if (k == 0) sts128(acc.at(M), make_double2(e.x - o.x, 0.0));  // w_N^M = -1; E[0], O[0] real
-      }
-    } else {
-      // Hermitian merge: Z[k] = E' + i O', E' = X[k] + conj X[M-k], O' = (X[k] - conj X[M-k]) conj(w^k)
-#pragma unroll
-      for (int m = 0; m < E; ++m) {
-        const int k = t + m * LP;
-        double2 xk = lds128(acc.at(k));
-        double2 xm = lds128(acc.at(M - k));
-        if (k == 0) {  // FFTW's c2r ignores the imaginary parts of the self-conjugate bins
-          xk.y = 0.0;
-          xm.y = 0.0;
-        }
-        const double2 e = make_double2(xk.x + xm.x, xk.y - xm.y);
-        const double2 d = make_double2(xk.x - xm.x, xk.y + xm.y);
-        const double2 o = cmul(d, cconj(split_twiddle(m)));
-        v[m] = make_double2(e.x - o.y, e.y + o.x);
-      }
-      wp_stages<M, E, 1, DIR, 0>(v, t, acc, twr);
-      __syncwarp();
-#pragma unroll
-      for (int m = 0; m < E; ++m) {
-        const int j = t + m * LP;
-        double2 x = make_double2(op.a * v[m].x, op.a * v[m].y);
-        if constexpr (AUX) {
-          const double2 y = lds128(smem0 + s * Z::stage_bytes + Z::main_bytes + row * (N * 8) + j * 16);
-          x.x *= y.x;
-          x.y *= y.y;
-        }
-        sts128(acc.at(j), x);
-      }
-    }
+    zrow_transform<N, E, C2R, AUX>(rbase, smem0 + s * Z::stage_bytes + Z::main_bytes + row * (N * 8), t, twr, wt, twN, op);
     fence_proxy_async();
     __syncthreads();
     if (tid < 32) {

@@ -45,7 +45,9 @@ enum KernelKind : int {
   KK_FFT_STRIDED_X = 9,
   KK_ALLTOALL = 10,
   KK_HALO = 11,
-  KK_COUNT = 12
+  KK_FFT_ZY_R2C = 12,  // fused z+y passes (fft_fused.cuh)
+  KK_FFT_ZY_C2R = 13,
+  KK_COUNT = 14
 };
 
 struct Profiler {

@@ -282,6 +282,9 @@ def run_ours(args):
         "fft_strided_pass_y": 2 * nh * 16, "fft_strided_pass_x": 2 * nh * 16,            # read + write the half-complex array once
         "fft_r2c_zpass": n * 8 + nh * 16,
         "fft_c2r_zpass": n * 8 + nh * 16,
+        # fused z+y passes: the real array and the half-complex array cross HBM once each; the
+        # intermediate between the two passes stays in L2
+        "fft_zy_fused_r2c": n * 8 + nh * 16, "fft_zy_fused_c2r": n * 8 + nh * 16,
         "scatter": 4 * n * 8,                       # Psi_x,y,z in, rho out
         "gather_adjoint": 7 * n * 8,
         "overdens_residual": 5 * n * 8,

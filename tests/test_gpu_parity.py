@@ -335,3 +335,31 @@ def test_tma_pass_matches_cp_async_pass(N, monkeypatch):
     assert rel_l2(out["1"][0], out["0"][0]) < 1e-13
     assert rel_l2(out["1"][1], out["0"][1]) < 1e-14
     assert abs(out["1"][2] - out["0"][2]) <= 1e-13 * abs(out["0"][2])
+
+
+def test_fused_zy_kernel_matches_separate_passes(monkeypatch):
+    """The opt-in fused z+y kernel (fft_fused.cuh, BGPU_FFT_FUSED=1: warp-specialised roles, the intermediate
+    array handed over through L2 with per-plane flags) against numpy and against the separate passes."""
+    from barcode_b200.chain import Chain, Params
+    from barcode_b200 import inputs
+    N = 256
+    L = inputs.box_length(N)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((N, N, N))
+    ref = np.fft.rfftn(x)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L)
+    n = N ** 3
+    s = 0.3 * rng.standard_normal(n)
+    nobs = 1.0 + 0.1 * rng.standard_normal(n)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("BGPU_FFT_FUSED", fused)
+        with Chain(Params(N1=N, L1=L, masskernel=1, likelihood=1, rsd_model=True, calc_h=0)) as ch:
+            if fused == "1":
+                assert rel_l2(ch.fft_r2c(x), ref) < 1e-14
+                assert rel_l2(ch.fft_c2r(ref), x) < 1e-14
+            ch.set_static(Power=P, nobs=nobs, noise=np.ones(n), window=np.ones(n))
+            ch.hamiltonian_mass()
+            out[fused] = (ch.gradient_psi(s), ch.kinetic_term(s))
+    assert rel_l2(out["1"][0], out["0"][0]) < 1e-13
+    assert abs(out["1"][1] - out["0"][1]) <= 1e-13 * abs(out["0"][1])
