@@ -344,7 +344,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   ROp sop;
   sop.kind = R_SCALE;
   sop.a = inv_n;
-  if (h->G > 1 && h->N >= 512) {
+  if (h->G > 1 && (h->N >= 512 || h->fft.force_generic)) {
     // the TMA-staged x pass cannot hold both operand tiles at this size: combine in a pass of its own
     launch_kfinal_combine(h->shat, h->inv_power, h->acc, h->acc, norm, h->N, h->nh, h->stream);
     h->fft.hooks = h->out_hooks;
@@ -544,8 +544,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   if (nranks > 1) {
     // the slab path runs on the TMA-staged FFT passes and covers what needs no particle
     // data across slabs beyond the density halo
-    require(p->N1 == 128 || p->N1 == 256 || p->N1 == 512,
-            "bgpu_slab_create: the slab-decomposed transform supports N = 128, 256, 512");
+    require(p->N1 == 128 || p->N1 == 256 || p->N1 == 512 || p->N1 == 1024,
+            "bgpu_slab_create: the slab-decomposed transform supports N = 128, 256, 512, 1024");
     require(rank >= 0 && rank < nranks && p->N1 % nranks == 0 && p->N1 / nranks >= 8,
             "bgpu_slab_create: N1 must be a multiple of the number of ranks, at least 8 planes per rank");
     require(p->calc_h == 0 || p->calc_h == 1,

@@ -15,6 +15,7 @@
 #include "fft.cuh"
 #include "fft_tma.cuh"
 #include "fft_fused.cuh"
+#include "fft_slab_generic.cuh"
 #include "util.h"
 
 namespace bgpu {
@@ -250,6 +251,38 @@ static bool try_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp
   }
 }
 
+// generic (cp.async) strided pass over slab layouts: N = 1024, and N = 128 for tests (fft_slab_generic.cuh)
+template <int N> constexpr bool slab_generic_has_size() { return N == 128 || N == 1024; }
+
+template <int N, int DIR, int AXIS>
+static void launch_strided_slab(const Fft3d &f, const double2 *in, double2 *out, KOp lop, KOp sop, const PassIo &io,
+                                cudaStream_t st) {
+  if constexpr (slab_generic_has_size<N>()) {
+    constexpr int T = Shape<N>::T;
+    constexpr int threads = T * N / 8;
+    constexpr int smem = 2 * N * T * (int)sizeof(double2);
+    auto kern = fft_strided_pass_slab<N, T, DIR, AXIS>;
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+      BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int occ = 0;
+      BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+      blocks_per_sm = occ > 0 ? occ : 1;
+    }
+    if (io.peer_out || lop.kind == K_FINAL || ((io.in_packed || io.out_packed) && AXIS != 1))
+      throw std::runtime_error("bgpu: layout not supported by the generic slab pass");
+    const int n_other = io.n_other ? io.n_other : N;
+    if (n_other % T) throw std::runtime_error("bgpu: planes per rank must be a multiple of the tile width");
+    SlabGeom geo{n_other, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0};
+    const int tiles = n_other * ((N / 2) / T) + n_other / T;
+    int blocks = f.sm_count * blocks_per_sm;
+    if (blocks > tiles) blocks = tiles;
+    ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
+    kern<<<blocks, threads, smem, st>>>(in, out, f.twN, lop, sop, geo);
+    BGPU_LAUNCHED(1);
+  }
+}
+
 template <int N, int DIR, int AXIS>
 static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, const double2 *tw, KOp lop, KOp sop,
                            cudaStream_t st, const PassIo &io = PassIo{}) {
@@ -257,6 +290,11 @@ static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, cons
   constexpr int threads = T * N / 8;
   constexpr int tiles = N * ((N / 2) / T) + N / T;
   constexpr size_t smem = (size_t)N * T * sizeof(double2);
+  const bool generic = slab_generic_has_size<N>() && (f.G > 1 || io.n_other) && (f.force_generic || !tma_has_size<N>());
+  if (generic) {
+    launch_strided_slab<N, DIR, AXIS>(f, in, out, lop, sop, io, st);
+    return;
+  }
   if (try_strided_tma<N, DIR, AXIS>(f, in, out, lop, sop, io, st)) return;
   if (f.G > 1 || io.n_other || io.other_count)
     throw std::runtime_error("bgpu: the slab-decomposed transform needs the TMA-staged pass (N = 128, 256 or 512)");
@@ -462,7 +500,7 @@ static void r2c_impl(const Fft3d &f, const double *in, double2 *out, double2 *xo
   PassIo x_io;
   x_io.n_other = f.Ns;
   x_io.other0 = f.rank * f.Ns;
-  if (f.p2p) {
+  if (f.p2p && tma_has_size<N>() && !f.force_generic) {
     // fused transpose: the y pass stores every tile straight into the peers' receive buffers (TMA over
     // NVLink); one cross-rank barrier, then the x pass reads what the peers wrote here.  Receive
     // buffers alternate between transforms, so the barrier of this transform also orders the next
@@ -502,7 +540,7 @@ static void c2r_impl(const Fft3d &f, const double2 *in, double2 *work, double *o
     y_io.in_packed = true;
     y_io.G = f.G;
     y_io.Ns = f.Ns;
-    if (f.p2p) {
+    if (f.p2p && tma_has_size<N>() && !f.force_generic) {
       double2 *const *peers = f.peer_recv[f.parity];
       x_io.peer_out = peers;
       x_io.my_rank = f.rank;
@@ -612,6 +650,8 @@ void Fft3d::init(int n, cudaStream_t st) {
     // fused z+y kernel (fft_fused.cuh).  Opt-in: measured on B200 at 256^3 it is correct but ~25 % slower than
     // the two separate passes -- the passes are bound by shared-memory bandwidth and
     // latency on the SM, not by HBM, so halving the HBM traffic does not pay by itself.
+    const char *fg = std::getenv("BGPU_FFT_SLAB_GENERIC");
+    force_generic = fg && fg[0] == '1';
     const char *fu = std::getenv("BGPU_FFT_FUSED");
     use_fused = fu && fu[0] == '1';
     const char *ld = std::getenv("BGPU_FFT_LEAD");

@@ -15,13 +15,15 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("p2p", ["1", "0"])
-def test_slab_chain_matches_single_gpu_chain(p2p):
+@pytest.mark.parametrize("p2p,generic", [("1", "0"), ("0", "0"), ("0", "1")])
+def test_slab_chain_matches_single_gpu_chain(p2p, generic):
+    """p2p: fused transpose over peer memory vs NCCL all-to-all; generic: the cp.async slab pass that
+    1024^3 runs on (fft_slab_generic.cuh), here at 128^3 where a single-GPU reference exists."""
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
     world = 4 if n >= 4 else 2
-    env = dict(os.environ, BGPU_SLAB_P2P=p2p)
+    env = dict(os.environ, BGPU_SLAB_P2P=p2p, BGPU_FFT_SLAB_GENERIC=generic)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", "29655",
                         os.path.join(ROOT, "tools", "slab_check.py"), "--grid", "128"],
