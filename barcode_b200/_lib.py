@@ -31,7 +31,8 @@ class BgpuParams(C.Structure):
         ("mass_factor", C.c_double),
         ("div_dH_by_N", C.c_int),
         ("device", C.c_int),
-        ("reserved", C.c_int * 8),
+        ("delta_min", C.c_double),
+        ("reserved", C.c_int * 6),
     ]
 
 

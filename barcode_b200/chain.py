@@ -48,6 +48,7 @@ class Params:
     correct_delta: bool = True
     mass_factor: float = 1.0
     div_dH_by_N: bool = False
+    delta_min: float = -0.999
     device: int = 0
 
     def to_c(self) -> BgpuParams:

@@ -151,8 +151,8 @@ void validate(const bgpu_params &p) {
   if (p.masskernel == 3)
     require(p.particle_kernel_h_rel > 0. && p.particle_kernel_h_rel <= p.N1 / 4.,
             "bgpu: particle_kernel_h_rel must be in (0, N1/4] for the SPH kernel (init_par.cc:373-375)");
-  require(p.likelihood == 0 || p.likelihood == 1,
-          "bgpu: likelihood must be 0 (Poisson) or 1 (Gaussian); lognormal / GRF are not implemented on the GPU path yet");
+  require(p.likelihood >= 0 && p.likelihood <= 3,
+          "bgpu: likelihood must be 0 (Poisson), 1 (Gaussian), 2 (log-normal) or 3 (Gaussian random field)");
   require(p.calc_h == 0 || p.calc_h == 1 || p.calc_h == 2 || p.calc_h == BGPU_CALC_H_EXACT,
           "bgpu: calc_h must be 0, 1, 2 (SPH adjoint) or 4 (NGP/CIC/TSC adjoint); 3 is not implemented");
   require(p.calc_h == 0 || p.calc_h == 1 || (p.calc_h == 2 && p.masskernel == 3) ||
@@ -272,6 +272,21 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   h->fft.hooks = h->in_hooks;   // rows of the signal may still be arriving from the host
   r2c_plain(h, d_s, h->shat);
   h->fft.hooks = nullptr;
+  if (p.likelihood == 3) {
+    // Gaussian random field (HMC.cc:159-160, gaussian_random_field.cpp:25-38): no structure formation at all,
+    // gradpsi = IFFT[(V/N)/P s^] + (s - nobs)/sigma^2
+    KOp lop;
+    lop.kind = K_MULREAL;
+    lop.real0 = h->inv_power;
+    ROp sop;
+    sop.kind = R_SCALE;
+    sop.a = inv_n;
+    h->fft.c2r(h->shat, h->work, d_out, lop, sop);
+    launch_grf_grad_add(d_out, d_s, h->nobs, h->noise, h->window, h->n, h->stream);
+    if (h->out_hooks && h->out_hooks->after)
+      for (int c = 0; c < h->out_hooks->chunks; ++c) h->out_hooks->after(h->out_hooks->ctx, c);
+    return;
+  }
   forward_from_shat(h, d_s, p.deltaQ_factor, p.rsd_model != 0, nullptr, nullptr, nullptr);
   LikeParams lp = h->like;
   lp.exact_sign = (p.calc_h == BGPU_CALC_H_EXACT) ? 1 : 0;
@@ -313,7 +328,11 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
         sop.aux = h->resid;
         h->fft.c2r(h->dhat, h->work, h->tmp, lop, sop);
       } else {
-        launch_findif_product(h->delta, h->resid, h->tmp, h->N, p.L1, c, h->stream);
+        // gradfindif of delta_x (Poisson, poissonian.cpp:37-42) or of f(delta_x) (log-normal,
+        // lognormal_independent.cpp:81-91; f goes to Psi_x, which is free once the density exists)
+        if (p.likelihood == 2 && c == 0)
+          launch_lognormal_f(h->delta, h->psi[0], h->n, p.rho_c, p.delta_min, h->stream);
+        launch_findif_product(p.likelihood == 2 ? h->psi[0] : h->delta, h->resid, h->tmp, h->N, p.L1, c, h->stream);
       }
       ROp lop2;
       lop2.kind = R_LOAD;
@@ -379,6 +398,11 @@ void psi_device(bgpu_handle *h, const double *d_s) {
   launch_half_dot(d_s, h->tmp, h->n, h->partials, h->dscal + S_PRIOR, h->stream);
   allreduce_scalar(h, S_PRIOR);
 
+  if (p.likelihood == 3) {  // gaussian_random_field.cpp:40-52: -lnL on the Lagrangian field itself
+    launch_grf_nll(d_s, h->nobs, h->noise, h->window, h->n, h->partials, h->dscal + S_NLL, h->stream);
+    allreduce_scalar(h, S_NLL);
+    return;
+  }
   const bool gauss = p.likelihood == 1;
   forward_from_shat(h, d_s, gauss ? p.deltaQ_factor : 1.0, gauss ? (p.rsd_model != 0) : false, nullptr, nullptr, nullptr);
   LikeParams lp = h->like;
@@ -533,6 +557,7 @@ void bgpu_default_params(bgpu_params *p) {
   p->mass_factor = 1.0;
   p->div_dH_by_N = 0;
   p->device = 0;
+  p->delta_min = -0.999;  // data/input.par:51
 }
 
 static int create_impl(const bgpu_params *p, int rank, int nranks, const void *nccl_id, bgpu_handle **out) {
@@ -553,8 +578,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
     require(p->sfmodel == 1 || p->rsd_model,
             "bgpu_slab_create: the 2LPT/ALPT model differentiates by finite differences across slabs; not built yet");
-    require(!(p->calc_h == 0 && p->likelihood == 0),
-            "bgpu_slab_create: Poisson + calc_h = 0 differentiates by finite differences across slabs; not built yet");
+    require(!(p->calc_h == 0 && (p->likelihood == 0 || p->likelihood == 2)),
+            "bgpu_slab_create: Poisson / log-normal + calc_h = 0 differentiate by finite differences across slabs; not built yet");
     require(nccl_id != nullptr, "bgpu_slab_create: a NCCL unique id is required");
   }
   int ndev = 0;
@@ -676,6 +701,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   h->like.rho_c = p->rho_c;
   h->like.biasP = p->biasP;
   h->like.biasE = p->biasE;
+  h->like.delta_min = p->delta_min;
   h->like.exact_sign = 0;
 
   dalloc(h->power, h->n); dalloc(h->nobs, h->n); dalloc(h->noise, h->n); dalloc(h->window, h->n);

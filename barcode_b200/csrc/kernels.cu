@@ -331,6 +331,20 @@ struct ResidualEval {
         const double q = __ddiv_rn(__dsub_rn(Lambda, n), sg);
         val = __dmul_rn(0.5, __dmul_rn(q, q));
       }
+    } else if (lp.likelihood == 2) {
+      // log-normal (lognormal_independent.cpp:41-55, 57-62, 112-122): the residual takes the log of the
+      // unclamped density (NaN / inf where 1 + delta <= 0, as in the reference), the value clamps at delta_min
+      if (w > 0.) {
+        const double base = __dadd_rn(1.0, __dmul_rn(lp.biasP, delta));
+        const double Lr = log(__dmul_rn(lp.rho_c, pow_bias<UNIT>(base, lp.biasE)));
+        const double dl = delta < lp.delta_min ? lp.delta_min : delta;
+        const double Lv = log(__dmul_rn(lp.rho_c, __dadd_rn(1.0, dl)));
+        r = __ddiv_rn(__dsub_rn(n, Lr), __dmul_rn(sg, sg));
+        if (lp.exact_sign)  // exact adjoint: -d(-lnL)/d delta of the clamped value, chain factor 1/(1 + delta) included
+          r = delta < lp.delta_min ? 0.0 : __ddiv_rn(__ddiv_rn(__dsub_rn(n, Lv), __dmul_rn(sg, sg)), __dadd_rn(1.0, delta));
+        const double q = __dsub_rn(Lv, n);
+        val = __ddiv_rn(__dmul_rn(__dmul_rn(0.5, q), q), __dmul_rn(sg, sg));
+      }
     } else {
       const double dens = __dadd_rn(1.0, __dmul_rn(lp.biasP, delta));
       const double Lambda = __dmul_rn(__dmul_rn(w, lp.rho_c), pow_bias<UNIT>(dens, lp.biasE));
@@ -400,6 +414,50 @@ void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const dou
       reinterpret_cast<double2 *>(resid), n2, ncells_global, scratch);
   final_sum_kernel<<<1, kReduceThreads, 0, st>>>(scratch, blocks, nll);
   BGPU_LAUNCHED(2);
+}
+
+__global__ void lognormal_f_kernel(const double *__restrict__ delta, double *__restrict__ out, size_t n, double rho_c,
+                                   double delta_min) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d = delta[i];
+  if (d < delta_min) d = delta_min;
+  out[i] = log(__dmul_rn(rho_c, __dadd_rn(1.0, d)));
+}
+
+void launch_lognormal_f(const double *delta, double *out, size_t n, double rho_c, double delta_min, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  lognormal_f_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(delta, out, n, rho_c, delta_min);
+  BGPU_LAUNCHED(1);
+}
+
+__global__ void grf_grad_add_kernel(double *__restrict__ grad, const double *__restrict__ s,
+                                    const double *__restrict__ nobs, const double *__restrict__ noise,
+                                    const double *__restrict__ window, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (window[i] > 0.) grad[i] = __dadd_rn(grad[i], __ddiv_rn(__dsub_rn(s[i], nobs[i]), __dmul_rn(noise[i], noise[i])));
+}
+
+void launch_grf_grad_add(double *grad, const double *s, const double *nobs, const double *noise, const double *window,
+                         size_t n, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  grf_grad_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grad, s, nobs, noise, window, n);
+  BGPU_LAUNCHED(1);
+}
+
+struct GrfNll {
+  const double *s, *nobs, *noise, *window;
+  __device__ __forceinline__ double operator()(size_t i) const {
+    if (!(window[i] > 0.)) return 0.0;
+    const double q = __ddiv_rn(__dsub_rn(s[i], nobs[i]), noise[i]);
+    return __dmul_rn(0.5, __dmul_rn(q, q));
+  }
+};
+
+void launch_grf_nll(const double *s, const double *nobs, const double *noise, const double *window, size_t n,
+                    double *scratch, double *out, cudaStream_t st) {
+  reduce(GrfNll{s, nobs, noise, window}, n, scratch, out, st);
 }
 
 // ---------------------------------------------------------------------------

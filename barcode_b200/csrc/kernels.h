@@ -26,8 +26,9 @@ struct GridGeom {
 };
 
 struct LikeParams {
-  int likelihood;  // 0 Poisson, 1 Gaussian
+  int likelihood;  // 0 Poisson, 1 Gaussian, 2 log-normal (3, Gaussian random field, never reaches the residual kernel)
   double rho_c, biasP, biasE;
+  double delta_min;  // log-normal density floor
   int exact_sign;  // Poisson residual in the Gaussian sign convention (exact adjoint only)
 };
 
@@ -37,6 +38,15 @@ constexpr int kReduceThreads = 256;
 
 // half-grid multiplier normFS / C(k) (0 where C <= 0), from a full real-indexed spectrum
 void launch_inverse_spectrum(const double *full, double *half, int N, double normFS, cudaStream_t st);
+
+// log-normal likelihood: f(delta_x) = log(rho_c (1 + max(delta_x, delta_min))) (lognormal_independent.cpp:57-79)
+void launch_lognormal_f(const double *delta, double *out, size_t n, double rho_c, double delta_min, cudaStream_t st);
+// Gaussian-random-field likelihood (gaussian_random_field.cpp:25-52): grad += (s - nobs)/sigma^2 where w > 0;
+// -lnL = sum 1/2 ((s - nobs)/sigma)^2 where w > 0
+void launch_grf_grad_add(double *grad, const double *s, const double *nobs, const double *noise, const double *window,
+                         size_t n, cudaStream_t st);
+void launch_grf_nll(const double *s, const double *nobs, const double *noise, const double *window, size_t n,
+                    double *scratch, double *out, cudaStream_t st);
 
 // particle scatter: Psi -> rho (zeroed here); optional positions out
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,

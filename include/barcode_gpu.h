@@ -51,7 +51,7 @@ typedef struct bgpu_params {
   double xobs, yobs, zobs;   /* observer (only plane-parallel RSD is supported, as in rsd.cc:60-62) */
   int planepar, periodic;
   int masskernel;            /* mk: 0 NGP, 1 CIC, 2 TSC, 3 SPH spline */
-  int likelihood;            /* 0 Poisson, 1 Gaussian */
+  int likelihood;            /* 0 Poisson, 1 Gaussian, 2 log-normal, 3 Gaussian random field (init_par.cc:534-559) */
   int sfmodel;               /* 1 Zel'dovich; else Lag2Eul_non_zeldovich (2LPT + spherical collapse, ALPT);
                               * with rsd_model the reference runs Zel'dovich for any value */
   int rsd_model;
@@ -66,7 +66,8 @@ typedef struct bgpu_params {
   double mass_factor;
   int div_dH_by_N;
   int device;                /* CUDA device ordinal */
-  int reserved[8];
+  double delta_min;          /* log-normal likelihood: density floor (input.par delta_min, default -0.999) */
+  int reserved[6];
 } bgpu_params;
 
 /* the reference's defaults (data/input.par, init_par.cc:574-578) */

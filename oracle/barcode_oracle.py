@@ -34,7 +34,7 @@ class Params:
     N1: int
     L1: float
     masskernel: int = 1        # 0 NGP, 1 CIC, 2 TSC (massFunctions.cc)
-    likelihood: int = 1        # 0 Poisson, 1 Gaussian (init_par.cc:534-559)
+    likelihood: int = 1        # 0 Poisson, 1 Gaussian, 2 log-normal, 3 Gaussian random field (init_par.cc:534-559)
     rsd_model: bool = False
     calc_h: int = 0            # 0, 1 reference; 4 = exact mass-assignment adjoint (new)
     mass_type: int = 1         # 0 ones (R), 1 1/P (FS), 4 P (FS)  (HMC_mass.cc:315-368)
@@ -56,6 +56,7 @@ class Params:
     biasP: float = 1.0
     biasE: float = 1.0
     div_dH_by_N: bool = False
+    delta_min: float = -0.999  # log-normal density floor (data/input.par:51)
 
     @property
     def N(self):
@@ -504,9 +505,25 @@ def partial_f(p: Params, deltaX, nobs, noise, window, exact_sign: bool = False) 
         out[ok] = (1 - n[ok] / Lam) * p.rho_c * p.biasE * p.biasP * np.power(dens[ok], p.biasE - 1)
         if exact_sign:
             out = -out
+    elif p.likelihood == 2:
+        # lognormal_independent.cpp:41-55: r = (n - Lambda)/sigma^2 where w > 0, Lambda = log(rho_c (1 + bP
+        # delta)^bE) of the UNCLAMPED density (nan / inf where it is not positive, as in the reference)
+        ok = w > 0.0
+        with np.errstate(invalid="ignore", divide="ignore"):
+            Lam = np.log(p.rho_c * np.power(1.0 + p.biasP * dX[ok], p.biasE))
+        out[ok] = (n[ok] - Lam) / (sg[ok] * sg[ok])
+        if exact_sign:  # NEW: -d(-lnL)/d delta of the clamped value the reference's log_like sums (:112-122)
+            dc = np.maximum(dX[ok], p.delta_min)
+            Lv = np.log(p.rho_c * (1.0 + dc))
+            out[ok] = np.where(dX[ok] < p.delta_min, 0.0, (n[ok] - Lv) / (sg[ok] * sg[ok]) / (1.0 + dX[ok]))
     else:
         raise NotImplementedError("likelihood %d" % p.likelihood)
     return out.reshape(deltaX.shape)
+
+
+def lognormal_f(p: Params, deltaX) -> np.ndarray:
+    """lognormal_likelihood_f_delta_x (lognormal_independent.cpp:57-79): log(rho_c (1 + max(delta, delta_min)))."""
+    return np.log(p.rho_c * (1.0 + np.maximum(deltaX, p.delta_min)))
 
 
 def neg_log_like_from_delta(p: Params, deltaX, nobs, noise, window) -> float:
@@ -523,6 +540,10 @@ def neg_log_like_from_delta(p: Params, deltaX, nobs, noise, window) -> float:
             Lam = w * p.rho_c * np.power(dens, p.biasE)
         ok = (w > 0.0) & (Lam > 0.0)
         return float(np.sum(Lam[ok] - n[ok] * np.log(Lam[ok])))
+    if p.likelihood == 2:  # lognormal_independent.cpp:112-122
+        ok = w > 0.0
+        res = lognormal_f(p, dX[ok]) - n[ok]
+        return float(np.sum(0.5 * res * res / (sg[ok] * sg[ok])))
     raise NotImplementedError
 
 
@@ -531,7 +552,11 @@ def log_like(p: Params, signal, nobs, noise, window):
     poissonian_likelihood_log_like (poissonian.cpp:44-74).  The Poisson path
     never applies deltaQ_factor or RSD (poissonian.cpp:54-56).  Returns
     (-lnL, deltaX)."""
-    if p.likelihood == 0:
+    if p.likelihood == 3:  # gaussian_random_field.cpp:40-52: the Lagrangian field itself, no forward model
+        s_, n, sg, w = signal.reshape(-1), nobs.reshape(-1), noise.reshape(-1), window.reshape(-1)
+        ok = w > 0.0
+        return float(np.sum(0.5 * ((s_[ok] - n[ok]) / sg[ok]) ** 2)), None
+    if p.likelihood in (0, 2):  # neither applies deltaQ_factor or RSD (poissonian.cpp:54-56, lognormal_independent.cpp:98-110)
         q = Params(**{**p.__dict__, "rsd_model": False, "deltaQ_factor": 1.0})
         dX, _, _ = forward(q, signal)
     else:
@@ -584,7 +609,8 @@ def calc_h0(p: Params, deltaX, nobs, noise, window) -> np.ndarray:
     or gradfindif (Poisson, poissonian.cpp:37-42)."""
     r = partial_f(p, deltaX, nobs, noise, window)
     g = gradfft if p.likelihood == 1 else gradfindif
-    return grad_inv_lap_sum(p, [r * g(p, deltaX, c) for c in (1, 2, 3)])
+    f = lognormal_f(p, deltaX) if p.likelihood == 2 else deltaX  # lognormal_independent.cpp:81-91
+    return grad_inv_lap_sum(p, [r * g(p, f, c) for c in (1, 2, 3)])
 
 
 def gather_adjoint(p: Params, r, x, y, z):
@@ -635,6 +661,10 @@ def gather_adjoint(p: Params, r, x, y, z):
 
 def grad_log_like(p: Params, signal, nobs, noise, window):
     """likelihood_grad_log_like (HMC_models.cc:377-471).  Returns (grad, deltaX)."""
+    if p.likelihood == 3:  # HMC.cc:159-160 -> grf_likelihood_grad_log_like (gaussian_random_field.cpp:25-38)
+        N = p.N1
+        s3, w, sg = signal.reshape(N, N, N), window.reshape(N, N, N), noise.reshape(N, N, N)
+        return np.where(w > 0.0, (s3 - nobs.reshape(N, N, N)) / (sg * sg), 0.0), None
     dX, (x, y, z), _ = forward(p, signal)
     if p.calc_h == 0:
         h = calc_h0(p, dX, nobs, noise, window)

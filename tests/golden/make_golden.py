@@ -50,6 +50,15 @@ CASES = {
     "za_sph_gauss_rsd_h2": dict(masskernel=3, likelihood=1, rsd_model=True, calc_h=2, mass_type=1,
                                 particle_kernel_h_rel=1.3),
     "za_sph_poisson_h2": dict(masskernel=3, likelihood=0, rsd_model=False, calc_h=2, mass_type=4),
+    # log-normal likelihood (lognormal_independent.cpp): h = r, and the gradfindif product form with RSD in the
+    # gradient's forward model but not in log_like's; a gentle signal keeps every cell occupied (the reference takes
+    # the log of the unclamped density in the residual)
+    "za_cic_lognormal_h1": dict(masskernel=1, likelihood=2, rsd_model=False, calc_h=1, mass_type=1, signal_scale=0.1,
+                                eps_fac=1e-4),
+    "za_tsc_lognormal_rsd": dict(masskernel=2, likelihood=2, rsd_model=True, calc_h=0, mass_type=1, signal_scale=0.1,
+                                 delta_min=-0.9, eps_fac=1e-4),
+    # Gaussian random field "likelihood" (gaussian_random_field.cpp, HMC.cc:159-160): no structure formation
+    "grf": dict(masskernel=1, likelihood=3, rsd_model=False, calc_h=0, mass_type=1),
     "alpt_tsc_poisson_h1": dict(masskernel=2, likelihood=0, rsd_model=False, calc_h=1, mass_type=1, sfmodel=3,
                                 slength=6.0, deltaQ_factor=0.95),
 }
@@ -67,7 +76,10 @@ def main():
     for name, kw in CASES.items():
         if only and name not in only:
             continue
-        cfg = ref.Config(N1=N1, L1=L1, N_eps_fac=8.0, eps_fac=1.0, **kw)
+        kw = dict(kw)
+        signal_scale = kw.pop("signal_scale", 0.5)
+        eps_fac = kw.pop("eps_fac", 1.0)   # eps = eps_fac * EPS_U
+        cfg = ref.Config(N1=N1, L1=L1, N_eps_fac=8.0, eps_fac=eps_fac, **kw)
         R = ref.Reference(cfg)
         P = R.readtab(CAMB)
         if kw.get("sfmodel", 1) != 1 and not kw.get("rsd_model", False):
@@ -82,6 +94,10 @@ def main():
         rng = np.random.default_rng(11)
         if cfg.likelihood == 1:
             nobs = np.maximum(0.0, 1.0 + dX_truth + rng.standard_normal(R.N))
+        elif cfg.likelihood == 2:   # barcoderunner.cc:163-183: log of the clamped density plus noise
+            nobs = np.log(1.0 + np.maximum(dX_truth, cfg.delta_min)) + 0.3 * rng.standard_normal(R.N)
+        elif cfg.likelihood == 3:   # the data ARE a noisy Lagrangian field
+            nobs = truth + rng.standard_normal(R.N)
         else:
             nobs = rng.poisson(np.maximum(1.0 + dX_truth, 0.0)).astype(np.float64)
         # a window with a masked corner exercises the w > 0 branches
@@ -90,7 +106,7 @@ def main():
         window = window.ravel()
         noise = 1.0 + 0.25 * rng.random(R.N)
         R.set_inputs(nobs=nobs, window=window, noise=noise)
-        s = 0.5 * R.create_garfield(2, P)
+        s = signal_scale * R.create_garfield(2, P)
         R.set_inputs(signal=s)
         mass_f, mass_r = R.hamiltonian_mass()
         mom = R.draw_momenta(3)
@@ -115,6 +131,8 @@ def main():
         out["D1"] = R.scalar("D1")
         out["D2"] = R.scalar("D2")
         out["cfg"] = np.array(repr({**kw, "N1": N1, "L1": L1}))
+        out["signal_scale"] = signal_scale
+        out["eps_fac"] = eps_fac
         np.savez_compressed(os.path.join(HERE, f"case_{name}.npz"), **out)
         print(name, "gradpsi norm", np.linalg.norm(out["gradpsi"]), "dH", dH, "Neps", out["Neps"])
         R.close()

@@ -67,7 +67,7 @@ def test_validation_errors_are_reported_not_swallowed(lib):
     from barcode_b200._lib import BgpuParams
     h = C.c_void_p()
     for field, val, needle in (("N1", 48, "power of two"), ("masskernel", 4, "masskernel"), ("calc_h", 2, "SPH"),
-                               ("calc_h", 3, "calc_h"), ("likelihood", 2, "likelihood"),
+                               ("calc_h", 3, "calc_h"), ("likelihood", 4, "likelihood"),
                                ("mass_type", 5, "mass_type")):
         p = BgpuParams()
         lib.bgpu_default_params(C.byref(p))
