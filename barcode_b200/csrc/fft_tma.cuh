@@ -154,11 +154,8 @@ __device__ __forceinline__ void butterfly(double2 &a0, double2 &a1, double2 &a2,
   }
 }
 
-// load the per-thread twiddles of every non-final stage: twr[stage][m] multiplies register m.
-// RECUR: only the first power w = tw^(base) of each butterfly is kept (twr[stage][j]); the stage
-// rebuilds w^2 .. w^(R-1) by multiplication, trading ~6 complex products per butterfly for 7/8 of
-// the twiddle registers, which is what lets a third CTA share the SM.
-template <int N, int E, int S, int DIR, int STG, bool RECUR = false>
+// load the per-thread twiddles of every non-final stage: twr[stage][m] multiplies register m
+template <int N, int E, int S, int DIR, int STG>
 __device__ __forceinline__ void wp_load_twiddles(double2 (*twr)[E], int t, const double2 *__restrict__ tw) {
   constexpr int LP = N / E;
   constexpr int R = StageRadix<N, S>::value;
@@ -168,14 +165,10 @@ __device__ __forceinline__ void wp_load_twiddles(double2 (*twr)[E], int t, const
     for (int j = 0; j < NB; ++j) {
       const int b = t + j * LP;
       const int base = b - (b & (S - 1));
-      if constexpr (RECUR) {
-        twr[STG][j] = twiddle<DIR>(tw, base);
-      } else {
 #pragma unroll
-        for (int k = 0; k < R; ++k) twr[STG][j + k * NB] = twiddle<DIR>(tw, base * k);
-      }
+      for (int k = 0; k < R; ++k) twr[STG][j + k * NB] = twiddle<DIR>(tw, base * k);
     }
-    wp_load_twiddles<N, E, S * R, DIR, STG + 1, RECUR>(twr, t, tw);
+    wp_load_twiddles<N, E, S * R, DIR, STG + 1>(twr, t, tw);
   }
 }
 
@@ -190,7 +183,7 @@ struct RowAccess {  // a contiguous row of double2 (z pass)
   __device__ __forceinline__ uint32_t at(int e) const { return row + (uint32_t)e * 16u; }
 };
 
-template <int N, int E, int S, int DIR, int STG, class Acc, bool RECUR = false>
+template <int N, int E, int S, int DIR, int STG, class Acc>
 __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc, const double2 (*twr)[E]) {
   constexpr int LP = N / E;
   constexpr int R = StageRadix<N, S>::value;
@@ -214,24 +207,10 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc
       const int b = t + j * LP;
       const int q = b & (S - 1);
       const int base = b - q;
-      double2 wk[R > 1 ? R : 2];
-      if constexpr (RECUR) {  // powers of the butterfly's base twiddle, depth <= 3 products
-        wk[1] = twr[STG][j];
-        if constexpr (R > 2) {
-          wk[2] = cmul(wk[1], wk[1]);
-          wk[3] = cmul(wk[2], wk[1]);
-        }
-        if constexpr (R > 4) {
-          wk[4] = cmul(wk[2], wk[2]);
-          wk[5] = cmul(wk[4], wk[1]);
-          wk[6] = cmul(wk[3], wk[3]);
-          wk[7] = cmul(wk[4], wk[3]);
-        }
-      }
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         double2 x = v[j + k * NB];
-        if (k > 0) x = cmul(x, RECUR ? wk[k] : twr[STG][j + k * NB]);
+        if (k > 0) x = cmul(x, twr[STG][j + k * NB]);
         int e = q + R * base + k * S;
         if constexpr (S == 1) e ^= (e >> 3) & 7;  // conflict-free stride-8 scatter
         sts128(acc.at(e), x);
@@ -244,7 +223,7 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc
       if constexpr (S == 1) e ^= (e >> 3) & 7;
       v[m] = lds128(acc.at(e));
     }
-    wp_stages<N, E, S * R, DIR, STG + 1, Acc, RECUR>(v, t, acc, twr);
+    wp_stages<N, E, S * R, DIR, STG + 1, Acc>(v, t, acc, twr);
   }
 }
 
@@ -344,7 +323,7 @@ struct RotCtx {
   }
 };
 
-template <int N, int E, int NSTAGE, int DIR, int AXIS, int AUX, int MINB, bool RECUR = false>
+template <int N, int E, int NSTAGE, int DIR, int AXIS, int AUX, int MINB>
 __global__ void __launch_bounds__(8 * (N / E), MINB)
     fft_strided_tma(const __grid_constant__ TmaMaps maps, const double2 *__restrict__ tw, KOp lop, KOp sop,
                     PassGeom geo) {
@@ -411,7 +390,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
 
   // tile-invariant twiddles
   double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
-  wp_load_twiddles<N, E, 1, DIR, 0, RECUR>(twr, t, tw);
+  wp_load_twiddles<N, E, 1, DIR, 0>(twr, t, tw);
 
   for (int i = 0; i < my_count; ++i) {
     const int s = i % NSTAGE;
@@ -452,7 +431,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
       for (int m = 0; m < E; ++m) v[m] = rc.apply(v[m], t + m * LP);
     }
 
-    wp_stages<N, E, 1, DIR, 0, ColAccess, RECUR>(v, t, ColAccess{tbase, p}, twr);
+    wp_stages<N, E, 1, DIR, 0>(v, t, ColAccess{tbase, p}, twr);
 
     if (sop.kind == K_INVLAP_SET || sop.kind == K_INVLAP_ADD) {
       RotCtx<N, AXIS> rc;
