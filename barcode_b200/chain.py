@@ -179,6 +179,21 @@ class Chain:
             None if g is None else _dp(g), _dp(out)))
         return out.reshape(self.shape)
 
+    def draw_momenta_device(self, seed: int, draw_index: int):
+        """Momenta ~ N(0, M) from the device generator (Philox4x32-10); not GSL-seed-compatible."""
+        out = np.empty(self.N)
+        _lib.check(self.L.bgpu_draw_momenta_device(self._h, int(seed), int(draw_index), _dp(out)))
+        return out.reshape(self.shape)
+
+    def draw_momenta_device_dev(self, seed: int, draw_index: int, d_momenta_ptr: int):
+        _lib.check(self.L.bgpu_draw_momenta_device_dev(self._h, int(seed), int(draw_index), C.c_void_p(d_momenta_ptr)))
+
+    def device_normals(self, seed: int, draw_index: int, stream: int, first: int, n: int):
+        out = np.empty(n)
+        _lib.check(self.L.bgpu_device_normals(self._h, int(seed), int(draw_index), int(stream), int(first), int(n),
+                                              _dp(out)))
+        return out
+
     def forward(self, signal, want_pos=False):
         s = _f64(signal, self.N)
         dX = np.empty(self.N)

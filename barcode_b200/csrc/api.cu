@@ -1028,6 +1028,57 @@ int bgpu_color_momenta(bgpu_handle *h, const double *white, const double *real_g
   BGPU_CATCH
 }
 
+// S5 with the generator on the device.  Same distribution as draw_momenta
+// (HMC_momenta.cc:42-92), different stream: the GSL mt19937 stream is serial by construction and costs
+// 2N host Gaussians per candidate (0.7 s at 256^3, ten times a whole trajectory on the GPU), so production
+// runs that do not need seed-for-seed agreement with the CPU code draw here instead.
+static void draw_momenta_device(bgpu_handle *h, uint64_t seed, uint64_t draw, double *d_out) {
+  require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
+  require(h->G == 1, "bgpu_draw_momenta_device: not available on a slab-decomposed chain yet");
+  if (h->mass_fs) {
+    launch_philox_normals(h->tmp, h->n, 0, seed, draw, 0, h->stream);
+    r2c_plain(h, h->tmp, h->work);
+    launch_colour_white(h->work, h->mass_f, h->N, h->ncells / (h->p.L1 * h->p.L2 * h->p.L3), h->stream);
+    ROp sop;
+    sop.kind = R_SCALE;
+    sop.a = 1.0 / h->ncells;
+    h->fft.c2r(h->work, h->work, d_out, KOp{}, sop);
+  } else {
+    launch_fill(d_out, 0.0, h->n, h->stream);
+  }
+  if (h->mass_rs) {
+    launch_philox_normals(h->tmp, h->n, 0, seed, draw, 1, h->stream);
+    launch_add_real_momenta(d_out, h->mass_r, h->tmp, h->n, h->stream);
+  }
+}
+
+int bgpu_draw_momenta_device_dev(bgpu_handle *h, uint64_t seed, uint64_t draw_index, double *d_momenta) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  draw_momenta_device(h, seed, draw_index, d_momenta);
+  BGPU_CATCH
+}
+
+int bgpu_draw_momenta_device(bgpu_handle *h, uint64_t seed, uint64_t draw_index, double *momenta) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  draw_momenta_device(h, seed, draw_index, h->mom);
+  d2h(h, momenta, h->mom, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_device_normals(bgpu_handle *h, uint64_t seed, uint64_t draw_index, unsigned stream, size_t first, size_t n,
+                        double *out) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(n <= h->n && n % 2 == 0 && first % 2 == 0, "bgpu_device_normals: n must be even, at most N^3; first even");
+  launch_philox_normals(h->tmp, n, first, seed, draw_index, stream, h->stream);
+  d2h(h, out, h->tmp, n);
+  sync(h);
+  BGPU_CATCH
+}
+
 int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *posx, double *posy, double *posz) {
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));

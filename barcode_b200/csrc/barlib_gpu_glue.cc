@@ -231,8 +231,22 @@ void Hamiltonian_EoM(struct HAMIL_DATA *hd, real_prec *signali, real_prec *momen
 // S5  draw_momenta, HMC_momenta.cc:42-92: GSL stream on the host in the reference's order
 // (2N ugaussians in shell order, then N gaussians if mass_rs), colouring + C2R on the device
 // ---------------------------------------------------------------------------
+//
+// BARCODE_GPU_DEVICE_RNG=1 (opt-in, NOT seed-compatible with the CPU code): the draw itself happens on the device
+// (bgpu_draw_momenta_device: Philox4x32-10, same distribution).  The host stream then only gives one 32-bit word
+// per candidate as the draw's key, so it stays in step for Neps, epsilon and the Metropolis uniform.
 void draw_momenta(struct HAMIL_DATA *hd, gsl_rng *seed, real_prec *momenta, struct DATA *data) {
   HAMIL_NUMERICAL *n = hd->numerical;
+  static const bool device_rng = [] {
+    const char *e = std::getenv("BARCODE_GPU_DEVICE_RNG");
+    return e && e[0] == '1';
+  }();
+  if (device_rng) {
+    static uint64_t draw_index = 0;
+    const uint64_t key = gsl_rng_get(seed);
+    check(bgpu_draw_momenta_device(session(hd, data), key, draw_index++, momenta), "bgpu_draw_momenta_device");
+    return;
+  }
   std::vector<std::complex<real_prec> > white;
   if (n->mass_fs) white = resolution_independent_random_grid_FS<real_prec>(n->N1, seed, false);
   std::vector<real_prec> gauss;

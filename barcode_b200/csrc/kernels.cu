@@ -567,6 +567,80 @@ void launch_findif_product(const double *delta, const double *resid, double *out
 }
 
 // ---------------------------------------------------------------------------
+// counter-based Gaussian generator: Philox4x32-10 (Salmon et al. 2011; constants and
+// known-answer vectors of Random123) + Box-Muller.  Element pair (2i, 2i+1) of draw `draw`, stream
+// `stream` comes from counter {i_lo, i_hi, draw_lo, draw_hi ^ stream << 24} under key {seed_lo, seed_hi}:
+// any element of any draw can be regenerated independently, on any number of GPUs.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// 53-bit uniform in (0, 1) from two 32-bit words
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void philox_normal_kernel(double2 *__restrict__ out, size_t npairs, size_t pair0, uint64_t seed, uint64_t draw,
+                                     uint32_t stream) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  const uint64_t g = (uint64_t)(pair0 + i);
+  uint32_t c[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)draw, (uint32_t)(draw >> 32) ^ (stream << 24)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double u1 = u53(c[0], c[1]), u2 = u53(c[2], c[3]);
+  const double r = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  out[i] = make_double2(r * cs, r * sn);
+}
+
+void launch_philox_normals(double *out, size_t n, size_t first, uint64_t seed, uint64_t draw, unsigned stream,
+                           cudaStream_t st) {
+  ProfScope prof(KK_COLOUR, st);
+  const size_t npairs = n / 2;  // n and first are even
+  philox_normal_kernel<<<blocks_for(npairs, 256), 256, 0, st>>>(reinterpret_cast<double2 *>(out), npairs, first / 2, seed,
+                                                               draw, stream);
+  BGPU_LAUNCHED(1);
+}
+
+// colour the transform of a real white field w (<|w^|^2> = N): A = w^ sqrt(N/V M) has <|A|^2> = N^2/V M, the
+// variance create_GARFIELD gives its modes (random.cpp:81-83); sigma is read at the folded index and the DC
+// mode is zeroed as there (:102-135, :347-351).
+__global__ void colour_white_kernel(double2 *__restrict__ W, const double *__restrict__ spec, int N, double c2) {
+  const int nzh = N / 2 + 1;
+  const size_t n = (size_t)N * N * nzh;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int k = (int)(idx % nzh);
+  const int j = (int)((idx / nzh) % N);
+  const int i = (int)(idx / ((size_t)nzh * N));
+  const int fi = i <= N / 2 ? i : N - i, fj = j <= N / 2 ? j : N - j;
+  double a = sqrt(c2 * spec[((size_t)fi * N + fj) * N + k]);
+  if ((i | j | k) == 0 || !(a == a)) a = 0.0;
+  const double2 w = W[idx];
+  W[idx] = make_double2(a * w.x, a * w.y);
+}
+
+void launch_colour_white(double2 *W, const double *spec_full, int N, double c2, cudaStream_t st) {
+  ProfScope prof(KK_COLOUR, st);
+  const size_t n = (size_t)N * N * (N / 2 + 1);
+  colour_white_kernel<<<blocks_for(n, 256), 256, 0, st>>>(W, spec_full, N, c2);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
 // streaming helpers
 // ---------------------------------------------------------------------------
 __global__ void inverse_spectrum_kernel(const double *__restrict__ full, double *__restrict__ half, int N,

@@ -2,6 +2,7 @@
 // (particles, likelihood, reductions, leapfrog, momentum colouring).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stddef.h>
 
 namespace bgpu {
@@ -47,6 +48,12 @@ void launch_grf_grad_add(double *grad, const double *s, const double *nobs, cons
                          size_t n, cudaStream_t st);
 void launch_grf_nll(const double *s, const double *nobs, const double *noise, const double *window, size_t n,
                     double *scratch, double *out, cudaStream_t st);
+
+// counter-based Gaussians (Philox4x32-10 + Box-Muller): out[0..n) = elements [first, first + n) of (seed, draw, stream)
+void launch_philox_normals(double *out, size_t n, size_t first, uint64_t seed, uint64_t draw, unsigned stream,
+                           cudaStream_t st);
+// W (half grid, transform of a real white field) *= sqrt(c2 * spec) at the folded index, DC = 0
+void launch_colour_white(double2 *W, const double *spec_full, int N, double c2, cudaStream_t st);
 
 // particle scatter: Psi -> rho (zeroed here); optional positions out
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,

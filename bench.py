@@ -280,8 +280,12 @@ def run_ours(args):
     total_prof = sum(v[0] for v in prof.values())
     dom = max(prof.items(), key=lambda kv: kv[1][0])
     nh = args.grid * args.grid * (args.grid // 2 + 1)
+    # x pass: every launch reads and writes the half-complex array once (32 B / element); the last one of an
+    # evaluation also reads its operands -- (V/N)/P (8 B) for calc_h = 1, plus the accumulated h^ (16 B) otherwise
+    x_launches = {0: 12, 1: 5, 4: 8}[args.calc_h]
+    x_bytes = ((x_launches - 1) * 32 + (40 if args.calc_h == 1 else 56)) * nh / x_launches
     alg_bytes = {  # algorithmic bytes per launch of each kernel class ("Kernels")
-        "fft_strided_pass_y": 2 * nh * 16, "fft_strided_pass_x": 2 * nh * 16,            # read + write the half-complex array once
+        "fft_strided_pass_y": 2 * nh * 16, "fft_strided_pass_x": x_bytes,
         "fft_r2c_zpass": n * 8 + nh * 16,
         "fft_c2r_zpass": n * 8 + nh * 16,
         # fused z+y passes: the real array and the half-complex array cross HBM once each; the

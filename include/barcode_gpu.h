@@ -85,8 +85,9 @@ void bgpu_destroy(bgpu_handle *h);
  * rank 0 calls bgpu_nccl_unique_id and the host program hands the 128 bytes to the other ranks
  * (MPI_Bcast, a file, torch.distributed ...).  The distributed FFT transposes with NCCL
  * all-to-all, the mass-assignment halo goes to the two x neighbours, scalars are all-reduced; every
- * rank must make the same sequence of calls.  Supported: N1 in {128, 256, 512}, calc_h 0 / 1
- * (Gaussian likelihood for calc_h 0), NGP / CIC / TSC, RSD; bgpu_color_momenta is not. */
+ * rank must make the same sequence of calls.  Supported: calc_h 0 / 1
+ * (Gaussian likelihood for calc_h 0), NGP / CIC / TSC, RSD; N1 in {128, 256, 512, 1024}; the momentum
+ * draws (bgpu_color_momenta, bgpu_draw_momenta_device) are not. */
 int bgpu_nccl_unique_id(void *out128);
 int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out);
 int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *nx_local);
@@ -114,6 +115,14 @@ int bgpu_leapfrog(bgpu_handle *h, const double *s_i, const double *p_i, uint64_t
  * real_gauss = the N gsl_ran_gaussian draws of draw_real_space_momenta, or NULL when !mass_rs */
 int bgpu_color_momenta(bgpu_handle *h, const double *white_complex_fullgrid, const double *real_gauss,
                        double *momenta);
+/* S5 with the generator on the device: the same distribution as draw_momenta -- Gaussian
+ * momenta with covariance M, DC mode zero -- from the counter-based Philox4x32-10 generator + Box-Muller,
+ * keyed by (seed, draw_index).  NOT seed-compatible with the reference's GSL mt19937 stream (which is serial
+ * and costs 2N host Gaussians per candidate); use bgpu_color_momenta when runs must reproduce the CPU code's.
+ * bgpu_device_normals exposes the raw generator (elements [first, first + n) of a draw) for tests. */
+int bgpu_draw_momenta_device(bgpu_handle *h, uint64_t seed, uint64_t draw_index, double *momenta);
+int bgpu_device_normals(bgpu_handle *h, uint64_t seed, uint64_t draw_index, unsigned stream, size_t first, size_t n,
+                        double *out);
 /* Lag2Eul / Lag2Eul_rsd_zeldovich as likelihood_grad_log_like calls them (HMC_models.cc:383-406);
  * pos* may be NULL */
 int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *posx, double *posy, double *posz);
@@ -133,6 +142,7 @@ int bgpu_gradient_psi_dev(bgpu_handle *h, const double *d_signal, double *d_grad
 int bgpu_psi_dev(bgpu_handle *h, const double *d_signal, double *psi_prior, double *psi_likeli, double *d_deltaX);
 int bgpu_kinetic_dev(bgpu_handle *h, const double *d_momenta, double *K);
 int bgpu_leapfrog_dev(bgpu_handle *h, double *d_signal, double *d_momenta, uint64_t Neps, double epsilon);
+int bgpu_draw_momenta_device_dev(bgpu_handle *h, uint64_t seed, uint64_t draw_index, double *d_momenta);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t bgpu_kernel_launches(void);

@@ -885,3 +885,45 @@ def draw_momenta(p: Params, white: np.ndarray, mass_f, mass_r, real_gauss=None) 
     if p.mass_rs:
         mom = mom + np.sqrt(mass_r.reshape(N, N, N)) * real_gauss.reshape(N, N, N)
     return mom
+
+
+# --------------------------------------------------------------------------
+# F4: counter-based Gaussians of the device momentum draw (no reference code: the reference draws from
+# GSL's serial mt19937).  Philox4x32-10 as published (Salmon, Moraes, Dror, Shaw, SC'11; Random123),
+# pinned by its known-answer vectors in tests/test_host.py.
+# --------------------------------------------------------------------------
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
+    """Vectorised over the counter words (uint64 arrays holding 32-bit values); returns four uint64 arrays."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3))
+    for _ in range(10):
+        p0, p1 = _PHILOX_M0 * c0, _PHILOX_M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & _MASK32, p1 >> np.uint64(32), p1 & _MASK32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + _PHILOX_W0) & 0xFFFFFFFF, (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def device_normals(seed: int, draw: int, stream: int, first: int, n: int) -> np.ndarray:
+    """Elements [first, first + n) of draw `draw`, stream `stream` under `seed` (kernels.cu philox_normal_kernel):
+    pair g = element // 2 uses counter {g_lo, g_hi, draw_lo, draw_hi ^ stream << 24}, key {seed_lo, seed_hi};
+    u = 53-bit uniforms in (0, 1); Box-Muller."""
+    g = np.arange(first // 2, (first + n) // 2, dtype=np.uint64)
+    z = np.zeros_like(g)
+    r = philox4x32_10(g & _MASK32, g >> np.uint64(32), z + np.uint64(draw & 0xFFFFFFFF),
+                      z + np.uint64(((draw >> 32) ^ (stream << 24)) & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+
+    def u53(hi, lo):
+        return ((hi >> np.uint64(5)).astype(np.float64) * 67108864.0 + (lo >> np.uint64(6)).astype(np.float64) + 0.5) \
+            / 9007199254740992.0
+
+    u1, u2 = u53(r[0], r[1]), u53(r[2], r[3])
+    rad = np.sqrt(-2.0 * np.log(u1))
+    out = np.empty(n)
+    out[0::2] = rad * np.cos(2.0 * np.pi * u2)
+    out[1::2] = rad * np.sin(2.0 * np.pi * u2)
+    return out

@@ -136,3 +136,29 @@ def test_unchanged_host_driver_runs_on_the_gpu_path(tmp_path, masskernel, likeli
         assert a.shape == b.shape == (16 ** 3,), name
         if np.linalg.norm(a) > 0:
             assert rel_l2(b, a) < 1e-7, name
+
+
+@pytest.mark.skipif(not os.path.exists(GPU), reason="oracle/_ref/barcode_gpu not built")
+def test_host_driver_with_the_device_momentum_generator(tmp_path, monkeypatch):
+    """BARCODE_GPU_DEVICE_RNG=1: the momentum draw itself runs on the device (Philox; not GSL-seed-compatible),
+    everything else of the reference's sampler unchanged.  The chain must run, accept candidates at a small step
+    and conserve energy as the CPU-stream run does (dH of the same order)."""
+    with np.load(os.path.join(GOLDEN, "pk_table.npz")) as f:
+        k, P = f["k"], f["P"]
+    pk = tmp_path / "pk.dat"
+    with open(pk, "w") as o:
+        for a, b in zip(k, P):
+            o.write(f"{a:.9g} {b:.9g}\n")
+    par = INPUT_PAR.format(calc_h=0, rsd="false", likelihood=1, eps_fac=0.004, mass_type=1, pk=pk, N=16, L=50.0,
+                           n_gibbs=4, masskernel=1)
+    _, log_host = run(GPU, str(tmp_path / "host_rng"), par)
+    monkeypatch.setenv("BARCODE_GPU_DEVICE_RNG", "1")
+    _, log_dev = run(GPU, str(tmp_path / "dev_rng"), par)
+    assert log_dev.shape[0] >= 4 and np.all(np.isfinite(log_dev))
+    assert log_dev[:, 0].sum() >= 1                                  # candidates are accepted
+    # kinetic energy of a draw is chi^2_(N-1)/2: both generators give ~ N/2 = 2048 +- a few sqrt(N/2)
+    # (performance_log.txt columns: accepted, epsilon, Neps, dH, dK, dE, dprior, dlikeli, psi_prior_i, ... H_kin_i, H_kin_f)
+    for log in (log_host, log_dev):
+        assert np.all(np.abs(log[:, -2] - 2047.5) < 6 * np.sqrt(2047.5))
+    a = np.fromfile(tmp_path / "dev_rng" / "data" / "deltaLAG_4")
+    assert a.shape == (16 ** 3,) and np.all(np.isfinite(a))

@@ -369,3 +369,46 @@ def test_fused_zy_kernel_matches_separate_passes(monkeypatch):
             out[fused] = (ch.gradient_psi(s), ch.kinetic_term(s))
     assert rel_l2(out["1"][0], out["0"][0]) < 1e-13
     assert abs(out["1"][1] - out["0"][1]) <= 1e-13 * abs(out["0"][1])
+
+
+# ---------------------------------------------------------------- device momentum draw
+def test_device_normals_match_oracle_generator():
+    """The Philox4x32-10 + Box-Muller stream on the GPU against its numpy restatement (itself pinned to the
+    published known-answer vectors, tests/test_host.py): same uniforms bit for bit, normals to libm rounding."""
+    from oracle import barcode_oracle as bo
+    from barcode_b200.chain import Chain, Params
+    with Chain(Params(N1=32, L1=100.0)) as ch:
+        for seed, draw, stream, first, n in ((1, 0, 0, 0, 4096), (0xDEADBEEFCAFE, (1 << 40) + 3, 1, 2048, 1024)):
+            got = ch.device_normals(seed, draw, stream, first, n)
+            want = bo.device_normals(seed, draw, stream, first, n)
+            assert np.max(np.abs(got - want)) < 1e-13
+
+
+@pytest.mark.parametrize("mass_type", [1, 4, 0])
+def test_device_momentum_draw_has_the_mass_as_covariance(mass_type):
+    """bgpu_draw_momenta_device: E[K] = (modes with mass)/2 with K from the parity-tested kinetic term, the draws
+    are reproducible per (seed, index) and differ between indices, the DC mode is zero (random.cpp:347-351)."""
+    from barcode_b200.chain import Chain, Params
+    from barcode_b200 import inputs
+    N = 64
+    L = inputs.box_length(N)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L)
+    with Chain(Params(N1=N, L1=L, mass_type=mass_type)) as ch:
+        ch.set_static(Power=P)
+        ch.hamiltonian_mass()
+        p0 = ch.draw_momenta_device(5, 0)
+        assert np.array_equal(p0, ch.draw_momenta_device(5, 0))
+        p1 = ch.draw_momenta_device(5, 1)
+        assert not np.array_equal(p0, p1)
+        nmodes = N ** 3 - (0 if mass_type == 0 else 1)
+        Ks = [ch.kinetic_term(ch.draw_momenta_device(5, i)) for i in range(4)]
+        # K is chi^2_nmodes / 2: mean nmodes/2, sigma sqrt(nmodes/2); four draws -> 5 sigma of the mean
+        assert abs(np.mean(Ks) - nmodes / 2) < 5 * np.sqrt(nmodes / 2) / 2
+        if mass_type != 0:
+            assert abs(p0.sum()) < 1e-6 * np.abs(p0).sum()
+            # binned spectrum follows the mass: <|p^|^2> = N^2/V M
+            ph = np.abs(np.fft.rfftn(p0.reshape(N, N, N))) ** 2
+            M = ch.hamiltonian_mass()[0].reshape(N, N, N)[:, :, :N // 2 + 1]
+            ok = M > 0
+            ratio = ph[ok] / (float(N) ** 6 / L ** 3 * M[ok])
+            assert abs(ratio.mean() - 1) < 0.02

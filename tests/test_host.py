@@ -45,3 +45,27 @@ def test_bench_reference_arm_small_grid():
     assert line["impl"] == "reference" and line["metric"] == "hmc_gradient_evals_per_s"
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 of the oracle (the generator behind bgpu_draw_momenta_device) against the published
+    known-answer vectors of Random123 (kat_vectors: zero, all-ones and pi-digit inputs)."""
+    from oracle import barcode_oracle as bo
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = bo.philox4x32_10(*[np.array([c], dtype=np.uint64) for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+
+
+def test_device_normals_oracle_statistics():
+    from oracle import barcode_oracle as bo
+    x = bo.device_normals(seed=12345, draw=7, stream=0, first=0, n=1 << 18)
+    assert abs(x.mean()) < 5 / np.sqrt(x.size) and abs(x.var() - 1) < 5 * np.sqrt(2 / x.size)
+    assert abs((x ** 4).mean() - 3) < 0.1
+    # any sub-range regenerates independently; draws and streams differ
+    assert np.array_equal(bo.device_normals(12345, 7, 0, 1000, 64), x[1000:1064])
+    assert not np.array_equal(bo.device_normals(12345, 8, 0, 0, 64), x[:64])
+    assert not np.array_equal(bo.device_normals(12345, 7, 1, 0, 64), x[:64])
