@@ -271,6 +271,14 @@ def run_ours(args):
     d_s2, d_p2 = d_s.clone(), d_p.clone()
     ms_leap = timed(lambda: ch.leapfrog_dev(d_s2.data_ptr(), d_p2.data_ptr(), 1, 1e-3), max(2, args.steps // 2), 1)
     leap_steps = max(2, args.steps // 2)
+    # momentum draw on the device (bgpu_draw_momenta_device: Philox normals -> r2c -> colour -> c2r); the reference
+    # draws 2 N^3 GSL Gaussians serially on the host for every candidate (random.cpp:99-101)
+    draw_i = [0]
+
+    def draw():
+        ch.draw_momenta_device_dev(1, draw_i[0], d_p2.data_ptr())
+        draw_i[0] += 1
+    ms_draw = timed(draw, max(2, args.steps // 2), 1)
 
     # roofline leg: the same K steps again with CUDA events around every kernel launch
     bc.profile_begin()
@@ -395,6 +403,7 @@ def run_ours(args):
             "also": {
                 f"gradient_evals_per_s_calc_h_{other_h}": world * args.steps / (ms_other * 1e-3),
                 "leapfrog_steps_per_s": world * leap_steps / (ms_leap * 1e-3),
+                "device_momentum_draw_ms": ms_draw / leap_steps,
                 "kernel_launches_total": int(bc.kernel_launches() - launches0),
             },
         }
