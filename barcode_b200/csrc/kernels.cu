@@ -131,9 +131,11 @@ __global__ void scatter_kernel(GridGeom g, const double *__restrict__ psix, cons
   const bool valid = idx < n;  // no early return: deposit() shuffles across the whole warp
   double x = 0., y = 0., z = 0.;
   if (valid) {
-    const int k = (int)(idx % g.N);
-    const int j = (int)((idx / g.N) % g.N);
-    const int il = (int)(idx / ((size_t)g.N * g.N));
+    // N is a power of two (the FFT's constraint): shifts, not three 64-bit divisions by a run-time N
+    const int sh = 31 - __clz(g.N);
+    const int k = (int)(idx & (size_t)(g.N - 1));
+    const int j = (int)((idx >> sh) & (size_t)(g.N - 1));
+    const int il = (int)(idx >> (2 * sh));
     const int i = g.x0 + il;
     double px = psix[idx], py = psiy[idx], pz = psiz[idx];
     if (g.cellbound) {
@@ -471,9 +473,10 @@ __global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, doubl
   const size_t n = (size_t)N * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  const int k = (int)(idx % N);
-  const int j = (int)((idx / N) % N);
-  const int i = (int)(idx / ((size_t)N * N));
+  const int sh = 31 - __clz(N);  // N is a power of two
+  const int k = (int)(idx & (size_t)(N - 1));
+  const int j = (int)((idx >> sh) & (size_t)(N - 1));
+  const int i = (int)(idx >> (2 * sh));
   double x, y, z;
   particle_position(g, i, j, k, ax[idx], ay[idx], az[idx], x, y, z);
   double vx = 0.0, vy = 0.0, vz = 0.0;
@@ -546,7 +549,8 @@ __global__ void findif_product_kernel(const double *__restrict__ in, const doubl
   const size_t n = (size_t)N * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  int c[3] = {(int)(idx / ((size_t)N * N)), (int)((idx / N) % N), (int)(idx % N)};
+  const int sh = 31 - __clz(N);  // N is a power of two
+  int c[3] = {(int)(idx >> (2 * sh)), (int)((idx >> sh) & (size_t)(N - 1)), (int)(idx & (size_t)(N - 1))};
   const size_t stride = comp == 0 ? (size_t)N * N : (comp == 1 ? (size_t)N : 1);
   const int ii = c[comp];
   const size_t base = idx - (size_t)ii * stride;
@@ -938,7 +942,8 @@ __global__ void lpt2_source_kernel(const double *__restrict__ phi, const double 
   const size_t n = (size_t)N * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  const int k = (int)(idx % N), j = (int)((idx / N) % N), i = (int)(idx / ((size_t)N * N));
+  const int sh = 31 - __clz(N);  // N is a power of two
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
   const double xx = findif2_at<0, 0>(phi, N, i, j, k, fac), yy = findif2_at<1, 1>(phi, N, i, j, k, fac),
                zz = findif2_at<2, 2>(phi, N, i, j, k, fac);
   const double xy = findif2_at<0, 1>(phi, N, i, j, k, fac), xz = findif2_at<0, 2>(phi, N, i, j, k, fac),
@@ -1023,7 +1028,8 @@ __global__ void scatter_sph_kernel(GridGeom g, const double *__restrict__ psix, 
   const size_t n = (size_t)N * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  const int k = (int)(idx % N), j = (int)((idx / N) % N), i = (int)(idx / ((size_t)N * N));
+  const int sh = 31 - __clz(N);  // N is a power of two
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
   double x, y, z;
   particle_position(g, i, j, k, psix[idx], psiy[idx], psiz[idx], x, y, z);
   if (posx) {
@@ -1085,7 +1091,8 @@ __global__ void gather_sph_kernel(GridGeom g, double *__restrict__ ax, double *_
   const size_t n = (size_t)N * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  const int k = (int)(idx % N), j = (int)((idx / N) % N), i = (int)(idx / ((size_t)N * N));
+  const int sh = 31 - __clz(N);  // N is a power of two
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
   double px, py, pz;
   particle_position(g, i, j, k, ax[idx], ay[idx], az[idx], px, py, pz);
   const double d = g.d, h = g.sph_h, h_inv = 1. / h, d_h = d * h_inv;

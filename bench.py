@@ -499,11 +499,20 @@ def run_slab(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON result: everything libraries print on file descriptor 1 while the
+    # bench runs (NCCL's "NCCL version ..." banner on some boxes) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
-        return run_reference(args)
-    if args.mode == "slab":
-        return run_slab(args)
-    return run_ours(args)
+        rc = run_reference(args)
+    elif args.mode == "slab":
+        rc = run_slab(args)
+    else:
+        rc = run_ours(args)
+    sys.stdout.flush()
+    return rc
 
 
 if __name__ == "__main__":
