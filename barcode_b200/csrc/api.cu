@@ -199,12 +199,29 @@ void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, d
     pois.kind = K_NEGINVK2;
     pois.a = dQ;
     pois.kfac = h->kfac;
-    h->fft.c2r(h->shat, h->work, h->psi[0], pois, scale_n);
-    launch_lpt2_source(h->psi[0], d_s, h->psi[1], h->N, h->p.L1, dQ, h->p.D1, h->p.D2, h->stream);
+    const size_t plane = (size_t)h->N * h->N;
+    if (h->G == 1) {
+      h->fft.c2r(h->shat, h->work, h->psi[0], pois, scale_n);
+      launch_lpt2_source(h->psi[0], d_s, h->psi[1], h->N, h->N, 0, h->p.L1, dQ, h->p.D1, h->p.D2, h->stream);
+    } else {
+      // slab: the twice-applied 4th-order stencil reaches 4 planes across the slab boundary.  phi^(1) goes into
+      // the (still unused) density tile with 4 halo planes each side, filled from the x neighbours.
+      constexpr int XH = 4;
+      double *ext = h->rho_ext, *phi = ext + XH * plane;
+      h->fft.c2r(h->shat, h->work, phi, pois, scale_n);
+      const int lo = (h->rank + h->G - 1) % h->G, hi = (h->rank + 1) % h->G;
+      {
+        ProfScope prof(KK_HALO, h->stream);
+        // my first planes are rank-1's upper halo, my last planes rank+1's lower halo
+        h->comm->exchange2(phi, lo, phi + (size_t)(h->Ns - XH) * plane, hi, ext + (size_t)(h->Ns + XH) * plane, hi, ext, lo,
+                           XH * plane, h->stream);
+      }
+      launch_lpt2_source(ext, d_s, h->psi[1], h->N, h->Ns, XH, h->p.L1, dQ, h->p.D1, h->p.D2, h->stream);
+    }
     r2c_plain(h, h->psi[1], h->dhat);
     launch_sc_divergence(d_s, h->psi[2], h->n, dQ, h->p.D1, h->stream);
     r2c_plain(h, h->psi[2], h->acc);
-    launch_alpt_combine(h->dhat, h->acc, h->N, h->kfac, h->p.slength, h->stream);
+    launch_alpt_combine(h->dhat, h->acc, h->N, h->Ns, h->G > 1 ? h->rank * h->Ns : 0, h->kfac, h->p.slength, h->stream);
     disp_src = h->dhat;
     disp_a = 1.0;  // theta2velcomp on +theta (Lag2Eul.cc:238): the sign differs from the Zel'dovich branch
   }
@@ -220,7 +237,17 @@ void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, d
   GridGeom g = h->geom;
   g.rsd = rsd ? 1 : 0;
   g.cellbound = zeldovich ? 0 : 1;
+  g.cb_lo = nullptr;
   const size_t plane = (size_t)h->N * h->N;
+  if (g.cellbound && h->G > 1) {
+    // cellboundcomp averages with the (i-1, j-1, k-1) neighbour: plane x0-1 of the three displacement
+    // components comes from the lower neighbour (its last plane), mine goes to the upper one
+    const int lo = (h->rank + h->G - 1) % h->G, hi = (h->rank + 1) % h->G;
+    ProfScope prof(KK_HALO, h->stream);
+    for (int c = 0; c < 3; ++c)
+      h->comm->shift(h->psi[c] + (size_t)(h->Ns - 1) * plane, hi, h->halo_recv + (size_t)c * plane, lo, plane, h->stream);
+    g.cb_lo = h->halo_recv;
+  }
   if (h->G > 1) {
     // halo width from the largest x displacement on any rank (+1 plane for the upper CIC / TSC
     // neighbour, +1 for the lower TSC neighbour and rounding)
@@ -576,8 +603,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     require(p->calc_h == 0 || p->calc_h == 1,
             "bgpu_slab_create: calc_h must be 0 or 1 (the exact adjoint's residual halo is not built yet)");
     require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
-    require(p->sfmodel == 1 || p->rsd_model,
-            "bgpu_slab_create: the 2LPT/ALPT model differentiates by finite differences across slabs; not built yet");
+    require(p->sfmodel == 1 || p->rsd_model || p->N1 / nranks >= 8,
+            "bgpu_slab_create: the 2LPT/ALPT model needs at least 8 planes per rank (4-plane stencil halo)");
     require(!(p->calc_h == 0 && (p->likelihood == 0 || p->likelihood == 2)),
             "bgpu_slab_create: Poisson / log-normal + calc_h = 0 differentiate by finite differences across slabs; not built yet");
     require(nccl_id != nullptr, "bgpu_slab_create: a NCCL unique id is required");
@@ -677,6 +704,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   g.H = 0;
   g.flag = h->dflag;
   g.cellbound = 0;
+  g.cb_lo = nullptr;
   g.sph_h = p->particle_kernel_h_rel * g.d;
   if (p->masskernel == 3) {
     // SPH_kernel_3D_cells + _hull_1 (SPH_kernel.cpp:62-139)

@@ -142,10 +142,18 @@ __global__ void scatter_kernel(GridGeom g, const double *__restrict__ psix, cons
       // cellboundcomp (massFunctions.cc:588-660): every displacement averaged with its (i-1, j-1, k-1)
       // neighbour, periodically -- folded into the read instead of a pass over three arrays
       const int N = g.N;
-      const size_t m = ((size_t)(il == 0 ? N - 1 : il - 1) * N + (j == 0 ? N - 1 : j - 1)) * N + (k == 0 ? N - 1 : k - 1);
-      px = 0.5 * (psix[m] + px);
-      py = 0.5 * (psiy[m] + py);
-      pz = 0.5 * (psiz[m] + pz);
+      const size_t jk = (size_t)(j == 0 ? N - 1 : j - 1) * N + (k == 0 ? N - 1 : k - 1);
+      if (il == 0 && g.cb_lo) {  // slab: the plane below my first one came from the lower neighbour
+        const size_t pl = (size_t)N * N;
+        px = 0.5 * (g.cb_lo[jk] + px);
+        py = 0.5 * (g.cb_lo[pl + jk] + py);
+        pz = 0.5 * (g.cb_lo[2 * pl + jk] + pz);
+      } else {
+        const size_t m = (size_t)(il == 0 ? N - 1 : il - 1) * N * N + jk;
+        px = 0.5 * (psix[m] + px);
+        py = 0.5 * (psiy[m] + py);
+        pz = 0.5 * (psiz[m] + pz);
+      }
     }
     particle_position(g, i, j, k, px, py, pz, x, y, z);
     if (posx) {
@@ -913,12 +921,14 @@ void launch_kfinal_combine(const double2 *s, const double *mult, const double2 *
 // with periodic wrap: -fac * ((4/3)(f[-1] - f[+1]) - (1/6)(f[-2] - f[+2]))
 __device__ __forceinline__ int wrap_idx(int i, int N) { return i < 0 ? i + N : (i >= N ? i - N : i); }
 
+// `xo` = planes of x halo in front of the local slab (0 on a cube, which wraps in x instead)
 template <int AX>
-__device__ __forceinline__ double findif_at(const double *__restrict__ f, int N, int i, int j, int k, double fac) {
+__device__ __forceinline__ double findif_at(const double *__restrict__ f, int N, int xo, int i, int j, int k,
+                                            double fac) {
   auto at = [&](int o) {
-    const int ii = AX == 0 ? wrap_idx(i + o, N) : i, jj = AX == 1 ? wrap_idx(j + o, N) : j,
+    const int ii = AX == 0 ? (xo ? i + o : wrap_idx(i + o, N)) : i, jj = AX == 1 ? wrap_idx(j + o, N) : j,
               kk = AX == 2 ? wrap_idx(k + o, N) : k;
-    return f[((size_t)ii * N + jj) * N + kk];
+    return f[((size_t)(ii + xo) * N + jj) * N + kk];
   };
   return -(fac * ((4.0 / 3) * (at(-1) - at(1)) - (1.0 / 6) * (at(-2) - at(2))));
 }
@@ -926,11 +936,12 @@ __device__ __forceinline__ double findif_at(const double *__restrict__ f, int N,
 // second derivative d_B d_A phi at (i, j, k): the same stencil applied twice, as calc_m2v_mem does with
 // GFINDIFF (EqSolvers.cc:396-407)
 template <int A, int B>
-__device__ __forceinline__ double findif2_at(const double *__restrict__ f, int N, int i, int j, int k, double fac) {
+__device__ __forceinline__ double findif2_at(const double *__restrict__ f, int N, int xo, int i, int j, int k,
+                                             double fac) {
   auto g = [&](int o) {  // d_A phi at the point shifted by o along B
-    const int ii = B == 0 ? wrap_idx(i + o, N) : i, jj = B == 1 ? wrap_idx(j + o, N) : j,
+    const int ii = B == 0 ? (xo ? i + o : wrap_idx(i + o, N)) : i, jj = B == 1 ? wrap_idx(j + o, N) : j,
               kk = B == 2 ? wrap_idx(k + o, N) : k;
-    return findif_at<A>(f, N, ii, jj, kk, fac);
+    return findif_at<A>(f, N, xo, ii, jj, kk, fac);
   };
   return -(fac * ((4.0 / 3) * (g(-1) - g(1)) - (1.0 / 6) * (g(-2) - g(2))));
 }
@@ -938,16 +949,16 @@ __device__ __forceinline__ double findif2_at(const double *__restrict__ f, int N
 // out = D1 * (dQ s) - D2 * delta2, delta2 = sum of the 2x2 minors of the Hessian of phi
 // (calc_m2v_mem, EqSolvers.cc:373-422; Lag2Eul.cc:196-198)
 __global__ void lpt2_source_kernel(const double *__restrict__ phi, const double *__restrict__ s, double *__restrict__ out,
-                                   int N, double fac, double dQ, double D1, double D2) {
-  const size_t n = (size_t)N * N * N;
+                                   int N, int Ns, int xo, double fac, double dQ, double D1, double D2) {
+  const size_t n = (size_t)Ns * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int sh = 31 - __clz(N);  // N is a power of two
   const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
-  const double xx = findif2_at<0, 0>(phi, N, i, j, k, fac), yy = findif2_at<1, 1>(phi, N, i, j, k, fac),
-               zz = findif2_at<2, 2>(phi, N, i, j, k, fac);
-  const double xy = findif2_at<0, 1>(phi, N, i, j, k, fac), xz = findif2_at<0, 2>(phi, N, i, j, k, fac),
-               yz = findif2_at<1, 2>(phi, N, i, j, k, fac);
+  const double xx = findif2_at<0, 0>(phi, N, xo, i, j, k, fac), yy = findif2_at<1, 1>(phi, N, xo, i, j, k, fac),
+               zz = findif2_at<2, 2>(phi, N, xo, i, j, k, fac);
+  const double xy = findif2_at<0, 1>(phi, N, xo, i, j, k, fac), xz = findif2_at<0, 2>(phi, N, xo, i, j, k, fac),
+               yz = findif2_at<1, 2>(phi, N, xo, i, j, k, fac);
   const double m2v = xx * yy - xy * xy + xx * zz - xz * xz + yy * zz - yz * yz;
   out[idx] = D1 * (dQ * s[idx]) - D2 * m2v;
 }
@@ -967,13 +978,13 @@ __global__ void sc_divergence_kernel(const double *__restrict__ s, double *__res
 // C^ = K D2^ + (1 - K) D4^ on the half grid, K = exp(-k^2 rS^2 / 2) (kernelcomp filtertype 1,
 // convolution.cpp:224-322; its normalisation, the k = 0 value, is 1): Psi_c = K o Psi^LPT_c +
 // Psi^SC_c - K o Psi^SC_c (Lag2Eul.cc:238-268) before the -i k_c / k^2 projection, which is linear
-__global__ void alpt_combine_kernel(double2 *__restrict__ d2, const double2 *__restrict__ d4, int N, double kfac,
-                                    double rS) {
+__global__ void alpt_combine_kernel(double2 *__restrict__ d2, const double2 *__restrict__ d4, int N, int Ns, int y0,
+                                    double kfac, double rS) {
   const int nzh = N / 2 + 1;
-  const size_t n = (size_t)N * N * nzh;
+  const size_t n = (size_t)N * Ns * nzh;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  const int z = (int)(idx % nzh), y = (int)((idx / nzh) % N), x = (int)(idx / ((size_t)nzh * N));
+  const int z = (int)(idx % nzh), y = y0 + (int)((idx / nzh) % Ns), x = (int)(idx / ((size_t)nzh * Ns));
   auto kv = [&](int i) { return (i <= N / 2) ? kfac * (double)i : -kfac * (double)(N - i); };
   const double kx = kv(x), ky = kv(y), kz = kv(z);
   const double K = exp(-(kx * kx + ky * ky + kz * kz) * (rS * rS) / 2.);
@@ -981,11 +992,11 @@ __global__ void alpt_combine_kernel(double2 *__restrict__ d2, const double2 *__r
   d2[idx] = make_double2(K * a.x + (b.x - K * b.x), K * a.y + (b.y - K * b.y));
 }
 
-void launch_lpt2_source(const double *phi, const double *s, double *out, int N, double L, double dQ, double D1,
-                        double D2, cudaStream_t st) {
+void launch_lpt2_source(const double *phi, const double *s, double *out, int N, int Ns, int xoff, double L, double dQ,
+                        double D1, double D2, cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);
-  const size_t n = (size_t)N * N * N;
-  lpt2_source_kernel<<<blocks_for(n, 256), 256, 0, st>>>(phi, s, out, N, (double)N / (2. * L), dQ, D1, D2);
+  const size_t n = (size_t)Ns * N * N;
+  lpt2_source_kernel<<<blocks_for(n, 256), 256, 0, st>>>(phi, s, out, N, Ns, xoff, (double)N / (2. * L), dQ, D1, D2);
   BGPU_LAUNCHED(1);
 }
 void launch_sc_divergence(const double *s, double *out, size_t n, double dQ, double D1, cudaStream_t st) {
@@ -993,10 +1004,11 @@ void launch_sc_divergence(const double *s, double *out, size_t n, double dQ, dou
   sc_divergence_kernel<<<blocks_for(n, 256), 256, 0, st>>>(s, out, n, dQ, D1);
   BGPU_LAUNCHED(1);
 }
-void launch_alpt_combine(double2 *d2, const double2 *d4, int N, double kfac, double rS, cudaStream_t st) {
+void launch_alpt_combine(double2 *d2, const double2 *d4, int N, int Ns, int y0, double kfac, double rS,
+                         cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);
-  const size_t n = (size_t)N * N * (N / 2 + 1);
-  alpt_combine_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d2, d4, N, kfac, rS);
+  const size_t n = (size_t)N * Ns * (N / 2 + 1);
+  alpt_combine_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d2, d4, N, Ns, y0, kfac, rS);
   BGPU_LAUNCHED(1);
 }
 

@@ -23,6 +23,7 @@ struct GridGeom {
   int H;           // halo planes each side of the density tile: rho is [(Ns + 2H)][N][N], plane 0 = global x0 - H
   int *flag;       // set to 1 if a particle left the halo (device int), may be null when H == 0 and Ns == N
   int cellbound;   // displacements are cell-boundary averaged on read (cellboundcomp; non-Zel'dovich model)
+  const double *cb_lo;  // slab: plane x0-1 of Psi_x, Psi_y, Psi_z ([3][N][N], from the lower neighbour); null on a cube
   double sph_h;    // SPH scale length particle_kernel_h = h_rel * d (init_par.cc:379), masskernel 3
 };
 
@@ -88,10 +89,13 @@ void launch_kfinal_combine(const double2 *s, const double *mult, const double2 *
 
 // Lag2Eul_non_zeldovich's real-space pieces (Lag2Eul.cc:138-268): 2LPT source D1 dQ s - D2 delta2(phi),
 // spherical-collapse divergence, and the ALPT combination K D2^ + (1 - K) D4^ (in place over d2)
-void launch_lpt2_source(const double *phi, const double *s, double *out, int N, double L, double dQ, double D1,
-                        double D2, cudaStream_t st);
+// Ns / xoff: phi holds planes [-xoff, Ns + xoff) of this rank's slab (xoff = 4 halo planes from the x neighbours,
+// the reach of the twice-applied stencil); a cube passes Ns = N, xoff = 0 and wraps in x
+void launch_lpt2_source(const double *phi, const double *s, double *out, int N, int Ns, int xoff, double L, double dQ,
+                        double D1, double D2, cudaStream_t st);
 void launch_sc_divergence(const double *s, double *out, size_t n, double dQ, double D1, cudaStream_t st);
-void launch_alpt_combine(double2 *d2, const double2 *d4, int N, double kfac, double rS, cudaStream_t st);
+// k-space layout [x][Ns][N/2+1] with y = y0 + y_local (a cube: Ns = N, y0 = 0)
+void launch_alpt_combine(double2 *d2, const double2 *d4, int N, int Ns, int y0, double kfac, double rS, cudaStream_t st);
 
 // deterministic sum of an array -> *out (device scalar); scratch: kReduceBlocks doubles
 void launch_sum(const double *a, size_t n, double *scratch, double *out, cudaStream_t st);

@@ -116,4 +116,13 @@ void NcclComm::exchange2(const double *a_, int to_a, const double *b_, int to_b,
   check(a.GroupEnd(), "ncclGroupEnd");
 }
 
+void NcclComm::shift(const double *send, int to, double *recv, int from, size_t count, cudaStream_t st) {
+  const Api &a = api();
+  ncclComm_t c = static_cast<ncclComm_t>(comm);
+  check(a.GroupStart(), "ncclGroupStart");
+  check(a.Send(send, count, ncclDouble, to, c, st), "ncclSend");
+  check(a.Recv(recv, count, ncclDouble, from, c, st), "ncclRecv");
+  check(a.GroupEnd(), "ncclGroupEnd");
+}
+
 }  // namespace bgpu

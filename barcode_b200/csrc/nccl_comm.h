@@ -28,6 +28,8 @@ struct NcclComm : SlabComm {
   // one grouped neighbour exchange: send a -> rank `to_a`, b -> `to_b`; receive ra <- `from_a`, rb <- `from_b`
   void exchange2(const double *a, int to_a, const double *b, int to_b, double *ra, int from_a, double *rb, int from_b,
                  size_t count, cudaStream_t st);
+  // one-directional ring shift: send -> rank `to`, receive <- rank `from`
+  void shift(const double *send, int to, double *recv, int from, size_t count, cudaStream_t st);
 };
 
 }  // namespace bgpu

@@ -99,3 +99,49 @@ def slab_density(p: bo.Params, psi_local, rank, world, dist):
     own[Ns - H:] += allh[hi][0].numpy()   # rank+1's lower halo are my last planes
     own[:H] += allh[lo][1].numpy()        # rank-1's upper halo are my first planes
     return own, H
+
+
+def _neighbour_planes(local, nplanes, rank, world, dist):
+    """(planes below my slab, planes above it): the last `nplanes` of rank-1 and the first of rank+1."""
+    import torch
+    edges = torch.from_numpy(np.ascontiguousarray(np.stack([local[:nplanes], local[-nplanes:]])))
+    alle = [torch.empty_like(edges) for _ in range(world)]
+    dist.all_gather(alle, edges)
+    lo, hi = (rank - 1) % world, (rank + 1) % world
+    return alle[lo][1].numpy(), alle[hi][0].numpy()
+
+
+def slab_calc_m2v(p: bo.Params, phi_local, rank, world, dist):
+    """calc_m2v (EqSolvers.cc:373-422, the 4th-order stencil applied twice) on an x slab: four halo planes
+    from each x neighbour (api.cu forward_from_shat / kernels.cu lpt2_source_kernel), periodic in y and z."""
+    N = p.N1
+    XH = 4
+    below, above = _neighbour_planes(phi_local, XH, rank, world, dist)
+    ext = np.concatenate([below, phi_local, above], axis=0)          # planes [-4, Ns + 4)
+    fac = N / (2.0 * p.L1)
+
+    def fd(a, ax):  # gradient.cpp:81-153; along x no wrap (halo planes are there), the result loses 2 planes a side
+        if ax == 0:
+            c = a[2:-2]
+            return -fac * ((4.0 / 3) * (a[1:-3] - a[3:-1]) - (1.0 / 6) * (a[:-4] - a[4:]))
+        return -fac * ((4.0 / 3) * (np.roll(a, 1, ax) - np.roll(a, -1, ax))
+                       - (1.0 / 6) * (np.roll(a, 2, ax) - np.roll(a, -2, ax)))
+
+    def second(a, b):  # d_b d_a phi on the owned planes
+        g = fd(ext, a)                      # a == 0: planes [-2, Ns+2); else all [-4, Ns+4)
+        h = fd(g, b)
+        lost = (2 if a == 0 else 0) + (2 if b == 0 else 0)
+        return h[XH - lost:h.shape[0] - (XH - lost)]
+
+    Lxx, Lxy, Lxz = second(0, 0), second(0, 1), second(0, 2)
+    Lyy, Lyz, Lzz = second(1, 1), second(1, 2), second(2, 2)
+    return Lxx * Lyy - Lxy * Lxy + Lxx * Lzz - Lxz * Lxz + Lyy * Lzz - Lyz * Lyz
+
+
+def slab_cellbound(psi_local, rank, world, dist):
+    """cellboundcomp (massFunctions.cc:588-660) on an x slab: 0.5 (Psi(i-1, j-1, k-1) + Psi(i, j, k)); plane
+    x0 - 1 is the lower neighbour's last plane (kernels.cu scatter_kernel, GridGeom::cb_lo)."""
+    below, _ = _neighbour_planes(psi_local, 1, rank, world, dist)
+    ext = np.concatenate([below, psi_local], axis=0)
+    shifted = np.roll(ext[:-1], (1, 1), (1, 2))                      # (i-1) by the halo, (j-1, k-1) periodic
+    return 0.5 * (shifted + psi_local)

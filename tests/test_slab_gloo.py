@@ -39,6 +39,13 @@ def _worker(rank, world, port, q):
         rho_ref = bo.density(p, x, y, z)
         rho, H = so.slab_density(p, psi[:, x0:x0 + Ns], rank, world, dist)
         e_rho = np.abs(rho - rho_ref[x0:x0 + Ns]).max()
+        # 2LPT/ALPT pieces that reach across slab faces: Hessian minors (4-plane halo), cell-boundary averaging
+        phi = rng.standard_normal((N, N, N))
+        e_m2v = np.abs(so.slab_calc_m2v(p, phi[x0:x0 + Ns], rank, world, dist) - bo.calc_m2v(p, phi)[x0:x0 + Ns]).max() \
+            / np.abs(bo.calc_m2v(p, phi)).max()
+        cb_ref = 0.5 * (np.roll(psi[0], (1, 1, 1), (0, 1, 2)) + psi[0])
+        e_cb = np.abs(so.slab_cellbound(psi[0][x0:x0 + Ns], rank, world, dist) - cb_ref[x0:x0 + Ns]).max()
+        assert e_m2v < 1e-13 and e_cb < 1e-15, (e_m2v, e_cb)
         q.put((rank, e_fwd, e_inv, e_rho, H, float(rho.sum())))
     except Exception as exc:  # surface the failure instead of letting the parent wait for its timeout
         q.put((rank, repr(exc)))

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--masskernel", type=int, default=1)
     ap.add_argument("--amp", type=float, default=0.5)
+    ap.add_argument("--sfmodel", type=int, default=1, help="2/3: Lag2Eul_non_zeldovich (forces rsd_model off)")
     a = ap.parse_args()
     info = multi.rank_info()
     torch.cuda.set_device(info.local_rank)
@@ -59,7 +60,8 @@ def main():
         return torch.cat(out, 0).cpu().numpy()
 
     for calc_h in (0, 1):
-        kw = dict(N1=N, L1=L, masskernel=a.masskernel, likelihood=1, rsd_model=True, calc_h=calc_h, mass_type=1)
+        kw = dict(N1=N, L1=L, masskernel=a.masskernel, likelihood=1, rsd_model=(a.sfmodel == 1), calc_h=calc_h,
+                  mass_type=1, sfmodel=a.sfmodel)
         sc = slab.SlabChain.create(bc.Params(device=info.local_rank, **kw), info.rank, info.world)
         sc.set_static(Power=sc.local(P), nobs=sc.local(nobs), noise=sc.local(noise), window=sc.local(window))
         sc.hamiltonian_mass()
