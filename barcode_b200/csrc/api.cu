@@ -80,6 +80,8 @@ struct bgpu_handle {
   int Hmax = 0;                 // halo planes allocated each side of rho_ext
   double *rho_ext = nullptr;    // [(Ns + 2 Hmax)][N][N]; delta points at the owned planes inside it
   double *halo_recv = nullptr;  // 2 * Hmax * N^2
+  double *resid_ext = nullptr;  // exact adjoint on a slab: the residual with H halo planes each side
+  int H_cur = 0;                // halo width of the evaluation in flight
   double2 *sendbuf = nullptr, *recvbuf = nullptr;
   int *dflag = nullptr;         // device flag: a particle left the halo
   int *hflag = nullptr;         // pinned copy
@@ -261,6 +263,7 @@ void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, d
       throw std::runtime_error("bgpu: displacement of " + std::to_string(h->hscal[S_MAXPSI] / g.d) +
                                " cells along x exceeds the slab halo (" + std::to_string(h->Hmax) + " planes)");
     g.H = H;
+    h->H_cur = H;
     h->delta = h->rho_ext + (size_t)H * plane;
   }
   if (g.masskernel == 3)
@@ -374,8 +377,25 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     if (p.calc_h == 2)
       launch_gather_sph(h->geom, h->psi[0], h->psi[1], h->psi[2], h->resid, h->sph_kmax, h->sph_R,
                         p.rho_c * (p.L1 * p.L2 * p.L3) / h->ncells, h->stream);
-    else
+    else if (h->G == 1)
       launch_gather_adjoint(h->geom, h->psi[0], h->psi[1], h->psi[2], h->resid, h->stream);
+    else {
+      // slab: a particle of mine may sit in cells of the neighbouring slabs (the same halo the scatter used),
+      // so the gather reads the residual from a tile extended by H planes of each x neighbour
+      const int H = h->H_cur, lo = (h->rank + h->G - 1) % h->G, hi = (h->rank + 1) % h->G;
+      const size_t plane = (size_t)h->N * h->N, cnt = (size_t)H * plane;
+      double *own = h->resid_ext + cnt;
+      BGPU_CUDA(cudaMemcpyAsync(own, h->resid, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      {
+        ProfScope prof(KK_HALO, h->stream);
+        // my first planes are rank-1's upper halo, my last planes rank+1's lower halo
+        h->comm->exchange2(own, lo, own + (size_t)(h->Ns - H) * plane, hi, own + (size_t)h->Ns * plane, hi, h->resid_ext, lo,
+                           cnt, h->stream);
+      }
+      GridGeom g = h->geom;
+      g.H = H;
+      launch_gather_adjoint(g, h->psi[0], h->psi[1], h->psi[2], h->resid_ext, h->stream);
+    }
     for (int c = 0; c < 3; ++c) {
       ROp lop2;
       lop2.kind = R_LOAD;
@@ -600,8 +620,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
             "bgpu_slab_create: the slab-decomposed transform supports N = 128, 256, 512, 1024");
     require(rank >= 0 && rank < nranks && p->N1 % nranks == 0 && p->N1 / nranks >= 8,
             "bgpu_slab_create: N1 must be a multiple of the number of ranks, at least 8 planes per rank");
-    require(p->calc_h == 0 || p->calc_h == 1,
-            "bgpu_slab_create: calc_h must be 0 or 1 (the exact adjoint's residual halo is not built yet)");
+    require(p->calc_h == 0 || p->calc_h == 1 || p->calc_h == BGPU_CALC_H_EXACT,
+            "bgpu_slab_create: calc_h must be 0, 1 or 4 (the SPH adjoint is not built for slabs yet)");
     require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
     require(p->sfmodel == 1 || p->rsd_model || p->N1 / nranks >= 8,
             "bgpu_slab_create: the 2LPT/ALPT model needs at least 8 planes per rank (4-plane stencil halo)");
@@ -640,6 +660,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     dalloc(h->recvbuf, 2 * h->nh);   // two receive buffers, alternating between transforms
     h->Hmax = h->Ns < 24 ? h->Ns : 24;
     dalloc(h->halo_recv, (size_t)2 * h->Hmax * h->N * h->N);
+    if (p->calc_h == BGPU_CALC_H_EXACT) dalloc(h->resid_ext, (size_t)(h->Ns + 2 * h->Hmax) * h->N * h->N);
     BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->dflag), sizeof(int)));
     BGPU_CUDA(cudaMemsetAsync(h->dflag, 0, sizeof(int), h->stream));
     BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hflag), sizeof(int)));
@@ -799,7 +820,7 @@ void bgpu_destroy(bgpu_handle *h) {
     }
   }
   double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->mass_f, h->mass_r, h->inv_mass,
-                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->tmp,
+                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->tmp,
                      h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
     if (q) cudaFree(q);

@@ -478,13 +478,22 @@ void launch_grf_nll(const double *s, const double *nobs, const double *noise, co
 __global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, double *__restrict__ ay,
                                       double *__restrict__ az, const double *__restrict__ resid) {
   const int N = g.N;
-  const size_t n = (size_t)N * N * N;
+  const size_t n = (size_t)g.Ns * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int sh = 31 - __clz(N);  // N is a power of two
   const int k = (int)(idx & (size_t)(N - 1));
   const int j = (int)((idx >> sh) & (size_t)(N - 1));
-  const int i = (int)(idx >> (2 * sh));
+  const int i = g.x0 + (int)(idx >> (2 * sh));
+  // plane of the (halo-extended, slab-local) residual tile that global cell plane c maps to (a cube: c itself);
+  // the scatter of the same positions has already checked that every cell lies inside the halo
+  const int lo_plane = g.x0 - g.H;
+  auto plane = [&](int c) {
+    int l = c - lo_plane;
+    if (l < 0) l += N;
+    if (l >= N) l -= N;
+    return l;
+  };
   double x, y, z;
   particle_position(g, i, j, k, ax[idx], ay[idx], az[idx], x, y, z);
   double vx = 0.0, vy = 0.0, vz = 0.0;
@@ -496,6 +505,8 @@ __global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, doubl
       cic_axis(x, g.d, g.L, N, ci[0], ci[1], wi[0], wi[1]);
       cic_axis(y, g.d, g.L, N, cj[0], cj[1], wj[0], wj[1]);
       cic_axis(z, g.d, g.L, N, ck[0], ck[1], wk[0], wk[1]);
+      ci[0] = plane(ci[0]);
+      ci[1] = plane(ci[1]);
       const double gsgn[2] = {-inv_d, inv_d};
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -516,6 +527,8 @@ __global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, doubl
       tsc_axis(x, g.min1, g.d, N, ci, wi, dx);
       tsc_axis(y, g.min2, g.d, N, cj, wj, dy);
       tsc_axis(z, g.min3, g.d, N, ck, wk, dz);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) ci[a] = plane(ci[a]);
       // d/dx of (1/2 (1/2 - D)^2, 3/4 - D^2, 1/2 (1/2 + D)^2), D = x/d - (i + 1/2)
       const double gi[3] = {-(0.5 - dx) * inv_d, -2.0 * dx * inv_d, (0.5 + dx) * inv_d};
       const double gj[3] = {-(0.5 - dy) * inv_d, -2.0 * dy * inv_d, (0.5 + dy) * inv_d};
@@ -544,7 +557,7 @@ __global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, doubl
 void launch_gather_adjoint(const GridGeom &g, double *ax, double *ay, double *az, const double *resid,
                            cudaStream_t st) {
   ProfScope prof(KK_GATHER, st);
-  const size_t n = (size_t)g.N * g.N * g.N;
+  const size_t n = (size_t)g.Ns * g.N * g.N;
   gather_adjoint_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, ax, ay, az, resid);
   BGPU_LAUNCHED(1);
 }

@@ -85,9 +85,10 @@ void bgpu_destroy(bgpu_handle *h);
  * rank 0 calls bgpu_nccl_unique_id and the host program hands the 128 bytes to the other ranks
  * (MPI_Bcast, a file, torch.distributed ...).  The distributed FFT transposes with NCCL
  * all-to-all, the mass-assignment halo goes to the two x neighbours, scalars are all-reduced; every
- * rank must make the same sequence of calls.  Supported: calc_h 0 / 1
- * (Gaussian likelihood for calc_h 0), NGP / CIC / TSC, RSD; N1 in {128, 256, 512, 1024}; the momentum
- * draws (bgpu_color_momenta, bgpu_draw_momenta_device) are not. */
+ * rank must make the same sequence of calls.  Supported: N1 in {128, 256, 512, 1024}; NGP / CIC / TSC;
+ * Zel'dovich and 2LPT/ALPT forward models, RSD; calc_h 0 (Gaussian likelihood), 1 and BGPU_CALC_H_EXACT.
+ * Not on slabs yet: the SPH kernel, the finite-difference product gradients (Poisson / log-normal with
+ * calc_h 0) and the momentum draws (bgpu_color_momenta, bgpu_draw_momenta_device). */
 int bgpu_nccl_unique_id(void *out128);
 int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out);
 int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *nx_local);

@@ -59,7 +59,7 @@ def main():
         dist.all_gather(out, t)
         return torch.cat(out, 0).cpu().numpy()
 
-    for calc_h in (0, 1):
+    for calc_h in (0, 1, 4):
         kw = dict(N1=N, L1=L, masskernel=a.masskernel, likelihood=1, rsd_model=(a.sfmodel == 1), calc_h=calc_h,
                   mass_type=1, sfmodel=a.sfmodel)
         sc = slab.SlabChain.create(bc.Params(device=info.local_rank, **kw), info.rank, info.world)
