@@ -194,6 +194,13 @@ class Chain:
                                               _dp(out)))
         return out
 
+    def measure_spectrum(self, signal, n_bin: int):
+        """measure_spectrum (field_statistics.cpp:20-90) -> (kmode[n_bin], power[n_bin])."""
+        s = _f64(signal, self.N)
+        kmode, power = np.empty(n_bin), np.empty(n_bin)
+        _lib.check(self.L.bgpu_measure_spectrum(self._h, _dp(s), int(n_bin), _dp(kmode), _dp(power)))
+        return kmode, power
+
     def forward(self, signal, want_pos=False):
         s = _f64(signal, self.N)
         dX = np.empty(self.N)

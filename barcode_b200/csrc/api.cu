@@ -1083,11 +1083,15 @@ int bgpu_color_momenta(bgpu_handle *h, const double *white, const double *real_g
 // runs that do not need seed-for-seed agreement with the CPU code draw here instead.
 static void draw_momenta_device(bgpu_handle *h, uint64_t seed, uint64_t draw, double *d_out) {
   require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
-  require(h->G == 1, "bgpu_draw_momenta_device: not available on a slab-decomposed chain yet");
+  // element e of the global grid always gets the same number, whatever the decomposition
+  const size_t first = (size_t)h->x0 * h->N * h->N;
   if (h->mass_fs) {
-    launch_philox_normals(h->tmp, h->n, 0, seed, draw, 0, h->stream);
+    launch_philox_normals(h->tmp, h->n, first, seed, draw, 0, h->stream);
     r2c_plain(h, h->tmp, h->work);
-    launch_colour_white(h->work, h->mass_f, h->N, h->ncells / (h->p.L1 * h->p.L2 * h->p.L3), h->stream);
+    if (h->G == 1)
+      launch_colour_white(h->work, h->mass_f, h->N, h->ncells / (h->p.L1 * h->p.L2 * h->p.L3), h->stream);
+    else  // transposed k-space slab: colour with the multiplier the kinetic term uses, (N/V) M = 1/inv_mass
+      launch_colour_white_rows(h->work, h->inv_mass, h->N, h->nh, h->stream);
     ROp sop;
     sop.kind = R_SCALE;
     sop.a = 1.0 / h->ncells;
@@ -1096,7 +1100,7 @@ static void draw_momenta_device(bgpu_handle *h, uint64_t seed, uint64_t draw, do
     launch_fill(d_out, 0.0, h->n, h->stream);
   }
   if (h->mass_rs) {
-    launch_philox_normals(h->tmp, h->n, 0, seed, draw, 1, h->stream);
+    launch_philox_normals(h->tmp, h->n, first, seed, draw, 1, h->stream);
     launch_add_real_momenta(d_out, h->mass_r, h->tmp, h->n, h->stream);
   }
 }
@@ -1124,6 +1128,22 @@ int bgpu_device_normals(bgpu_handle *h, uint64_t seed, uint64_t draw_index, unsi
   require(n <= h->n && n % 2 == 0 && first % 2 == 0, "bgpu_device_normals: n must be even, at most N^3; first even");
   launch_philox_normals(h->tmp, n, first, seed, draw_index, stream, h->stream);
   d2h(h, out, h->tmp, n);
+  sync(h);
+  BGPU_CATCH
+}
+
+// measure_spectrum (field_statistics.cpp:20-90), the per-sample P(k) diagnostic
+int bgpu_measure_spectrum(bgpu_handle *h, const double *signal, uint64_t N_bin, double *kmode, double *power) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(h->G == 1, "bgpu_measure_spectrum: not available on a slab-decomposed chain yet");
+  require(N_bin >= 1 && N_bin <= 2048 && 3 * N_bin <= h->n, "bgpu_measure_spectrum: N_bin must be in [1, 2048]");
+  h2d(h, h->tmp, signal, h->n);
+  r2c_plain(h, h->tmp, h->work);
+  double *acc = h->grad;  // scratch: 3 * N_bin doubles
+  launch_measure_spectrum(h->work, h->N, h->p.L1, (int)N_bin, acc, h->stream);
+  d2h(h, power, acc, N_bin);
+  d2h(h, kmode, acc + N_bin, N_bin);
   sync(h);
   BGPU_CATCH
 }

@@ -658,11 +658,91 @@ __global__ void colour_white_kernel(double2 *__restrict__ W, const double *__res
   W[idx] = make_double2(a * w.x, a * w.y);
 }
 
+// The same colouring from the half-grid multiplier the kinetic term uses, inv = (V/N)/M (0 where M <= 0):
+// (N/V) M = 1/inv, so A = w^ / sqrt(inv).  Works on any row layout with the multiplier's padded pitch
+// (cube [x][y][.] and the transposed slab [x][y_local][.] alike) and keeps the draw and K consistent.
+__global__ void colour_white_rows_kernel(double2 *__restrict__ W, const double *__restrict__ inv, int nzh, size_t n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const size_t row = idx / nzh;
+  const int z = (int)(idx - row * nzh);
+  const double m = inv[row * (nzh + 1) + z];
+  const double a = m > 0.0 ? rsqrt(m) : 0.0;
+  const double2 w = W[idx];
+  W[idx] = make_double2(a * w.x, a * w.y);
+}
+
+void launch_colour_white_rows(double2 *W, const double *inv_half, int N, size_t n_half, cudaStream_t st) {
+  ProfScope prof(KK_COLOUR, st);
+  colour_white_rows_kernel<<<blocks_for(n_half, 256), 256, 0, st>>>(W, inv_half, N / 2 + 1, n_half);
+  BGPU_LAUNCHED(1);
+}
+
 void launch_colour_white(double2 *W, const double *spec_full, int N, double c2, cudaStream_t st) {
   ProfScope prof(KK_COLOUR, st);
   const size_t n = (size_t)N * N * (N / 2 + 1);
   colour_white_kernel<<<blocks_for(n, 256), 256, 0, st>>>(W, spec_full, N, c2);
   BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// F3: measure_spectrum (field_statistics.cpp:20-90): spherically binned power of a field's transform.
+// The reference loops over the FULL complex grid; here one thread takes one half-grid mode and counts it
+// twice where its mirror (N-i, N-j, N-k) is not in the half array (0 < k < N/2): same |k|, same |F|^2.
+// acc = [power | kmode | nmode], 3 * nbin doubles, zeroed by the launcher.
+// ---------------------------------------------------------------------------
+__global__ void spectrum_bin_kernel(const double2 *__restrict__ F, int N, double kfac, double dk, int nbin,
+                                    double *__restrict__ acc) {
+  extern __shared__ double sh_acc[];  // 3 * nbin
+  for (int b = threadIdx.x; b < 3 * nbin; b += blockDim.x) sh_acc[b] = 0.0;
+  __syncthreads();
+  const int nzh = N / 2 + 1;
+  const size_t n = (size_t)N * N * nzh;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % nzh);
+    const int j = (int)((idx / nzh) % N);
+    const int i = (int)(idx / ((size_t)nzh * N));
+    auto kv = [&](int m) { return (m <= N / 2) ? kfac * (double)m : -kfac * (double)(N - m); };  // scale_space.cpp:41-51
+    const double kx = kv(i), ky = kv(j), kz = kv(k);
+    // k_squared (scale_space.cpp:16-39) without FMA contraction: modes that sit exactly on a bin edge
+    // (|k|/dk an integer up to rounding) must fall on the reference's side of it
+    const double ktot = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)), __dmul_rn(kz, kz)));
+    const unsigned long long b = (unsigned long long)__ddiv_rn(ktot, dk);
+    if (b < (unsigned long long)nbin) {
+      const double w = (k > 0 && k < N / 2) ? 2.0 : 1.0;
+      const double2 f = F[idx];
+      atomicAdd(sh_acc + b, w * (f.x * f.x + f.y * f.y));
+      atomicAdd(sh_acc + nbin + b, w * ktot);
+      atomicAdd(sh_acc + 2 * nbin + b, w);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < 3 * nbin; b += blockDim.x)
+    if (sh_acc[b] != 0.0) atomicAdd(acc + b, sh_acc[b]);
+}
+
+__global__ void spectrum_finish_kernel(double *__restrict__ acc, int nbin, double norm) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbin) return;
+  const double nm = acc[2 * nbin + b];
+  if (nm > 0.0) {
+    acc[nbin + b] = acc[nbin + b] / nm;
+    acc[b] = acc[b] / nm * norm;
+  }
+}
+
+void launch_measure_spectrum(const double2 *F, int N, double L, int nbin, double *acc, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  const double kfac = 2.0 * M_PI / L;
+  const double kny = kfac * (double)(N / 2);
+  const double dk = std::sqrt((kny * kny + kny * kny) + kny * kny) / (double)nbin;   // kmax = |k| of (N/2, N/2, N/2)
+  BGPU_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * nbin, st));
+  const size_t n = (size_t)N * N * (N / 2 + 1);
+  const int blocks = (int)(blocks_for(n, 256) < 1184u ? blocks_for(n, 256) : 1184u);
+  spectrum_bin_kernel<<<blocks, 256, sizeof(double) * 3 * nbin, st>>>(F, N, kfac, dk, nbin, acc);
+  const double V = L * L * L, nn = (double)N * N * N;
+  spectrum_finish_kernel<<<(nbin + 255) / 256, 256, 0, st>>>(acc, nbin, V / nn / nn);  // FOURIER_DEF_2 norm
+  BGPU_LAUNCHED(2);
 }
 
 // ---------------------------------------------------------------------------

@@ -55,6 +55,11 @@ void launch_philox_normals(double *out, size_t n, size_t first, uint64_t seed, u
                            cudaStream_t st);
 // W (half grid, transform of a real white field) *= sqrt(c2 * spec) at the folded index, DC = 0
 void launch_colour_white(double2 *W, const double *spec_full, int N, double c2, cudaStream_t st);
+// W *= 1/sqrt(inv) with inv = the padded half-grid multiplier (V/N)/M of the kinetic term, 0 where inv <= 0
+void launch_colour_white_rows(double2 *W, const double *inv_half, int N, size_t n_half, cudaStream_t st);
+
+// measure_spectrum (field_statistics.cpp:20-90) of a half-complex transform F; acc = [power | kmode | nmode] (3 nbin, device)
+void launch_measure_spectrum(const double2 *F, int N, double L, int nbin, double *acc, cudaStream_t st);
 
 // particle scatter: Psi -> rho (zeroed here); optional positions out
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,

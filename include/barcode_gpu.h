@@ -88,7 +88,7 @@ void bgpu_destroy(bgpu_handle *h);
  * rank must make the same sequence of calls.  Supported: N1 in {128, 256, 512, 1024}; NGP / CIC / TSC;
  * Zel'dovich and 2LPT/ALPT forward models, RSD; calc_h 0 (Gaussian likelihood), 1 and BGPU_CALC_H_EXACT.
  * Not on slabs yet: the SPH kernel, the finite-difference product gradients (Poisson / log-normal with
- * calc_h 0) and the momentum draws (bgpu_color_momenta, bgpu_draw_momenta_device). */
+ * calc_h 0) and the host-stream momentum draw (bgpu_color_momenta; bgpu_draw_momenta_device works). */
 int bgpu_nccl_unique_id(void *out128);
 int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out);
 int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *nx_local);
@@ -127,6 +127,9 @@ int bgpu_device_normals(bgpu_handle *h, uint64_t seed, uint64_t draw_index, unsi
 /* Lag2Eul / Lag2Eul_rsd_zeldovich as likelihood_grad_log_like calls them (HMC_models.cc:383-406);
  * pos* may be NULL */
 int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *posx, double *posy, double *posz);
+/* measure_spectrum (field_statistics.cpp:20-90): spherically binned power spectrum of a real field, N_bin bins
+ * up to |k| of the cube's corner mode; the per-sample diagnostic behind powSpecit<it>.dat */
+int bgpu_measure_spectrum(bgpu_handle *h, const double *signal, uint64_t N_bin, double *kmode, double *power);
 
 /* building blocks exposed for parity tests */
 int bgpu_assign_density(bgpu_handle *h, const double *x, const double *y, const double *z, double *rho);

@@ -888,6 +888,30 @@ def draw_momenta(p: Params, white: np.ndarray, mass_f, mass_r, real_gauss=None) 
 
 
 # --------------------------------------------------------------------------
+# F3: measure_spectrum (field_statistics.cpp:20-90)
+# --------------------------------------------------------------------------
+def measure_spectrum(p: Params, signal, n_bin: int):
+    """Spherically binned power of the FULL complex transform: bin = (ULONG)(|k| / dk), dk = |k(N/2, N/2, N/2)| /
+    n_bin, modes at or beyond kmax dropped; kmode = mean |k| of a bin, power = mean |F|^2 * V / N^2
+    (FOURIER_DEF_2); empty bins stay 0.  Returns (kmode, power)."""
+    N = p.N1
+    F = np.fft.fftn(signal.reshape(N, N, N))
+    k = calc_ki(N, p.L1)
+    ktot = np.sqrt((k[:, None, None] ** 2 + k[None, :, None] ** 2) + k[None, None, :] ** 2)
+    kny = k[N // 2]
+    dk = np.sqrt(3.0 * kny * kny) / float(n_bin)
+    b = (ktot / dk).astype(np.int64).ravel()
+    ok = b < n_bin
+    nmode = np.bincount(b[ok], minlength=n_bin).astype(np.float64)
+    kmode = np.bincount(b[ok], weights=ktot.ravel()[ok], minlength=n_bin)
+    power = np.bincount(b[ok], weights=(np.abs(F) ** 2).ravel()[ok], minlength=n_bin)
+    have = nmode > 0
+    kmode[have] /= nmode[have]
+    power[have] = power[have] / nmode[have] * (p.vol / float(N) ** 3 / float(N) ** 3)
+    return kmode, power
+
+
+# --------------------------------------------------------------------------
 # F4: counter-based Gaussians of the device momentum draw (no reference code: the reference draws from
 # GSL's serial mt19937).  Philox4x32-10 as published (Salmon, Moraes, Dror, Shaw, SC'11; Random123),
 # pinned by its known-answer vectors in tests/test_host.py.

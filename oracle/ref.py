@@ -88,6 +88,7 @@ def lib():
             "ref_fft_c2r": [C.c_int, dp, dp],
             "ref_gradfft": [C.c_int, C.c_double, dp, dp, C.c_uint],
             "ref_gradfindif": [C.c_int, C.c_double, dp, dp, C.c_uint],
+            "ref_measure_spectrum": [C.c_int, C.c_double, dp, C.c_ulong, dp, dp],
             "ref_time_gradient_psi": [C.c_void_p, dp, C.c_int, dp],
         }.items():
             fn = getattr(L, name)
@@ -321,6 +322,15 @@ def gradfft(a, L1, dim):
     out = np.empty(N1 ** 3)
     _chk(lib().ref_gradfft(N1, L1, _p(a.ravel()), _p(out), dim))
     return out.reshape(a.shape)
+
+
+def measure_spectrum(a, L1, n_bin):
+    """measure_spectrum (field_statistics.cpp:20-90) -> (kmode[n_bin], power[n_bin])."""
+    N1 = a.shape[0]
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    kmode, power = np.empty(n_bin), np.empty(n_bin)
+    _chk(lib().ref_measure_spectrum(N1, L1, _p(a.ravel()), n_bin, _p(kmode), _p(power)))
+    return kmode, power
 
 
 def gradfindif(a, L1, dim):

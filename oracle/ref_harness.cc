@@ -543,6 +543,13 @@ int ref_gradfindif(int N1, double L1, const double *in, double *out, unsigned di
   REF_CATCH
 }
 
+/* measure_spectrum, field_statistics.cpp:20-90 (per-sample diagnostics) */
+int ref_measure_spectrum(int N1, double L1, const double *signal, unsigned long N_bin, double *kmode, double *power) {
+  REF_TRY
+  measure_spectrum(N1, N1, N1, L1, L1, L1, const_cast<double *>(signal), kmode, power, N_bin);
+  REF_CATCH
+}
+
 /* CPU baseline timing: seconds per gradient_psi call, 1 warm-up + reps timed (omp_get_wtime) */
 int ref_time_gradient_psi(void *hv, const double *signal, int reps, double *seconds_per_call) {
   auto *h = static_cast<ref_handle *>(hv);

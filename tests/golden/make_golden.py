@@ -13,6 +13,7 @@ for the hot path, so these files are the pin.
                       in the float32 precision of calc_power.cc:41-42
   case_<name>.npz     inputs + reference outputs of one configuration at 16^3
   garfield_n8.npz     white-noise stream, coloured field and momenta at 8^3
+  spectrum_n16.npz    measure_spectrum of a coloured field at 16^3
 """
 from __future__ import annotations
 
@@ -137,6 +138,19 @@ def main():
         print(name, "gradpsi norm", np.linalg.norm(out["gradpsi"]), "dH", dH, "Neps", out["Neps"])
         R.close()
 
+    if only and "spectrum" not in only:
+        return
+    # measure_spectrum (field_statistics.cpp:20-90) of a coloured field at 16^3, 20 and 200 bins (the latter
+    # leaves bins empty)
+    R = ref.Reference(ref.Config(N1=N1, L1=L1))
+    P = R.readtab(CAMB)
+    field = R.create_garfield(5, P)
+    R.close()
+    out = dict(signal=field, L1=L1)
+    for nb in (20, 200):
+        km, pw = ref.measure_spectrum(field.reshape(N1, N1, N1), L1, nb)
+        out[f"kmode_{nb}"], out[f"power_{nb}"] = km, pw
+    np.savez_compressed(os.path.join(HERE, "spectrum_n16.npz"), **out)
     if only:
         return
     # momentum draw at 8^3: the white-noise stream, its colouring with P and with 1/P

@@ -412,3 +412,26 @@ def test_device_momentum_draw_has_the_mass_as_covariance(mass_type):
             ok = M > 0
             ratio = ph[ok] / (float(N) ** 6 / L ** 3 * M[ok])
             assert abs(ratio.mean() - 1) < 0.02
+
+
+# ---------------------------------------------------------------- P(k) diagnostic
+def test_measure_spectrum_matches_reference_and_oracle():
+    import os
+    from conftest import GOLDEN
+    from oracle import barcode_oracle as bo
+    from barcode_b200.chain import Chain, Params
+    with np.load(os.path.join(GOLDEN, "spectrum_n16.npz")) as f:
+        g = {k: f[k] for k in f.files}
+    with Chain(Params(N1=16, L1=float(g["L1"]))) as ch:
+        for nb in (20, 200):
+            km, pw = ch.measure_spectrum(g["signal"], nb)
+            assert np.allclose(km, g[f"kmode_{nb}"], rtol=1e-12, atol=0)
+            assert np.allclose(pw, g[f"power_{nb}"], rtol=1e-11, atol=0)
+    N, L = 128, 400.0
+    x = np.random.default_rng(8).standard_normal((N, N, N))
+    with Chain(Params(N1=N, L1=L)) as ch:
+        km, pw = ch.measure_spectrum(x, 200)
+    km0, pw0 = bo.measure_spectrum(bo.Params(N1=N, L1=L), x, 200)
+    assert np.allclose(km, km0, rtol=1e-12, atol=0) and np.allclose(pw, pw0, rtol=1e-11, atol=0)
+    # white noise of unit variance: P = V / N^3 in every bin
+    assert abs(pw[20:150].mean() / (L ** 3 / N ** 3) - 1) < 0.01

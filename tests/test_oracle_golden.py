@@ -128,3 +128,14 @@ def test_exact_adjoint_is_the_derivative_of_psi():
         fd = (f(s + v) - f(s - v)) / 2.0
         an = float(np.sum(g * v))
         assert abs(fd - an) <= 2e-5 * abs(an) + 1e-9
+
+
+def test_measure_spectrum_golden():
+    """measure_spectrum (field_statistics.cpp:20-90): the numpy restatement against the compiled reference."""
+    with np.load(os.path.join(GOLDEN, "spectrum_n16.npz")) as f:
+        g = {k: f[k] for k in f.files}
+    p = bo.Params(N1=16, L1=float(g["L1"]))
+    for nb in (20, 200):
+        km, pw = bo.measure_spectrum(p, g["signal"], nb)
+        assert np.allclose(km, g[f"kmode_{nb}"], rtol=1e-13, atol=0)
+        assert np.allclose(pw, g[f"power_{nb}"], rtol=1e-12, atol=0)

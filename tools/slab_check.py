@@ -76,6 +76,7 @@ def main():
             res["kinetic"] = np.array([sc.kinetic_term(sc.local(p0))])
             sf, pf = sc.leapfrog(sc.local(s), sc.local(p0), 2, 1e-3)
             res["leap_s"], res["leap_p"] = gather(sf), gather(pf)
+            res["device_draw"] = gather(sc.draw_momenta_device(5, 3))
         res["gradient"] = gather(sc.gradient_psi(sc.local(s)))
         sc.close()
         if info.rank == 0:
@@ -93,6 +94,7 @@ def main():
                     ref["kinetic"] = np.array([ch.kinetic_term(p0)])
                     sf, pf = ch.leapfrog(s, p0, 2, 1e-3)
                     ref["leap_s"], ref["leap_p"] = sf, pf
+                    ref["device_draw"] = ch.draw_momenta_device(5, 3)
                 ref["gradient"] = ch.gradient_psi(s)
             for k in ref:
                 e = rel(res[k], ref[k])
