@@ -80,6 +80,7 @@ struct bgpu_handle {
   int Hmax = 0;                 // halo planes allocated each side of rho_ext
   double *rho_ext = nullptr;    // [(Ns + 2 Hmax)][N][N]; delta points at the owned planes inside it
   double *halo_recv = nullptr;  // 2 * Hmax * N^2
+  double *phi1 = nullptr, *xa = nullptr, *xb = nullptr, *xc = nullptr;  // exact 2LPT/ALPT adjoint: phi^(1) + 3 scratch arrays
   double *resid_ext = nullptr;  // exact adjoint on a slab: the residual with H halo planes each side
   int H_cur = 0;                // halo width of the evaluation in flight
   double2 *sendbuf = nullptr, *recvbuf = nullptr;
@@ -166,7 +167,11 @@ void validate(const bgpu_params &p) {
   if (p.sfmodel != 1 && !p.rsd_model) {
     // Lag2Eul_non_zeldovich (2LPT + spherical collapse split at slength).  The reference has no adjoint
     // for it (HMC_models.cc:458): its gradients are calc_h 0 / 1 on the forward density.
-    require(p.calc_h == 0 || p.calc_h == 1, "bgpu: sfmodel != 1 supports calc_h 0 and 1 (no exact adjoint of the 2LPT/ALPT model yet)");
+    // calc_h 0 / 1 are the reference's gradients on the forward density; calc_h = 4 is the exact adjoint (new)
+    require(p.calc_h == 0 || p.calc_h == 1 || (p.calc_h == BGPU_CALC_H_EXACT && p.masskernel != 3),
+            "bgpu: sfmodel != 1 supports calc_h 0, 1 and 4 (NGP / CIC / TSC)");
+    if (p.calc_h == BGPU_CALC_H_EXACT)
+      require(p.correct_delta != 0, "bgpu: the exact adjoint of the 2LPT/ALPT model needs correct_delta = true");
     require(p.slength > 0., "bgpu: sfmodel != 1 needs slength > 0 (the ALPT smoothing radius, input.par slength)");
   }
   if (p.rsd_model) {
@@ -203,8 +208,9 @@ void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, d
     pois.kfac = h->kfac;
     const size_t plane = (size_t)h->N * h->N;
     if (h->G == 1) {
-      h->fft.c2r(h->shat, h->work, h->psi[0], pois, scale_n);
-      launch_lpt2_source(h->psi[0], d_s, h->psi[1], h->N, h->N, 0, h->p.L1, dQ, h->p.D1, h->p.D2, h->stream);
+      double *phi = h->phi1 ? h->phi1 : h->psi[0];  // the exact adjoint needs phi^(1) again
+      h->fft.c2r(h->shat, h->work, phi, pois, scale_n);
+      launch_lpt2_source(phi, d_s, h->psi[1], h->N, h->N, 0, h->p.L1, dQ, h->p.D1, h->p.D2, h->stream);
     } else {
       // slab: the twice-applied 4th-order stencil reaches 4 planes across the slab boundary.  phi^(1) goes into
       // the (still unused) density tile with 4 halo planes each side, filled from the x neighbours.
@@ -372,6 +378,53 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
       sop2.kfac = h->kfac;
       h->fft.r2c(h->tmp, h->work, h->acc, lop2, sop2);
     }
+  } else if (p.calc_h == BGPU_CALC_H_EXACT && h->phi1) {
+    // exact adjoint of Lag2Eul_non_zeldovich (new; oracle: non_zeldovich_adjoint, FD-validated):
+    //   W_c = CB^T V_c;  A^ = sum_c T_c W^_c;  u_lpt = IFFT[K A^], u_sc = IFFT[(1 - K) A^];
+    //   grad = dQ (D1 u_lpt - D2 Poisson[sum_ab FD_a FD_b (dm2v/dL_ab u_lpt)] + theta_SC' u_sc)
+    GridGeom g = h->geom;
+    g.cellbound = 1;
+    launch_gather_adjoint_to(g, h->psi[0], h->psi[1], h->psi[2], h->xa, h->xb, h->tmp, h->resid, h->stream);
+    double *V[3] = {h->xa, h->xb, h->tmp};
+    for (int c = 0; c < 3; ++c) launch_cellbound_transpose(V[c], h->psi[c], h->N, h->stream);
+    for (int c = 0; c < 3; ++c) {
+      ROp lop2;
+      lop2.kind = R_LOAD;
+      KOp sop2;
+      sop2.kind = (c == 0) ? K_INVLAP_SET : K_INVLAP_ADD;
+      sop2.comp = c;
+      sop2.kfac = h->kfac;
+      h->fft.r2c(h->psi[c], h->work, h->acc, lop2, sop2);
+    }
+    ROp unit;
+    unit.kind = R_SCALE;
+    unit.a = inv_n;
+    KOp kg;
+    kg.kfac = h->kfac;
+    kg.a = p.slength;
+    kg.kind = K_GAUSS;
+    h->fft.c2r(h->acc, h->work, h->xa, kg, unit);            // u_lpt
+    kg.kind = K_ONE_MINUS_GAUSS;
+    h->fft.c2r(h->acc, h->work, h->xb, kg, unit);            // u_sc
+    double *P6[6] = {h->psi[0], h->psi[1], h->psi[2], h->resid, h->tmp, h->xc};
+    launch_lpt2_adjoint_coef(h->phi1, h->xa, P6, h->N, p.L1, h->stream);
+    launch_lpt2_adjoint_div(P6, h->phi1, h->N, p.L1, h->stream);   // G over phi^(1), which is done
+    r2c_plain(h, h->phi1, h->dhat);
+    KOp pois;
+    pois.kind = K_NEGINVK2;
+    pois.a = 1.0;
+    pois.kfac = h->kfac;
+    h->fft.c2r(h->dhat, h->work, h->phi1, pois, unit);          // q = Poisson[G]
+    launch_alpt_adjoint_combine(h->tmp, h->xa, h->phi1, h->xb, d_s, h->n, p.deltaQ_factor, p.D1, p.D2, h->stream);
+    // gradpsi = IFFT[(V/N)/P s^] + that
+    KOp lop;
+    lop.kind = K_MULREAL;
+    lop.real0 = h->inv_power;
+    h->fft.c2r(h->shat, h->work, d_out, lop, unit);
+    launch_axpy(d_out, h->tmp, 1.0, h->n, h->stream);
+    if (h->out_hooks && h->out_hooks->after)
+      for (int c = 0; c < h->out_hooks->chunks; ++c) h->out_hooks->after(h->out_hooks->ctx, c);
+    return;
   } else {
     // exact adjoint: V = gather(r) in place over Psi, then the same back-projection
     if (p.calc_h == 2)
@@ -620,6 +673,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
             "bgpu_slab_create: the slab-decomposed transform supports N = 128, 256, 512, 1024");
     require(rank >= 0 && rank < nranks && p->N1 % nranks == 0 && p->N1 / nranks >= 8,
             "bgpu_slab_create: N1 must be a multiple of the number of ranks, at least 8 planes per rank");
+    require(!(p->calc_h == BGPU_CALC_H_EXACT && p->sfmodel != 1 && !p->rsd_model),
+            "bgpu_slab_create: the exact adjoint of the 2LPT/ALPT model is not built for slabs yet");
     require(p->calc_h == 0 || p->calc_h == 1 || p->calc_h == BGPU_CALC_H_EXACT,
             "bgpu_slab_create: calc_h must be 0, 1 or 4 (the SPH adjoint is not built for slabs yet)");
     require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
@@ -761,6 +816,9 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   dalloc(h->rho_ext, (size_t)(h->Ns + 2 * h->Hmax) * h->N * h->N);
   h->delta = h->rho_ext;   // a cube has no halo; a slab moves delta to its owned planes per evaluation
   dalloc(h->resid, h->n); dalloc(h->tmp, h->n);
+  if (p->sfmodel != 1 && !p->rsd_model && p->calc_h == BGPU_CALC_H_EXACT) {
+    dalloc(h->phi1, h->n); dalloc(h->xa, h->n); dalloc(h->xb, h->n); dalloc(h->xc, h->n);
+  }
   dalloc(h->shat, h->nh); dalloc(h->dhat, h->nh); dalloc(h->work, h->nh); dalloc(h->acc, h->nh);
   dalloc(h->partials, (size_t)kReduceBlocks); dalloc(h->dscal, (size_t)S_COUNT);
   BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hscal), S_COUNT * sizeof(double)));
@@ -820,7 +878,7 @@ void bgpu_destroy(bgpu_handle *h) {
     }
   }
   double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->mass_f, h->mass_r, h->inv_mass,
-                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->tmp,
+                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->tmp, h->phi1, h->xa, h->xb, h->xc,
                      h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
     if (q) cudaFree(q);

@@ -198,6 +198,13 @@ __device__ __forceinline__ double2 kop_load(const KOp &op, double2 v, size_t off
       const double f = ksq > 0.0 ? -op.a * __drcp_rn(ksq) : 0.0;
       return make_double2(f * v.x, f * v.y);
     }
+    case K_GAUSS:
+    case K_ONE_MINUS_GAUSS: {
+      const double kx = kval(ix, N, op.kfac), ky = kval(iy, N, op.kfac), kz = kval(iz, N, op.kfac);
+      const double K = exp(-(kx * kx + ky * ky + kz * kz) * (op.a * op.a) / 2.);
+      const double f = op.kind == K_GAUSS ? K : 1.0 - K;
+      return make_double2(f * v.x, f * v.y);
+    }
     default:
       return v;
   }

@@ -15,7 +15,9 @@ enum KKind : int {
   K_FINAL = 4,       // v * real0[off] + a * cplx0[off]   (prior + norm * h, HMC.cc:205)
   K_INVLAP_SET = 5,  // store: out[off]  = (k_c/k^2)(Im v, -Re v); k^2 == 0 -> 0, Nyquist -> 0 (gradient.cpp:167-210)
   K_INVLAP_ADD = 6,  // store: out[off] += same
-  K_NEGINVK2 = 7     // a * v * (-1/k^2), 0 at k^2 == 0, no Nyquist zeroing (PoissonSolver, EqSolvers.cc:29-64)
+  K_NEGINVK2 = 7,    // a * v * (-1/k^2), 0 at k^2 == 0, no Nyquist zeroing (PoissonSolver, EqSolvers.cc:29-64)
+  K_GAUSS = 8,       // v * K,       K = exp(-k^2 a^2 / 2), a = smoothing radius (kernelcomp filtertype 1, convolution.cpp:224-322)
+  K_ONE_MINUS_GAUSS = 9  // v * (1 - K)
 };
 
 struct KOp {

@@ -304,6 +304,11 @@ struct RotCtx {
       const double g = ksq > 0.0 ? -a * __drcp_rn(ksq) : 0.0;
       return make_double2(g * v.x, g * v.y);
     }
+    if (kind == K_GAUSS || kind == K_ONE_MINUS_GAUSS) {  // the ALPT smoothing kernel and its complement
+      const double K = exp(-(kr * kr + c2) * (a * a) / 2.);
+      const double g = kind == K_GAUSS ? K : 1.0 - K;
+      return make_double2(g * v.x, g * v.y);
+    }
     const double kc = sel == 0 ? kr : (sel == 1 ? k_oth : k_z);
     double f;
     if (kind == K_GRAD) {

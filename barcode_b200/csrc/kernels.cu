@@ -475,8 +475,10 @@ void launch_grf_nll(const double *s, const double *nobs, const double *noise, co
 // particle, pure gather: V_c = sum_cells r_cell * dW_cell/dx_c.  Deterministic.
 // The particle's own displacement is read and its V written in place.
 // ---------------------------------------------------------------------------
-__global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, double *__restrict__ ay,
-                                      double *__restrict__ az, const double *__restrict__ resid) {
+// Under the cell-boundary averaging of the 2LPT model (g.cellbound) the positions come from Psi averaged with
+// its (i-1, j-1, k-1) neighbour, so V must not overwrite Psi: (ox, oy, oz) are then separate arrays.
+__global__ void gather_adjoint_kernel(GridGeom g, const double *ax, const double *ay, const double *az,
+                                      double *ox, double *oy, double *oz, const double *__restrict__ resid) {
   const int N = g.N;
   const size_t n = (size_t)g.Ns * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -495,7 +497,15 @@ __global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, doubl
     return l;
   };
   double x, y, z;
-  particle_position(g, i, j, k, ax[idx], ay[idx], az[idx], x, y, z);
+  double px = ax[idx], py = ay[idx], pz = az[idx];
+  if (g.cellbound) {  // cube only (the slab path keeps to the Zel'dovich model for the exact adjoint)
+    const int il = (int)(idx >> (2 * sh));
+    const size_t m = ((size_t)(il == 0 ? N - 1 : il - 1) * N + (j == 0 ? N - 1 : j - 1)) * N + (k == 0 ? N - 1 : k - 1);
+    px = 0.5 * (ax[m] + px);
+    py = 0.5 * (ay[m] + py);
+    pz = 0.5 * (az[m] + pz);
+  }
+  particle_position(g, i, j, k, px, py, pz, x, y, z);
   double vx = 0.0, vy = 0.0, vz = 0.0;
   if (in_domain(g, x, y, z)) {
     const double inv_d = 1.0 / g.d;
@@ -549,16 +559,24 @@ __global__ void gather_adjoint_kernel(GridGeom g, double *__restrict__ ax, doubl
     }  // NGP: piecewise-constant weights, derivative identically zero
   }
   if (g.rsd) vz += g.fgrow * vz;  // d z_s / d Psi_z = 1 + f (cf. HMC_models.cc:295-301)
-  ax[idx] = vx;
-  ay[idx] = vy;
-  az[idx] = vz;
+  ox[idx] = vx;
+  oy[idx] = vy;
+  oz[idx] = vz;
 }
 
 void launch_gather_adjoint(const GridGeom &g, double *ax, double *ay, double *az, const double *resid,
                            cudaStream_t st) {
   ProfScope prof(KK_GATHER, st);
   const size_t n = (size_t)g.Ns * g.N * g.N;
-  gather_adjoint_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, ax, ay, az, resid);
+  gather_adjoint_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, ax, ay, az, ax, ay, az, resid);
+  BGPU_LAUNCHED(1);
+}
+
+void launch_gather_adjoint_to(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *vx,
+                              double *vy, double *vz, const double *resid, cudaStream_t st) {
+  ProfScope prof(KK_GATHER, st);
+  const size_t n = (size_t)g.Ns * g.N * g.N;
+  gather_adjoint_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, psix, psiy, psiz, vx, vy, vz, resid);
   BGPU_LAUNCHED(1);
 }
 
@@ -1102,6 +1120,97 @@ void launch_alpt_combine(double2 *d2, const double2 *d4, int N, int Ns, int y0, 
   ProfScope prof(KK_STREAM, st);
   const size_t n = (size_t)N * Ns * (N / 2 + 1);
   alpt_combine_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d2, d4, N, Ns, y0, kfac, rS);
+  BGPU_LAUNCHED(1);
+}
+
+// ---------------------------------------------------------------------------
+// Exact adjoint of Lag2Eul_non_zeldovich (new: the reference has none, HMC_models.cc:458; derivation in
+// oracle/barcode_oracle.py non_zeldovich_adjoint, validated there by finite differences of psi()).
+// ---------------------------------------------------------------------------
+// transpose of cellboundcomp: W(x) = 1/2 (V(x) + V(x + (1, 1, 1))), periodic
+__global__ void cellbound_transpose_kernel(const double *__restrict__ v, double *__restrict__ w, int N) {
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int sh = 31 - __clz(N);
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
+  const size_t m = ((size_t)wrap_idx(i + 1, N) * N + wrap_idx(j + 1, N)) * N + wrap_idx(k + 1, N);
+  w[idx] = 0.5 * (v[m] + v[idx]);
+}
+
+// P_ab = (d m2v / d L_ab) u: (Lyy + Lzz) u, (Lxx + Lzz) u, (Lxx + Lyy) u, -2 Lxy u, -2 Lxz u, -2 Lyz u
+struct Six {
+  double *p[6];
+};
+__global__ void lpt2_adjoint_coef_kernel(const double *__restrict__ phi, const double *__restrict__ u, Six out, int N,
+                                         double fac) {
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int sh = 31 - __clz(N);
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
+  const double xx = findif2_at<0, 0>(phi, N, 0, i, j, k, fac), yy = findif2_at<1, 1>(phi, N, 0, i, j, k, fac),
+               zz = findif2_at<2, 2>(phi, N, 0, i, j, k, fac);
+  const double xy = findif2_at<0, 1>(phi, N, 0, i, j, k, fac), xz = findif2_at<0, 2>(phi, N, 0, i, j, k, fac),
+               yz = findif2_at<1, 2>(phi, N, 0, i, j, k, fac);
+  const double uu = u[idx];
+  out.p[0][idx] = (yy + zz) * uu;
+  out.p[1][idx] = (xx + zz) * uu;
+  out.p[2][idx] = (xx + yy) * uu;
+  out.p[3][idx] = -2.0 * xy * uu;
+  out.p[4][idx] = -2.0 * xz * uu;
+  out.p[5][idx] = -2.0 * yz * uu;
+}
+
+// G = sum_ab FD_a FD_b P_ab (the stencil is antisymmetric: the transpose of FD_b FD_a is FD_a FD_b)
+__global__ void lpt2_adjoint_div_kernel(Six in, double *__restrict__ out, int N, double fac) {
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int sh = 31 - __clz(N);
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
+  out[idx] = findif2_at<0, 0>(in.p[0], N, 0, i, j, k, fac) + findif2_at<1, 1>(in.p[1], N, 0, i, j, k, fac) +
+             findif2_at<2, 2>(in.p[2], N, 0, i, j, k, fac) + findif2_at<0, 1>(in.p[3], N, 0, i, j, k, fac) +
+             findif2_at<0, 2>(in.p[4], N, 0, i, j, k, fac) + findif2_at<1, 2>(in.p[5], N, 0, i, j, k, fac);
+}
+
+// out = dQ (D1 u_lpt - D2 q + theta_SC'(dQ s) u_sc), theta_SC' = D1 / sqrt(1 - 2/3 D1 dQ s) where positive, else 0
+__global__ void alpt_adjoint_combine_kernel(double *__restrict__ out, const double *__restrict__ u_lpt,
+                                            const double *__restrict__ q, const double *__restrict__ u_sc,
+                                            const double *__restrict__ s, size_t n, double dQ, double D1, double D2) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const double arg = 1. - 2. / 3. * D1 * (dQ * s[idx]);
+  const double dsc = arg > 0. ? D1 / sqrt(arg) : 0.;
+  out[idx] = dQ * (D1 * u_lpt[idx] - D2 * q[idx] + dsc * u_sc[idx]);
+}
+
+void launch_cellbound_transpose(const double *v, double *w, int N, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  const size_t n = (size_t)N * N * N;
+  cellbound_transpose_kernel<<<blocks_for(n, 256), 256, 0, st>>>(v, w, N);
+  BGPU_LAUNCHED(1);
+}
+void launch_lpt2_adjoint_coef(const double *phi, const double *u, double *const out[6], int N, double L, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  Six o;
+  for (int a = 0; a < 6; ++a) o.p[a] = out[a];
+  const size_t n = (size_t)N * N * N;
+  lpt2_adjoint_coef_kernel<<<blocks_for(n, 256), 256, 0, st>>>(phi, u, o, N, (double)N / (2. * L));
+  BGPU_LAUNCHED(1);
+}
+void launch_lpt2_adjoint_div(double *const in[6], double *out, int N, double L, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  Six o;
+  for (int a = 0; a < 6; ++a) o.p[a] = in[a];
+  const size_t n = (size_t)N * N * N;
+  lpt2_adjoint_div_kernel<<<blocks_for(n, 256), 256, 0, st>>>(o, out, N, (double)N / (2. * L));
+  BGPU_LAUNCHED(1);
+}
+void launch_alpt_adjoint_combine(double *out, const double *u_lpt, const double *q, const double *u_sc, const double *s,
+                                 size_t n, double dQ, double D1, double D2, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  alpt_adjoint_combine_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, u_lpt, q, u_sc, s, n, dQ, D1, D2);
   BGPU_LAUNCHED(1);
 }
 

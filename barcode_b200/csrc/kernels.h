@@ -99,6 +99,13 @@ void launch_kfinal_combine(const double2 *s, const double *mult, const double2 *
 void launch_lpt2_source(const double *phi, const double *s, double *out, int N, int Ns, int xoff, double L, double dQ,
                         double D1, double D2, cudaStream_t st);
 void launch_sc_divergence(const double *s, double *out, size_t n, double dQ, double D1, cudaStream_t st);
+// exact adjoint of the 2LPT/ALPT model (cube): transpose of the cell-boundary average; P_ab = dm2v/dL_ab * u
+// (six arrays); G = sum_ab FD_a FD_b P_ab; out = dQ (D1 u_lpt - D2 q + theta_SC' u_sc)
+void launch_cellbound_transpose(const double *v, double *w, int N, cudaStream_t st);
+void launch_lpt2_adjoint_coef(const double *phi, const double *u, double *const out[6], int N, double L, cudaStream_t st);
+void launch_lpt2_adjoint_div(double *const in[6], double *out, int N, double L, cudaStream_t st);
+void launch_alpt_adjoint_combine(double *out, const double *u_lpt, const double *q, const double *u_sc, const double *s,
+                                 size_t n, double dQ, double D1, double D2, cudaStream_t st);
 // k-space layout [x][Ns][N/2+1] with y = y0 + y_local (a cube: Ns = N, y0 = 0)
 void launch_alpt_combine(double2 *d2, const double2 *d4, int N, int Ns, int y0, double kfac, double rS, cudaStream_t st);
 
@@ -119,6 +126,9 @@ void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const dou
 // exact adjoint of the mass assignment: V_c(p) = sum_cells r_c dW_c/dx_c, in place over Psi
 void launch_gather_adjoint(const GridGeom &g, double *psix_Vx, double *psiy_Vy, double *psiz_Vz,
                            const double *resid, cudaStream_t st);
+// the same out of place (required under g.cellbound, where a particle's position also reads its neighbour's Psi)
+void launch_gather_adjoint_to(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *vx,
+                              double *vy, double *vz, const double *resid, cudaStream_t st);
 
 // out = resid * d_c(delta) with the 4th-order finite difference of gradient.cpp:81-153
 void launch_findif_product(const double *delta, const double *resid, double *out, int N, double L, int comp,

@@ -55,7 +55,8 @@ typedef struct bgpu_params {
   int sfmodel;               /* 1 Zel'dovich; else Lag2Eul_non_zeldovich (2LPT + spherical collapse, ALPT);
                               * with rsd_model the reference runs Zel'dovich for any value */
   int rsd_model;
-  int calc_h;                /* 0, 1, 2 (SPH adjoint, needs masskernel 3) as the reference; BGPU_CALC_H_EXACT */
+  int calc_h;                /* 0, 1, 2 (SPH adjoint, needs masskernel 3) as the reference; BGPU_CALC_H_EXACT =
+                              * exact adjoint of NGP / CIC / TSC under the Zel'dovich or the 2LPT/ALPT model */
   int mass_type;             /* 0 ones (R), 1 1/P (FS), 4 P (FS) */
   double D1, D2, ascale, OM, OL;
   double particle_kernel_h_rel; /* SPH scale length in cells (input.par particle_kernel_h_rel); masskernel 3 */

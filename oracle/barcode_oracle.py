@@ -678,6 +678,8 @@ def grad_log_like(p: Params, signal, nobs, noise, window):
         r = partial_f(p, dX, nobs, noise, window, exact_sign=True)
         mean = 1.0  # rho/mean: mean == 1 analytically for NGP/CIC/TSC
         V = gather_adjoint(p, r / mean, x, y, z)
+        if not (p.sfmodel == 1 or p.rsd_model):
+            return p.deltaQ_factor * non_zeldovich_adjoint(p, p.deltaQ_factor * signal, V), dX
         h = grad_inv_lap_sum(p, V)
     else:
         raise NotImplementedError("calc_h %d" % p.calc_h)
@@ -685,6 +687,38 @@ def grad_log_like(p: Params, signal, nobs, noise, window):
     if p.correct_delta:
         norm *= p.D1                       # :467-469
     return norm * h, dX
+
+
+def non_zeldovich_adjoint(p: Params, s_in, V) -> np.ndarray:
+    """NEW (the reference has no adjoint of Lag2Eul_non_zeldovich, HMC_models.cc:458): the exact transpose of
+    displacement_non_zeldovich applied to the particle forces V_c = -d(-lnL)/dx_c.  With P_c = IFFT T_c FFT the
+    projection (T_c = -i k_c/k^2, P_c^T = -P_c), CB the cell-boundary average and C = K o theta_LPT + (1 - K) o
+    theta_SC:   d(-lnL)/d in = (dC/d in)^T sum_c P_c CB^T V_c
+      theta_SC' = D1 / sqrt(1 - 2/3 D1 in) where the root's argument is positive, else 0
+      theta_LPT = D1 in - D2 m2v(phi), phi = IFFT[-in^/k^2]:  (d theta_LPT/d in)^T u = D1 u - D2 Poisson[G(u)],
+      G(u) = sum_ab FD_a FD_b (dm2v/dL_ab u)   (the 4th-order stencil is antisymmetric, so (FD_b FD_a)^T = FD_a FD_b)
+    `s_in` = deltaQ_factor * signal, the model's input."""
+    N = p.N1
+    s_in = s_in.reshape(N, N, N)
+    W = [0.5 * (np.roll(v.reshape(N, N, N), (-1, -1, -1), (0, 1, 2)) + v.reshape(N, N, N)) for v in V]   # CB^T
+    hW = grad_inv_lap_sum(p, W)
+    kern = alpt_kernel(p)
+    Ah = rfft(hW)
+    u_lpt = irfft(kern * Ah, N)
+    u_sc = irfft((1.0 - kern) * Ah, N)
+    arg = 1.0 - 2.0 / 3.0 * p.D1 * s_in
+    dsc = np.where(arg > 0.0, p.D1 / np.sqrt(np.where(arg > 0.0, arg, 1.0)), 0.0)
+    phi = poisson_solver(p, s_in)
+    dx, dy, dz = gradfindif(p, phi, 1), gradfindif(p, phi, 2), gradfindif(p, phi, 3)
+    Lxx, Lxy, Lxz = gradfindif(p, dx, 1), gradfindif(p, dx, 2), gradfindif(p, dx, 3)
+    Lyy, Lyz, Lzz = gradfindif(p, dy, 2), gradfindif(p, dy, 3), gradfindif(p, dz, 3)
+
+    def dd(a, b, f):
+        return gradfindif(p, gradfindif(p, f, a), b)
+
+    G = (dd(1, 1, (Lyy + Lzz) * u_lpt) + dd(2, 2, (Lxx + Lzz) * u_lpt) + dd(3, 3, (Lxx + Lyy) * u_lpt)
+         - 2.0 * dd(1, 2, Lxy * u_lpt) - 2.0 * dd(1, 3, Lxz * u_lpt) - 2.0 * dd(2, 3, Lyz * u_lpt))
+    return p.D1 * u_lpt - p.D2 * poisson_solver(p, G) + dsc * u_sc
 
 
 def gradient_psi(p: Params, signal, power, nobs, noise, window) -> np.ndarray:
