@@ -32,7 +32,8 @@ class BgpuParams(C.Structure):
         ("div_dH_by_N", C.c_int),
         ("device", C.c_int),
         ("delta_min", C.c_double),
-        ("reserved", C.c_int * 6),
+        ("N_bin", C.c_int),
+        ("reserved", C.c_int * 5),
     ]
 
 
@@ -59,6 +60,7 @@ SIGNATURES = {
     "bgpu_color_momenta": (C.c_int, [_h, _dp, _dp, _dp]),
     "bgpu_draw_momenta_device": (C.c_int, [_h, C.c_uint64, C.c_uint64, _dp]),
     "bgpu_draw_momenta_device_dev": (C.c_int, [_h, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bgpu_hamiltonian_mass_x": (C.c_int, [_h, _dp, _dp, _dp]),
     "bgpu_measure_spectrum": (C.c_int, [_h, _dp, C.c_uint64, _dp, _dp]),
     "bgpu_device_normals": (C.c_int, [_h, C.c_uint64, C.c_uint64, C.c_uint, C.c_size_t, C.c_size_t, _dp]),
     "bgpu_forward": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp]),

@@ -49,6 +49,7 @@ class Params:
     mass_factor: float = 1.0
     div_dH_by_N: bool = False
     delta_min: float = -0.999
+    N_bin: int = 200
     device: int = 0
 
     def to_c(self) -> BgpuParams:
@@ -121,10 +122,14 @@ class Chain:
         arrs = [None if a is None else _f64(a, self.N) for a in (mass_f, mass_r)]
         _lib.check(self.L.bgpu_set_mass(self._h, *[None if a is None else _dp(a) for a in arrs]))
 
-    def hamiltonian_mass(self):
-        """Hamiltonian_mass (HMC_mass.cc:315-368): returns (mass_f, mass_r)."""
+    def hamiltonian_mass(self, signal=None):
+        """Hamiltonian_mass (HMC_mass.cc:315-368): returns (mass_f, mass_r).  `signal` (hd->x) is needed by the
+        likelihood-force masses, mass_type 2 / 3."""
         mf, mr = np.zeros(self.N), np.zeros(self.N)
-        _lib.check(self.L.bgpu_hamiltonian_mass(self._h, _dp(mf), _dp(mr)))
+        if signal is None:
+            _lib.check(self.L.bgpu_hamiltonian_mass(self._h, _dp(mf), _dp(mr)))
+        else:
+            _lib.check(self.L.bgpu_hamiltonian_mass_x(self._h, _dp(_f64(signal, self.N)), _dp(mf), _dp(mr)))
         return mf.reshape(self.shape), mr.reshape(self.shape)
 
     # -- the seams S1..S5 -------------------------------------------------

@@ -60,6 +60,8 @@ struct bgpu_handle {
   // static inputs
   double *power = nullptr, *nobs = nullptr, *noise = nullptr, *window = nullptr;
   double *inv_power = nullptr;               // half grid, (V/N)/P
+  double *zero_half = nullptr;               // half grid of zeros: the prior switched off (mass types 2 / 3)
+  bool like_only = false;                    // gradient_device leaves the prior out (likelihood force)
   double *mass_f = nullptr, *mass_r = nullptr;
   double *inv_mass = nullptr;                // half grid, (V/N)/M_f
   // state / scratch (real)
@@ -162,8 +164,10 @@ void validate(const bgpu_params &p) {
               (p.calc_h == BGPU_CALC_H_EXACT && p.masskernel != 3),
           "Must use SPH mass kernel (masskernel = 3) when using likelihood_calc_h_SPH (calc_h = 2); the exact "
           "adjoint of the SPH kernel is calc_h = 2, of NGP/CIC/TSC calc_h = 4");
-  require(p.mass_type == 0 || p.mass_type == 1 || p.mass_type == 4,
-          "bgpu: mass_type must be 0, 1 or 4 on the GPU path (2/3/5/6/60 are cold set-up paths)");
+  require(p.mass_type >= 0 && p.mass_type <= 4,
+          "bgpu: mass_type must be 0 ... 4 on the GPU path (5/6/60, the first-order likelihood-force expansion, are O(N) FFTs of cold set-up)");
+  if (p.mass_type == 2 || p.mass_type == 3)
+    require(p.N_bin >= 1 && p.N_bin <= 2048, "bgpu: N_bin must be in [1, 2048] for mass_type 2 / 3");
   if (p.sfmodel != 1 && !p.rsd_model) {
     // Lag2Eul_non_zeldovich (2LPT + spherical collapse split at slength).  The reference has no adjoint
     // for it (HMC_models.cc:458): its gradients are calc_h 0 / 1 on the forward density.
@@ -305,6 +309,8 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   require(h->have_power && h->have_obs, "bgpu: bgpu_set_static (Power, nobs, noise, window) must be called first");
   const bgpu_params &p = h->p;
   const double inv_n = 1.0 / h->ncells;
+  // the prior's multiplier (V/N)/P -- or zeros when only the likelihood force is wanted (mass types 2 / 3)
+  const double *prior_mult = h->like_only ? h->zero_half : h->inv_power;
   h->fft.hooks = h->in_hooks;   // rows of the signal may still be arriving from the host
   r2c_plain(h, d_s, h->shat);
   h->fft.hooks = nullptr;
@@ -313,7 +319,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     // gradpsi = IFFT[(V/N)/P s^] + (s - nobs)/sigma^2
     KOp lop;
     lop.kind = K_MULREAL;
-    lop.real0 = h->inv_power;
+    lop.real0 = prior_mult;
     ROp sop;
     sop.kind = R_SCALE;
     sop.a = inv_n;
@@ -338,7 +344,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     // h = r (HMC_models.cc:413-415): gradpsi = IFFT[(V/N)/P s^] + norm * r
     KOp lop;
     lop.kind = K_MULREAL;
-    lop.real0 = h->inv_power;
+    lop.real0 = prior_mult;
     ROp sop;
     sop.kind = R_SCALE;
     sop.a = inv_n;
@@ -419,7 +425,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     // gradpsi = IFFT[(V/N)/P s^] + that
     KOp lop;
     lop.kind = K_MULREAL;
-    lop.real0 = h->inv_power;
+    lop.real0 = prior_mult;
     h->fft.c2r(h->shat, h->work, d_out, lop, unit);
     launch_axpy(d_out, h->tmp, 1.0, h->n, h->stream);
     if (h->out_hooks && h->out_hooks->after)
@@ -465,7 +471,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   sop.a = inv_n;
   if (h->G > 1 && (h->N >= 512 || h->fft.force_generic)) {
     // the TMA-staged x pass cannot hold both operand tiles at this size: combine in a pass of its own
-    launch_kfinal_combine(h->shat, h->inv_power, h->acc, h->acc, norm, h->N, h->nh, h->stream);
+    launch_kfinal_combine(h->shat, prior_mult, h->acc, h->acc, norm, h->N, h->nh, h->stream);
     h->fft.hooks = h->out_hooks;
     h->fft.c2r(h->acc, h->work, d_out, KOp{}, sop);
     h->fft.hooks = nullptr;
@@ -474,7 +480,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   KOp lop;
   lop.kind = K_FINAL;
   lop.a = norm;
-  lop.real0 = h->inv_power;
+  lop.real0 = prior_mult;
   lop.cplx0 = h->acc;
   h->fft.hooks = h->out_hooks;  // rows of the gradient leave for the host as the last z pass produces them
   h->fft.c2r(h->shat, h->work, d_out, lop, sop);
@@ -658,6 +664,7 @@ void bgpu_default_params(bgpu_params *p) {
   p->div_dH_by_N = 0;
   p->device = 0;
   p->delta_min = -0.999;  // data/input.par:51
+  p->N_bin = 200;         // data/input.par:129
 }
 
 static int create_impl(const bgpu_params *p, int rank, int nranks, const void *nccl_id, bgpu_handle **out) {
@@ -758,7 +765,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   h->fft.init(h->N, h->stream);
   h->kfac = 2. * M_PI / p->L1;                                      // scale_space.cpp:42
   h->normFS = (p->L1 * p->L2 * p->L3) / h->ncells;                  // HMC_help.cc:26
-  h->mass_fs = (p->mass_type == 1 || p->mass_type == 4);            // struct_hamil.h:276-296
+  h->mass_fs = (p->mass_type >= 1 && p->mass_type <= 4);            // struct_hamil.h:276-296
   h->mass_rs = (p->mass_type == 0);
 
   GridGeom &g = h->geom;
@@ -810,6 +817,10 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
 
   dalloc(h->power, h->n); dalloc(h->nobs, h->n); dalloc(h->noise, h->n); dalloc(h->window, h->n);
   dalloc(h->inv_power, h->nhp);
+  if (p->mass_type == 2 || p->mass_type == 3) {
+    dalloc(h->zero_half, h->nhp);
+    BGPU_CUDA(cudaMemsetAsync(h->zero_half, 0, h->nhp * sizeof(double), h->stream));
+  }
   dalloc(h->mass_f, h->n); dalloc(h->mass_r, h->n); dalloc(h->inv_mass, h->nhp);
   dalloc(h->sig, h->n); dalloc(h->mom, h->n); dalloc(h->grad, h->n);
   for (int c = 0; c < 3; ++c) dalloc(h->psi[c], h->n);
@@ -877,7 +888,7 @@ void bgpu_destroy(bgpu_handle *h) {
     } catch (...) {
     }
   }
-  double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->mass_f, h->mass_r, h->inv_mass,
+  double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->zero_half, h->mass_f, h->mass_r, h->inv_mass,
                      h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->tmp, h->phi1, h->xa, h->xb, h->xc,
                      h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
@@ -957,11 +968,56 @@ int bgpu_hamiltonian_mass(bgpu_handle *h, double *mass_f_out, double *mass_r_out
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
   require(h->have_power || h->p.mass_type == 0, "bgpu_hamiltonian_mass: Power must be set first");
+  require(h->p.mass_type != 2 && h->p.mass_type != 3,
+          "bgpu_hamiltonian_mass: mass types 2 / 3 depend on the signal; call bgpu_hamiltonian_mass_x");
   launch_mass(h->power, h->mass_f, h->mass_r, h->p.mass_type, h->p.mass_factor, h->n, h->stream);
   if (h->mass_fs) update_inverse(h, h->mass_f, h->inv_mass);
   h->have_mass = true;
   if (mass_f_out && h->mass_fs) d2h(h, mass_f_out, h->mass_f, h->n);
   if (mass_r_out && h->mass_rs) d2h(h, mass_r_out, h->mass_r, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+// Hamiltonian_mass for every supported type (HMC_mass.cc:315-368); types 2 / 3 measure the spectrum of the
+// likelihood force at `signal` (likeli_force_power, :39-51)
+int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f_out, double *mass_r_out) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  const bgpu_params &p = h->p;
+  if (p.mass_type != 2 && p.mass_type != 3) return bgpu_hamiltonian_mass(h, mass_f_out, mass_r_out);
+  require(h->G == 1, "bgpu_hamiltonian_mass_x: mass types 2 / 3 are not available on a slab-decomposed chain yet");
+  require(signal != nullptr && h->have_power && h->have_obs,
+          "bgpu_hamiltonian_mass_x: signal, Power and the observations are needed for mass types 2 / 3");
+  h2d(h, h->sig, signal, h->n);
+  h->like_only = true;
+  try {
+    gradient_device(h, h->sig, h->grad);   // likelihood_grad_log_like alone
+  } catch (...) {
+    h->like_only = false;
+    throw;
+  }
+  h->like_only = false;
+  r2c_plain(h, h->grad, h->work);
+  const int nb = p.N_bin;
+  double *acc = h->tmp;                     // [power | kmode | nmode]
+  launch_measure_spectrum(h->work, h->N, p.L1, nb, acc, h->stream);
+  double mean = 0.0;
+  if (p.mass_type == 3) {                   // Hamiltonian_mass_mean_likeli_force, HMC_mass.cc:86-114
+    std::vector<double> spec(2 * (size_t)nb);
+    d2h(h, spec.data(), acc, 2 * (size_t)nb);
+    sync(h);
+    const double kfac = 2. * M_PI / p.L1, kny = kfac * (double)(h->N / 2);
+    const double dk = std::sqrt((kny * kny + kny * kny) + kny * kny) / (double)nb;
+    double fm = 0.0, kv = 0.0;
+    for (int i = 0; i < nb; ++i) fm += 4. * M_PI * spec[nb + i] * spec[nb + i] * dk * spec[i];
+    for (int i = 0; i < nb; ++i) kv += 4. * M_PI * spec[nb + i] * spec[nb + i] * dk;
+    mean = fm / kv;
+  }
+  launch_force_mass(h->power, acc, h->mass_f, h->N, p.L1, nb, p.mass_type, mean, p.mass_factor, h->stream);
+  update_inverse(h, h->mass_f, h->inv_mass);
+  h->have_mass = true;
+  if (mass_f_out) d2h(h, mass_f_out, h->mass_f, h->n);
   sync(h);
   BGPU_CATCH
 }

@@ -79,7 +79,7 @@ bool same_params(const bgpu_params &a, const bgpu_params &b) {
          a.slength == b.slength && a.particle_kernel_h_rel == b.particle_kernel_h_rel && a.ascale == b.ascale &&
          a.OM == b.OM && a.OL == b.OL && a.rho_c == b.rho_c && a.biasP == b.biasP && a.biasE == b.biasE &&
          a.deltaQ_factor == b.deltaQ_factor && a.correct_delta == b.correct_delta &&
-         a.mass_factor == b.mass_factor && a.delta_min == b.delta_min;
+         a.mass_factor == b.mass_factor && a.delta_min == b.delta_min && a.N_bin == b.N_bin;
 }
 
 bgpu_params params_from(struct HAMIL_DATA *hd, struct DATA *data) {
@@ -109,6 +109,7 @@ bgpu_params params_from(struct HAMIL_DATA *hd, struct DATA *data) {
   p.mass_factor = n->mass_factor;
   p.div_dH_by_N = n->div_dH_by_N;
   p.delta_min = hd->delta_min;
+  p.N_bin = (int)n->N_bin;
   const char *dev = std::getenv("BARCODE_GPU_DEVICE");
   p.device = dev ? std::atoi(dev) : 0;
   return p;

@@ -852,6 +852,41 @@ __global__ void mass_kernel(const double *__restrict__ power, double *__restrict
   }
 }
 
+// mass types 2 / 3 (HMC_mass.cc:52-160): mass_f = factor (2/P + sqrt(F/P)) with F = the likelihood-force spectrum
+// at the cell's |k| bin (type 2; 0 at k = 0, and at the one corner mode whose bin index equals N_bin, where the
+// reference reads past its array) or its mean over k-space shells (type 3, `mean`)
+__global__ void force_mass_kernel(const double *__restrict__ power, const double *__restrict__ force_spec,
+                                  double *__restrict__ mass_f, int N, double kfac, double dk, int nbin, int type,
+                                  double mean, double factor) {
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const double P = power[idx];
+  const double invP = P > 0.0 ? 1. / P : 0.;
+  double F = mean;
+  if (type == 2) {
+    const int sh = 31 - __clz(N);
+    const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
+    auto kv = [&](int m) { return (m <= N / 2) ? kfac * (double)m : -kfac * (double)(N - m); };
+    const double kx = kv(i), ky = kv(j), kz = kv(k);
+    const double kr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)), __dmul_rn(kz, kz)));
+    const unsigned long long b = (unsigned long long)__ddiv_rn(kr, dk);
+    F = (kr > 0. && b < (unsigned long long)nbin) ? force_spec[b] : 0.0;
+  }
+  mass_f[idx] = factor * (1.0 * (2 * invP + sqrt(invP * F)));
+}
+
+void launch_force_mass(const double *power, const double *force_spec, double *mass_f, int N, double L, int nbin, int type,
+                       double mean, double factor, cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  const double kfac = 2.0 * M_PI / L;
+  const double kny = kfac * (double)(N / 2);
+  const double dk = std::sqrt((kny * kny + kny * kny) + kny * kny) / (double)nbin;
+  const size_t n = (size_t)N * N * N;
+  force_mass_kernel<<<blocks_for(n, 256), 256, 0, st>>>(power, force_spec, mass_f, N, kfac, dk, nbin, type, mean, factor);
+  BGPU_LAUNCHED(1);
+}
+
 void launch_mass(const double *power, double *mass_f, double *mass_r, int mass_type, double mass_factor, size_t n,
                  cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);

@@ -61,6 +61,10 @@ void launch_colour_white_rows(double2 *W, const double *inv_half, int N, size_t 
 // measure_spectrum (field_statistics.cpp:20-90) of a half-complex transform F; acc = [power | kmode | nmode] (3 nbin, device)
 void launch_measure_spectrum(const double2 *F, int N, double L, int nbin, double *acc, cudaStream_t st);
 
+// mass types 2 / 3: factor (2/P + sqrt(F/P)), F = force_spec[bin(|k|)] (type 2) or `mean` (type 3)
+void launch_force_mass(const double *power, const double *force_spec, double *mass_f, int N, double L, int nbin, int type,
+                       double mean, double factor, cudaStream_t st);
+
 // particle scatter: Psi -> rho (zeroed here); optional positions out
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
                     double *posx, double *posy, double *posz, cudaStream_t st);

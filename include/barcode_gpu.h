@@ -57,7 +57,8 @@ typedef struct bgpu_params {
   int rsd_model;
   int calc_h;                /* 0, 1, 2 (SPH adjoint, needs masskernel 3) as the reference; BGPU_CALC_H_EXACT =
                               * exact adjoint of NGP / CIC / TSC under the Zel'dovich or the 2LPT/ALPT model */
-  int mass_type;             /* 0 ones (R), 1 1/P (FS), 4 P (FS) */
+  int mass_type;             /* 0 ones (R), 1 1/P (FS), 4 P (FS); 2 / 3: 1/P + likelihood-force spectrum / its mean (FS,
+                              * HMC_mass.cc:39-160; bgpu_hamiltonian_mass_x) */
   double D1, D2, ascale, OM, OL;
   double particle_kernel_h_rel; /* SPH scale length in cells (input.par particle_kernel_h_rel); masskernel 3 */
   double slength;            /* ALPT smoothing radius [Mpc/h] (input.par slength -> n->kth, struct_hamil.h:259); sfmodel != 1 */
@@ -68,7 +69,8 @@ typedef struct bgpu_params {
   int div_dH_by_N;
   int device;                /* CUDA device ordinal */
   double delta_min;          /* log-normal likelihood: density floor (input.par delta_min, default -0.999) */
-  int reserved[6];
+  int N_bin;                 /* bins of measure_spectrum (input.par N_bin, default 200); mass types 2 / 3 */
+  int reserved[5];
 } bgpu_params;
 
 /* the reference's defaults (data/input.par, init_par.cc:574-578) */
@@ -102,6 +104,9 @@ int bgpu_set_static(bgpu_handle *h, const double *Power, const double *nobs, con
 int bgpu_set_mass(bgpu_handle *h, const double *mass_f, const double *mass_r);
 /* S6 Hamiltonian_mass (HMC_mass.cc:315-368), types 0/1/4; outputs may be NULL */
 int bgpu_hamiltonian_mass(bgpu_handle *h, double *mass_f_out, double *mass_r_out);
+/* the same for every supported mass type; types 2 / 3 measure the spectrum of the likelihood force at `signal`
+ * (hd->x; likeli_force_power, HMC_mass.cc:39-51) */
+int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f_out, double *mass_r_out);
 
 /* S1 gradient_psi (HMC.cc:146-206): writes hd->gradpsi */
 int bgpu_gradient_psi(bgpu_handle *h, const double *signal, double *gradpsi);

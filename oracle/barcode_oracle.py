@@ -57,6 +57,7 @@ class Params:
     biasE: float = 1.0
     div_dH_by_N: bool = False
     delta_min: float = -0.999  # log-normal density floor (data/input.par:51)
+    N_bin: int = 200           # measure_spectrum bins (data/input.par:129)
 
     @property
     def N(self):
@@ -735,8 +736,9 @@ def psi(p: Params, signal, power, nobs, noise, window):
 # --------------------------------------------------------------------------
 # A16/A17: mass, kinetic energy, leapfrog
 # --------------------------------------------------------------------------
-def hamiltonian_mass(p: Params, power):
-    """HMC_mass.cc:315-368 types 0/1/4: (mass_f, mass_r)."""
+def hamiltonian_mass(p: Params, power, signal=None, nobs=None, noise=None, window=None):
+    """HMC_mass.cc:315-368 types 0/1/4, and 2/3 (the likelihood-force masses, :39-160, which need the signal and
+    the observations): (mass_f, mass_r)."""
     N = p.N1
     mass_f = np.zeros((N, N, N))
     mass_r = np.zeros((N, N, N))
@@ -747,6 +749,21 @@ def hamiltonian_mass(p: Params, power):
         mass_f = np.where(P > 0.0, 1.0 / np.where(P > 0.0, P, 1.0), 0.0)  # inv_ps, HMC_mass.cc
     elif p.mass_type == 4:
         mass_f = power.reshape(N, N, N).copy()
+    elif p.mass_type in (2, 3):
+        force = grad_log_like(p, signal.reshape(N, N, N), nobs, noise, window)[0]     # likeli_force_power, :39-51
+        kmode, fspec = measure_spectrum(p, force, p.N_bin)
+        P = power.reshape(N, N, N)
+        invP = np.where(P > 0.0, 1.0 / np.where(P > 0.0, P, 1.0), 0.0)
+        k = calc_ki(N, p.L1)
+        dk = np.sqrt(3.0 * k[N // 2] * k[N // 2]) / float(p.N_bin)
+        if p.mass_type == 2:   # Hamiltonian_mass_likeli_force, :54-83
+            kr = np.sqrt((k[:, None, None] ** 2 + k[None, :, None] ** 2) + k[None, None, :] ** 2)
+            b = (kr / dk).astype(np.int64)
+            # the corner mode's bin index equals N_bin: the reference reads one past its array there; 0 here
+            F = np.where((kr > 0.0) & (b < p.N_bin), fspec[np.minimum(b, p.N_bin - 1)], 0.0)
+        else:                  # Hamiltonian_mass_mean_likeli_force, :86-114
+            F = np.sum(4.0 * np.pi * kmode * kmode * dk * fspec) / np.sum(4.0 * np.pi * kmode * kmode * dk)
+        mass_f = 2.0 * invP + np.sqrt(invP * F)
     else:
         raise NotImplementedError("mass_type %d is off the hot path (SURVEY section 2 row 5)" % p.mass_type)
     if p.mass_fs:

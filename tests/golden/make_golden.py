@@ -60,6 +60,9 @@ CASES = {
                                  delta_min=-0.9, eps_fac=1e-4),
     # Gaussian random field "likelihood" (gaussian_random_field.cpp, HMC.cc:159-160): no structure formation
     "grf": dict(masskernel=1, likelihood=3, rsd_model=False, calc_h=0, mass_type=1),
+    # likelihood-force Hamiltonian masses (HMC_mass.cc:39-160): 1/P + force spectrum (2), + its mean (3)
+    "za_cic_gauss_mass2": dict(masskernel=1, likelihood=1, rsd_model=False, calc_h=0, mass_type=2, N_bin=20),
+    "za_tsc_gauss_rsd_mass3": dict(masskernel=2, likelihood=1, rsd_model=True, calc_h=0, mass_type=3, N_bin=20),
     "alpt_tsc_poisson_h1": dict(masskernel=2, likelihood=0, rsd_model=False, calc_h=1, mass_type=1, sfmodel=3,
                                 slength=6.0, deltaQ_factor=0.95),
 }

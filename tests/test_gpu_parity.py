@@ -23,7 +23,7 @@ def make_chain(cfg, **over):
               sfmodel=cfg.get("sfmodel", 1), deltaQ_factor=cfg.get("deltaQ_factor", 1.0),
               mass_factor=cfg.get("mass_factor", 1.0), slength=cfg.get("slength", 4.0),
               particle_kernel_h_rel=cfg.get("particle_kernel_h_rel", 1.0),
-              delta_min=cfg.get("delta_min", -0.999))
+              delta_min=cfg.get("delta_min", -0.999), N_bin=cfg.get("N_bin", 200))
     kw.update(over)
     return Chain(Params(**kw))
 
@@ -35,7 +35,7 @@ def oracle_params(cfg, **over):
               deltaQ_factor=cfg.get("deltaQ_factor", 1.0), mass_factor=cfg.get("mass_factor", 1.0),
               sfmodel=cfg.get("sfmodel", 1), slength=cfg.get("slength", 4.0),
               particle_kernel_h_rel=cfg.get("particle_kernel_h_rel", 1.0),
-              delta_min=cfg.get("delta_min", -0.999))
+              delta_min=cfg.get("delta_min", -0.999), N_bin=cfg.get("N_bin", 200))
     kw.update(over)
     return bo.Params(**kw)
 
@@ -161,6 +161,13 @@ def test_kinetic_term(case):
 
 def test_hamiltonian_mass(case):
     with make_chain(case["cfg"]) as ch:
+        if case["cfg"]["mass_type"] in (2, 3):
+            # likelihood-force masses (HMC_mass.cc:39-160): gradient of the likelihood at the signal, its binned
+            # spectrum, 2/P + sqrt(F/P) -- equal to the order of the spectrum's sums
+            ch.set_static(Power=case["Power"], nobs=case["nobs"], noise=case["noise"], window=case["window"])
+            mf, mr = ch.hamiltonian_mass(case["signal"])
+            assert rel_l2(mf, case["mass_f"]) < TOL
+            return
         ch.set_static(Power=case["Power"])
         mf, mr = ch.hamiltonian_mass()
     assert np.array_equal(mf.ravel(), case["mass_f"]) and np.array_equal(mr.ravel(), case["mass_r"])
