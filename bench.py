@@ -269,8 +269,11 @@ def run_ours(args):
     # one leapfrog step = kick, M^-1 p, drift, gradient, kick (HMC.cc:289-352)
     ch.hamiltonian_mass()
     d_s2, d_p2 = d_s.clone(), d_p.clone()
-    ms_leap = timed(lambda: ch.leapfrog_dev(d_s2.data_ptr(), d_p2.data_ptr(), 1, 1e-3), max(2, args.steps // 2), 1)
-    leap_steps = max(2, args.steps // 2)
+    # a trajectory of Neps = 8 steps (9 gradient evaluations, 8 M^-1 p): steps / s = 8 / time per call
+    NEPS = 8
+    leap_calls = max(2, args.steps // 4)
+    ms_leap = timed(lambda: ch.leapfrog_dev(d_s2.data_ptr(), d_p2.data_ptr(), NEPS, 1e-3), leap_calls, 1)
+    leap_steps = leap_calls * NEPS
     # momentum draw on the device (bgpu_draw_momenta_device: Philox normals -> r2c -> colour -> c2r); the reference
     # draws 2 N^3 GSL Gaussians serially on the host for every candidate (random.cpp:99-101)
     draw_i = [0]
@@ -278,7 +281,8 @@ def run_ours(args):
     def draw():
         ch.draw_momenta_device_dev(1, draw_i[0], d_p2.data_ptr())
         draw_i[0] += 1
-    ms_draw = timed(draw, max(2, args.steps // 2), 1)
+    draw_calls = max(2, args.steps // 2)
+    ms_draw = timed(draw, draw_calls, 1)
 
     # roofline leg: the same K steps again with CUDA events around every kernel launch
     bc.profile_begin()
@@ -403,7 +407,7 @@ def run_ours(args):
             "also": {
                 f"gradient_evals_per_s_calc_h_{other_h}": world * args.steps / (ms_other * 1e-3),
                 "leapfrog_steps_per_s": world * leap_steps / (ms_leap * 1e-3),
-                "device_momentum_draw_ms": ms_draw / leap_steps,
+                "device_momentum_draw_ms": ms_draw / draw_calls,
                 "kernel_launches_total": int(bc.kernel_launches() - launches0),
             },
         }

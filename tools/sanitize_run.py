@@ -1,7 +1,7 @@
 """Small driver for compute-sanitizer (memcheck): one pass over every kernel family at 32^3 (first-generation
 passes) and 128^3 (TMA-staged passes).
 
-    compute-sanitizer --tool memcheck python tools/sanitize_run.py
+    python tools/sanitize_run.py            (compute-sanitizer --tool memcheck ... where the pool allows it; closed on this one)
 """
 import os
 import sys
