@@ -83,6 +83,7 @@ struct bgpu_handle {
   double *rho_ext = nullptr;    // [(Ns + 2 Hmax)][N][N]; delta points at the owned planes inside it
   double *halo_recv = nullptr;  // 2 * Hmax * N^2
   double *phi1 = nullptr, *xa = nullptr, *xb = nullptr, *xc = nullptr;  // exact 2LPT/ALPT adjoint: phi^(1) + 3 scratch arrays
+  double *fext = nullptr;       // log-normal + calc_h 0 on a slab: f(delta_x) with 2 halo planes each side
   double *resid_ext = nullptr;  // exact adjoint on a slab: the residual with H halo planes each side
   int H_cur = 0;                // halo width of the evaluation in flight
   double2 *sendbuf = nullptr, *recvbuf = nullptr;
@@ -358,6 +359,33 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   if (p.calc_h == 0) {
     // likelihood_calc_h (HMC_models_testing.cpp:25-50): g_c = r * d_c(delta)
     if (p.likelihood == 1) r2c_plain(h, h->delta, h->dhat);  // gradfft shares one forward transform
+    // gradfindif of delta_x (Poisson, poissonian.cpp:37-42) or of f(delta_x) (log-normal,
+    // lognormal_independent.cpp:81-91).  On a slab the 4th-order stencil reaches 2 planes into the x neighbours:
+    // their delta goes into the halo planes of the density tile (free once the deposits there have been added).
+    const double *fd_field = h->delta;
+    int fd_xo = 0;
+    if (p.likelihood != 1) {
+      const size_t plane = (size_t)h->N * h->N;
+      if (h->G > 1) {
+        constexpr int XH = 2;
+        const int lo = (h->rank + h->G - 1) % h->G, hi = (h->rank + 1) % h->G;
+        double *own = h->delta;
+        ProfScope prof(KK_HALO, h->stream);
+        h->comm->exchange2(own, lo, own + (size_t)(h->Ns - XH) * plane, hi, own + (size_t)h->Ns * plane, hi,
+                           own - (size_t)XH * plane, lo, XH * plane, h->stream);
+        fd_xo = XH;
+      }
+      if (p.likelihood == 2) {  // f goes to Psi_x (free once the density exists) / to its own halo-extended buffer
+        if (h->G == 1) {
+          launch_lognormal_f(h->delta, h->psi[0], h->n, p.rho_c, p.delta_min, h->stream);
+          fd_field = h->psi[0];
+        } else {
+          launch_lognormal_f(h->delta - (size_t)fd_xo * plane, h->fext, h->n + (size_t)2 * fd_xo * plane, p.rho_c,
+                             p.delta_min, h->stream);
+          fd_field = h->fext + (size_t)fd_xo * plane;
+        }
+      }
+    }
     for (int c = 0; c < 3; ++c) {
       if (p.likelihood == 1) {
         KOp lop;
@@ -370,11 +398,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
         sop.aux = h->resid;
         h->fft.c2r(h->dhat, h->work, h->tmp, lop, sop);
       } else {
-        // gradfindif of delta_x (Poisson, poissonian.cpp:37-42) or of f(delta_x) (log-normal,
-        // lognormal_independent.cpp:81-91; f goes to Psi_x, which is free once the density exists)
-        if (p.likelihood == 2 && c == 0)
-          launch_lognormal_f(h->delta, h->psi[0], h->n, p.rho_c, p.delta_min, h->stream);
-        launch_findif_product(p.likelihood == 2 ? h->psi[0] : h->delta, h->resid, h->tmp, h->N, p.L1, c, h->stream);
+        launch_findif_product(fd_field, h->resid, h->tmp, h->N, h->Ns, fd_xo, p.L1, c, h->stream);
       }
       ROp lop2;
       lop2.kind = R_LOAD;
@@ -687,8 +711,6 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
     require(p->sfmodel == 1 || p->rsd_model || p->N1 / nranks >= 8,
             "bgpu_slab_create: the 2LPT/ALPT model needs at least 8 planes per rank (4-plane stencil halo)");
-    require(!(p->calc_h == 0 && (p->likelihood == 0 || p->likelihood == 2)),
-            "bgpu_slab_create: Poisson / log-normal + calc_h = 0 differentiate by finite differences across slabs; not built yet");
     require(nccl_id != nullptr, "bgpu_slab_create: a NCCL unique id is required");
   }
   int ndev = 0;
@@ -723,6 +745,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     h->Hmax = h->Ns < 24 ? h->Ns : 24;
     dalloc(h->halo_recv, (size_t)2 * h->Hmax * h->N * h->N);
     if (p->calc_h == BGPU_CALC_H_EXACT) dalloc(h->resid_ext, (size_t)(h->Ns + 2 * h->Hmax) * h->N * h->N);
+    if (p->calc_h == 0 && p->likelihood == 2) dalloc(h->fext, (size_t)(h->Ns + 4) * h->N * h->N);
     BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->dflag), sizeof(int)));
     BGPU_CUDA(cudaMemsetAsync(h->dflag, 0, sizeof(int), h->stream));
     BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hflag), sizeof(int)));
@@ -889,7 +912,7 @@ void bgpu_destroy(bgpu_handle *h) {
     }
   }
   double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->zero_half, h->mass_f, h->mass_r, h->inv_mass,
-                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->tmp, h->phi1, h->xa, h->xb, h->xc,
+                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->fext, h->tmp, h->phi1, h->xa, h->xb, h->xc,
                      h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
     if (q) cudaFree(q);
@@ -986,7 +1009,6 @@ int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f
   BGPU_CUDA(cudaSetDevice(h->p.device));
   const bgpu_params &p = h->p;
   if (p.mass_type != 2 && p.mass_type != 3) return bgpu_hamiltonian_mass(h, mass_f_out, mass_r_out);
-  require(h->G == 1, "bgpu_hamiltonian_mass_x: mass types 2 / 3 are not available on a slab-decomposed chain yet");
   require(signal != nullptr && h->have_power && h->have_obs,
           "bgpu_hamiltonian_mass_x: signal, Power and the observations are needed for mass types 2 / 3");
   h2d(h, h->sig, signal, h->n);
@@ -1001,7 +1023,9 @@ int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f
   r2c_plain(h, h->grad, h->work);
   const int nb = p.N_bin;
   double *acc = h->tmp;                     // [power | kmode | nmode]
-  launch_measure_spectrum(h->work, h->N, p.L1, nb, acc, h->stream);
+  launch_measure_spectrum_bin(h->work, h->N, h->Ns, h->G > 1 ? h->rank * h->Ns : 0, p.L1, nb, acc, h->stream);
+  if (h->G > 1) h->comm->all_reduce_sum(acc, 3 * (size_t)nb, h->stream);
+  launch_measure_spectrum_finish(acc, h->N, p.L1, nb, h->stream);
   double mean = 0.0;
   if (p.mass_type == 3) {                   // Hamiltonian_mass_mean_likeli_force, HMC_mass.cc:86-114
     std::vector<double> spec(2 * (size_t)nb);
@@ -1014,7 +1038,7 @@ int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f
     for (int i = 0; i < nb; ++i) kv += 4. * M_PI * spec[nb + i] * spec[nb + i] * dk;
     mean = fm / kv;
   }
-  launch_force_mass(h->power, acc, h->mass_f, h->N, p.L1, nb, p.mass_type, mean, p.mass_factor, h->stream);
+  launch_force_mass(h->power, acc, h->mass_f, h->N, h->Ns, h->x0, p.L1, nb, p.mass_type, mean, p.mass_factor, h->stream);
   update_inverse(h, h->mass_f, h->inv_mass);
   h->have_mass = true;
   if (mass_f_out) d2h(h, mass_f_out, h->mass_f, h->n);
@@ -1250,12 +1274,13 @@ int bgpu_device_normals(bgpu_handle *h, uint64_t seed, uint64_t draw_index, unsi
 int bgpu_measure_spectrum(bgpu_handle *h, const double *signal, uint64_t N_bin, double *kmode, double *power) {
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
-  require(h->G == 1, "bgpu_measure_spectrum: not available on a slab-decomposed chain yet");
   require(N_bin >= 1 && N_bin <= 2048 && 3 * N_bin <= h->n, "bgpu_measure_spectrum: N_bin must be in [1, 2048]");
   h2d(h, h->tmp, signal, h->n);
   r2c_plain(h, h->tmp, h->work);
   double *acc = h->grad;  // scratch: 3 * N_bin doubles
-  launch_measure_spectrum(h->work, h->N, h->p.L1, (int)N_bin, acc, h->stream);
+  launch_measure_spectrum_bin(h->work, h->N, h->Ns, h->G > 1 ? h->rank * h->Ns : 0, h->p.L1, (int)N_bin, acc, h->stream);
+  if (h->G > 1) h->comm->all_reduce_sum(acc, 3 * (size_t)N_bin, h->stream);
+  launch_measure_spectrum_finish(acc, h->N, h->p.L1, (int)N_bin, h->stream);
   d2h(h, power, acc, N_bin);
   d2h(h, kmode, acc + N_bin, N_bin);
   sync(h);

@@ -583,29 +583,36 @@ void launch_gather_adjoint_to(const GridGeom &g, const double *psix, const doubl
 // ---------------------------------------------------------------------------
 // K5: r * d_c(delta), 4th-order central difference, gradient.cpp:81-153
 // ---------------------------------------------------------------------------
+// Slab: `in` points at the first OWNED plane of an array that carries xo >= 2 valid planes of the x neighbours on
+// each side (no wrap along x); a cube passes Ns = N, xo = 0 and wraps.
 __global__ void findif_product_kernel(const double *__restrict__ in, const double *__restrict__ resid,
-                                      double *__restrict__ out, int N, double fac, int comp) {
-  const size_t n = (size_t)N * N * N;
+                                      double *__restrict__ out, int N, int Ns, int xo, double fac, int comp) {
+  const size_t n = (size_t)Ns * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int sh = 31 - __clz(N);  // N is a power of two
   int c[3] = {(int)(idx >> (2 * sh)), (int)((idx >> sh) & (size_t)(N - 1)), (int)(idx & (size_t)(N - 1))};
-  const size_t stride = comp == 0 ? (size_t)N * N : (comp == 1 ? (size_t)N : 1);
+  const ptrdiff_t stride = comp == 0 ? (ptrdiff_t)N * N : (comp == 1 ? (ptrdiff_t)N : 1);
   const int ii = c[comp];
-  const size_t base = idx - (size_t)ii * stride;
-  const int r = ii + 1 >= N ? ii + 1 - N : ii + 1, rr = ii + 2 >= N ? ii + 2 - N : ii + 2;
-  const int l = ii - 1 < 0 ? ii - 1 + N : ii - 1, ll = ii - 2 < 0 ? ii - 2 + N : ii - 2;
+  const ptrdiff_t base = (ptrdiff_t)idx - (ptrdiff_t)ii * stride;
+  int r = ii + 1, rr = ii + 2, l = ii - 1, ll = ii - 2;
+  if (!(comp == 0 && xo)) {  // periodic along this axis
+    r = r >= N ? r - N : r;
+    rr = rr >= N ? rr - N : rr;
+    l = l < 0 ? l + N : l;
+    ll = ll < 0 ? ll + N : ll;
+  }
   const double g = -(fac * ((4.0 / 3) * (in[base + l * stride] - in[base + r * stride]) -
                             (1.0 / 6) * (in[base + ll * stride] - in[base + rr * stride])));
   out[idx] = resid[idx] * g;
 }
 
-void launch_findif_product(const double *delta, const double *resid, double *out, int N, double L, int comp,
-                           cudaStream_t st) {
+void launch_findif_product(const double *delta, const double *resid, double *out, int N, int Ns, int xo, double L,
+                           int comp, cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);
-  const size_t n = (size_t)N * N * N;
+  const size_t n = (size_t)Ns * N * N;
   const double fac = (double)N / (2. * L);
-  findif_product_kernel<<<blocks_for(n, 256), 256, 0, st>>>(delta, resid, out, N, fac, comp);
+  findif_product_kernel<<<blocks_for(n, 256), 256, 0, st>>>(delta, resid, out, N, Ns, xo, fac, comp);
   BGPU_LAUNCHED(1);
 }
 
@@ -709,17 +716,17 @@ void launch_colour_white(double2 *W, const double *spec_full, int N, double c2, 
 // twice where its mirror (N-i, N-j, N-k) is not in the half array (0 < k < N/2): same |k|, same |F|^2.
 // acc = [power | kmode | nmode], 3 * nbin doubles, zeroed by the launcher.
 // ---------------------------------------------------------------------------
-__global__ void spectrum_bin_kernel(const double2 *__restrict__ F, int N, double kfac, double dk, int nbin,
+__global__ void spectrum_bin_kernel(const double2 *__restrict__ F, int N, int Ns, int y0, double kfac, double dk, int nbin,
                                     double *__restrict__ acc) {
   extern __shared__ double sh_acc[];  // 3 * nbin
   for (int b = threadIdx.x; b < 3 * nbin; b += blockDim.x) sh_acc[b] = 0.0;
   __syncthreads();
   const int nzh = N / 2 + 1;
-  const size_t n = (size_t)N * N * nzh;
+  const size_t n = (size_t)N * Ns * nzh;   // a cube: Ns = N, y0 = 0; a slab: the transposed layout [x][y_local][z]
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(idx % nzh);
-    const int j = (int)((idx / nzh) % N);
-    const int i = (int)(idx / ((size_t)nzh * N));
+    const int j = y0 + (int)((idx / nzh) % Ns);
+    const int i = (int)(idx / ((size_t)nzh * Ns));
     auto kv = [&](int m) { return (m <= N / 2) ? kfac * (double)m : -kfac * (double)(N - m); };  // scale_space.cpp:41-51
     const double kx = kv(i), ky = kv(j), kz = kv(k);
     // k_squared (scale_space.cpp:16-39) without FMA contraction: modes that sit exactly on a bin edge
@@ -749,18 +756,24 @@ __global__ void spectrum_finish_kernel(double *__restrict__ acc, int nbin, doubl
   }
 }
 
-void launch_measure_spectrum(const double2 *F, int N, double L, int nbin, double *acc, cudaStream_t st) {
+// bin this rank's modes into acc (zeroed here); a slab all-reduces acc over the ranks before the finish
+void launch_measure_spectrum_bin(const double2 *F, int N, int Ns, int y0, double L, int nbin, double *acc,
+                                 cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);
   const double kfac = 2.0 * M_PI / L;
   const double kny = kfac * (double)(N / 2);
   const double dk = std::sqrt((kny * kny + kny * kny) + kny * kny) / (double)nbin;   // kmax = |k| of (N/2, N/2, N/2)
   BGPU_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * nbin, st));
-  const size_t n = (size_t)N * N * (N / 2 + 1);
+  const size_t n = (size_t)N * Ns * (N / 2 + 1);
   const int blocks = (int)(blocks_for(n, 256) < 1184u ? blocks_for(n, 256) : 1184u);
-  spectrum_bin_kernel<<<blocks, 256, sizeof(double) * 3 * nbin, st>>>(F, N, kfac, dk, nbin, acc);
+  spectrum_bin_kernel<<<blocks, 256, sizeof(double) * 3 * nbin, st>>>(F, N, Ns, y0, kfac, dk, nbin, acc);
+  BGPU_LAUNCHED(1);
+}
+
+void launch_measure_spectrum_finish(double *acc, int N, double L, int nbin, cudaStream_t st) {
   const double V = L * L * L, nn = (double)N * N * N;
   spectrum_finish_kernel<<<(nbin + 255) / 256, 256, 0, st>>>(acc, nbin, V / nn / nn);  // FOURIER_DEF_2 norm
-  BGPU_LAUNCHED(2);
+  BGPU_LAUNCHED(1);
 }
 
 // ---------------------------------------------------------------------------
@@ -856,9 +869,9 @@ __global__ void mass_kernel(const double *__restrict__ power, double *__restrict
 // at the cell's |k| bin (type 2; 0 at k = 0, and at the one corner mode whose bin index equals N_bin, where the
 // reference reads past its array) or its mean over k-space shells (type 3, `mean`)
 __global__ void force_mass_kernel(const double *__restrict__ power, const double *__restrict__ force_spec,
-                                  double *__restrict__ mass_f, int N, double kfac, double dk, int nbin, int type,
-                                  double mean, double factor) {
-  const size_t n = (size_t)N * N * N;
+                                  double *__restrict__ mass_f, int N, int Ns, int x0, double kfac, double dk, int nbin,
+                                  int type, double mean, double factor) {
+  const size_t n = (size_t)Ns * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const double P = power[idx];
@@ -866,7 +879,7 @@ __global__ void force_mass_kernel(const double *__restrict__ power, const double
   double F = mean;
   if (type == 2) {
     const int sh = 31 - __clz(N);
-    const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
+    const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = x0 + (int)(idx >> (2 * sh));
     auto kv = [&](int m) { return (m <= N / 2) ? kfac * (double)m : -kfac * (double)(N - m); };
     const double kx = kv(i), ky = kv(j), kz = kv(k);
     const double kr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)), __dmul_rn(kz, kz)));
@@ -876,14 +889,15 @@ __global__ void force_mass_kernel(const double *__restrict__ power, const double
   mass_f[idx] = factor * (1.0 * (2 * invP + sqrt(invP * F)));
 }
 
-void launch_force_mass(const double *power, const double *force_spec, double *mass_f, int N, double L, int nbin, int type,
-                       double mean, double factor, cudaStream_t st) {
+void launch_force_mass(const double *power, const double *force_spec, double *mass_f, int N, int Ns, int x0, double L,
+                       int nbin, int type, double mean, double factor, cudaStream_t st) {
   ProfScope prof(KK_STREAM, st);
   const double kfac = 2.0 * M_PI / L;
   const double kny = kfac * (double)(N / 2);
   const double dk = std::sqrt((kny * kny + kny * kny) + kny * kny) / (double)nbin;
-  const size_t n = (size_t)N * N * N;
-  force_mass_kernel<<<blocks_for(n, 256), 256, 0, st>>>(power, force_spec, mass_f, N, kfac, dk, nbin, type, mean, factor);
+  const size_t n = (size_t)Ns * N * N;
+  force_mass_kernel<<<blocks_for(n, 256), 256, 0, st>>>(power, force_spec, mass_f, N, Ns, x0, kfac, dk, nbin, type, mean,
+                                                        factor);
   BGPU_LAUNCHED(1);
 }
 

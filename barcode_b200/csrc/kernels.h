@@ -59,11 +59,14 @@ void launch_colour_white(double2 *W, const double *spec_full, int N, double c2, 
 void launch_colour_white_rows(double2 *W, const double *inv_half, int N, size_t n_half, cudaStream_t st);
 
 // measure_spectrum (field_statistics.cpp:20-90) of a half-complex transform F; acc = [power | kmode | nmode] (3 nbin, device)
-void launch_measure_spectrum(const double2 *F, int N, double L, int nbin, double *acc, cudaStream_t st);
+// (two steps: bin this rank's modes of the [x][Ns][N/2+1] layout, y = y0 + y_local; then -- after a slab has
+// all-reduced acc -- normalise)
+void launch_measure_spectrum_bin(const double2 *F, int N, int Ns, int y0, double L, int nbin, double *acc, cudaStream_t st);
+void launch_measure_spectrum_finish(double *acc, int N, double L, int nbin, cudaStream_t st);
 
 // mass types 2 / 3: factor (2/P + sqrt(F/P)), F = force_spec[bin(|k|)] (type 2) or `mean` (type 3)
-void launch_force_mass(const double *power, const double *force_spec, double *mass_f, int N, double L, int nbin, int type,
-                       double mean, double factor, cudaStream_t st);
+void launch_force_mass(const double *power, const double *force_spec, double *mass_f, int N, int Ns, int x0, double L,
+                       int nbin, int type, double mean, double factor, cudaStream_t st);
 
 // particle scatter: Psi -> rho (zeroed here); optional positions out
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
@@ -135,8 +138,8 @@ void launch_gather_adjoint_to(const GridGeom &g, const double *psix, const doubl
                               double *vy, double *vz, const double *resid, cudaStream_t st);
 
 // out = resid * d_c(delta) with the 4th-order finite difference of gradient.cpp:81-153
-void launch_findif_product(const double *delta, const double *resid, double *out, int N, double L, int comp,
-                           cudaStream_t st);
+void launch_findif_product(const double *delta, const double *resid, double *out, int N, int Ns, int xo, double L,
+                           int comp, cudaStream_t st);
 
 // y += a * x ; y = a * x ; y += a * x / m (m <= 0 -> 0)
 void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st);

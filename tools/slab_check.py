@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--masskernel", type=int, default=1)
     ap.add_argument("--amp", type=float, default=0.5)
     ap.add_argument("--sfmodel", type=int, default=1, help="2/3: Lag2Eul_non_zeldovich (forces rsd_model off)")
+    ap.add_argument("--likelihood", type=int, default=1)
+    ap.add_argument("--mass-type", type=int, default=1)
     a = ap.parse_args()
     info = multi.rank_info()
     torch.cuda.set_device(info.local_rank)
@@ -60,13 +62,17 @@ def main():
         return torch.cat(out, 0).cpu().numpy()
 
     for calc_h in (0, 1, 4):
-        kw = dict(N1=N, L1=L, masskernel=a.masskernel, likelihood=1, rsd_model=(a.sfmodel == 1), calc_h=calc_h,
-                  mass_type=1, sfmodel=a.sfmodel)
+        kw = dict(N1=N, L1=L, masskernel=a.masskernel, likelihood=a.likelihood, rsd_model=(a.sfmodel == 1),
+                  calc_h=calc_h, mass_type=a.mass_type, sfmodel=a.sfmodel, N_bin=40)
         sc = slab.SlabChain.create(bc.Params(device=info.local_rank, **kw), info.rank, info.world)
         sc.set_static(Power=sc.local(P), nobs=sc.local(nobs), noise=sc.local(noise), window=sc.local(window))
-        sc.hamiltonian_mass()
+        res_mass = gather(sc.hamiltonian_mass(sc.local(s))[0]) if a.mass_type in (1, 2, 3, 4) else None
         res = {}
+        if res_mass is not None:
+            res["mass_f"] = res_mass
         if calc_h == 0:
+            km, pw = sc.measure_spectrum(sc.local(s), 40)
+            res["spectrum"] = np.concatenate([km, pw])
             res["fft_roundtrip"] = gather(sc.fft_c2r(sc.fft_r2c(sc.local(s))))
             res["convolve"] = gather(sc.convolve_inv_corr(sc.local(s), sc.local(P)))
             res["forward"] = gather(sc.forward(sc.local(s)))
@@ -82,9 +88,13 @@ def main():
         if info.rank == 0:
             with bc.Chain(bc.Params(device=info.local_rank, **kw)) as ch:
                 ch.set_static(Power=P, nobs=nobs, noise=noise, window=window)
-                ch.hamiltonian_mass()
                 ref = {}
+                m = ch.hamiltonian_mass(s)[0]
+                if res_mass is not None:
+                    ref["mass_f"] = m
                 if calc_h == 0:
+                    km, pw = ch.measure_spectrum(s, 40)
+                    ref["spectrum"] = np.concatenate([km, pw])
                     ref["fft_roundtrip"] = s
                     ref["convolve"] = ch.convolve_inv_corr(s, P)
                     ref["forward"] = ch.forward(s)
