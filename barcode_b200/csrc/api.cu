@@ -1004,13 +1004,13 @@ int bgpu_hamiltonian_mass(bgpu_handle *h, double *mass_f_out, double *mass_r_out
 
 // Hamiltonian_mass for every supported type (HMC_mass.cc:315-368); types 2 / 3 measure the spectrum of the
 // likelihood force at `signal` (likeli_force_power, :39-51)
-int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f_out, double *mass_r_out) {
-  BGPU_TRY
-  BGPU_CUDA(cudaSetDevice(h->p.device));
+// likeli_force_power (HMC_mass.cc:39-51): spectrum of the likelihood gradient at `signal` -> h->tmp as
+// [power | kmode | nmode], N_bin entries each
+static void likeli_force_power_device(bgpu_handle *h, const double *signal) {
   const bgpu_params &p = h->p;
-  if (p.mass_type != 2 && p.mass_type != 3) return bgpu_hamiltonian_mass(h, mass_f_out, mass_r_out);
   require(signal != nullptr && h->have_power && h->have_obs,
-          "bgpu_hamiltonian_mass_x: signal, Power and the observations are needed for mass types 2 / 3");
+          "bgpu: signal, Power and the observations are needed for the likelihood-force spectrum");
+  require(h->zero_half != nullptr, "bgpu: the likelihood-force spectrum needs a handle created with mass_type 2 or 3");
   h2d(h, h->sig, signal, h->n);
   h->like_only = true;
   try {
@@ -1022,10 +1022,30 @@ int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f
   h->like_only = false;
   r2c_plain(h, h->grad, h->work);
   const int nb = p.N_bin;
-  double *acc = h->tmp;                     // [power | kmode | nmode]
+  double *acc = h->tmp;
   launch_measure_spectrum_bin(h->work, h->N, h->Ns, h->G > 1 ? h->rank * h->Ns : 0, p.L1, nb, acc, h->stream);
   if (h->G > 1) h->comm->all_reduce_sum(acc, 3 * (size_t)nb, h->stream);
   launch_measure_spectrum_finish(acc, h->N, p.L1, nb, h->stream);
+}
+
+int bgpu_likeli_force_power(bgpu_handle *h, const double *signal, double *kmode, double *power) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  likeli_force_power_device(h, signal);
+  d2h(h, power, h->tmp, (size_t)h->p.N_bin);
+  d2h(h, kmode, h->tmp + h->p.N_bin, (size_t)h->p.N_bin);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f_out, double *mass_r_out) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  const bgpu_params &p = h->p;
+  if (p.mass_type != 2 && p.mass_type != 3) return bgpu_hamiltonian_mass(h, mass_f_out, mass_r_out);
+  likeli_force_power_device(h, signal);
+  const int nb = p.N_bin;
+  double *acc = h->tmp;                     // [power | kmode | nmode]
   double mean = 0.0;
   if (p.mass_type == 3) {                   // Hamiltonian_mass_mean_likeli_force, HMC_mass.cc:86-114
     std::vector<double> spec(2 * (size_t)nb);

@@ -35,6 +35,7 @@
 
 #include "fftw_array.h"
 #include "IOfunctionsGen.h"
+#include "IOfunctions.h"
 #include "HMC.h"
 #include "HMC_mass.h"
 #include "HMC_momenta.h"
@@ -275,7 +276,16 @@ void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
   const ULONG massnum = (n->iGibbs > n->massnum_burn) ? n->massnum_burn : n->massnum_init;
   const std::string name_r = dn->dir + std::string("auxmass_r"), name_f = dn->dir + std::string("auxmass_f");
   if (0 == n->iGibbs % massnum || n->iGibbs == 1) {
-    Hamiltonian_mass(hd, hd->x, data);   // host, unchanged (types 0/1/4 are one pass over Power)
+    if (n->mass_type == 2 || n->mass_type == 3) {
+      // the likelihood-force masses (HMC_mass.cc:39-160) need likelihood_grad_log_like + measure_spectrum: on the
+      // device, with the forcespec.dat dump the reference writes (likeli_force_power, :48-50)
+      std::vector<real_prec> kmode(n->N_bin), fpower(n->N_bin);
+      check(bgpu_likeli_force_power(h, hd->x, kmode.data(), fpower.data()), "bgpu_likeli_force_power");
+      dump_measured_spec(kmode.data(), fpower.data(), dn->dir + std::string("forcespec.dat"), n->N_bin);
+      check(bgpu_hamiltonian_mass_x(h, hd->x, hd->mass_f, nullptr), "bgpu_hamiltonian_mass_x");
+    } else {
+      Hamiltonian_mass(hd, hd->x, data);   // host, unchanged (types 0/1/4 are one pass over Power)
+    }
     if (n->mass_rs) {
       if (contains_nan(hd->mass_r, n->N)) throw std::runtime_error("auxmass_r contains a NaN! aborting.");
       write_array(name_r, hd->mass_r, n->N1, n->N2, n->N3);

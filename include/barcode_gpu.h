@@ -108,6 +108,9 @@ int bgpu_hamiltonian_mass(bgpu_handle *h, double *mass_f_out, double *mass_r_out
 /* the same for every supported mass type; types 2 / 3 measure the spectrum of the likelihood force at `signal`
  * (hd->x; likeli_force_power, HMC_mass.cc:39-51) */
 int bgpu_hamiltonian_mass_x(bgpu_handle *h, const double *signal, double *mass_f_out, double *mass_r_out);
+/* likeli_force_power (HMC_mass.cc:39-51): binned spectrum of likelihood_grad_log_like(signal), N_bin entries each
+ * (what the reference dumps as forcespec.dat); needs a handle created with mass_type 2 or 3 */
+int bgpu_likeli_force_power(bgpu_handle *h, const double *signal, double *kmode, double *power);
 
 /* S1 gradient_psi (HMC.cc:146-206): writes hd->gradpsi */
 int bgpu_gradient_psi(bgpu_handle *h, const double *signal, double *gradpsi);

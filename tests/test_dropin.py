@@ -106,7 +106,8 @@ def run(exe, d, par):
 
 
 @pytest.mark.skipif(not (os.path.exists(CPU) and os.path.exists(GPU)), reason="oracle/_ref binaries not built")
-@pytest.mark.parametrize("masskernel,likelihood,rsd,mass_type", [(1, 1, "false", 1), (2, 1, "true", 1), (1, 0, "false", 0)])
+@pytest.mark.parametrize("masskernel,likelihood,rsd,mass_type", [(1, 1, "false", 1), (2, 1, "true", 1), (1, 0, "false", 0),
+                                                                  (1, 1, "false", 2)])
 def test_unchanged_host_driver_runs_on_the_gpu_path(tmp_path, masskernel, likelihood, rsd, mass_type):
     with np.load(os.path.join(GOLDEN, "pk_table.npz")) as f:
         k, P = f["k"], f["P"]
@@ -129,7 +130,7 @@ def test_unchanged_host_driver_runs_on_the_gpu_path(tmp_path, masskernel, likeli
     assert np.all(np.abs(log_c[:, 3:8] - log_g[:, 3:8]) <= 2e-5 * scale + 2e-5 * np.abs(log_c[:, 3:8]))
     # output array files: identical format (headerless float64), same content
     # (write_array appends ".dat" only when the name holds no "." -- and "./data/" does, IOfunctionsGen.cc:185-230)
-    for name in ("deltaLAG_1", "deltaLAG_3", "deltaEUL_3", "auxmass_f" if mass_type == 1 else "auxmass_r", "nobs",
+    for name in ("deltaLAG_1", "deltaLAG_3", "deltaEUL_3", "auxmass_r" if mass_type == 0 else "auxmass_f", "nobs",
                  "deltaLAGtest"):
         a = np.fromfile(tmp_path / "cpu" / "data" / name)
         b = np.fromfile(tmp_path / "gpu" / "data" / name)
