@@ -1205,7 +1205,7 @@ int bgpu_color_momenta(bgpu_handle *h, const double *white, const double *real_g
   require(h->G == 1, "bgpu_color_momenta: not available on a slab-decomposed chain yet (colour on the host or a cube handle)");
   if (h->mass_fs) {
     require(white != nullptr, "bgpu_color_momenta: white noise is required for a Fourier-space mass");
-    // the full complex grid (2N doubles) is staged through dhat+acc's storage? no: own temporary
+    // the full complex white-noise grid (2 N^3 doubles) does not fit any resident scratch array: own temporary
     double2 *d_white = nullptr;
     dalloc(d_white, h->n);
     try {

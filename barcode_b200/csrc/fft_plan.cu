@@ -174,7 +174,6 @@ constexpr bool tma_supported() {
 struct PassIo {
   int n_other = 0;      // pencils' "other" extent; 0 = N (cube)
   int other0 = 0;       // global index of other == 0
-  int other_begin = 0, other_count = 0;  // this launch walks others [begin, begin + count); count 0 = all
   bool in_packed = false, out_packed = false;
   int G = 1, Ns = 0;
   double2 *const *peer_out = nullptr;  // fused transpose: receive buffer of every rank, as mapped here
@@ -209,10 +208,9 @@ static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, 
   maps.auxc = AUX >= 2 ? f.tensor_map(lop.cplx0, AXIS, true, 0, n_slow, n_mid) : maps.in;
   if (io.peer_out)
     for (int h = 0; h < io.G; ++h) maps.peer[h] = f.tensor_map(io.peer_out[h], AXIS, true, 1, io.G, io.Ns);
-  const int count = io.other_count ? io.other_count : n_other;
-  PassGeom geo{count, io.other_begin, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0,
-               io.peer_out ? io.Ns : 0, io.my_rank};
-  const int tiles = count * ((N / 2 + 1 + 7) / 8);
+  PassGeom geo{n_other, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0, io.peer_out ? io.Ns : 0,
+               io.my_rank};
+  const int tiles = n_other * ((N / 2 + 1 + 7) / 8);
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > tiles) blocks = tiles;
   ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
@@ -296,7 +294,7 @@ static void launch_strided(const Fft3d &f, const double2 *in, double2 *out, cons
     return;
   }
   if (try_strided_tma<N, DIR, AXIS>(f, in, out, lop, sop, io, st)) return;
-  if (f.G > 1 || io.n_other || io.other_count)
+  if (f.G > 1 || io.n_other)
     throw std::runtime_error("bgpu: the slab-decomposed transform needs the TMA-staged pass (N = 128, 256 or 512)");
   ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
   if constexpr (N >= 128) {

@@ -253,8 +253,7 @@ struct TmaMaps {
 // all-to-all buffers directly: `*_packed` = rows per peer block of the rank-4 tensor map
 // [z][y_local][x_local][peer], 0 for the plain rank-3 map.
 struct PassGeom {
-  int n_other;      // "other" indices walked by this launch ...
-  int first_other;  // ... starting here (a launch may cover a range of x planes / y rows only)
+  int n_other;
   int other0;
   int in_packed;
   int out_packed;
@@ -356,7 +355,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
   auto issue_load = [&](int i) {
     const int tile = blockIdx.x + i * gridDim.x;
     const int s = i % NSTAGE;
-    const int other = tile / ZT + geo.first_other, zt = tile % ZT;
+    const int other = tile / ZT, zt = tile % ZT;
     uint8_t *dst = smem_al + s * Tile::stage_bytes;
     mbar_expect_tx(&full[s], Tile::stage_bytes);
     if (AXIS == 1 && geo.in_packed) {  // rows arrive grouped by the peer that sent them
@@ -400,7 +399,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
   for (int i = 0; i < my_count; ++i) {
     const int s = i % NSTAGE;
     const int tile = blockIdx.x + i * gridDim.x;
-    const int other = tile / ZT + geo.first_other, zt = tile % ZT;
+    const int other = tile / ZT, zt = tile % ZT;
     const int iz = zt * T + p;
     const uint32_t tbase = smem0 + s * Tile::stage_bytes;
     if constexpr (EARLY) {
