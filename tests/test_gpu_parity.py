@@ -446,3 +446,62 @@ def test_measure_spectrum_matches_reference_and_oracle():
     assert np.allclose(km, km0, rtol=1e-12, atol=0) and np.allclose(pw, pw0, rtol=1e-11, atol=0)
     # white noise of unit variance: P = V / N^3 in every bin
     assert abs(pw[20:150].mean() / (L ** 3 / N ** 3) - 1) < 0.01
+
+
+# ---------------------------------------------------------------- BASELINE.json configs[0] against the LIVE reference
+@pytest.mark.parametrize("mk,like,rsd,calc_h,mass_type,sfmodel", [
+    (1, 1, False, 0, 1, 1),     # configs[0]: 64^3 ZA + CIC, Gaussian, real space
+    (1, 1, True, 0, 1, 2),      # configs[1]'s physics at 64^3 (RSD => the reference runs Zel'dovich)
+    (2, 0, False, 0, 1, 1),     # configs[2]'s physics at 64^3 (TSC, Poisson)
+    (3, 1, False, 2, 1, 1),     # the shipped default: SPH + its exact adjoint
+])
+def test_64_cubed_against_the_compiled_reference(mk, like, rsd, calc_h, mass_type, sfmodel):
+    """The CUDA path against oracle/_ref (the unmodified reference sources compiled in the build container; the .so
+    travels with the snapshot) at 64^3, the size of BASELINE.json configs[0] and of the reference's own
+    data/input.par: forward density, both energies, the gradient, the kinetic energy, a 3-step trajectory and dH."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libbarcode_ref.so not built")
+    from barcode_b200 import inputs
+    from barcode_b200.chain import Chain, Params
+    N, L = 64, 200.0
+    cfg = ref.Config(N1=N, L1=L, masskernel=mk, likelihood=like, rsd_model=rsd, calc_h=calc_h, mass_type=mass_type,
+                     sfmodel=sfmodel, N_eps_fac=8.0, eps_fac=1.0)
+    R = ref.Reference(cfg)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L).ravel()
+    rng = np.random.default_rng(64 + mk)
+    one = np.ones(R.N)
+    R.set_inputs(Power=P, window=one, noise=one, nobs=one)
+    truth = R.create_garfield(21, P)
+    dX_truth = R.forward(truth, want_pos=False)
+    nobs = np.maximum(0, 1 + dX_truth + rng.standard_normal(R.N)) if like == 1 else \
+        rng.poisson(np.maximum(1 + dX_truth, 0)) * 1.0
+    noise = 1.0 + 0.5 * rng.random(R.N)
+    R.set_inputs(nobs=nobs, noise=noise)
+    s = 0.5 * R.create_garfield(22, P)
+    R.set_inputs(signal=s)
+    mf, mr = R.hamiltonian_mass()
+    mom = R.draw_momenta(23)
+    g_ref = R.gradient_psi(s)
+    pp_ref, pl_ref = R.psi(s)
+    dX_ref = R.array("deltaX").copy()
+    K_ref = R.kinetic(mom)
+    sf_ref, pf_ref = R.EoM(s, mom, 0.3, 1e-5)          # Neps = floor(8 * 0.3) + 1 = 3, eps = 1e-5
+    neps, eps = int(R.scalar("Neps")), R.scalar("epsilon")
+    dH_ref, sc_ref = R.delta_hamiltonian(s, mom, sf_ref, pf_ref)
+    R.close()
+    with Chain(Params(N1=N, L1=L, masskernel=mk, likelihood=like, rsd_model=rsd, calc_h=calc_h, mass_type=mass_type,
+                      sfmodel=sfmodel)) as ch:
+        ch.set_static(Power=P, nobs=nobs, noise=noise, window=one)
+        mf_g, mr_g = ch.hamiltonian_mass()
+        assert np.array_equal(mf_g.ravel(), mf) and np.array_equal(mr_g.ravel(), mr)
+        assert rel_l2(ch.gradient_psi(s), g_ref) < TOL
+        pp, pl, dX = ch.psi(s)
+        assert abs(pp - pp_ref) <= TOL * abs(pp_ref) and abs(pl - pl_ref) <= TOL * abs(pl_ref)
+        assert rel_l2(dX, dX_ref) < TOL
+        assert abs(ch.kinetic_term(mom) - K_ref) <= TOL * abs(K_ref)
+        sf, pf = ch.leapfrog(s, mom, neps, eps)
+        assert rel_l2(sf, sf_ref) < 1e-8 and rel_l2(pf, pf_ref) < 1e-8
+        dH, sc, _ = ch.delta_hamiltonian(s, mom, sf, pf)
+        floor = 1e-13 * (abs(sc_ref["H_kin_i"]) + abs(sc_ref["psi_prior_i"]) + abs(sc_ref["psi_likeli_i"]))
+        assert abs(dH - dH_ref) <= 1e-8 * abs(dH_ref) + floor
