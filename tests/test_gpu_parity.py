@@ -6,6 +6,8 @@ Checked against (a) the golden vectors the compiled reference produced
 integer cell indices bit-exact; density, log-posterior and gradient within
 1e-10 relative L2 (FP64); Delta-H over the fixed trajectory within 1e-8 relative.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -449,25 +451,36 @@ def test_measure_spectrum_matches_reference_and_oracle():
 
 
 # ---------------------------------------------------------------- BASELINE.json configs[0] against the LIVE reference
-@pytest.mark.parametrize("mk,like,rsd,calc_h,mass_type,sfmodel", [
-    (1, 1, False, 0, 1, 1),     # configs[0]: 64^3 ZA + CIC, Gaussian, real space
-    (1, 1, True, 0, 1, 2),      # configs[1]'s physics at 64^3 (RSD => the reference runs Zel'dovich)
-    (2, 0, False, 0, 1, 1),     # configs[2]'s physics at 64^3 (TSC, Poisson)
-    (3, 1, False, 2, 1, 1),     # the shipped default: SPH + its exact adjoint
+@pytest.mark.parametrize("N,mk,like,rsd,calc_h,mass_type,sfmodel", [
+    (64, 1, 1, False, 0, 1, 1),     # configs[0]: 64^3 ZA + CIC, Gaussian, real space
+    (64, 1, 1, True, 0, 1, 2),      # configs[1]'s physics at 64^3 (RSD => the reference runs Zel'dovich)
+    (64, 2, 0, False, 0, 1, 1),     # configs[2]'s physics at 64^3 (TSC, Poisson)
+    (64, 3, 1, False, 2, 1, 1),     # the shipped default: SPH + its exact adjoint
+    (128, 2, 0, False, 0, 1, 1),    # configs[2] at its own size: 128^3 ZA + TSC, Poisson
+    (256, 1, 1, True, 0, 1, 2),     # configs[1] at its own size: 256^3 (2LPT requested ->) ZA + CIC, Gaussian, RSD
+    (128, 1, 1, False, 0, 1, 3),    # configs[3]'s physics at 128^3: ALPT + CIC (Lag2Eul_non_zeldovich)
+    pytest.param(512, 1, 1, False, 0, 1, 3, marks=pytest.mark.skipif(
+        not os.environ.get("BGPU_HEAVY_TESTS"), reason="configs[3] at its own size, 512^3 ALPT + CIC: minutes of "
+        "reference CPU time; set BGPU_HEAVY_TESTS=1 (run once per round, log under profiles/)")),
 ])
-def test_64_cubed_against_the_compiled_reference(mk, like, rsd, calc_h, mass_type, sfmodel):
+def test_against_the_compiled_reference_at_baseline_sizes(N, mk, like, rsd, calc_h, mass_type, sfmodel, tmp_path,
+                                                          monkeypatch):
     """The CUDA path against oracle/_ref (the unmodified reference sources compiled in the build container; the .so
-    travels with the snapshot) at 64^3, the size of BASELINE.json configs[0] and of the reference's own
-    data/input.par: forward density, both energies, the gradient, the kinetic energy, a 3-step trajectory and dH."""
+    travels with the snapshot) at the sizes of BASELINE.json configs[0-2] (64^3 is also the reference's own
+    data/input.par): forward density, both energies, the gradient, the kinetic energy, a 3-step trajectory and dH."""
     from oracle import ref
     if not ref.available():
         pytest.skip("oracle/_ref/libbarcode_ref.so not built")
     from barcode_b200 import inputs
     from barcode_b200.chain import Chain, Params
-    N, L = 64, 200.0
+    L = inputs.box_length(N)
     cfg = ref.Config(N1=N, L1=L, masskernel=mk, likelihood=like, rsd_model=rsd, calc_h=calc_h, mass_type=mass_type,
                      sfmodel=sfmodel, N_eps_fac=8.0, eps_fac=1.0)
     R = ref.Reference(cfg)
+    if sfmodel != 1 and not rsd:
+        # the reference re-reads its ALPT kernel file from the working directory on every forward evaluation
+        monkeypatch.chdir(tmp_path)
+        R.kernelcomp()
     P = inputs.power_on_grid(*inputs.load_pk_table(), N, L).ravel()
     rng = np.random.default_rng(64 + mk)
     one = np.ones(R.N)
@@ -486,12 +499,14 @@ def test_64_cubed_against_the_compiled_reference(mk, like, rsd, calc_h, mass_typ
     pp_ref, pl_ref = R.psi(s)
     dX_ref = R.array("deltaX").copy()
     K_ref = R.kinetic(mom)
-    sf_ref, pf_ref = R.EoM(s, mom, 0.3, 1e-5)          # Neps = floor(8 * 0.3) + 1 = 3, eps = 1e-5
-    neps, eps = int(R.scalar("Neps")), R.scalar("epsilon")
-    dH_ref, sc_ref = R.delta_hamiltonian(s, mom, sf_ref, pf_ref)
+    traj = N <= 256                                     # (the 512^3 case stops here: minutes of CPU per evaluation)
+    if traj:
+        sf_ref, pf_ref = R.EoM(s, mom, 0.3, 1e-5)      # Neps = floor(8 * 0.3) + 1 = 3, eps = 1e-5
+        neps, eps = int(R.scalar("Neps")), R.scalar("epsilon")
+        dH_ref, sc_ref = R.delta_hamiltonian(s, mom, sf_ref, pf_ref)
     R.close()
     with Chain(Params(N1=N, L1=L, masskernel=mk, likelihood=like, rsd_model=rsd, calc_h=calc_h, mass_type=mass_type,
-                      sfmodel=sfmodel)) as ch:
+                      sfmodel=sfmodel, slength=cfg.slength)) as ch:
         ch.set_static(Power=P, nobs=nobs, noise=noise, window=one)
         mf_g, mr_g = ch.hamiltonian_mass()
         assert np.array_equal(mf_g.ravel(), mf) and np.array_equal(mr_g.ravel(), mr)
@@ -500,6 +515,8 @@ def test_64_cubed_against_the_compiled_reference(mk, like, rsd, calc_h, mass_typ
         assert abs(pp - pp_ref) <= TOL * abs(pp_ref) and abs(pl - pl_ref) <= TOL * abs(pl_ref)
         assert rel_l2(dX, dX_ref) < TOL
         assert abs(ch.kinetic_term(mom) - K_ref) <= TOL * abs(K_ref)
+        if not traj:
+            return
         sf, pf = ch.leapfrog(s, mom, neps, eps)
         assert rel_l2(sf, sf_ref) < 1e-8 and rel_l2(pf, pf_ref) < 1e-8
         dH, sc, _ = ch.delta_hamiltonian(s, mom, sf, pf)
