@@ -63,6 +63,9 @@ SIGNATURES = {
     "bgpu_hamiltonian_mass_x": (C.c_int, [_h, _dp, _dp, _dp]),
     "bgpu_likeli_force_power": (C.c_int, [_h, _dp, _dp, _dp]),
     "bgpu_measure_spectrum": (C.c_int, [_h, _dp, C.c_uint64, _dp, _dp]),
+    "bgpu_set_signal": (C.c_int, [_h, _dp]),
+    "bgpu_candidate": (C.c_int, [_h, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, _dp, _dp]),
+    "bgpu_accept": (C.c_int, [_h, _dp, _dp]),
     "bgpu_device_normals": (C.c_int, [_h, C.c_uint64, C.c_uint64, C.c_uint, C.c_size_t, C.c_size_t, _dp]),
     "bgpu_forward": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp]),
     "bgpu_assign_density": (C.c_int, [_h, _dp, _dp, _dp, _dp]),

@@ -82,6 +82,8 @@ struct bgpu_handle {
   int Hmax = 0;                 // halo planes allocated each side of rho_ext
   double *rho_ext = nullptr;    // [(Ns + 2 Hmax)][N][N]; delta points at the owned planes inside it
   double *halo_recv = nullptr;  // 2 * Hmax * N^2
+  double *cand_s = nullptr, *cand_p = nullptr;  // device-resident HMC candidate (bgpu_candidate)
+  bool have_signal = false;
   double *phi1 = nullptr, *xa = nullptr, *xb = nullptr, *xc = nullptr;  // exact 2LPT/ALPT adjoint: phi^(1) + 3 scratch arrays
   double *fext = nullptr;       // log-normal + calc_h 0 on a slab: f(delta_x) with 2 halo planes each side
   double *resid_ext = nullptr;  // exact adjoint on a slab: the residual with H halo planes each side
@@ -912,7 +914,7 @@ void bgpu_destroy(bgpu_handle *h) {
     }
   }
   double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->zero_half, h->mass_f, h->mass_r, h->inv_mass,
-                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->fext, h->tmp, h->phi1, h->xa, h->xb, h->xc,
+                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->fext, h->tmp, h->cand_s, h->cand_p, h->phi1, h->xa, h->xb, h->xc,
                      h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
     if (q) cudaFree(q);
@@ -1303,6 +1305,63 @@ int bgpu_measure_spectrum(bgpu_handle *h, const double *signal, uint64_t N_bin, 
   launch_measure_spectrum_finish(acc, h->N, h->p.L1, (int)N_bin, h->stream);
   d2h(h, power, acc, N_bin);
   d2h(h, kmode, acc + N_bin, N_bin);
+  sync(h);
+  BGPU_CATCH
+}
+
+// ---------------------------------------------------------------------------
+// One HMC candidate without the signal or the momenta ever leaving the device: the body of HamiltonianMC's loop
+// (HMC.cc:436-506) between the host's RNG draws and its Metropolis decision -- S5 (device generator), S4, S3, S2.
+// ---------------------------------------------------------------------------
+int bgpu_set_signal(bgpu_handle *h, const double *x) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(x != nullptr, "bgpu_set_signal: null signal");
+  if (!h->cand_s) {
+    dalloc(h->cand_s, h->n);
+    dalloc(h->cand_p, h->n);
+  }
+  h2d(h, h->sig, x, h->n);
+  h->have_signal = true;
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_candidate(bgpu_handle *h, uint64_t seed, uint64_t draw_index, uint64_t Neps, double epsilon, double *energies6,
+                   double *p_f0) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(h->have_signal, "bgpu_candidate: bgpu_set_signal must be called first");
+  require(energies6 != nullptr, "bgpu_candidate: null output");
+  draw_momenta_device(h, seed, draw_index, h->cand_p);                       // HMC.cc:449
+  // delta_Hamiltonian's initial energies (HMC.cc:214-215): the ends of the trajectory do not change them
+  kinetic_device(h, h->cand_p);
+  psi_device(h, h->sig);
+  BGPU_CUDA(cudaMemcpyAsync(h->hscal, h->dscal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  BGPU_CUDA(cudaMemcpyAsync(h->cand_s, h->sig, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  sync(h);
+  energies6[0] = h->hscal[S_KIN];
+  energies6[1] = h->hscal[S_PRIOR];
+  energies6[2] = h->hscal[S_NLL];
+  leapfrog_device(h, h->cand_s, h->cand_p, Neps, epsilon);                   // HMC.cc:455
+  kinetic_device(h, h->cand_p);                                              // :224-225; deltaX is left at s_f's
+  psi_device(h, h->cand_s);
+  BGPU_CUDA(cudaMemcpyAsync(h->hscal, h->dscal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (p_f0) BGPU_CUDA(cudaMemcpyAsync(p_f0, h->cand_p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+  energies6[3] = h->hscal[S_KIN];
+  energies6[4] = h->hscal[S_PRIOR];
+  energies6[5] = h->hscal[S_NLL];
+  BGPU_CATCH
+}
+
+int bgpu_accept(bgpu_handle *h, double *x_out, double *deltaX_out) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(h->have_signal && h->cand_s, "bgpu_accept: no candidate");
+  BGPU_CUDA(cudaMemcpyAsync(h->sig, h->cand_s, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (x_out) d2h(h, x_out, h->sig, h->n);
+  if (deltaX_out) d2h(h, deltaX_out, h->delta, h->n);
   sync(h);
   BGPU_CATCH
 }

@@ -237,16 +237,20 @@ void Hamiltonian_EoM(struct HAMIL_DATA *hd, real_prec *signali, real_prec *momen
 // BARCODE_GPU_DEVICE_RNG=1 (opt-in, NOT seed-compatible with the CPU code): the draw itself happens on the device
 // (bgpu_draw_momenta_device: Philox4x32-10, same distribution).  The host stream then only gives one 32-bit word
 // per candidate as the draw's key, so it stays in step for Neps, epsilon and the Metropolis uniform.
-void draw_momenta(struct HAMIL_DATA *hd, gsl_rng *seed, real_prec *momenta, struct DATA *data) {
-  HAMIL_NUMERICAL *n = hd->numerical;
-  static const bool device_rng = [] {
+static bool device_rng_enabled() {
+  static const bool on = [] {
     const char *e = std::getenv("BARCODE_GPU_DEVICE_RNG");
     return e && e[0] == '1';
   }();
-  if (device_rng) {
-    static uint64_t draw_index = 0;
+  return on;
+}
+static uint64_t g_draw_index = 0;  // device generator: one counter per momentum draw of the process
+
+void draw_momenta(struct HAMIL_DATA *hd, gsl_rng *seed, real_prec *momenta, struct DATA *data) {
+  HAMIL_NUMERICAL *n = hd->numerical;
+  if (device_rng_enabled()) {
     const uint64_t key = gsl_rng_get(seed);
-    check(bgpu_draw_momenta_device(session(hd, data), key, draw_index++, momenta), "bgpu_draw_momenta_device");
+    check(bgpu_draw_momenta_device(session(hd, data), key, g_draw_index++, momenta), "bgpu_draw_momenta_device");
     return;
   }
   std::vector<std::complex<real_prec> > white;
@@ -300,18 +304,60 @@ void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
   wprintw(data->curses->status, "starting Hamiltonian sampling (GPU path)");
   wrefresh(data->curses->status);
 
-  fftw_array<real_prec> momentai(n->N), momentaf(n->N), signali(n->N), signalf(n->N);
+  // With the device generator (BARCODE_GPU_DEVICE_RNG=1) nothing of a candidate needs the host: the signal is
+  // uploaded once per sample and every candidate -- momenta, trajectory, the four energies -- stays on the device
+  // (bgpu_candidate); only the accepted field comes back.  The host stream is consumed exactly as in the separate
+  // calls: one word as the draw's key, then Neps and epsilon, then the Metropolis uniform.
+  static const bool fused_off = [] {   // BARCODE_GPU_FUSED=0: device generator, but the separate host-array calls
+    const char *e = std::getenv("BARCODE_GPU_FUSED");
+    return e && e[0] == '0';
+  }();
+  const bool fused = device_rng_enabled() && !fused_off;
+  fftw_array<real_prec> momentai(fused ? 1 : n->N), momentaf(fused ? 1 : n->N), signali(fused ? 1 : n->N),
+      signalf(fused ? 1 : n->N);
+  if (fused) check(bgpu_set_signal(h, hd->x), "bgpu_set_signal");
   bool accepted = false;
   for (ULONG iter = 1; iter <= n->itmax && !accepted; ++iter) {
     wprintw(data->curses->table, "%6lu ", n->iGibbs);
     wprintw(data->curses->table, "%4lu ", iter);
     wrefresh(data->curses->table);
 
-    copyArray(hd->x, signali, n->N);                                           // :445
-    draw_momenta(hd, seed, momentai, data);                                    // :449
-    update_eps_fac(hd, data);                                                  // :453
-    Hamiltonian_EoM(hd, signali, momentai, signalf, momentaf, seed, data);     // :455
-    const real_prec dH = delta_Hamiltonian(hd, signali, momentai, signalf, momentaf, data);
+    real_prec dH;
+    if (fused) {
+      const uint64_t key = gsl_rng_get(seed);                                  // draw_momenta's key
+      update_eps_fac(hd, data);                                                // :453
+      n->Neps = static_cast<ULONG>(n->N_eps_fac * (gsl_rng_uniform(seed))) + 1;  // :260-263
+      n->epsilon = static_cast<real_prec>(n->eps_fac * gsl_rng_uniform(seed));
+      if (n->epsilon > 2.) n->epsilon = 2.;
+      wprintw(data->curses->table, "%5.0e ", n->epsilon);
+      wprintw(data->curses->table, "%4lu ", n->Neps);
+      wrefresh(data->curses->table);
+      double E[6], pf0 = 0.;
+      check(bgpu_candidate(h, key, g_draw_index++, n->Neps, n->epsilon, E, &pf0), "bgpu_candidate");
+      if (std::abs(pf0) > 1e50) {
+        wprintw(data->curses->message, "\nLeap-frogging ... stopped, momentum too high (momenta[0] = %e)", pf0);
+        wrefresh(data->curses->message);
+      }
+      data->numerical->count_attempts++;
+      // delta_Hamiltonian, :209-248
+      n->H_kin_i = E[0]; n->psi_prior_i = E[1]; n->psi_likeli_i = E[2];
+      n->H_kin_f = E[3]; n->psi_prior_f = E[4]; n->psi_likeli_f = E[5];
+      n->psi_prior = E[4]; n->psi_likeli = E[5];
+      n->dprior = E[4] - E[1];
+      n->dlikeli = E[5] - E[2];
+      const real_prec Hami = E[0] + (E[1] + E[2]), Hamf = E[3] + (E[4] + E[5]);
+      dH = Hamf - Hami;
+      if (n->div_dH_by_N) dH /= static_cast<real_prec>(n->N);
+      n->dH = dH;
+      n->dK = E[3] - E[0];
+      n->dE = (E[4] + E[5]) - (E[1] + E[2]);
+    } else {
+      copyArray(hd->x, signali, n->N);                                           // :445
+      draw_momenta(hd, seed, momentai, data);                                    // :449
+      update_eps_fac(hd, data);                                                  // :453
+      Hamiltonian_EoM(hd, signali, momentai, signalf, momentaf, seed, data);     // :455
+      dH = delta_Hamiltonian(hd, signali, momentai, signalf, momentaf, data);
+    }
 
     // acceptance probability, :462-467
     real_prec p_acceptance = 1.;
@@ -330,10 +376,12 @@ void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
     wprintw(data->curses->table, accepted ? "y " : "n ");
     wrefresh(data->curses->table);
 
-    if (accepted)
-      copyArray(signalf, hd->x, n->N);
-    else
+    if (accepted) {
+      if (fused) check(bgpu_accept(h, hd->x, hd->deltaX), "bgpu_accept");
+      else copyArray(signalf, hd->x, n->N);
+    } else {
       n->rejections++;
+    }
     n->accepted = accepted;
 
     write_to_performance_log(data, hd);

@@ -134,6 +134,17 @@ int bgpu_color_momenta(bgpu_handle *h, const double *white_complex_fullgrid, con
 int bgpu_draw_momenta_device(bgpu_handle *h, uint64_t seed, uint64_t draw_index, double *momenta);
 int bgpu_device_normals(bgpu_handle *h, uint64_t seed, uint64_t draw_index, unsigned stream, size_t first, size_t n,
                         double *out);
+/* One HMC candidate with the signal and the momenta resident on the device -- the body of HamiltonianMC's loop
+ * (HMC.cc:436-506) between the host's RNG draws and its Metropolis decision: momenta from the device generator
+ * (seed, draw_index), the Neps-step trajectory from the signal given to bgpu_set_signal, and the six energies of
+ * delta_Hamiltonian: {H_kin_i, psi_prior_i, psi_likeli_i, H_kin_f, psi_prior_f, psi_likeli_f}.  p_f0 (optional)
+ * receives momenta_f[0] for the reference's run-away message.  bgpu_accept makes the candidate the current signal
+ * and copies it (and its deltaX, as psi() leaves it in hd->deltaX) to the host.  Per candidate only scalars cross
+ * PCIe; with host arrays (bgpu_leapfrog, bgpu_psi, ...) it is ~10 array transfers from pageable memory. */
+int bgpu_set_signal(bgpu_handle *h, const double *x);
+int bgpu_candidate(bgpu_handle *h, uint64_t seed, uint64_t draw_index, uint64_t Neps, double epsilon, double *energies6,
+                   double *p_f0);
+int bgpu_accept(bgpu_handle *h, double *x_out, double *deltaX_out);
 /* Lag2Eul / Lag2Eul_rsd_zeldovich as likelihood_grad_log_like calls them (HMC_models.cc:383-406);
  * pos* may be NULL */
 int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *posx, double *posy, double *posz);

@@ -155,6 +155,18 @@ def test_host_driver_with_the_device_momentum_generator(tmp_path, monkeypatch):
     _, log_host = run(GPU, str(tmp_path / "host_rng"), par)
     monkeypatch.setenv("BARCODE_GPU_DEVICE_RNG", "1")
     _, log_dev = run(GPU, str(tmp_path / "dev_rng"), par)
+    # the device-resident candidate (bgpu_candidate: only scalars cross PCIe) and the separate host-array calls
+    # consume the host stream identically and must walk the same chain
+    monkeypatch.setenv("BARCODE_GPU_FUSED", "0")
+    _, log_sep = run(GPU, str(tmp_path / "dev_rng_separate"), par)
+    assert log_sep.shape == log_dev.shape
+    assert np.array_equal(log_sep[:, 0], log_dev[:, 0]) and np.array_equal(log_sep[:, 2], log_dev[:, 2])
+    scale = np.abs(log_sep[:, 8:]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(log_sep[:, 8:] - log_dev[:, 8:]) <= 2e-5 * scale)
+    assert rel_l2(np.fromfile(tmp_path / "dev_rng" / "data" / "deltaLAG_4"),
+                  np.fromfile(tmp_path / "dev_rng_separate" / "data" / "deltaLAG_4")) < 1e-9
+    assert rel_l2(np.fromfile(tmp_path / "dev_rng" / "data" / "deltaEUL_4"),
+                  np.fromfile(tmp_path / "dev_rng_separate" / "data" / "deltaEUL_4")) < 1e-9
     assert log_dev.shape[0] >= 4 and np.all(np.isfinite(log_dev))
     assert log_dev[:, 0].sum() >= 1                                  # candidates are accepted
     # kinetic energy of a draw is chi^2_(N-1)/2: both generators give ~ N/2 = 2048 +- a few sqrt(N/2)

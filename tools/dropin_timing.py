@@ -1,0 +1,62 @@
+"""Wall-clock time per HMC sample of the reference's OWN program, CPU build vs GPU drop-in (run on the GPU box):
+
+    python tools/dropin_timing.py --grid 64 --samples 6
+
+oracle/_ref/barcode_cpu (every barlib source unmodified) and oracle/_ref/barcode_gpu (HMC.cc + HMC_momenta.cc
+replaced by barcode_b200/csrc/barlib_gpu_glue.cc) run the same input.par (tests/test_dropin.py's) with N_Gibbs = 1
+and N_Gibbs = samples; the difference of the two wall times is the cost of samples - 1 samples without the set-up
+(mock data, initial guess).  Also with BARCODE_GPU_DEVICE_RNG=1.
+"""
+import argparse
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_dropin import CPU, GPU, INPUT_PAR  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--grid", type=int, default=64)
+ap.add_argument("--samples", type=int, default=6)
+a = ap.parse_args()
+N = a.grid
+L = N * 200.0 / 64
+tmp = tempfile.mkdtemp(prefix="dropin_timing_")
+with np.load(os.path.join(ROOT, "tests", "golden", "pk_table.npz")) as f:
+    k, P = f["k"], f["P"]
+pk = os.path.join(tmp, "pk.dat")
+with open(pk, "w") as o:
+    for x, y in zip(k, P):
+        o.write(f"{x:.9g} {y:.9g}\n")
+
+
+def run(exe, tag, n_gibbs, env=None):
+    d = os.path.join(tmp, f"{tag}_{n_gibbs}")
+    os.makedirs(os.path.join(d, "data"))
+    par = INPUT_PAR.format(calc_h=0, rsd="true", likelihood=1, eps_fac=0.004, mass_type=1, pk=pk, N=N, L=L,
+                           n_gibbs=n_gibbs, masskernel=1)
+    open(os.path.join(d, "input.par"), "w").write(par)
+    t0 = time.time()
+    r = subprocess.run([exe], cwd=d, capture_output=True, text=True, env=dict(os.environ, **(env or {})))
+    dt = time.time() - t0
+    if r.returncode != 0:
+        raise SystemExit(r.stdout[-2000:] + r.stderr[-2000:])
+    rows = open(os.path.join(d, "performance_log.txt")).read().strip().splitlines()[1:]
+    neps = [float(x.split("\t")[2]) for x in rows]
+    return dt, len(rows), sum(neps)
+
+
+print(f"grid {N}^3, ZA + CIC, Gaussian likelihood, RSD; host cores: {os.cpu_count()}")
+for exe, tag, env in ((CPU, "reference CPU build", None), (GPU, "GPU drop-in (GSL stream on the host)", None),
+                      (GPU, "GPU drop-in, BARCODE_GPU_DEVICE_RNG=1", {"BARCODE_GPU_DEVICE_RNG": "1"})):
+    t1, c1, e1 = run(exe, tag.split()[0] + str(len(tag)), 1, env)
+    tn, cn, en = run(exe, tag.split()[0] + str(len(tag)), a.samples, env)
+    per = (tn - t1) / max(1, (a.samples - 1))
+    print(f"  {tag:42s} {per * 1e3:10.1f} ms / sample   ({cn - c1} candidates, {en - e1:.0f} leapfrog steps in "
+          f"{tn - t1:.2f} s; set-up + first sample {t1:.2f} s)")
