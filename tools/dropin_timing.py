@@ -24,6 +24,7 @@ from test_dropin import CPU, GPU, INPUT_PAR  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--grid", type=int, default=64)
 ap.add_argument("--samples", type=int, default=6)
+ap.add_argument("--skip", nargs="*", default=[], help="variants to leave out: cpu, host_rng, separate")
 a = ap.parse_args()
 N = a.grid
 L = N * 200.0 / 64
@@ -53,10 +54,16 @@ def run(exe, tag, n_gibbs, env=None):
 
 
 print(f"grid {N}^3, ZA + CIC, Gaussian likelihood, RSD; host cores: {os.cpu_count()}")
-for exe, tag, env in ((CPU, "reference CPU build", None), (GPU, "GPU drop-in (GSL stream on the host)", None),
-                      (GPU, "GPU drop-in, BARCODE_GPU_DEVICE_RNG=1", {"BARCODE_GPU_DEVICE_RNG": "1"})):
-    t1, c1, e1 = run(exe, tag.split()[0] + str(len(tag)), 1, env)
-    tn, cn, en = run(exe, tag.split()[0] + str(len(tag)), a.samples, env)
+variants = [("cpu", CPU, "reference CPU build", None),
+            ("host_rng", GPU, "GPU drop-in (GSL stream on the host)", None),
+            ("separate", GPU, "GPU drop-in, device RNG, host-array calls",
+             {"BARCODE_GPU_DEVICE_RNG": "1", "BARCODE_GPU_FUSED": "0"}),
+            ("fused", GPU, "GPU drop-in, device RNG, device-resident candidates", {"BARCODE_GPU_DEVICE_RNG": "1"})]
+for key, exe, tag, env in variants:
+    if key in a.skip:
+        continue
+    t1, c1, e1 = run(exe, key, 1, env)
+    tn, cn, en = run(exe, key, a.samples, env)
     per = (tn - t1) / max(1, (a.samples - 1))
-    print(f"  {tag:42s} {per * 1e3:10.1f} ms / sample   ({cn - c1} candidates, {en - e1:.0f} leapfrog steps in "
+    print(f"  {tag:52s} {per * 1e3:10.1f} ms / sample   ({cn - c1} candidates, {en - e1:.0f} leapfrog steps in "
           f"{tn - t1:.2f} s; set-up + first sample {t1:.2f} s)")
