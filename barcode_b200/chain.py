@@ -193,6 +193,30 @@ class Chain:
     def draw_momenta_device_dev(self, seed: int, draw_index: int, d_momenta_ptr: int):
         _lib.check(self.L.bgpu_draw_momenta_device_dev(self._h, int(seed), int(draw_index), C.c_void_p(d_momenta_ptr)))
 
+    # -- device-resident HMC candidate (HamiltonianMC's loop body, HMC.cc:436-506) ---------------------------
+    def set_signal(self, x):
+        _lib.check(self.L.bgpu_set_signal(self._h, _dp(_f64(x, self.N))))
+
+    def candidate(self, seed: int, draw_index: int, Neps: int, epsilon: float):
+        """Momenta from the device generator, Neps leapfrog steps from the current signal, the six energies of
+        delta_Hamiltonian -> dict; nothing but scalars crosses PCIe."""
+        E = (C.c_double * 6)()
+        pf0 = C.c_double()
+        _lib.check(self.L.bgpu_candidate(self._h, int(seed), int(draw_index), int(Neps), float(epsilon), E,
+                                         C.byref(pf0)))
+        keys = ("H_kin_i", "psi_prior_i", "psi_likeli_i", "H_kin_f", "psi_prior_f", "psi_likeli_f")
+        out = dict(zip(keys, (float(v) for v in E)))
+        out["dH"] = (out["H_kin_f"] + (out["psi_prior_f"] + out["psi_likeli_f"])) - \
+            (out["H_kin_i"] + (out["psi_prior_i"] + out["psi_likeli_i"]))
+        out["momenta_f0"] = pf0.value
+        return out
+
+    def accept(self):
+        """Make the candidate the current signal; returns (x, deltaX)."""
+        x, dX = np.empty(self.N), np.empty(self.N)
+        _lib.check(self.L.bgpu_accept(self._h, _dp(x), _dp(dX)))
+        return x.reshape(self.shape), dX.reshape(self.shape)
+
     def device_normals(self, seed: int, draw_index: int, stream: int, first: int, n: int):
         out = np.empty(n)
         _lib.check(self.L.bgpu_device_normals(self._h, int(seed), int(draw_index), int(stream), int(first), int(n),

@@ -288,6 +288,16 @@ def run_ours(args):
     draw_calls = max(2, args.steps // 2)
     ms_draw = timed(draw, draw_calls, 1)
 
+    # one whole HMC candidate on the device (bgpu_candidate: device momentum draw, Neps = 8 trajectory, the four
+    # energy evaluations), wall clock including the scalar read-backs -- what the glue's sampler loop costs
+    ch.set_signal(prob["signal"])
+    ch.candidate(1, 0, NEPS, 1e-5)
+    t0 = time.perf_counter()
+    n_cand = max(2, args.steps // 4)
+    for i in range(n_cand):
+        ch.candidate(1, 1 + i, NEPS, 1e-5)
+    cand_ms = (time.perf_counter() - t0) * 1e3 / n_cand
+
     # roofline leg: the same K steps again with CUDA events around every kernel launch
     bc.profile_begin()
     for _ in range(args.steps):
@@ -412,6 +422,7 @@ def run_ours(args):
                 f"gradient_evals_per_s_calc_h_{other_h}": world * args.steps / (ms_other * 1e-3),
                 "leapfrog_steps_per_s": world * leap_steps / (ms_leap * 1e-3),
                 "device_momentum_draw_ms": ms_draw / draw_calls,
+                "hmc_candidate_ms_neps8_device_resident": cand_ms,
                 "kernel_launches_total": int(bc.kernel_launches() - launches0),
             },
         }

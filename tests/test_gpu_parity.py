@@ -522,3 +522,29 @@ def test_against_the_compiled_reference_at_baseline_sizes(N, mk, like, rsd, calc
         dH, sc, _ = ch.delta_hamiltonian(s, mom, sf, pf)
         floor = 1e-13 * (abs(sc_ref["H_kin_i"]) + abs(sc_ref["psi_prior_i"]) + abs(sc_ref["psi_likeli_i"]))
         assert abs(dH - dH_ref) <= 1e-8 * abs(dH_ref) + floor
+
+
+def test_device_resident_candidate_equals_the_separate_calls():
+    """bgpu_candidate (momenta, trajectory and energies without leaving the device) against the same steps through
+    the host-array entry points: draw_momenta_device -> kinetic / psi -> leapfrog -> kinetic / psi."""
+    c = load_case("za_cic_gauss_rsd")
+    with loaded_chain(c) as ch:
+        s = c["signal"]
+        neps, eps = 3, 1e-5
+        mom = ch.draw_momenta_device(9, 4)
+        Ki = ch.kinetic_term(mom)
+        ppi, pli, _ = ch.psi(s)
+        sf, pf = ch.leapfrog(s, mom, neps, eps)
+        Kf = ch.kinetic_term(pf)
+        ppf, plf, dXf = ch.psi(sf)
+        ch.set_signal(s)
+        E = ch.candidate(9, 4, neps, eps)
+        for got, want in ((E["H_kin_i"], Ki), (E["psi_prior_i"], ppi), (E["psi_likeli_i"], pli), (E["H_kin_f"], Kf),
+                          (E["psi_prior_f"], ppf), (E["psi_likeli_f"], plf)):
+            assert abs(got - want) <= 1e-12 * abs(want)
+        assert abs(E["momenta_f0"] - pf.ravel()[0]) <= 1e-13 * abs(pf.ravel()[0])
+        x, dX = ch.accept()
+        assert rel_l2(x, sf) < 1e-14 and rel_l2(dX, dXf) < 1e-13
+        # the accepted field is the new current signal: the next candidate starts from it
+        E2 = ch.candidate(9, 5, 1, eps)
+        assert abs(E2["psi_prior_i"] - ppf) <= 1e-12 * abs(ppf)
