@@ -145,3 +145,78 @@ def slab_cellbound(psi_local, rank, world, dist):
     ext = np.concatenate([below, psi_local], axis=0)
     shifted = np.roll(ext[:-1], (1, 1), (1, 2))                      # (i-1) by the halo, (j-1, k-1) periodic
     return 0.5 * (shifted + psi_local)
+
+
+def slab_gather_adjoint_cic(p: bo.Params, r_local, psi_local, rank, world, dist):
+    """Exact CIC adjoint on an x slab (api.cu gradient_device, kernels.cu gather_adjoint_kernel): the residual of my
+    planes is extended by H planes of each x neighbour (the halo width of the scatter), and my particles gather
+    from that tile through slab.ext_plane.  Returns V (3 arrays over my Lagrangian planes)."""
+    import torch
+    N, d, L = p.N1, p.d, p.L1
+    x0, Ns = slab.slab_range(N, rank, world)
+    g = d * np.arange(N, dtype=np.float64) + 0.5 * d
+    x = bo.pacman(g[x0:x0 + Ns, None, None] + psi_local[0], L)
+    y = bo.pacman(g[None, :, None] + psi_local[1], L) + 0 * x
+    z = bo.pacman(g[None, None, :] + psi_local[2], L) + 0 * x
+    if p.rsd_model:
+        vez = bo.c_pecvel(p.ascale, p.OM, p.OL) * psi_local[2]
+        OC = 1.0 - p.OM - p.OL
+        Hub = 100.0 * np.sqrt(p.OM / p.ascale / p.ascale / p.ascale + p.OL + OC / p.ascale / p.ascale)
+        z = bo.pacman(z + vez * (1.0 / Hub / p.ascale), L)
+    m = torch.tensor([float(np.abs(psi_local[0]).max())], dtype=torch.float64)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    H = slab.halo_planes(float(m.item()), d)
+    below, above = _neighbour_planes(r_local, H, rank, world, dist)
+    ext = np.concatenate([below, r_local, above], axis=0).reshape(-1)      # planes [x0 - H, x0 + Ns + H)
+    xs, ys, zs = x.ravel(), y.ravel(), z.ravel()
+    i0, i1, tx, dx = bo.cic_cells_weights(p, xs)
+    j0, j1, ty, dy = bo.cic_cells_weights(p, ys)
+    k0, k1, tz, dz = bo.cic_cells_weights(p, zs)
+    V = [np.zeros_like(xs) for _ in range(3)]
+    for ii, wx, gx in ((i0, tx, -1.0 / d), (i1, dx, 1.0 / d)):
+        li = slab.ext_plane(ii, x0, H, N)
+        assert (li < Ns + 2 * H).all(), "a particle left the halo"
+        for jj, wy, gy in ((j0, ty, -1.0 / d), (j1, dy, 1.0 / d)):
+            for kk, wz, gz in ((k0, tz, -1.0 / d), (k1, dz, 1.0 / d)):
+                rc = ext[kk + N * (jj + N * li)]
+                V[0] += rc * gx * wy * wz
+                V[1] += rc * wx * gy * wz
+                V[2] += rc * wx * wy * gz
+    if p.rsd_model:
+        V[2] = V[2] + bo.fgrow(p.ascale, p.OM, p.OL) * V[2]
+    return [v.reshape(x.shape) for v in V]
+
+
+def slab_findif_x(p: bo.Params, a_local, rank, world, dist):
+    """gradfindif along x (gradient.cpp:81-153) on an x slab: two halo planes from each neighbour
+    (kernels.cu findif_product_kernel with xo = 2)."""
+    below, above = _neighbour_planes(a_local, 2, rank, world, dist)
+    e = np.concatenate([below, a_local, above], axis=0)
+    fac = p.N1 / (2.0 * p.L1)
+    return -fac * ((4.0 / 3) * (e[1:-3] - e[3:-1]) - (1.0 / 6) * (e[:-4] - e[4:]))
+
+
+def slab_measure_spectrum(p: bo.Params, kslab, n_bin, rank, world, dist):
+    """measure_spectrum (field_statistics.cpp:20-90) from the transposed k-space slab [x][y_local][z <= N/2]: modes with
+    0 < z < N/2 count twice (their mirror is not stored), bins are summed over the ranks, then normalised
+    (kernels.cu spectrum_bin_kernel / spectrum_finish_kernel)."""
+    import torch
+    N = p.N1
+    y0, Ns = slab.slab_range(N, rank, world)
+    k = bo.calc_ki(N, p.L1)
+    nzh = N // 2 + 1
+    ktot = np.sqrt((k[:, None, None] ** 2 + k[None, y0:y0 + Ns, None] ** 2) + k[None, None, :nzh] ** 2)
+    dk = np.sqrt(3.0 * k[N // 2] * k[N // 2]) / float(n_bin)
+    b = (ktot / dk).astype(np.int64)
+    w = np.where((np.arange(nzh) > 0) & (np.arange(nzh) < N // 2), 2.0, 1.0)[None, None, :] + 0 * ktot
+    ok = b < n_bin
+    acc = np.stack([np.bincount(b[ok], weights=(w * np.abs(kslab) ** 2)[ok], minlength=n_bin),
+                    np.bincount(b[ok], weights=(w * ktot)[ok], minlength=n_bin),
+                    np.bincount(b[ok], weights=w[ok], minlength=n_bin)])
+    t = torch.from_numpy(acc)
+    dist.all_reduce(t)
+    power, kmode, nmode = t.numpy()
+    have = nmode > 0
+    kmode[have] /= nmode[have]
+    power[have] = power[have] / nmode[have] * (p.vol / float(N) ** 3 / float(N) ** 3)
+    return kmode, power

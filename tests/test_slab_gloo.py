@@ -46,6 +46,17 @@ def _worker(rank, world, port, q):
         cb_ref = 0.5 * (np.roll(psi[0], (1, 1, 1), (0, 1, 2)) + psi[0])
         e_cb = np.abs(so.slab_cellbound(psi[0][x0:x0 + Ns], rank, world, dist) - cb_ref[x0:x0 + Ns]).max()
         assert e_m2v < 1e-13 and e_cb < 1e-15, (e_m2v, e_cb)
+        # exact CIC adjoint with the residual's halo, finite difference along x with its 2-plane halo, binned spectrum
+        r = rng.standard_normal((N, N, N))
+        V = so.slab_gather_adjoint_cic(p, r[x0:x0 + Ns], psi[:, x0:x0 + Ns], rank, world, dist)
+        Vref = bo.gather_adjoint(p, r, x, y, z)
+        e_V = max(np.abs(V[c] - Vref[c][x0:x0 + Ns]).max() for c in range(3)) / max(np.abs(v).max() for v in Vref)
+        e_fd = np.abs(so.slab_findif_x(p, phi[x0:x0 + Ns], rank, world, dist) - bo.gradfindif(p, phi, 1)[x0:x0 + Ns]).max() \
+            / np.abs(bo.gradfindif(p, phi, 1)).max()
+        km, pw = so.slab_measure_spectrum(p, k, 12, rank, world, dist)
+        km0, pw0 = bo.measure_spectrum(p, a, 12)
+        e_sp = max(np.abs(km - km0).max() / km0.max(), np.abs(pw - pw0).max() / pw0.max())
+        assert e_V < 1e-13 and e_fd < 1e-14 and e_sp < 1e-13, (e_V, e_fd, e_sp)
         q.put((rank, e_fwd, e_inv, e_rho, H, float(rho.sum())))
     except Exception as exc:  # surface the failure instead of letting the parent wait for its timeout
         q.put((rank, repr(exc)))
