@@ -160,10 +160,12 @@ def run_reference(args):
     s = reference_problem(R, args.grid, cfg["L1"], 1)
     for _ in range(max(1, args.warmup)):
         R.gradient_psi(s)
+    ref.fft_stats(reset=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         R.gradient_psi(s)
     dt = time.perf_counter() - t0
+    fft_s, fft_calls = ref.fft_stats()
     value = args.steps / dt
     cores = ref.num_threads()
     line = {
@@ -171,6 +173,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "fft_backend": ref.fft_backend(),
+                   "fft_share_of_step": fft_s / dt, "fft_calls_per_step": fft_calls / args.steps,
                    "note": "the reference's own gradient_psi (calc_h=0) on the host cores, OpenMP threads = cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": f"{args.steps} full gradient_psi calls at {args.grid}^3 after {max(1, args.warmup)} warm-up"},

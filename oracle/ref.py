@@ -347,3 +347,14 @@ def fft_backend() -> str:
 
 def num_threads() -> int:
     return int(lib().ref_num_threads())
+
+
+def fft_stats(reset: bool = False):
+    """(wall seconds inside fftw_execute, number of calls) since the last reset -- the FFT shim's own counters,
+    so that a timing of the reference can say how much of it is the substitute FFT."""
+    fn = lib().shim_fftw_stats
+    fn.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]
+    fn.restype = None
+    sec, calls = C.c_double(), C.c_long()
+    fn(C.byref(sec), C.byref(calls), 1 if reset else 0)
+    return sec.value, calls.value

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -345,7 +346,22 @@ fftw_plan fftw_plan_dft_3d(int n0, int n1, int n2, fftw_complex *in, fftw_comple
   return make_plan(C2C, n0, n1, n2, in, out, sign);
 }
 
+static double g_exec_seconds = 0.0;
+static long g_exec_calls = 0;
+static double now_seconds() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+/* wall time spent inside fftw_execute since the last reset (called from one host thread, as the reference does) */
+void shim_fftw_stats(double *seconds, long *calls, int reset) {
+  if (seconds) *seconds = g_exec_seconds;
+  if (calls) *calls = g_exec_calls;
+  if (reset) { g_exec_seconds = 0.0; g_exec_calls = 0; }
+}
+
 void fftw_execute(const fftw_plan p) {
+  const double t_begin = now_seconds();
   const int n0 = p->n0, n1 = p->n1, n2 = p->n2;
   const int nc = n2 / 2 + 1;
   switch (p->kind) {
@@ -374,6 +390,8 @@ void fftw_execute(const fftw_plan p) {
       break;
     }
   }
+  g_exec_seconds += now_seconds() - t_begin;
+  ++g_exec_calls;
 }
 
 void fftw_destroy_plan(fftw_plan p) { delete p; }
