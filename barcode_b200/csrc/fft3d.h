@@ -47,6 +47,7 @@ struct Fft3d {
   mutable const ChunkHooks *hooks = nullptr;  // set around ONE transform by the caller, consumed by its z pass
   // fused z+y kernel (fft_fused.cuh): per-plane completion counters, their running target, producer lead
   bool use_fused = false;  // BGPU_FFT_FUSED=1
+  bool two_warp = false;   // BGPU_FFT_2WARP=1: 512-point strided pencils over two warps (fft_tma.cuh, ColAccessWide)
   bool force_generic = false;  // BGPU_FFT_SLAB_GENERIC=1: slab passes through fft_slab_generic.cuh even where TMA fits
   unsigned long long *zy_ready = nullptr;
   mutable unsigned long long zy_epoch = 0;

@@ -180,10 +180,17 @@ struct PassIo {
   int my_rank = 0;
 };
 
-template <int N, int DIR, int AXIS, int AUX>
+// E = elements per lane: TmaShape<N>::E puts a pencil inside one warp; half of it spreads a 512-point pencil over
+// two warps (16 warps per SM instead of 8, <= 128 registers; BGPU_FFT_2WARP=1, opt-in until measured)
+template <int N, int DIR, int AXIS, int AUX, int E = TmaShape<N>::E>
 static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, KOp lop, KOp sop, const PassIo &io,
                                cudaStream_t st) {
-  constexpr int E = TmaShape<N>::E;
+  if constexpr (N == 512 && E == TmaShape<N>::E) {
+    if (f.two_warp) {
+      launch_strided_tma<N, DIR, AXIS, AUX, TmaShape<N>::E / 2>(f, in, out, lop, sop, io, st);
+      return;
+    }
+  }
   constexpr int MINB = AUX == 0 ? TmaShape<N>::MINB : 1;
   constexpr int NSTAGE = TmaStages<N, AUX>::value;
   constexpr int threads = 8 * (N / E);
@@ -650,6 +657,8 @@ void Fft3d::init(int n, cudaStream_t st) {
     // latency on the SM, not by HBM, so halving the HBM traffic does not pay by itself.
     const char *fg = std::getenv("BGPU_FFT_SLAB_GENERIC");
     force_generic = fg && fg[0] == '1';
+    const char *tw2 = std::getenv("BGPU_FFT_2WARP");
+    two_warp = tw2 && tw2[0] == '1';
     const char *fu = std::getenv("BGPU_FFT_FUSED");
     use_fused = fu && fu[0] == '1';
     const char *ld = std::getenv("BGPU_FFT_LEAD");

@@ -32,6 +32,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "fft.cuh"
 
 namespace bgpu {
@@ -172,15 +174,36 @@ __device__ __forceinline__ void wp_load_twiddles(double2 (*twr)[E], int t, const
   }
 }
 
-// where a pencil's elements live in shared memory
-struct ColAccess {  // column p of a 128-byte-swizzled tile (strided pass)
+// the lanes of one pencil meet: a warp, or -- a pencil spread over two warps -- named barrier 1 + p
+// (barrier 0 is __syncthreads'; a CTA has 16)
+template <int LANES>
+__device__ __forceinline__ void pencil_sync(int p) {
+  if constexpr (LANES <= 32) {
+    __syncwarp();
+  } else {
+    static_assert(LANES % 32 == 0, "a named barrier counts whole warps");
+    asm volatile("bar.sync %0, %1;\n" ::"r"(p + 1), "n"(LANES) : "memory");
+  }
+}
+
+// where a pencil's elements live in shared memory, and how its lanes synchronise
+struct ColAccess {  // column p of a 128-byte-swizzled tile (strided pass), pencil inside one warp
   uint32_t tile;
   int p;
   __device__ __forceinline__ uint32_t at(int e) const { return tile_addr(tile, e, p); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+template <int LANES>
+struct ColAccessWide {  // the same column, pencil spread over LANES / 32 warps
+  uint32_t tile;
+  int p;
+  __device__ __forceinline__ uint32_t at(int e) const { return tile_addr(tile, e, p); }
+  __device__ __forceinline__ void sync() const { pencil_sync<LANES>(p); }
 };
 struct RowAccess {  // a contiguous row of double2 (z pass)
   uint32_t row;
   __device__ __forceinline__ uint32_t at(int e) const { return row + (uint32_t)e * 16u; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
 template <int N, int E, int S, int DIR, int STG, class Acc>
@@ -201,7 +224,7 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc
       bf2<DIR>(v[j], v[j + NB]);
   }
   if constexpr (!last) {
-    __syncwarp();  // every lane has lifted its inputs out of the pencil's storage
+    acc.sync();  // every lane has lifted its inputs out of the pencil's storage
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const int b = t + j * LP;
@@ -216,7 +239,7 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc
         sts128(acc.at(e), x);
       }
     }
-    __syncwarp();
+    acc.sync();
 #pragma unroll
     for (int m = 0; m < E; ++m) {
       int e = t + m * LP;
@@ -339,7 +362,8 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
   constexpr int NSTG = StageCount<N>::value;
   constexpr int ROWS_PER_BOX = N > 256 ? 256 : N;
   using Tile = TmaTile<N, AUX>;
-  static_assert(LP <= 32 && LP >= 8, "a pencil must live inside one warp");
+  static_assert(LP >= 8 && (LP <= 32 || LP == 64), "a pencil lives inside one warp, or in two (named barrier per pencil)");
+  using Col = typename std::conditional<(LP <= 32), ColAccess, ColAccessWide<LP>>::type;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -435,7 +459,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
       for (int m = 0; m < E; ++m) v[m] = rc.apply(v[m], t + m * LP);
     }
 
-    wp_stages<N, E, 1, DIR, 0>(v, t, ColAccess{tbase, p}, twr);
+    wp_stages<N, E, 1, DIR, 0>(v, t, Col{tbase, p}, twr);
 
     if (sop.kind == K_INVLAP_SET || sop.kind == K_INVLAP_ADD) {
       RotCtx<N, AXIS> rc;
@@ -443,7 +467,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
 #pragma unroll
       for (int m = 0; m < E; ++m) v[m] = rc.apply(v[m], t + m * LP);
     }
-    __syncwarp();  // the last exchange's reads are done
+    pencil_sync<LP>(p);  // the last exchange's reads are done
 #pragma unroll
     for (int m = 0; m < E; ++m) sts128(tile_addr(tbase, t + m * LP, p), v[m]);
     fence_proxy_async();

@@ -356,6 +356,28 @@ def test_tma_pass_matches_cp_async_pass(N, monkeypatch):
     assert abs(out["1"][2] - out["0"][2]) <= 1e-13 * abs(out["0"][2])
 
 
+@pytest.mark.skipif(not os.environ.get("BGPU_HEAVY_TESTS"), reason="512^3: two 22 GB chains; set BGPU_HEAVY_TESTS=1 "
+                    "(the same comparison runs without Python in tools/native/fft_ab.cc, "
+                    "profiles/fft_ab_r01f_2warp_512.log)")
+def test_two_warp_pencils_match_one_warp_pencils_512(monkeypatch):
+    """BGPU_FFT_2WARP=1 spreads a 512-point strided pencil over two warps (named barrier per pencil,
+    fft_tma.cuh ColAccessWide).  Same radix sequence and twiddles, so the transforms are bit-identical."""
+    from barcode_b200.chain import Chain, Params
+    from barcode_b200 import inputs
+    N = 512
+    L = inputs.box_length(N)
+    a = np.random.default_rng(9).standard_normal((N, N, N))
+    out = {}
+    for v in ("0", "1"):
+        monkeypatch.setenv("BGPU_FFT_2WARP", v)
+        with Chain(Params(N1=N, L1=L, masskernel=1, likelihood=1, rsd_model=True, calc_h=0)) as ch:
+            c = ch.fft_r2c(a)
+            out[v] = (c, ch.fft_c2r(c))
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1])
+    assert rel_l2(out["1"][1], a) < 1e-14
+
+
 def test_fused_zy_kernel_matches_separate_passes(monkeypatch):
     """The opt-in fused z+y kernel (fft_fused.cuh, BGPU_FFT_FUSED=1: warp-specialised roles, the intermediate
     array handed over through L2 with per-plane flags) against numpy and against the separate passes."""
