@@ -70,6 +70,7 @@ struct bgpu_handle {
   double *delta = nullptr, *resid = nullptr, *tmp = nullptr;
   // scratch (half-complex)
   double2 *shat = nullptr, *dhat = nullptr, *work = nullptr, *acc = nullptr;
+  double2 *ubuf = nullptr;  // BGPU_SHARE_X=1: the x-passed field / the y-passed sum that a component triple shares
   // reductions
   double *partials = nullptr, *dscal = nullptr;
   double *hscal = nullptr;  // pinned
@@ -241,6 +242,25 @@ void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, d
     disp_a = 1.0;  // theta2velcomp on +theta (Lag2Eul.cc:238): the sign differs from the Zel'dovich branch
   }
   // Psi^_c = a (k_c/k^2)(Im f^, -Re f^)
+  if (h->ubuf) {
+    // shared x pass: k_y and k_z are constant along an x pencil, so B = IFFT_x[a/k^2 (Im f^, -Re f^)] (same zeroing
+    // rules) serves both: Psi_y = IFFT_zy[k_y B], Psi_z = IFFT_zy[k_z B] -- 2 x passes instead of 3
+    KOp lop;
+    lop.kind = K_DISP;
+    lop.comp = K_COMP_UNIT;
+    lop.a = disp_a;
+    lop.kfac = h->kfac;
+    h->fft.xpass(disp_src, h->ubuf, +1, lop, KOp{});
+    for (int c = 2; c >= 1; --c) {
+      KOp yl;
+      yl.kind = K_MULK;
+      yl.comp = c;
+      yl.kfac = h->kfac;
+      h->fft.c2r_yz(h->ubuf, h->work, h->psi[c], yl, scale_n);
+    }
+    lop.comp = 0;
+    h->fft.c2r(disp_src, h->work, h->psi[0], lop, scale_n);
+  } else
   for (int c = 2; c >= 0; --c) {
     KOp lop;
     lop.kind = K_DISP;
@@ -304,6 +324,37 @@ void r2c_plain(bgpu_handle *h, const double *in, double2 *out) {
   ROp lop;
   lop.kind = R_LOAD;
   h->fft.r2c(in, out, nullptr, lop, KOp{});
+}
+
+// h->acc = sum_c (k_c/k^2)(Im V^_c, -Re V^_c) (grad_inv_lap_FS + add_to_array, gradient.cpp:157-211): three forward
+// transforms whose x passes accumulate -- or, with the shared x pass, (k_x V^_x + FFT_x[k_y V~_y + k_z V~_z]) / k^2
+// with the sum of the y and z components formed after their y passes: 2 x passes instead of 3
+void backproject(bgpu_handle *h, double *const V[3]) {
+  ROp lop2;
+  lop2.kind = R_LOAD;
+  KOp sop2;
+  sop2.kfac = h->kfac;
+  if (h->ubuf) {
+    sop2.kind = K_INVLAP_SET;
+    sop2.comp = 0;
+    h->fft.r2c(V[0], h->work, h->acc, lop2, sop2);
+    for (int c = 1; c < 3; ++c) {
+      KOp ys;
+      ys.kind = (c == 1) ? K_MULK_SET : K_MULK_ADD;
+      ys.comp = c;
+      ys.kfac = h->kfac;
+      h->fft.r2c_zy(V[c], h->work, h->ubuf, lop2, ys);
+    }
+    sop2.kind = K_INVLAP_ADD;
+    sop2.comp = K_COMP_UNIT;
+    h->fft.xpass(h->ubuf, h->acc, -1, KOp{}, sop2);
+    return;
+  }
+  for (int c = 0; c < 3; ++c) {
+    sop2.kind = (c == 0) ? K_INVLAP_SET : K_INVLAP_ADD;
+    sop2.comp = c;
+    h->fft.r2c(V[c], h->work, h->acc, lop2, sop2);
+  }
 }
 
 // likelihood_grad_log_like + prior + sum (HMC.cc:146-206, HMC_models.cc:377-471):
@@ -388,6 +439,43 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
         }
       }
     }
+    if (p.likelihood == 1 && h->ubuf) {
+      // shared x passes on both sides: d_c(delta) = IFFT_zy[k_c IFFT_x[-(Im, -Re) delta^]] for c = y, z, and the
+      // products r d_y(delta), r d_z(delta) are summed after their forward y passes (see backproject)
+      KOp lop;
+      lop.kind = K_GRAD;
+      lop.comp = 0;
+      lop.kfac = h->kfac;
+      ROp sop;
+      sop.kind = R_SCALE_MUL;
+      sop.a = inv_n;
+      sop.aux = h->resid;
+      h->fft.c2r(h->dhat, h->work, h->tmp, lop, sop);
+      ROp lop2;
+      lop2.kind = R_LOAD;
+      KOp sop2;
+      sop2.kind = K_INVLAP_SET;
+      sop2.comp = 0;
+      sop2.kfac = h->kfac;
+      h->fft.r2c(h->tmp, h->work, h->acc, lop2, sop2);
+      lop.comp = K_COMP_UNIT;
+      h->fft.xpass(h->dhat, h->dhat, +1, lop, KOp{});   // in place: delta^ is not needed again
+      for (int c = 1; c < 3; ++c) {
+        KOp yl;
+        yl.kind = K_MULK;
+        yl.comp = c;
+        yl.kfac = h->kfac;
+        h->fft.c2r_yz(h->dhat, h->work, h->tmp, yl, sop);
+        KOp ys;
+        ys.kind = (c == 1) ? K_MULK_SET : K_MULK_ADD;
+        ys.comp = c;
+        ys.kfac = h->kfac;
+        h->fft.r2c_zy(h->tmp, h->work, h->ubuf, lop2, ys);
+      }
+      sop2.kind = K_INVLAP_ADD;
+      sop2.comp = K_COMP_UNIT;
+      h->fft.xpass(h->ubuf, h->acc, -1, KOp{}, sop2);
+    } else
     for (int c = 0; c < 3; ++c) {
       if (p.likelihood == 1) {
         KOp lop;
@@ -419,15 +507,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     launch_gather_adjoint_to(g, h->psi[0], h->psi[1], h->psi[2], h->xa, h->xb, h->tmp, h->resid, h->stream);
     double *V[3] = {h->xa, h->xb, h->tmp};
     for (int c = 0; c < 3; ++c) launch_cellbound_transpose(V[c], h->psi[c], h->N, h->stream);
-    for (int c = 0; c < 3; ++c) {
-      ROp lop2;
-      lop2.kind = R_LOAD;
-      KOp sop2;
-      sop2.kind = (c == 0) ? K_INVLAP_SET : K_INVLAP_ADD;
-      sop2.comp = c;
-      sop2.kfac = h->kfac;
-      h->fft.r2c(h->psi[c], h->work, h->acc, lop2, sop2);
-    }
+    backproject(h, h->psi);
     ROp unit;
     unit.kind = R_SCALE;
     unit.a = inv_n;
@@ -481,15 +561,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
       g.H = H;
       launch_gather_adjoint(g, h->psi[0], h->psi[1], h->psi[2], h->resid_ext, h->stream);
     }
-    for (int c = 0; c < 3; ++c) {
-      ROp lop2;
-      lop2.kind = R_LOAD;
-      KOp sop2;
-      sop2.kind = (c == 0) ? K_INVLAP_SET : K_INVLAP_ADD;
-      sop2.comp = c;
-      sop2.kfac = h->kfac;
-      h->fft.r2c(h->psi[c], h->work, h->acc, lop2, sop2);
-    }
+    backproject(h, h->psi);
   }
   // gradpsi = IFFT[(V/N)/P s^ + norm * h^]
   ROp sop;
@@ -856,6 +928,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     dalloc(h->phi1, h->n); dalloc(h->xa, h->n); dalloc(h->xb, h->n); dalloc(h->xc, h->n);
   }
   dalloc(h->shat, h->nh); dalloc(h->dhat, h->nh); dalloc(h->work, h->nh); dalloc(h->acc, h->nh);
+  if (h->fft.can_share_x()) dalloc(h->ubuf, h->nh);
   dalloc(h->partials, (size_t)kReduceBlocks); dalloc(h->dscal, (size_t)S_COUNT);
   BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hscal), S_COUNT * sizeof(double)));
   BGPU_CUDA(cudaMemsetAsync(h->dscal, 0, S_COUNT * sizeof(double), h->stream));
@@ -918,7 +991,7 @@ void bgpu_destroy(bgpu_handle *h) {
                      h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
     if (q) cudaFree(q);
-  double2 *cplx[] = {h->shat, h->dhat, h->work, h->acc, h->sendbuf, h->recvbuf};
+  double2 *cplx[] = {h->shat, h->dhat, h->work, h->acc, h->ubuf, h->sendbuf, h->recvbuf};
   for (double2 *q : cplx)
     if (q) cudaFree(q);
   if (h->copy_stream) {

@@ -48,6 +48,7 @@ struct Fft3d {
   // fused z+y kernel (fft_fused.cuh): per-plane completion counters, their running target, producer lead
   bool use_fused = false;  // BGPU_FFT_FUSED=1
   bool two_warp = false;   // BGPU_FFT_2WARP=1: 512-point strided pencils over two warps (fft_tma.cuh, ColAccessWide)
+  bool share_x = false;    // BGPU_SHARE_X=1: the y and z components of a K_DISP / K_GRAD / K_INVLAP triple share one x pass
   bool force_generic = false;  // BGPU_FFT_SLAB_GENERIC=1: slab passes through fft_slab_generic.cuh even where TMA fits
   unsigned long long *zy_ready = nullptr;
   mutable unsigned long long zy_epoch = 0;
@@ -91,6 +92,15 @@ struct Fft3d {
   //   lop : k-space load functor of the first (x) pass
   //   sop : real-space store functor of the z pass (carries the 1/N)
   void c2r(const double2 *in, double2 *work, double *out, KOp lop, ROp sop) const;
+
+  // Single passes for transforms that share their x pass (fft_ops.h K_MULK*, K_COMP_UNIT; single GPU, TMA sizes).
+  //   xpass   one x pass in -> out, dir = -1 forward / +1 inverse, load and store functors of RotCtxX
+  //   c2r_yz  the rest of an inverse transform: y pass in -> work with load functor ylop (in is preserved), z pass -> out
+  //   r2c_zy  the start of a forward transform: z pass in -> work, y pass work -> yout with store functor ysop
+  bool can_share_x() const;
+  void xpass(const double2 *in, double2 *out, int dir, KOp lop, KOp sop) const;
+  void c2r_yz(const double2 *in, double2 *work, double *out, KOp ylop, ROp sop) const;
+  void r2c_zy(const double *in, double2 *work, double2 *yout, ROp lop, KOp ysop) const;
 };
 
 }  // namespace bgpu

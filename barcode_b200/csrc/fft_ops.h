@@ -17,8 +17,16 @@ enum KKind : int {
   K_INVLAP_ADD = 6,  // store: out[off] += same
   K_NEGINVK2 = 7,    // a * v * (-1/k^2), 0 at k^2 == 0, no Nyquist zeroing (PoissonSolver, EqSolvers.cc:29-64)
   K_GAUSS = 8,       // v * K,       K = exp(-k^2 a^2 / 2), a = smoothing radius (kernelcomp filtertype 1, convolution.cpp:224-322)
-  K_ONE_MINUS_GAUSS = 9  // v * (1 - K)
+  K_ONE_MINUS_GAUSS = 9, // v * (1 - K)
+  // Shared x pass (BGPU_SHARE_X=1; understood by the extended strided kernels only, fft_tma.cuh RotCtxX).  The three
+  // components of a K_DISP / K_GRAD / K_INVLAP triple differ by the REAL factor k_c, and k_y, k_z are constant along
+  // an x pencil, so the y and z components can share one x pass run with comp = K_COMP_UNIT (k_c := 1, same
+  // zeroing rules) and pick up k_y / k_z in their y passes:
+  K_MULK = 10,       // load:  v * k_c                  (comp 1 or 2)
+  K_MULK_SET = 11,   // store: out[off]  = v * k_c
+  K_MULK_ADD = 12    // store: out[off] += v * k_c
 };
+constexpr int K_COMP_UNIT = 3;  // KOp::comp value: k_c := 1
 
 struct KOp {
   int kind = K_NONE;

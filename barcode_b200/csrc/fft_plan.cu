@@ -157,7 +157,7 @@ template <> struct TmaShape<512> { static constexpr int E = 16, MINB = 1; };
 // ring depth: as many stages (at most 3) as fit beside the co-resident CTAs
 template <int N, int AUX>
 struct TmaStages {
-  static constexpr int per_cta = (227 * 1024 - 2048) / (AUX == 0 ? TmaShape<N>::MINB : 1);
+  static constexpr int per_cta = (227 * 1024 - 2048) / (AUX <= 0 ? TmaShape<N>::MINB : 1);
   static constexpr int fit = per_cta / TmaTile<N, AUX>::stage_bytes;
   static constexpr int value = fit >= 3 ? 3 : fit;
 };
@@ -191,7 +191,7 @@ static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, 
       return;
     }
   }
-  constexpr int MINB = AUX == 0 ? TmaShape<N>::MINB : 1;
+  constexpr int MINB = AUX <= 0 ? TmaShape<N>::MINB : 1;
   constexpr int NSTAGE = TmaStages<N, AUX>::value;
   constexpr int threads = 8 * (N / E);
   constexpr int smem = NSTAGE * TmaTile<N, AUX>::stage_bytes + 1024 + 64;
@@ -657,6 +657,8 @@ void Fft3d::init(int n, cudaStream_t st) {
     // latency on the SM, not by HBM, so halving the HBM traffic does not pay by itself.
     const char *fg = std::getenv("BGPU_FFT_SLAB_GENERIC");
     force_generic = fg && fg[0] == '1';
+    const char *sx = std::getenv("BGPU_SHARE_X");
+    share_x = sx && sx[0] == '1';
     const char *tw2 = std::getenv("BGPU_FFT_2WARP");
     two_warp = tw2 && tw2[0] == '1';
     const char *fu = std::getenv("BGPU_FFT_FUSED");
@@ -692,6 +694,61 @@ void Fft3d::barrier() const {
 }
 
 bool Fft3d::supported(int n) { return n >= 8 && n <= 1024 && (n & (n - 1)) == 0; }
+
+// ---------------------------------------------------------------------------
+// shared x pass (BGPU_SHARE_X=1): single passes with the extended functors (fft_tma.cuh RotCtxX, AUX = -1)
+// ---------------------------------------------------------------------------
+bool Fft3d::can_share_x() const { return share_x && G == 1 && use_tma && !use_fused && (N == 128 || N == 256 || N == 512); }
+
+template <int N>
+static void xpass_impl(const Fft3d &f, const double2 *in, double2 *out, int dir, KOp lop, KOp sop) {
+  if constexpr (tma_has_size<N>()) {
+    if (dir > 0)
+      launch_strided_tma<N, +1, 0, -1>(f, in, out, lop, sop, PassIo{}, f.stream);
+    else
+      launch_strided_tma<N, -1, 0, -1>(f, in, out, lop, sop, PassIo{}, f.stream);
+  } else {
+    throw std::runtime_error("bgpu: the shared x pass needs the TMA-staged strided pass (N = 128, 256 or 512)");
+  }
+}
+
+template <int N>
+static void c2r_yz_impl(const Fft3d &f, const double2 *in, double2 *work, double *out, KOp ylop, ROp sop) {
+  if constexpr (tma_has_size<N>()) {
+    launch_strided_tma<N, +1, 1, -1>(f, in, work, ylop, KOp{}, PassIo{}, f.stream);
+    if (!try_c2r_zpass_tma<N>(f, work, out, sop)) throw std::runtime_error("bgpu: shared x pass: no bulk-copy z pass");
+  } else {
+    throw std::runtime_error("bgpu: the shared x pass needs the TMA-staged strided pass (N = 128, 256 or 512)");
+  }
+}
+
+template <int N>
+static void r2c_zy_impl(const Fft3d &f, const double *in, double2 *work, double2 *yout, ROp lop, KOp ysop) {
+  if constexpr (tma_has_size<N>()) {
+    if (!try_r2c_zpass_tma<N>(f, in, work, lop)) throw std::runtime_error("bgpu: shared x pass: no bulk-copy z pass");
+    launch_strided_tma<N, -1, 1, -1>(f, work, yout, KOp{}, ysop, PassIo{}, f.stream);
+  } else {
+    throw std::runtime_error("bgpu: the shared x pass needs the TMA-staged strided pass (N = 128, 256 or 512)");
+  }
+}
+
+void Fft3d::xpass(const double2 *in, double2 *out, int dir, KOp lop, KOp sop) const {
+#define CALL(n) xpass_impl<n>(*this, in, out, dir, lop, sop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
+
+void Fft3d::c2r_yz(const double2 *in, double2 *work, double *out, KOp ylop, ROp sop) const {
+#define CALL(n) c2r_yz_impl<n>(*this, in, work, out, ylop, sop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
+
+void Fft3d::r2c_zy(const double *in, double2 *work, double2 *yout, ROp lop, KOp ysop) const {
+#define CALL(n) r2c_zy_impl<n>(*this, in, work, yout, lop, ysop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
 
 void Fft3d::r2c(const double *in, double2 *out, double2 *xout, ROp lop, KOp sop) const {
 #define CALL(n) r2c_impl<n>(*this, in, out, xout, lop, sop)

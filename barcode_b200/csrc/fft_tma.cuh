@@ -350,6 +350,47 @@ struct RotCtx {
   }
 };
 
+// RotCtx plus the kinds of the shared x pass (fft_ops.h): comp = K_COMP_UNIT and the real k_c multipliers.
+// A separate struct so that the kernels of the default path compile to the same code as before.
+template <int N, int AXIS>
+struct RotCtxX {
+  double k_oth, k_z, c2, kfac, a;
+  int sel;       // 0 = k along the pencil, 1 = the other strided axis, 2 = z, 3 = unit
+  int kind;
+  bool masked;
+  __device__ __forceinline__ void setup(const KOp &op, int other, int iz) {
+    kind = op.kind;
+    kfac = op.kfac;
+    a = op.a;
+    k_oth = kval(other, N, op.kfac);
+    k_z = kval(iz, N, op.kfac);
+    c2 = k_oth * k_oth + k_z * k_z;
+    masked = (other == N / 2) || (iz == N / 2);
+    sel = (op.comp == K_COMP_UNIT) ? 3 : ((op.comp == 2) ? 2 : ((op.comp == (AXIS == 0 ? 0 : 1)) ? 0 : 1));
+  }
+  __device__ __forceinline__ double2 apply(double2 v, int r) const {
+    const double kr = kval(r, N, kfac);
+    const double kc = sel == 3 ? 1.0 : (sel == 0 ? kr : (sel == 1 ? k_oth : k_z));
+    if (kind == K_MULK || kind == K_MULK_SET || kind == K_MULK_ADD) return make_double2(kc * v.x, kc * v.y);
+    double f;
+    if (kind == K_GRAD) {
+      f = -kc;
+    } else {  // K_DISP, K_INVLAP_SET, K_INVLAP_ADD
+      const double ksq = kr * kr + c2;
+      f = kc * __drcp_rn(ksq);
+      if (kind == K_DISP) {
+        f *= a;
+        if (!(ksq > 1.e-14)) f = 0.0;
+      } else if (!(ksq > 0.0)) {
+        f = 0.0;
+      }
+    }
+    if (masked || r == N / 2) f = 0.0;
+    return make_double2(f * v.y, -(f * v.x));
+  }
+};
+
+// AUX: 0 none, 1 real multiplier tile (K_MULREAL), 2 real + complex (K_FINAL), -1 none + the functors of RotCtxX
 template <int N, int E, int NSTAGE, int DIR, int AXIS, int AUX, int MINB>
 __global__ void __launch_bounds__(8 * (N / E), MINB)
     fft_strided_tma(const __grid_constant__ TmaMaps maps, const double2 *__restrict__ tw, KOp lop, KOp sop,
@@ -453,7 +494,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
         }
       }
     } else if (lop.kind != K_NONE) {
-      RotCtx<N, AXIS> rc;
+      typename std::conditional<AUX == -1, RotCtxX<N, AXIS>, RotCtx<N, AXIS>>::type rc;
       rc.setup(lop, other + geo.other0, iz);
 #pragma unroll
       for (int m = 0; m < E; ++m) v[m] = rc.apply(v[m], t + m * LP);
@@ -461,8 +502,8 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
 
     wp_stages<N, E, 1, DIR, 0>(v, t, Col{tbase, p}, twr);
 
-    if (sop.kind == K_INVLAP_SET || sop.kind == K_INVLAP_ADD) {
-      RotCtx<N, AXIS> rc;
+    if (AUX == -1 ? sop.kind != K_NONE : (sop.kind == K_INVLAP_SET || sop.kind == K_INVLAP_ADD)) {
+      typename std::conditional<AUX == -1, RotCtxX<N, AXIS>, RotCtx<N, AXIS>>::type rc;
       rc.setup(sop, other + geo.other0, iz);
 #pragma unroll
       for (int m = 0; m < E; ++m) v[m] = rc.apply(v[m], t + m * LP);
@@ -491,7 +532,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
       for (int r0 = 0; r0 < N; r0 += ROWS_PER_BOX) {
         const int c1 = AXIS == 0 ? other : r0, c2 = AXIS == 0 ? r0 : other;
         const void *src = smem_al + s * Tile::stage_bytes + r0 * 128;
-        if (sop.kind == K_INVLAP_ADD)
+        if (sop.kind == K_INVLAP_ADD || (AUX == -1 && sop.kind == K_MULK_ADD))
           tma_reduce_add_3d(&maps.out, zt * 2 * T, c1, c2, src);
         else
           tma_store_3d(&maps.out, zt * 2 * T, c1, c2, src);

@@ -378,6 +378,35 @@ def test_two_warp_pencils_match_one_warp_pencils_512(monkeypatch):
     assert rel_l2(out["1"][1], a) < 1e-14
 
 
+@pytest.mark.skipif(not os.environ.get("BGPU_UNVERIFIED_TESTS"), reason="BGPU_SHARE_X=1 was written after the round's GPU "
+                    "budget was spent (default kernels are SASS-identical, tools/sass_identity.py); its algebra is "
+                    "checked on the CPU in tests/test_host.py; run this first thing next round")
+@pytest.mark.parametrize("calc_h,sfmodel,rsd", [(0, 1, True), (4, 1, True), (4, 1, False), (0, 3, False), (4, 3, False)])
+def test_shared_x_pass_matches_separate_transforms(calc_h, sfmodel, rsd, monkeypatch):
+    """BGPU_SHARE_X=1: the y and z components of the displacement, gradient and back-projection triples share one
+    x pass (fft_ops.h K_MULK*, K_COMP_UNIT) -- 9 x passes per calc_h = 0 evaluation instead of 12, same result to rounding."""
+    from barcode_b200.chain import Chain, Params
+    from barcode_b200 import inputs
+    N = 128
+    L = inputs.box_length(N)
+    rng = np.random.default_rng(21)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L)
+    n = N ** 3
+    s = 0.3 * rng.standard_normal(n)
+    nobs = 1.0 + 0.1 * rng.standard_normal(n)
+    out = {}
+    for v in ("0", "1"):
+        monkeypatch.setenv("BGPU_SHARE_X", v)
+        with Chain(Params(N1=N, L1=L, masskernel=1, likelihood=1, rsd_model=rsd, sfmodel=sfmodel, calc_h=calc_h,
+                          correct_delta=True)) as ch:
+            ch.set_static(Power=P, nobs=nobs, noise=np.ones(n), window=np.ones(n))
+            out[v] = (ch.gradient_psi(s), ch.forward(s), ch.psi(s)[:2])
+    assert rel_l2(out["1"][1], out["0"][1]) < 1e-13
+    assert rel_l2(out["1"][0], out["0"][0]) < 1e-12
+    for a, b in zip(out["1"][2], out["0"][2]):
+        assert abs(a - b) <= 1e-12 * abs(b)
+
+
 def test_fused_zy_kernel_matches_separate_passes(monkeypatch):
     """The opt-in fused z+y kernel (fft_fused.cuh, BGPU_FFT_FUSED=1: warp-specialised roles, the intermediate
     array handed over through L2 with per-plane flags) against numpy and against the separate passes."""

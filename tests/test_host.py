@@ -69,3 +69,47 @@ def test_device_normals_oracle_statistics():
     assert np.array_equal(bo.device_normals(12345, 7, 0, 1000, 64), x[1000:1064])
     assert not np.array_equal(bo.device_normals(12345, 8, 0, 0, 64), x[:64])
     assert not np.array_equal(bo.device_normals(12345, 7, 1, 0, 64), x[:64])
+
+
+def test_shared_x_pass_algebra():
+    """The pass sequence behind BGPU_SHARE_X=1 (api.cu forward_from_shat / backproject, fft_ops.h K_MULK*,
+    K_COMP_UNIT), emulated pass by pass with numpy, against the three separate transforms it replaces: k_y and k_z
+    are constant along an x pencil, so the y and z components of a displacement / gradient / back-projection triple
+    can share one x pass (same Nyquist and k^2 zeroing rules, EqSolvers.cc:208-268, gradient.cpp:38-74,167-210)."""
+    from barcode_b200 import inputs
+    N, L, a = 16, 50.0, -0.7
+    rng = np.random.default_rng(3)
+    k1 = inputs.calc_ki(N, L)
+    nzh = N // 2 + 1
+    kx, ky, kz = k1[:, None, None], k1[None, :, None], k1[None, None, :nzh]
+    k2 = kx ** 2 + ky ** 2 + kz ** 2
+    idx = np.arange(N)
+    nyq = (idx[:, None, None] == N // 2) | (idx[None, :, None] == N // 2) | (idx[None, None, :nzh] == N // 2)
+    rot = lambda v: v.imag - 1j * v.real                        # (Im v, -Re v)
+    inv_disp = np.where((k2 > 1e-14) & ~nyq, a / np.where(k2 > 0, k2, 1.0), 0.0)
+    inv_lap = np.where((k2 > 0) & ~nyq, 1.0 / np.where(k2 > 0, k2, 1.0), 0.0)
+    kc = (kx, ky, kz)
+
+    # displacement triple: Psi_c = IFFT[a k_c / k^2 (Im s^, -Re s^)]
+    shat = np.fft.rfftn(rng.standard_normal((N, N, N)))
+    B = np.fft.ifft(inv_disp * rot(shat), axis=0)                # the shared x pass, comp = K_COMP_UNIT
+    for c in (1, 2):
+        direct = np.fft.irfftn(kc[c] * inv_disp * rot(shat), s=(N, N, N))
+        shared = np.fft.irfft(np.fft.ifft(kc[c] * B, axis=1), n=N, axis=2)   # K_MULK on the y pass's load, z pass
+        assert np.abs(shared - direct).max() < 1e-13 * np.abs(direct).max()
+
+    # gradient triple (gradfft): d_c = IFFT[-k_c (Im d^, -Re d^)], zero on the Nyquist planes
+    G = np.fft.ifft(np.where(nyq, 0.0, -1.0) * rot(shat), axis=0)
+    for c in (1, 2):
+        direct = np.fft.irfftn(np.where(nyq, 0.0, -kc[c]) * rot(shat) + 0 * k2, s=(N, N, N))
+        shared = np.fft.irfft(np.fft.ifft(kc[c] * G, axis=1), n=N, axis=2)
+        assert np.abs(shared - direct).max() < 1e-13 * np.abs(direct).max()
+
+    # back-projection triple: acc = sum_c k_c / k^2 (Im V^_c, -Re V^_c)
+    V = [rng.standard_normal((N, N, N)) for _ in range(3)]
+    direct = sum(kc[c] * inv_lap * rot(np.fft.rfftn(V[c])) for c in range(3))
+    zy = lambda v: np.fft.fft(np.fft.rfft(v, axis=2), axis=1)    # z pass, y pass
+    U = ky * zy(V[1])                                            # K_MULK_SET on the y pass's store
+    U = U + kz * zy(V[2])                                        # K_MULK_ADD (TMA reduce-add)
+    shared = kx * inv_lap * rot(np.fft.rfftn(V[0])) + inv_lap * rot(np.fft.fft(U, axis=0))   # K_INVLAP_ADD, unit
+    assert np.abs(shared - direct).max() < 1e-13 * np.abs(direct).max()
