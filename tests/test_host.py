@@ -94,14 +94,14 @@ def test_shared_x_pass_algebra():
     shat = np.fft.rfftn(rng.standard_normal((N, N, N)))
     B = np.fft.ifft(inv_disp * rot(shat), axis=0)                # the shared x pass, comp = K_COMP_UNIT
     for c in (1, 2):
-        direct = np.fft.irfftn(kc[c] * inv_disp * rot(shat), s=(N, N, N))
+        direct = np.fft.irfftn(kc[c] * inv_disp * rot(shat), s=(N, N, N), axes=(0, 1, 2))
         shared = np.fft.irfft(np.fft.ifft(kc[c] * B, axis=1), n=N, axis=2)   # K_MULK on the y pass's load, z pass
         assert np.abs(shared - direct).max() < 1e-13 * np.abs(direct).max()
 
     # gradient triple (gradfft): d_c = IFFT[-k_c (Im d^, -Re d^)], zero on the Nyquist planes
     G = np.fft.ifft(np.where(nyq, 0.0, -1.0) * rot(shat), axis=0)
     for c in (1, 2):
-        direct = np.fft.irfftn(np.where(nyq, 0.0, -kc[c]) * rot(shat) + 0 * k2, s=(N, N, N))
+        direct = np.fft.irfftn(np.where(nyq, 0.0, -kc[c]) * rot(shat) + 0 * k2, s=(N, N, N), axes=(0, 1, 2))
         shared = np.fft.irfft(np.fft.ifft(kc[c] * G, axis=1), n=N, axis=2)
         assert np.abs(shared - direct).max() < 1e-13 * np.abs(direct).max()
 
