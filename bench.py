@@ -43,9 +43,12 @@ def parse():
     ap.add_argument("--calc-h", type=int, default=0, choices=[0, 1, 4])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="chains", choices=["chains", "slab"],
+    ap.add_argument("--mode", default="chains", choices=["chains", "slab", "e2e_chains"],
                     help="N > 1 GPUs: independent chains (weak scaling, default) or ONE chain, x-slab decomposed "
-                         "(strong scaling; BASELINE.json configs[3], [4])")
+                         "(strong scaling; BASELINE.json configs[3], [4]).  e2e_chains (internal, one GPU): the "
+                         "host-buffer call of several independent chains interleaved on ONE GPU, see run_e2e_chains")
+    ap.add_argument("--chains", type=int, default=2, help="e2e_chains: chains (handles, host threads) on the GPU")
+    ap.add_argument("--no-e2e-chains", action="store_true", help="skip the interleaved-chains e2e leg")
     return ap.parse_args()
 
 
@@ -409,6 +412,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = cpu_baseline(args, cfg)
     ch.close()
+    if rank == 0 and world == 1 and not args.no_e2e_chains:
+        # independent chains interleaved on the GPU hide the PCIe transfers of one under the kernels of another;
+        # measured in a child process with a timeout, reported beside (not instead of) the single-chain e2e.value
+        e2e["interleaved_chains"] = e2e_chains_leg(args)
 
     if rank == 0:
         line = {
@@ -432,6 +439,114 @@ def run_ours(args):
         print(json.dumps(line))
     multi.finalize()
     return 0
+
+
+def run_e2e_chains(args):
+    """Host-buffer gradient evaluations of `--chains` independent chains interleaved on ONE GPU.
+
+    A single synchronous bgpu_gradient_psi(host -> host) call is PCIe-bound: the signal goes up, the evaluation
+    runs, the gradient comes down (e2e.value).  Independent chains -- the reference's own multi-chain mode, SURVEY
+    8e -- do not depend on each other, so one host thread per chain, each with its own handle, stream and pinned
+    buffers, lets chain B's transfers ride under chain A's kernels (two copy engines + the SMs).  Every call is
+    still the reference-facing C-ABI call with host buffers, H2D and D2H inside the timed region; value = all
+    chains' evaluations / wall time.  Runs in its own process (bench.py spawns it with a timeout) so that the
+    headline numbers cannot depend on it."""
+    import ctypes as C
+    import threading
+    import torch
+    from barcode_b200 import chain as bc
+    from barcode_b200 import inputs
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    cfg, name = workload(args.grid, args.calc_h)
+    n = args.grid ** 3
+    nch = max(1, args.chains)
+    chains = [bc.Chain(bc.Params(device=dev, **cfg)) for _ in range(nch)]
+    prob = inputs.synthetic_problem(chains[0], seed=1)
+    for ch in chains[1:]:
+        ch.set_static(Power=prob["Power"], nobs=prob["nobs"], noise=prob["noise"], window=prob["window"])
+    dp = C.POINTER(C.c_double)
+    sig = np.ascontiguousarray(prob["signal"]).reshape(-1)
+    h_s = [torch.from_numpy(sig.copy()).pin_memory() for _ in range(nch)]
+    h_g = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(nch)]
+
+    def step(i):
+        ch = chains[i]
+        rc = ch.L.bgpu_gradient_psi(ch._h, C.cast(h_s[i].data_ptr(), dp), C.cast(h_g[i].data_ptr(), dp))
+        if rc != 0:
+            raise RuntimeError(ch.L.bgpu_last_error().decode())
+
+    # warm-up one chain at a time (this also initialises the library's per-kernel launch configuration serially)
+    for i in range(nch):
+        for _ in range(max(1, args.warmup)):
+            step(i)
+    torch.cuda.synchronize()
+    ref_g = h_g[0].clone()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(0)
+    torch.cuda.synchronize()
+    dt_single = time.perf_counter() - t0
+
+    errors = []
+    gate = threading.Barrier(nch + 1)
+
+    def worker(i):
+        try:
+            gate.wait()
+            for _ in range(args.steps):
+                step(i)
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"chain {i}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(nch)]
+    for t in threads:
+        t.start()
+    gate.wait()
+    t0 = time.perf_counter()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if errors:
+        raise RuntimeError("; ".join(errors))
+    # every chain evaluated the same signal on the same data: the results must agree with the lone call
+    # (to rounding: the scatter's atomics are not ordered)
+    worst = max(float(torch.linalg.vector_norm(g - ref_g) / torch.linalg.vector_norm(ref_g)) for g in h_g)
+    for ch in chains:
+        ch.close()
+    print(json.dumps({
+        "value": nch * args.steps / dt, "unit": UNIT, "chains_per_gpu": nch, "steps_per_chain": args.steps,
+        "ms_per_eval": 1e3 * dt / (nch * args.steps), "single_chain_same_process": args.steps / dt_single,
+        "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+        "max_rel_l2_vs_lone_call": worst, "workload": name,
+        "api": "bgpu_gradient_psi(host signal -> host gradpsi), pinned host buffers, one host thread + handle + "
+               "stream per chain"}))
+    return 0 if worst < 1e-10 else 1
+
+
+def e2e_chains_leg(args, timeout_s=240):
+    """Run run_e2e_chains in a child process; returns its JSON or {"error": ...} -- never raises, never hangs."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--mode", "e2e_chains", "--grid", str(args.grid),
+           "--calc-h", str(args.calc_h), "--steps", str(args.steps), "--warmup", str(args.warmup),
+           "--chains", str(args.chains)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if not lines:
+            return {"error": f"exit {r.returncode}: {r.stderr.strip()[-300:]}"}
+        out = json.loads(lines[-1])
+        if r.returncode != 0:
+            out["error"] = f"exit {r.returncode}"
+        return out
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout_s} s"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def run_slab(args):
@@ -529,6 +644,8 @@ def main():
     sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         rc = run_reference(args)
+    elif args.mode == "e2e_chains":
+        rc = run_e2e_chains(args)
     elif args.mode == "slab":
         rc = run_slab(args)
     else:

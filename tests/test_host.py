@@ -113,3 +113,17 @@ def test_shared_x_pass_algebra():
     U = U + kz * zy(V[2])                                        # K_MULK_ADD (TMA reduce-add)
     shared = kx * inv_lap * rot(np.fft.rfftn(V[0])) + inv_lap * rot(np.fft.fft(U, axis=0))   # K_INVLAP_ADD, unit
     assert np.abs(shared - direct).max() < 1e-13 * np.abs(direct).max()
+
+
+def test_e2e_chains_leg_never_raises_without_a_gpu():
+    """bench.py's interleaved-chains e2e leg runs in a child process with a timeout: where it cannot run (no GPU
+    here) the bench line gets an error string, not an exception -- and no CPU fallback number."""
+    import argparse
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is visible; the failure path is exercised on the CPU box")
+    sys.path.insert(0, ROOT)
+    import bench
+    out = bench.e2e_chains_leg(argparse.Namespace(grid=32, calc_h=0, steps=2, warmup=1, chains=2), timeout_s=120)
+    assert set(out) == {"error"} and "no CUDA device" in out["error"]
