@@ -315,6 +315,8 @@ def run_ours(args):
     # x pass: every launch reads and writes the half-complex array once (32 B / element); the last one of an
     # evaluation also reads its operands -- (V/N)/P (8 B) for calc_h = 1, plus the accumulated h^ (16 B) otherwise
     x_launches = {0: 12, 1: 5, 4: 8}[args.calc_h]
+    if os.environ.get("BGPU_SHARE_X") == "1":   # opt-in shared x pass: two x passes per component triple
+        x_launches = {0: 9, 1: 5, 4: 6}[args.calc_h]
     x_bytes = ((x_launches - 1) * 32 + (40 if args.calc_h == 1 else 56)) * nh / x_launches
     alg_bytes = {  # algorithmic bytes per launch of each kernel class ("Kernels")
         "fft_strided_pass_y": 2 * nh * 16, "fft_strided_pass_x": x_bytes,
