@@ -493,9 +493,21 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
       ROp lop2;
       lop2.kind = R_LOAD;
       KOp sop2;
+      sop2.kfac = h->kfac;
+      if (h->ubuf && c > 0) {
+        // shared x pass of the back-projection (see backproject): the y and z products meet after their y passes
+        sop2.kind = (c == 1) ? K_MULK_SET : K_MULK_ADD;
+        sop2.comp = c;
+        h->fft.r2c_zy(h->tmp, h->work, h->ubuf, lop2, sop2);
+        if (c == 2) {
+          sop2.kind = K_INVLAP_ADD;
+          sop2.comp = K_COMP_UNIT;
+          h->fft.xpass(h->ubuf, h->acc, -1, KOp{}, sop2);
+        }
+        continue;
+      }
       sop2.kind = (c == 0) ? K_INVLAP_SET : K_INVLAP_ADD;
       sop2.comp = c;
-      sop2.kfac = h->kfac;
       h->fft.r2c(h->tmp, h->work, h->acc, lop2, sop2);
     }
   } else if (p.calc_h == BGPU_CALC_H_EXACT && h->phi1) {

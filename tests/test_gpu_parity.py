@@ -381,8 +381,9 @@ def test_two_warp_pencils_match_one_warp_pencils_512(monkeypatch):
 @pytest.mark.skipif(not os.environ.get("BGPU_UNVERIFIED_TESTS"), reason="BGPU_SHARE_X=1 was written after the round's GPU "
                     "budget was spent (default kernels are SASS-identical, tools/sass_identity.py); its algebra is "
                     "checked on the CPU in tests/test_host.py; run this first thing next round")
-@pytest.mark.parametrize("calc_h,sfmodel,rsd", [(0, 1, True), (4, 1, True), (4, 1, False), (0, 3, False), (4, 3, False)])
-def test_shared_x_pass_matches_separate_transforms(calc_h, sfmodel, rsd, monkeypatch):
+@pytest.mark.parametrize("calc_h,sfmodel,rsd,like", [(0, 1, True, 1), (4, 1, True, 1), (4, 1, False, 1), (0, 3, False, 1),
+                                                     (4, 3, False, 1), (0, 1, False, 0), (0, 1, False, 2)])
+def test_shared_x_pass_matches_separate_transforms(calc_h, sfmodel, rsd, like, monkeypatch):
     """BGPU_SHARE_X=1: the y and z components of the displacement, gradient and back-projection triples share one
     x pass (fft_ops.h K_MULK*, K_COMP_UNIT) -- 9 x passes per calc_h = 0 evaluation instead of 12, same result to rounding."""
     from barcode_b200.chain import Chain, Params
@@ -397,7 +398,7 @@ def test_shared_x_pass_matches_separate_transforms(calc_h, sfmodel, rsd, monkeyp
     out = {}
     for v in ("0", "1"):
         monkeypatch.setenv("BGPU_SHARE_X", v)
-        with Chain(Params(N1=N, L1=L, masskernel=1, likelihood=1, rsd_model=rsd, sfmodel=sfmodel, calc_h=calc_h,
+        with Chain(Params(N1=N, L1=L, masskernel=1, likelihood=like, rsd_model=rsd, sfmodel=sfmodel, calc_h=calc_h,
                           correct_delta=True)) as ch:
             ch.set_static(Power=P, nobs=nobs, noise=np.ones(n), window=np.ones(n))
             out[v] = (ch.gradient_psi(s), ch.forward(s), ch.psi(s)[:2])
