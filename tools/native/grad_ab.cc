@@ -3,7 +3,7 @@
 // bgpu_gradient_psi and bgpu_psi on a default handle and on a handle created with VAR=1; prints the relative L2
 // difference of the gradients, the two energies, and the per-kernel-class device times of one evaluation each.
 //   g++ -O2 -fopenmp -I include tools/native/grad_ab.cc -L barcode_b200 -lbarcode_b200 -Wl,-rpath,'$ORIGIN/../../barcode_b200' -o tools/native/grad_ab
-//   tools/native/grad_ab BGPU_SHARE_X 256 [calc_h [sfmodel [rsd]]]
+//   tools/native/grad_ab BGPU_SHARE_X 256 [calc_h [sfmodel [rsd [likelihood]]]]
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -57,6 +57,7 @@ int main(int argc, char **argv) {
   const int calc_h = argc > 3 ? std::atoi(argv[3]) : 0;
   const int sfmodel = argc > 4 ? std::atoi(argv[4]) : 1;
   const int rsd = argc > 5 ? std::atoi(argv[5]) : (sfmodel == 1 ? 1 : 0);
+  const int likelihood = argc > 6 ? std::atoi(argv[6]) : 1;
   const double t0 = now();
   const size_t n = (size_t)N * N * N;
   bgpu_params p;
@@ -66,6 +67,7 @@ int main(int argc, char **argv) {
   p.calc_h = calc_h;
   p.sfmodel = sfmodel;
   p.rsd_model = rsd;
+  p.likelihood = likelihood;
   p.correct_delta = 1;
   p.deltaQ_factor = 1.0;
   bgpu_handle *H[2] = {nullptr, nullptr};
@@ -74,8 +76,8 @@ int main(int argc, char **argv) {
   setenv(var, "1", 1);
   CHECK(bgpu_create(&p, &H[1]));
   unsetenv(var);
-  std::printf("%s A/B at %d^3, calc_h %d, sfmodel %d, rsd %d: handles up at %.2f s\n", var, N, calc_h, sfmodel, rsd,
-              now() - t0);
+  std::printf("%s A/B at %d^3, calc_h %d, sfmodel %d, rsd %d, likelihood %d: handles up at %.2f s\n", var, N, calc_h,
+              sfmodel, rsd, likelihood, now() - t0);
 
   std::vector<double> power(n), nobs(n), ones(n, 1.0), sig(n), grad[2];
   const double kf = 2.0 * M_PI / p.L1;

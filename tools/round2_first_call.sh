@@ -6,7 +6,7 @@
 OUT=gpurun_out/r02_first
 mkdir -p $OUT
 # 1. shared x pass: parity + per-kernel times, Python-free, seconds each
-for cfg in "256 0" "256 4" "128 0 3 0" "128 4 3 0" "512 0"; do
+for cfg in "256 0" "256 4" "128 0 3 0" "128 4 3 0" "128 0 1 0 0" "512 0"; do
   timeout 120 tools/native/grad_ab BGPU_SHARE_X $cfg > "$OUT/grad_ab_share_x_${cfg// /_}.log" 2>&1
   tail -4 "$OUT/grad_ab_share_x_${cfg// /_}.log"
 done
