@@ -43,8 +43,8 @@ initial_guess = 0
 initial_guess_file = deltaLAGtest
 initial_guess_smoothing_type = 1
 initial_guess_smoothing_scale = 20.
-N_eps_fac = 4.0
-eps_fac_update_type = 0
+N_eps_fac = {n_eps_fac}
+eps_fac_update_type = {eps_update}
 eps_fac = {eps_fac}
 eps_fac_initial = 0.5
 eps_fac_power = 2
@@ -67,7 +67,7 @@ slength = 4.
 Nx = {N}
 Lx = {L}
 z  = .0
-N_bin = 20
+N_bin = {n_bin}
 N_Gibbs = {n_gibbs}
 total_steps_lim = 0
 masskernel = {masskernel}
@@ -94,6 +94,13 @@ s_eps_total_scaling = 0.5
 """
 
 
+PAR_DEFAULTS = dict(n_eps_fac=4.0, eps_update=0, n_bin=20)
+
+
+def make_par(**kw):
+    return INPUT_PAR.format(**{**PAR_DEFAULTS, **kw})
+
+
 def run(exe, d, par):
     os.makedirs(os.path.join(d, "data"), exist_ok=True)
     open(os.path.join(d, "input.par"), "w").write(par)
@@ -115,7 +122,7 @@ def test_unchanged_host_driver_runs_on_the_gpu_path(tmp_path, masskernel, likeli
     with open(pk, "w") as o:
         for a, b in zip(k, P):
             o.write(f"{a:.9g} {b:.9g}\n")
-    par = INPUT_PAR.format(calc_h=0, rsd=rsd, likelihood=likelihood, eps_fac=0.004, mass_type=mass_type, pk=pk,
+    par = make_par(calc_h=0, rsd=rsd, likelihood=likelihood, eps_fac=0.004, mass_type=mass_type, pk=pk,
                            N=16, L=50.0, n_gibbs=3, masskernel=masskernel)
     hdr_c, log_c = run(CPU, str(tmp_path / "cpu"), par)
     hdr_g, log_g = run(GPU, str(tmp_path / "gpu"), par)
@@ -150,7 +157,7 @@ def test_host_driver_with_the_device_momentum_generator(tmp_path, monkeypatch):
     with open(pk, "w") as o:
         for a, b in zip(k, P):
             o.write(f"{a:.9g} {b:.9g}\n")
-    par = INPUT_PAR.format(calc_h=0, rsd="false", likelihood=1, eps_fac=0.004, mass_type=1, pk=pk, N=16, L=50.0,
+    par = make_par(calc_h=0, rsd="false", likelihood=1, eps_fac=0.004, mass_type=1, pk=pk, N=16, L=50.0,
                            n_gibbs=4, masskernel=1)
     _, log_host = run(GPU, str(tmp_path / "host_rng"), par)
     monkeypatch.setenv("BARCODE_GPU_DEVICE_RNG", "1")
@@ -175,3 +182,32 @@ def test_host_driver_with_the_device_momentum_generator(tmp_path, monkeypatch):
         assert np.all(np.abs(log[:, -2] - 2047.5) < 6 * np.sqrt(2047.5))
     a = np.fromfile(tmp_path / "dev_rng" / "data" / "deltaLAG_4")
     assert a.shape == (16 ** 3,) and np.all(np.isfinite(a))
+
+
+@pytest.mark.skipif(not (os.path.exists(CPU) and os.path.exists(GPU)), reason="oracle/_ref binaries not built")
+@pytest.mark.skipif(not os.environ.get("BGPU_UNVERIFIED_TESTS"), reason="added after the round's GPU budget was spent; its CPU "
+                    "half runs in tests/test_oracle_ref.py::test_reference_smoke_config_runs; run the GPU half next round")
+def test_the_reference_smoke_config_on_the_gpu_path(tmp_path):
+    """The reference's only integration test (test/run/input.par, .travis.yml:75-80): its shipped data/input.par --
+    SPH kernel, calc_h = 2, adaptive step size (eps_fac_update_type 3), N_eps_fac 8, N_bin 200 -- at Nx = 8,
+    Lx = 500, N_Gibbs = 5.  The reference only checks that the process exits; here the GPU drop-in must also
+    write the same log and fields as the CPU build."""
+    with np.load(os.path.join(GOLDEN, "pk_table.npz")) as f:
+        k, P = f["k"], f["P"]
+    pk = tmp_path / "pk.dat"
+    with open(pk, "w") as o:
+        for a, b in zip(k, P):
+            o.write(f"{a:.9g} {b:.9g}\n")
+    par = make_par(calc_h=2, rsd="false", likelihood=1, eps_fac=0.0, mass_type=1, pk=pk, N=8, L=500.0, n_gibbs=5,
+                   masskernel=3, n_eps_fac=8.0, eps_update=3, n_bin=200)
+    hdr_c, log_c = run(CPU, str(tmp_path / "cpu"), par)
+    hdr_g, log_g = run(GPU, str(tmp_path / "gpu"), par)
+    assert hdr_c == hdr_g and log_c.shape == log_g.shape and log_c.shape[0] >= 5
+    assert np.array_equal(log_c[:, 0], log_g[:, 0]) and np.array_equal(log_c[:, 2], log_g[:, 2])
+    scale = np.abs(log_c[:, 8:]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(log_c[:, 8:] - log_g[:, 8:]) <= 2e-5 * scale)
+    for name in ("deltaLAG_5", "deltaEUL_5", "auxmass_f"):
+        a = np.fromfile(tmp_path / "cpu" / "data" / name)
+        b = np.fromfile(tmp_path / "gpu" / "data" / name)
+        assert a.shape == b.shape == (8 ** 3,), name
+        assert rel_l2(b, a) < 1e-7, name

@@ -76,3 +76,30 @@ def test_reference_vs_restatement(mk, like, rsd, calc_h, mass_type):
     assert rel_l2(momo, mom) < 1e-13
     assert abs(bo.kinetic_term(p, mom, mf, mr) - R.kinetic(mom)) <= 1e-12 * abs(R.kinetic(mom))
     R.close()
+
+
+def test_reference_smoke_config_runs(tmp_path):
+    """The reference's only integration test (test/run/input.par via .travis.yml:75-80: its shipped data/input.par
+    at Nx = 8, Lx = 500, N_Gibbs = 5 -- SPH kernel, calc_h = 2, adaptive step size; passes if the process exits).
+    Here: the unmodified reference program built by oracle/Makefile runs it to completion and writes the log and
+    the per-sample fields; tests/test_dropin.py compares the GPU drop-in against exactly this run."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    td = importlib.import_module("test_dropin")
+    if not os.path.exists(td.CPU):
+        pytest.skip("oracle/_ref/barcode_cpu not built")
+    with np.load(os.path.join(td.GOLDEN, "pk_table.npz")) as f:
+        k, P = f["k"], f["P"]
+    pk = tmp_path / "pk.dat"
+    with open(pk, "w") as o:
+        for a, b in zip(k, P):
+            o.write(f"{a:.9g} {b:.9g}\n")
+    par = td.make_par(calc_h=2, rsd="false", likelihood=1, eps_fac=0.0, mass_type=1, pk=pk, N=8, L=500.0, n_gibbs=5,
+                      masskernel=3, n_eps_fac=8.0, eps_update=3, n_bin=200)
+    hdr, log = td.run(td.CPU, str(tmp_path / "cpu"), par)
+    assert hdr.split("\t")[:3] == ["accepted", "epsilon", "Neps"]
+    assert log.shape[1] == 14 and log[:, 0].sum() == 5 and np.all(np.isfinite(log))
+    for name in ("deltaLAG_5", "deltaEUL_5", "auxmass_f", "nobs"):
+        assert np.fromfile(tmp_path / "cpu" / "data" / name).shape == (8 ** 3,)

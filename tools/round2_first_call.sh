@@ -12,6 +12,8 @@ for cfg in "256 0" "256 4" "128 0 3 0" "128 4 3 0" "128 0 1 0 0" "512 0"; do
 done
 # 2. its gated parity tests
 BGPU_UNVERIFIED_TESTS=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "shared_x" 2>&1 | tail -5 | tee $OUT/pytest_shared_x.log
+# 2b. the reference's own integration smoke configuration (8^3, SPH, calc_h = 2) through the drop-in
+BGPU_UNVERIFIED_TESTS=1 timeout 600 python -m pytest tests/test_dropin.py -m gpu -q -k "smoke_config" 2>&1 | tail -5 | tee $OUT/pytest_smoke_config.log
 # 3. bench with and without it (the default line also carries e2e.interleaved_chains for the first time)
 timeout 600 python bench.py --grid 256 --no-cpu-baseline > $OUT/bench256_default.json 2> $OUT/bench256_default.err
 BGPU_SHARE_X=1 timeout 600 python bench.py --grid 256 --no-cpu-baseline --no-e2e-chains > $OUT/bench256_share_x.json 2> $OUT/bench256_share_x.err
