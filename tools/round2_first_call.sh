@@ -5,6 +5,10 @@
 # (g++ -O2 -fopenmp -I include tools/native/X.cc -L barcode_b200 -lbarcode_b200 -Wl,-rpath,'$ORIGIN/../../barcode_b200' -o tools/native/X).
 OUT=gpurun_out/r02_first
 mkdir -p $OUT
+for t in fft_ab grad_ab; do   # the binaries are git-ignored: rebuild them where they are missing (g++ is on the box)
+  [ -x tools/native/$t ] || g++ -O2 -fopenmp -I include tools/native/$t.cc -L barcode_b200 -lbarcode_b200 \
+      -Wl,-rpath,'$ORIGIN/../../barcode_b200' -o tools/native/$t
+done
 # 1. shared x pass: parity + per-kernel times, Python-free, seconds each
 for cfg in "256 0" "256 4" "128 0 3 0" "128 4 3 0" "128 0 1 0 0" "512 0"; do
   timeout 120 tools/native/grad_ab BGPU_SHARE_X $cfg > "$OUT/grad_ab_share_x_${cfg// /_}.log" 2>&1
