@@ -43,6 +43,7 @@ struct Fft3d {
   cudaStream_t stream = nullptr;
   int strided_blocks = 0;  // persistent grid of the pipelined strided pass: SMs x resident CTAs
   int sm_count = 0;
+  int device = 0;          // CUDA device this plan lives on (kernel attributes and occupancy are per device)
   bool use_tma = true;     // TMA-staged strided pass (fft_tma.cuh); BGPU_FFT_TMA=0 selects the cp.async one
   mutable const ChunkHooks *hooks = nullptr;  // set around ONE transform by the caller, consumed by its z pass
   // fused z+y kernel (fft_fused.cuh): per-plane completion counters, their running target, producer lead

@@ -149,6 +149,8 @@ const CUtensorMap &Fft3d::tensor_map(const void *base, int axis, bool cplx, int 
   return maps_.back().map;
 }
 
+constexpr int kMaxDevices = 16;  // GPUs one process may drive (per-device launch configuration below)
+
 template <int N> struct TmaShape;
 template <> struct TmaShape<128> { static constexpr int E = 8,  MINB = 4; };
 template <> struct TmaShape<256> { static constexpr int E = 8,  MINB = 2; };
@@ -196,7 +198,8 @@ static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, 
   constexpr int threads = 8 * (N / E);
   constexpr int smem = NSTAGE * TmaTile<N, AUX>::stage_bytes + 1024 + 64;
   auto kern = fft_strided_tma<N, E, NSTAGE, DIR, AXIS, AUX, MINB>;
-  static int blocks_per_sm = 0;  // per instantiation; attribute set once per process and device 0..n share the value
+  static int blocks_per_sm_dev[kMaxDevices] = {};  // per instantiation AND device: the attribute is a per-device setting
+  int &blocks_per_sm = blocks_per_sm_dev[f.device % kMaxDevices];
   if (!blocks_per_sm) {
     BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
@@ -267,7 +270,8 @@ static void launch_strided_slab(const Fft3d &f, const double2 *in, double2 *out,
     constexpr int threads = T * N / 8;
     constexpr int smem = 2 * N * T * (int)sizeof(double2);
     auto kern = fft_strided_pass_slab<N, T, DIR, AXIS>;
-    static int blocks_per_sm = 0;
+    static int blocks_per_sm_dev[kMaxDevices] = {};
+    int &blocks_per_sm = blocks_per_sm_dev[f.device % kMaxDevices];
     if (!blocks_per_sm) {
       BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       int occ = 0;
@@ -336,7 +340,8 @@ static void launch_zpass_tma(const Fft3d &f, const void *in, void *out, ROp op, 
   constexpr int smem = Z::smem_bytes;
   static_assert(smem <= 227 * 1024, "z-pass ring does not fit");
   auto kern = fft_zpass_tma<N, E, TR, NSTAGE, C2R, AUX, MINB>;
-  static int blocks_per_sm = 0;
+  static int blocks_per_sm_dev[kMaxDevices] = {};
+  int &blocks_per_sm = blocks_per_sm_dev[f.device % kMaxDevices];
   if (!blocks_per_sm) {
     BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
@@ -427,7 +432,8 @@ static void launch_zy_fused(const Fft3d &f, const void *zsrc, void *zdst, const 
     constexpr int NS = AUX ? 2 : 3;
     using L = ZySmem<N, S::TR, NS, NS, AUX>;
     auto kern = fft_zy_fused<N, S::EZ, S::TR, S::EY, NS, NS, C2R, AUX>;
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+    bool &configured = configured_dev[f.device % kMaxDevices];
     if (!configured) {
       BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::bytes));
       int occ = 0;
@@ -648,6 +654,7 @@ void Fft3d::init(int n, cudaStream_t st) {
   {
     int dev = 0;
     BGPU_CUDA(cudaGetDevice(&dev));
+    device = dev;
     BGPU_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     const char *e = std::getenv("BGPU_FFT_TMA");
     use_tma = !(e && e[0] == '0');
