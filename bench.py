@@ -47,7 +47,9 @@ def parse():
                     help="N > 1 GPUs: independent chains (weak scaling, default) or ONE chain, x-slab decomposed "
                          "(strong scaling; BASELINE.json configs[3], [4]).  e2e_chains (internal, one GPU): the "
                          "host-buffer call of several independent chains interleaved on ONE GPU, see run_e2e_chains")
-    ap.add_argument("--chains", type=int, default=2, help="e2e_chains: chains (handles, host threads) on the GPU")
+    ap.add_argument("--chains", type=int, default=3,
+                    help="e2e_chains: chains (handles, host threads) on the GPU; 3 = one uploading, one computing, one "
+                         "downloading (each phase takes about as long at PCIe 5 x16 rates)")
     ap.add_argument("--no-e2e-chains", action="store_true", help="skip the interleaved-chains e2e leg")
     return ap.parse_args()
 
