@@ -14,6 +14,11 @@ for cfg in "256 0" "256 4" "128 0 3 0" "128 4 3 0" "128 0 1 0 0" "512 0"; do
   timeout 120 tools/native/grad_ab BGPU_SHARE_X $cfg > "$OUT/grad_ab_share_x_${cfg// /_}.log" 2>&1
   tail -4 "$OUT/grad_ab_share_x_${cfg// /_}.log"
 done
+# 1b. memcheck of the new kernels (two-warp pencils, extended functors) at a small grid
+for v in BGPU_SHARE_X BGPU_FFT_2WARP; do
+  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 tools/native/grad_ab $v 128 0 > "$OUT/memcheck_$v.log" 2>&1
+  echo "memcheck $v: exit $?"; tail -2 "$OUT/memcheck_$v.log"
+done
 # 2. its gated parity tests
 BGPU_UNVERIFIED_TESTS=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "shared_x" 2>&1 | tail -5 | tee $OUT/pytest_shared_x.log
 # 2b. the reference's own integration smoke configuration (8^3, SPH, calc_h = 2) through the drop-in
