@@ -83,8 +83,15 @@ struct bgpu_handle {
   int Hmax = 0;                 // halo planes allocated each side of rho_ext
   double *rho_ext = nullptr;    // [(Ns + 2 Hmax)][N][N]; delta points at the owned planes inside it
   double *halo_recv = nullptr;  // 2 * Hmax * N^2
-  double *cand_s = nullptr, *cand_p = nullptr;  // device-resident HMC candidate (bgpu_candidate)
+  double *cand_s = nullptr, *cand_p = nullptr, *cur_s = nullptr;  // device-resident HMC candidate and current signal (bgpu_candidate)
   bool have_signal = false;
+  bool constructed = false;
+  // fused leapfrog (HMC.cc:251-369): the kick p += kick_a * gradpsi rides on the store of the gradient's last z pass
+  // (bulk f64 reduce-add), the drift on the store of M^-1 p's; a device flag stops a run-away trajectory
+  bool kick_on = false;          // gradient_device: apply kick_a * gradpsi to d_out (+=) instead of storing gradpsi
+  double kick_a = 0.0;
+  int *stopflag = nullptr;       // device: set once |momenta[0]| > 1e50 (cube: honoured by every later update)
+  bool fused_leapfrog = true;    // BGPU_LEAPFROG_FUSED=0: the step-by-step form with separate kicks and a host test per step     // create_impl ran to completion (the destructor's collectives are safe)
   double *phi1 = nullptr, *xa = nullptr, *xb = nullptr, *xc = nullptr;  // exact 2LPT/ALPT adjoint: phi^(1) + 3 scratch arrays
   double *fext = nullptr;       // log-normal + calc_h 0 on a slab: f(delta_x) with 2 halo planes each side
   double *resid_ext = nullptr;  // exact adjoint on a slab: the residual with H halo planes each side
@@ -363,6 +370,17 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   require(h->have_power && h->have_obs, "bgpu: bgpu_set_static (Power, nobs, noise, window) must be called first");
   const bgpu_params &p = h->p;
   const double inv_n = 1.0 / h->ncells;
+  if (h->kick_on) {
+    // only the evaluations that end in the prior + likelihood x pass can fuse the kick into their last store
+    const bool alpt_exact = p.calc_h == BGPU_CALC_H_EXACT && h->phi1;
+    if (p.likelihood == 3 || p.calc_h == 1 || alpt_exact) {
+      const double a = h->kick_a;
+      h->kick_on = false;
+      gradient_device(h, d_s, h->grad);
+      launch_axpy(d_out, h->grad, a, h->n, h->stream, h->G == 1 ? h->stopflag : nullptr);
+      return;
+    }
+  }
   // the prior's multiplier (V/N)/P -- or zeros when only the likelihood force is wanted (mass types 2 / 3)
   const double *prior_mult = h->like_only ? h->zero_half : h->inv_power;
   h->fft.hooks = h->in_hooks;   // rows of the signal may still be arriving from the host
@@ -579,6 +597,12 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   ROp sop;
   sop.kind = R_SCALE;
   sop.a = inv_n;
+  if (h->kick_on) {  // d_out += kick_a * gradpsi, in the store of the last z pass
+    sop.kind = R_AXPY;
+    sop.a = h->kick_a * inv_n;
+    sop.skip = h->G == 1 ? h->stopflag : nullptr;
+    h->kick_on = false;
+  }
   if (h->G > 1 && (h->N >= 512 || h->fft.force_generic)) {
     // the TMA-staged x pass cannot hold both operand tiles at this size: combine in a pass of its own
     launch_kfinal_combine(h->shat, prior_mult, h->acc, h->acc, norm, h->N, h->nh, h->stream);
@@ -650,8 +674,51 @@ void kinetic_device(bgpu_handle *h, const double *d_p) {
   allreduce_scalar(h, S_KIN);
 }
 
-// Hamiltonian_EoM (HMC.cc:251-369) after the RNG draws, in place on device
+// p += a * gradpsi(s): the kick of the leapfrog, fused into the gradient's last store where the path allows
+void kick_device(bgpu_handle *h, const double *d_s, double *d_p, double a) {
+  h->kick_on = true;
+  h->kick_a = a;
+  try {
+    gradient_device(h, d_s, d_p);
+  } catch (...) {
+    h->kick_on = false;
+    throw;
+  }
+  h->kick_on = false;
+}
+
+// Hamiltonian_EoM (HMC.cc:251-369) after the RNG draws, in place on device.
+//
+// Fused form (default): the two half kicks that meet between steps are one kick p -= eps * gradpsi (half kicks only
+// at the two ends, :293-294 / :351-352), applied by the gradient's last z pass (bulk f64 reduce-add); the drift
+// s += eps * M^-1 p (:338-339) is the store of M^-1 p's last z pass.  No host round trip inside the trajectory: the
+// run-away test (:360-364) raises a device flag that every later update of the trajectory honours (a cube; a slab
+// chain evaluates it once at the end -- a run-away trajectory is rejected either way).  The merged kick rounds
+// p - eps g once where the reference rounds two half kicks: a relative 1e-16 per step.
 void leapfrog_device(bgpu_handle *h, double *d_s, double *d_p, uint64_t Neps, double eps) {
+  if (h->fused_leapfrog) {
+    const int *skip = h->G == 1 ? h->stopflag : nullptr;
+    BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
+    kick_device(h, d_s, d_p, -(0.5 * eps));
+    for (uint64_t jj = 0; jj < Neps; ++jj) {
+      if (h->mass_fs) {
+        require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
+        r2c_plain(h, d_p, h->work);
+        KOp lop;
+        lop.kind = K_MULREAL;
+        lop.real0 = h->inv_mass;
+        ROp sop;
+        sop.kind = R_AXPY;
+        sop.a = eps / h->ncells;
+        sop.skip = skip;
+        h->fft.c2r(h->work, h->work, d_s, lop, sop);
+      }
+      if (h->mass_rs) launch_axpy_div(d_s, d_p, h->mass_r, eps, h->n, h->stream, skip);
+      kick_device(h, d_s, d_p, jj + 1 == Neps ? -(0.5 * eps) : -eps);
+      if (h->G == 1) launch_runaway_guard(d_p, h->stopflag, h->stream);
+    }
+    return;
+  }
   gradient_device(h, d_s, h->grad);
   for (uint64_t jj = 0; jj < Neps; ++jj) {
     launch_axpy(d_p, h->grad, -(0.5 * eps), h->n, h->stream);   // :293-294
@@ -898,6 +965,10 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   g.cellbound = 0;
   g.cb_lo = nullptr;
   g.sph_h = p->particle_kernel_h_rel * g.d;
+  {
+    const char *sw = std::getenv("BGPU_SWEEP");  // 0 = first-generation particle-per-thread kernels; n > 1 = segment length
+    g.sweep = sw ? std::atoi(sw) : 1;
+  }
   if (p->masskernel == 3) {
     // SPH_kernel_3D_cells + _hull_1 (SPH_kernel.cpp:62-139)
     const double d = g.d, reach_len = 2. * g.sph_h;
@@ -942,15 +1013,33 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   dalloc(h->shat, h->nh); dalloc(h->dhat, h->nh); dalloc(h->work, h->nh); dalloc(h->acc, h->nh);
   if (h->fft.can_share_x()) dalloc(h->ubuf, h->nh);
   dalloc(h->partials, (size_t)kReduceBlocks); dalloc(h->dscal, (size_t)S_COUNT);
+  BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->stopflag), sizeof(int)));
+  BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
+  {
+    const char *lf = std::getenv("BGPU_LEAPFROG_FUSED");
+    h->fused_leapfrog = !(lf && lf[0] == '0');
+  }
   BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hscal), S_COUNT * sizeof(double)));
   BGPU_CUDA(cudaMemsetAsync(h->dscal, 0, S_COUNT * sizeof(double), h->stream));
   sync(h);
+  h->constructed = true;
   *out = h;
   h = nullptr;
   }
   catch (const std::exception &e) {
     g_last_error = e.what();
-    if (h) bgpu_destroy(h);
+    if (h) {
+      h->constructed = false;  // no collective in the destructor: the peers may not be there
+      bgpu_destroy(h);
+    }
+    return 1;
+  }
+  catch (...) {
+    g_last_error = "bgpu: unknown error while creating the handle";
+    if (h) {
+      h->constructed = false;
+      bgpu_destroy(h);
+    }
     return 1;
   }
   return 0;
@@ -981,7 +1070,8 @@ int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *n
 void bgpu_destroy(bgpu_handle *h) {
   if (!h) return;
   cudaSetDevice(h->p.device);
-  if (h->comm && h->stream) {
+  // (a handle whose creation failed half way skips the collectives: its peers may never arrive)
+  if (h->comm && h->stream && h->constructed) {
     // collective: nobody unmaps or frees a receive buffer a peer may still be writing to
     try {
       h->comm->barrier(h->stream);
@@ -991,7 +1081,7 @@ void bgpu_destroy(bgpu_handle *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void *q : h->peer_base)
     if (q) cudaIpcCloseMemHandle(q);
-  if (h->comm && h->stream) {
+  if (h->comm && h->stream && h->constructed) {
     try {
       h->comm->barrier(h->stream);
       cudaStreamSynchronize(h->stream);
@@ -999,7 +1089,7 @@ void bgpu_destroy(bgpu_handle *h) {
     }
   }
   double *reals[] = {h->power, h->nobs, h->noise, h->window, h->inv_power, h->zero_half, h->mass_f, h->mass_r, h->inv_mass,
-                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->fext, h->tmp, h->cand_s, h->cand_p, h->phi1, h->xa, h->xb, h->xc,
+                     h->sig, h->mom, h->grad, h->psi[0], h->psi[1], h->psi[2], h->rho_ext, h->resid, h->resid_ext, h->fext, h->tmp, h->cand_s, h->cand_p, h->cur_s, h->phi1, h->xa, h->xb, h->xc,
                      h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
     if (q) cudaFree(q);
@@ -1016,6 +1106,7 @@ void bgpu_destroy(bgpu_handle *h) {
   }
   if (h->sph_kmax) cudaFree(h->sph_kmax);
   if (h->dflag) cudaFree(h->dflag);
+  if (h->stopflag) cudaFree(h->stopflag);
   if (h->hflag) cudaFreeHost(h->hflag);
   if (h->hscal) cudaFreeHost(h->hscal);
   h->fft.destroy();
@@ -1098,6 +1189,7 @@ static void likeli_force_power_device(bgpu_handle *h, const double *signal) {
   require(signal != nullptr && h->have_power && h->have_obs,
           "bgpu: signal, Power and the observations are needed for the likelihood-force spectrum");
   require(h->zero_half != nullptr, "bgpu: the likelihood-force spectrum needs a handle created with mass_type 2 or 3");
+  require(3 * (size_t)p.N_bin <= h->n, "bgpu: N_bin is too large for this grid (3 * N_bin doubles of bin scratch must fit one local array)");
   h2d(h, h->sig, signal, h->n);
   h->like_only = true;
   try {
@@ -1333,10 +1425,9 @@ static void draw_momenta_device(bgpu_handle *h, uint64_t seed, uint64_t draw, do
   if (h->mass_fs) {
     launch_philox_normals(h->tmp, h->n, first, seed, draw, 0, h->stream);
     r2c_plain(h, h->tmp, h->work);
-    if (h->G == 1)
-      launch_colour_white(h->work, h->mass_f, h->N, h->ncells / (h->p.L1 * h->p.L2 * h->p.L3), h->stream);
-    else  // transposed k-space slab: colour with the multiplier the kinetic term uses, (N/V) M = 1/inv_mass
-      launch_colour_white_rows(h->work, h->inv_mass, h->N, h->nh, h->stream);
+    // colour with the multiplier the kinetic term uses, (N/V) M = 1/inv_mass, on the cube [x][y][.] and on the
+    // transposed k-space slab [x][y_local][.] alike: the draw is bitwise independent of the decomposition
+    launch_colour_white_rows(h->work, h->inv_mass, h->N, h->nh, h->rank == 0, h->stream);
     ROp sop;
     sop.kind = R_SCALE;
     sop.a = 1.0 / h->ncells;
@@ -1405,8 +1496,9 @@ int bgpu_set_signal(bgpu_handle *h, const double *x) {
   if (!h->cand_s) {
     dalloc(h->cand_s, h->n);
     dalloc(h->cand_p, h->n);
+    dalloc(h->cur_s, h->n);   // the chain's current signal has its own buffer: every other entry point may overwrite h->sig
   }
-  h2d(h, h->sig, x, h->n);
+  h2d(h, h->cur_s, x, h->n);
   h->have_signal = true;
   sync(h);
   BGPU_CATCH
@@ -1421,9 +1513,9 @@ int bgpu_candidate(bgpu_handle *h, uint64_t seed, uint64_t draw_index, uint64_t 
   draw_momenta_device(h, seed, draw_index, h->cand_p);                       // HMC.cc:449
   // delta_Hamiltonian's initial energies (HMC.cc:214-215): the ends of the trajectory do not change them
   kinetic_device(h, h->cand_p);
-  psi_device(h, h->sig);
+  psi_device(h, h->cur_s);
   BGPU_CUDA(cudaMemcpyAsync(h->hscal, h->dscal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  BGPU_CUDA(cudaMemcpyAsync(h->cand_s, h->sig, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  BGPU_CUDA(cudaMemcpyAsync(h->cand_s, h->cur_s, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   sync(h);
   energies6[0] = h->hscal[S_KIN];
   energies6[1] = h->hscal[S_PRIOR];
@@ -1444,8 +1536,8 @@ int bgpu_accept(bgpu_handle *h, double *x_out, double *deltaX_out) {
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
   require(h->have_signal && h->cand_s, "bgpu_accept: no candidate");
-  BGPU_CUDA(cudaMemcpyAsync(h->sig, h->cand_s, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  if (x_out) d2h(h, x_out, h->sig, h->n);
+  BGPU_CUDA(cudaMemcpyAsync(h->cur_s, h->cand_s, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (x_out) d2h(h, x_out, h->cur_s, h->n);
   if (deltaX_out) d2h(h, deltaX_out, h->delta, h->n);
   sync(h);
   BGPU_CATCH
@@ -1479,6 +1571,8 @@ int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *p
 int bgpu_assign_density(bgpu_handle *h, const double *x, const double *y, const double *z, double *rho) {
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(h->G == 1, "bgpu_assign_density: arbitrary particle lists are not available on a slab-decomposed chain "
+                     "(its density tile holds the local planes and their halo only); use a cube handle");
   h2d(h, h->psi[0], x, h->n);
   h2d(h, h->psi[1], y, h->n);
   h2d(h, h->psi[2], z, h->n);
@@ -1492,7 +1586,7 @@ int bgpu_cell_indices(bgpu_handle *h, const double *x, const double *y, const do
                       int *ck) {
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
-  require(n <= h->n, "bgpu_cell_indices: at most N1*N2*N3 positions per call");
+  require(n <= h->n, "bgpu_cell_indices: at most as many positions per call as the handle has local cells");
   h2d(h, h->psi[0], x, n);
   h2d(h, h->psi[1], y, n);
   h2d(h, h->psi[2], z, n);

@@ -528,6 +528,7 @@ __global__ void __launch_bounds__(TR *N / 16)
     fft_c2r_zpass(const double2 *__restrict__ in, double *__restrict__ out, const double2 *__restrict__ twN,
                   const double2 *__restrict__ twM, ROp sop, size_t nrows) {
   extern __shared__ double2 smem[];
+  if (sop.skip && *sop.skip) return;
   constexpr int M = N / 2;
   constexpr int ROWP = M + M / 8 + 1;
   const int t = threadIdx.x % (M / 8);

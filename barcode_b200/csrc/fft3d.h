@@ -49,7 +49,7 @@ struct Fft3d {
   // fused z+y kernel (fft_fused.cuh): per-plane completion counters, their running target, producer lead
   bool use_fused = false;  // BGPU_FFT_FUSED=1
   bool two_warp = false;   // BGPU_FFT_2WARP=1: 512-point strided pencils over two warps (fft_tma.cuh, ColAccessWide)
-  bool share_x = false;    // BGPU_SHARE_X=1: the y and z components of a K_DISP / K_GRAD / K_INVLAP triple share one x pass
+  bool share_x = true;     // (BGPU_SHARE_X=0 turns it off) the y and z components of a K_DISP / K_GRAD / K_INVLAP triple share one x pass
   bool force_generic = false;  // BGPU_FFT_SLAB_GENERIC=1: slab passes through fft_slab_generic.cuh even where TMA fits
   unsigned long long *zy_ready = nullptr;
   mutable unsigned long long zy_epoch = 0;

@@ -49,6 +49,9 @@ struct ROp {
   int kind = R_SCALE;
   double a = 1.0;
   const double *aux = nullptr;
+  // c2r store only: when non-null and *skip != 0 the z pass stores nothing at all (a leapfrog trajectory that has
+  // been stopped by its run-away guard leaves the state where it was, HMC.cc:360-364)
+  const int *skip = nullptr;
 };
 
 }  // namespace bgpu

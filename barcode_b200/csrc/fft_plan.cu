@@ -53,7 +53,7 @@ template <int N>
 __global__ void tiny_c2r_zpass(const double2 *__restrict__ in, double *__restrict__ out,
                                const double2 *__restrict__ twN, ROp sop, size_t nrows) {
   const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= nrows) return;
+  if (row >= nrows || (sop.skip && *sop.skip)) return;
   double2 X[N / 2 + 1];
   for (int k = 0; k <= N / 2; ++k) X[k] = in[row * (N / 2 + 1) + k];
   X[0].y = 0.0;
@@ -665,7 +665,7 @@ void Fft3d::init(int n, cudaStream_t st) {
     const char *fg = std::getenv("BGPU_FFT_SLAB_GENERIC");
     force_generic = fg && fg[0] == '1';
     const char *sx = std::getenv("BGPU_SHARE_X");
-    share_x = sx && sx[0] == '1';
+    share_x = !(sx && sx[0] == '0');  // default since round 2 (measured +7 % at 256^3, parity-green); BGPU_SHARE_X=0 = three x passes
     const char *tw2 = std::getenv("BGPU_FFT_2WARP");
     two_warp = tw2 && tw2[0] == '1';
     const char *fu = std::getenv("BGPU_FFT_FUSED");

@@ -691,6 +691,9 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
   constexpr uint32_t in_row_bytes = C2R ? (M + 1) * 16 : N * 8;
   constexpr uint32_t out_row_bytes = C2R ? N * 8 : (M + 1) * 16;
   static_assert(LP >= 8 && LP <= 32 && TR <= 32, "row must live inside one warp; warp 0 issues one copy per row");
+  if constexpr (C2R) {
+    if (op.skip && *op.skip) return;  // uniform over the grid; nothing has been issued yet
+  }
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;

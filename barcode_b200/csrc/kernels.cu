@@ -197,6 +197,10 @@ static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n 
 
 void launch_scatter(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
                     double *posx, double *posy, double *posz, cudaStream_t st) {
+  if (scatter_sweep_applicable(g, posx)) {
+    launch_scatter_sweep(g, psix, psiy, psiz, rho, st);
+    return;
+  }
   ProfScope prof(KK_SCATTER, st);
   const size_t n = (size_t)g.Ns * g.N * g.N;
   BGPU_CUDA(cudaMemsetAsync(rho, 0, (size_t)(g.Ns + 2 * g.H) * g.N * g.N * sizeof(double), st));
@@ -566,6 +570,10 @@ __global__ void gather_adjoint_kernel(GridGeom g, const double *ax, const double
 
 void launch_gather_adjoint(const GridGeom &g, double *ax, double *ay, double *az, const double *resid,
                            cudaStream_t st) {
+  if (gather_sweep_applicable(g)) {
+    launch_gather_sweep(g, ax, ay, az, resid, st);
+    return;
+  }
   ProfScope prof(KK_GATHER, st);
   const size_t n = (size_t)g.Ns * g.N * g.N;
   gather_adjoint_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, ax, ay, az, ax, ay, az, resid);
@@ -686,20 +694,24 @@ __global__ void colour_white_kernel(double2 *__restrict__ W, const double *__res
 // The same colouring from the half-grid multiplier the kinetic term uses, inv = (V/N)/M (0 where M <= 0):
 // (N/V) M = 1/inv, so A = w^ / sqrt(inv).  Works on any row layout with the multiplier's padded pitch
 // (cube [x][y][.] and the transposed slab [x][y_local][.] alike) and keeps the draw and K consistent.
-__global__ void colour_white_rows_kernel(double2 *__restrict__ W, const double *__restrict__ inv, int nzh, size_t n) {
+__global__ void colour_white_rows_kernel(double2 *__restrict__ W, const double *__restrict__ inv, int nzh, size_t n,
+                                         int zero_dc) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const size_t row = idx / nzh;
   const int z = (int)(idx - row * nzh);
   const double m = inv[row * (nzh + 1) + z];
-  const double a = m > 0.0 ? rsqrt(m) : 0.0;
+  // 1 / sqrt (correctly rounded operations, not rsqrt): the cube and every slab decomposition round alike.
+  // The DC mode carries no momentum (random.cpp:347-351), whatever M(0) is: element 0 of the rank that owns y = 0.
+  double a = m > 0.0 ? __ddiv_rn(1.0, __dsqrt_rn(m)) : 0.0;
+  if (zero_dc && idx == 0) a = 0.0;
   const double2 w = W[idx];
   W[idx] = make_double2(a * w.x, a * w.y);
 }
 
-void launch_colour_white_rows(double2 *W, const double *inv_half, int N, size_t n_half, cudaStream_t st) {
+void launch_colour_white_rows(double2 *W, const double *inv_half, int N, size_t n_half, bool owns_dc, cudaStream_t st) {
   ProfScope prof(KK_COLOUR, st);
-  colour_white_rows_kernel<<<blocks_for(n_half, 256), 256, 0, st>>>(W, inv_half, N / 2 + 1, n_half);
+  colour_white_rows_kernel<<<blocks_for(n_half, 256), 256, 0, st>>>(W, inv_half, N / 2 + 1, n_half, owns_dc ? 1 : 0);
   BGPU_LAUNCHED(1);
 }
 
@@ -804,16 +816,24 @@ void launch_inverse_spectrum(const double *full, double *half, int N, double nor
   BGPU_LAUNCHED(1);
 }
 
-__global__ void axpy_kernel(double *__restrict__ y, const double *__restrict__ x, double a, size_t n) {
+__global__ void axpy_kernel(double *__restrict__ y, const double *__restrict__ x, double a, size_t n,
+                            const int *__restrict__ skip) {
+  if (skip && *skip) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));  // HMC.cc:294,339,352 (two roundings)
+}
+// HMC.cc:360-364: a trajectory whose momentum has run away is stopped -- on the device by raising a flag that
+// every later update of the trajectory honours (ROp::skip, launch_axpy's skip)
+__global__ void runaway_guard_kernel(const double *__restrict__ p, int *__restrict__ flag) {
+  if (fabs(p[0]) > 1e50) *flag = 1;
 }
 __global__ void scale_kernel(double *__restrict__ y, const double *__restrict__ x, double a, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = a * x[i];
 }
 __global__ void axpy_div_kernel(double *__restrict__ y, const double *__restrict__ x, const double *__restrict__ m,
-                                double a, size_t n) {
+                                double a, size_t n, const int *__restrict__ skip) {
+  if (skip && *skip) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const double mm = m[i];
@@ -826,9 +846,13 @@ __global__ void fill_kernel(double *__restrict__ y, double v, size_t n) {
   if (i < n) y[i] = v;
 }
 
-void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st) {
+void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st, const int *skip) {
   ProfScope prof(KK_STREAM, st);
-  axpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n);
+  axpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n, skip);
+  BGPU_LAUNCHED(1);
+}
+void launch_runaway_guard(const double *p, int *flag, cudaStream_t st) {
+  runaway_guard_kernel<<<1, 1, 0, st>>>(p, flag);
   BGPU_LAUNCHED(1);
 }
 void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t st) {
@@ -836,9 +860,9 @@ void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t s
   scale_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n);
   BGPU_LAUNCHED(1);
 }
-void launch_axpy_div(double *y, const double *x, const double *m, double a, size_t n, cudaStream_t st) {
+void launch_axpy_div(double *y, const double *x, const double *m, double a, size_t n, cudaStream_t st, const int *skip) {
   ProfScope prof(KK_STREAM, st);
-  axpy_div_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, m, a, n);
+  axpy_div_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, m, a, n, skip);
   BGPU_LAUNCHED(1);
 }
 void launch_fill(double *y, double v, size_t n, cudaStream_t st) {
@@ -1056,8 +1080,9 @@ void launch_inverse_spectrum_unpack(const double2 *transposed, double *half, int
 
 // out = a_real * s + norm * h on the (transposed) half grid: the K_FINAL combination as its own pass,
 // for the configurations whose strided pass cannot stage both operand tiles (N = 512 on a slab)
+// (hh and out may be the same array: no __restrict__ on them)
 __global__ void kfinal_combine_kernel(const double2 *__restrict__ s, const double *__restrict__ mult,
-                                      const double2 *__restrict__ hh, double2 *__restrict__ out, double norm, int nzh,
+                                      const double2 *hh, double2 *out, double norm, int nzh,
                                       size_t n) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;

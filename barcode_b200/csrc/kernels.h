@@ -24,6 +24,7 @@ struct GridGeom {
   int *flag;       // set to 1 if a particle left the halo (device int), may be null when H == 0 and Ns == N
   int cellbound;   // displacements are cell-boundary averaged on read (cellboundcomp; non-Zel'dovich model)
   const double *cb_lo;  // slab: plane x0-1 of Psi_x, Psi_y, Psi_z ([3][N][N], from the lower neighbour); null on a cube
+  int sweep;       // x-sweep scatter / gather (particles_sweep.cu): 0 off, 1 on, > 1 = planes per sweep segment
   double sph_h;    // SPH scale length particle_kernel_h = h_rel * d (init_par.cc:379), masskernel 3
 };
 
@@ -56,7 +57,7 @@ void launch_philox_normals(double *out, size_t n, size_t first, uint64_t seed, u
 // W (half grid, transform of a real white field) *= sqrt(c2 * spec) at the folded index, DC = 0
 void launch_colour_white(double2 *W, const double *spec_full, int N, double c2, cudaStream_t st);
 // W *= 1/sqrt(inv) with inv = the padded half-grid multiplier (V/N)/M of the kinetic term, 0 where inv <= 0
-void launch_colour_white_rows(double2 *W, const double *inv_half, int N, size_t n_half, cudaStream_t st);
+void launch_colour_white_rows(double2 *W, const double *inv_half, int N, size_t n_half, bool owns_dc, cudaStream_t st);
 
 // measure_spectrum (field_statistics.cpp:20-90) of a half-complex transform F; acc = [power | kmode | nmode] (3 nbin, device)
 // (two steps: bin this rank's modes of the [x][Ns][N/2+1] layout, y = y0 + y_local; then -- after a slab has
@@ -130,6 +131,14 @@ void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const dou
                               const double *noise, const double *window, double *resid, size_t n, double ncells_global,
                               double *scratch, double *nll, cudaStream_t st);
 
+// x-sweep variants (particles_sweep.cu): full cube, Lagrangian lattice without cell-boundary averaging, N >= 32.
+// launch_scatter / launch_gather_adjoint dispatch to them where they apply (BGPU_SWEEP=0 keeps the first-generation kernels).
+bool scatter_sweep_applicable(const GridGeom &g, const double *posx);
+void launch_scatter_sweep(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
+                          cudaStream_t st);
+bool gather_sweep_applicable(const GridGeom &g);
+void launch_gather_sweep(const GridGeom &g, double *ax, double *ay, double *az, const double *resid, cudaStream_t st);
+
 // exact adjoint of the mass assignment: V_c(p) = sum_cells r_c dW_c/dx_c, in place over Psi
 void launch_gather_adjoint(const GridGeom &g, double *psix_Vx, double *psiy_Vy, double *psiz_Vz,
                            const double *resid, cudaStream_t st);
@@ -142,9 +151,12 @@ void launch_findif_product(const double *delta, const double *resid, double *out
                            int comp, cudaStream_t st);
 
 // y += a * x ; y = a * x ; y += a * x / m (m <= 0 -> 0)
-void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st);
+void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st, const int *skip = nullptr);
+// *flag = 1 if |p[0]| > 1e50 (the run-away test of Hamiltonian_EoM, HMC.cc:360-364)
+void launch_runaway_guard(const double *p, int *flag, cudaStream_t st);
 void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t st);
-void launch_axpy_div(double *y, const double *x, const double *m, double a, size_t n, cudaStream_t st);
+void launch_axpy_div(double *y, const double *x, const double *m, double a, size_t n, cudaStream_t st,
+                     const int *skip = nullptr);
 void launch_fill(double *y, double v, size_t n, cudaStream_t st);
 
 // Hamiltonian mass types 0 / 1 / 4 (HMC_mass.cc:315-368)

@@ -185,8 +185,6 @@ def test_host_driver_with_the_device_momentum_generator(tmp_path, monkeypatch):
 
 
 @pytest.mark.skipif(not (os.path.exists(CPU) and os.path.exists(GPU)), reason="oracle/_ref binaries not built")
-@pytest.mark.skipif(not os.environ.get("BGPU_UNVERIFIED_TESTS"), reason="added after the round's GPU budget was spent; its CPU "
-                    "half runs in tests/test_oracle_ref.py::test_reference_smoke_config_runs; run the GPU half next round")
 def test_the_reference_smoke_config_on_the_gpu_path(tmp_path):
     """The reference's only integration test (test/run/input.par, .travis.yml:75-80): its shipped data/input.par --
     SPH kernel, calc_h = 2, adaptive step size (eps_fac_update_type 3), N_eps_fac 8, N_bin 200 -- at Nx = 8,

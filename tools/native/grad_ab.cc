@@ -3,13 +3,14 @@
 // bgpu_gradient_psi and bgpu_psi on a default handle and on a handle created with VAR=1; prints the relative L2
 // difference of the gradients, the two energies, and the per-kernel-class device times of one evaluation each.
 //   g++ -O2 -fopenmp -I include tools/native/grad_ab.cc -L barcode_b200 -lbarcode_b200 -Wl,-rpath,'$ORIGIN/../../barcode_b200' -o tools/native/grad_ab
-//   tools/native/grad_ab BGPU_SHARE_X 256 [calc_h [sfmodel [rsd [likelihood]]]]
+//   tools/native/grad_ab BGPU_SHARE_X[=value] 256 [calc_h [sfmodel [rsd [likelihood [masskernel]]]]]
 #include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "barcode_gpu.h"
@@ -52,12 +53,19 @@ static void report(const char *tag) {
 }
 
 int main(int argc, char **argv) {
-  const char *var = argc > 1 ? argv[1] : "BGPU_SHARE_X";
+  // NAME (variant = NAME=1 against NAME unset) or NAME=VALUE (variant = that assignment against NAME unset)
+  std::string var_s = argc > 1 ? argv[1] : "BGPU_SHARE_X", val_s = "1";
+  if (var_s.find('=') != std::string::npos) {
+    val_s = var_s.substr(var_s.find('=') + 1);
+    var_s = var_s.substr(0, var_s.find('='));
+  }
+  const char *var = var_s.c_str();
   const int N = argc > 2 ? std::atoi(argv[2]) : 256;
   const int calc_h = argc > 3 ? std::atoi(argv[3]) : 0;
   const int sfmodel = argc > 4 ? std::atoi(argv[4]) : 1;
   const int rsd = argc > 5 ? std::atoi(argv[5]) : (sfmodel == 1 ? 1 : 0);
   const int likelihood = argc > 6 ? std::atoi(argv[6]) : 1;
+  const int masskernel = argc > 7 ? std::atoi(argv[7]) : 1;
   const double t0 = now();
   const size_t n = (size_t)N * N * N;
   bgpu_params p;
@@ -68,12 +76,13 @@ int main(int argc, char **argv) {
   p.sfmodel = sfmodel;
   p.rsd_model = rsd;
   p.likelihood = likelihood;
+  p.masskernel = masskernel;
   p.correct_delta = 1;
   p.deltaQ_factor = 1.0;
   bgpu_handle *H[2] = {nullptr, nullptr};
   unsetenv(var);
   CHECK(bgpu_create(&p, &H[0]));
-  setenv(var, "1", 1);
+  setenv(var, val_s.c_str(), 1);
   CHECK(bgpu_create(&p, &H[1]));
   unsetenv(var);
   std::printf("%s A/B at %d^3, calc_h %d, sfmodel %d, rsd %d, likelihood %d: handles up at %.2f s\n", var, N, calc_h,
