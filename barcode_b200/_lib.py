@@ -84,7 +84,7 @@ SIGNATURES = {
     "bgpu_profile_end": (C.c_int, [_dp, C.POINTER(C.c_uint64), C.c_int]),
     "bgpu_profile_kind_name": (C.c_char_p, [C.c_int]),
 }
-PROFILE_KINDS = 14
+PROFILE_KINDS = 15
 
 _lib = None
 

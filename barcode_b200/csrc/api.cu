@@ -90,7 +90,8 @@ struct bgpu_handle {
   // (bulk f64 reduce-add), the drift on the store of M^-1 p's; a device flag stops a run-away trajectory
   bool kick_on = false;          // gradient_device: apply kick_a * gradpsi to d_out (+=) instead of storing gradpsi
   double kick_a = 0.0;
-  int *stopflag = nullptr;       // device: set once |momenta[0]| > 1e50 (cube: honoured by every later update)
+  int *stopflag = nullptr;       // device: the step after which |momenta[0]| > 1e50 stopped the trajectory, 0 = running
+  int *hflag2 = nullptr;         // pinned copy
   bool fused_leapfrog = true;    // BGPU_LEAPFROG_FUSED=0: the step-by-step form with separate kicks and a host test per step     // create_impl ran to completion (the destructor's collectives are safe)
   double *phi1 = nullptr, *xa = nullptr, *xb = nullptr, *xc = nullptr;  // exact 2LPT/ALPT adjoint: phi^(1) + 3 scratch arrays
   double *fext = nullptr;       // log-normal + calc_h 0 on a slab: f(delta_x) with 2 halo planes each side
@@ -114,7 +115,7 @@ struct bgpu_handle {
 
 namespace {
 
-enum Scal { S_SUMRHO = 0, S_NLL = 1, S_PRIOR = 2, S_KIN = 3, S_P0 = 4, S_MAXPSI = 5, S_COUNT = 8 };
+enum Scal { S_SUMRHO = 0, S_NLL = 1, S_PRIOR = 2, S_KIN = 3, S_P0 = 4, S_MAXPSI = 5, S_STOP = 6, S_P0PREV = 7, S_COUNT = 8 };
 
 template <class T>
 void dalloc(T *&ptr, size_t count) {
@@ -377,7 +378,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
       const double a = h->kick_a;
       h->kick_on = false;
       gradient_device(h, d_s, h->grad);
-      launch_axpy(d_out, h->grad, a, h->n, h->stream, h->G == 1 ? h->stopflag : nullptr);
+      launch_axpy(d_out, h->grad, a, h->n, h->stream, h->stopflag);
       return;
     }
   }
@@ -457,7 +458,47 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
         }
       }
     }
-    if (p.likelihood == 1 && h->ubuf) {
+    if (p.likelihood == 1 && h->ubuf && h->fft.can_zround()) {
+      // As below (shared x passes on both sides), and the two z passes that meet in real space around the product
+      // r * d_c(delta) run as ONE pass on the row in shared memory (fft_tma.cuh fft_zround_tma): per component
+      //   x (c = 0 only) -> y -> [c2r z, * r / N, r2c z] -> y -> x (accumulating; shared by c = 1, 2)
+      KOp lop;
+      lop.kind = K_GRAD;
+      lop.comp = 0;
+      lop.kfac = h->kfac;
+      ROp mul;
+      mul.kind = R_SCALE_MUL;
+      mul.a = inv_n;
+      mul.aux = h->resid;
+      KOp none;
+      h->fft.xpass(h->dhat, h->work, +1, lop, none);
+      h->fft.ypass(h->work, h->work, +1, none, none);
+      h->fft.zround(h->work, mul);
+      h->fft.ypass(h->work, h->work, -1, none, none);
+      KOp sop2;
+      sop2.kind = K_INVLAP_SET;
+      sop2.comp = 0;
+      sop2.kfac = h->kfac;
+      h->fft.xpass(h->work, h->acc, -1, none, sop2);
+      lop.comp = K_COMP_UNIT;
+      h->fft.xpass(h->dhat, h->dhat, +1, lop, none);   // in place: delta^ is not needed again
+      for (int c = 1; c < 3; ++c) {
+        KOp yl;
+        yl.kind = K_MULK;
+        yl.comp = c;
+        yl.kfac = h->kfac;
+        h->fft.ypass(h->dhat, h->work, +1, yl, none);
+        h->fft.zround(h->work, mul);
+        KOp ys;
+        ys.kind = (c == 1) ? K_MULK_SET : K_MULK_ADD;
+        ys.comp = c;
+        ys.kfac = h->kfac;
+        h->fft.ypass(h->work, h->ubuf, -1, none, ys);
+      }
+      sop2.kind = K_INVLAP_ADD;
+      sop2.comp = K_COMP_UNIT;
+      h->fft.xpass(h->ubuf, h->acc, -1, none, sop2);
+    } else     if (p.likelihood == 1 && h->ubuf) {
       // shared x passes on both sides: d_c(delta) = IFFT_zy[k_c IFFT_x[-(Im, -Re) delta^]] for c = y, z, and the
       // products r d_y(delta), r d_z(delta) are summed after their forward y passes (see backproject)
       KOp lop;
@@ -600,7 +641,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   if (h->kick_on) {  // d_out += kick_a * gradpsi, in the store of the last z pass
     sop.kind = R_AXPY;
     sop.a = h->kick_a * inv_n;
-    sop.skip = h->G == 1 ? h->stopflag : nullptr;
+    sop.skip = h->stopflag;
     h->kick_on = false;
   }
   if (h->G > 1 && (h->N >= 512 || h->fft.force_generic)) {
@@ -692,14 +733,29 @@ void kick_device(bgpu_handle *h, const double *d_s, double *d_p, double a) {
 // Fused form (default): the two half kicks that meet between steps are one kick p -= eps * gradpsi (half kicks only
 // at the two ends, :293-294 / :351-352), applied by the gradient's last z pass (bulk f64 reduce-add); the drift
 // s += eps * M^-1 p (:338-339) is the store of M^-1 p's last z pass.  No host round trip inside the trajectory: the
-// run-away test (:360-364) raises a device flag that every later update of the trajectory honours (a cube; a slab
-// chain evaluates it once at the end -- a run-away trajectory is rejected either way).  The merged kick rounds
-// p - eps g once where the reference rounds two half kicks: a relative 1e-16 per step.
+// run-away test (:360-364) runs on the device (kernels.cu runaway_guard_kernel: the value the reference tests is the
+// midpoint of momenta[0] before and after a merged kick) and raises a flag that every later update of the trajectory
+// honours; a slab chain shares rank 0's verdict with a one-element all-reduce per step.  The host reads the flag
+// once, after the trajectory.  The merged kick rounds p - eps g once where the reference rounds two half kicks: a
+// relative 1e-16 per step.
 void leapfrog_device(bgpu_handle *h, double *d_s, double *d_p, uint64_t Neps, double eps) {
   if (h->fused_leapfrog) {
-    const int *skip = h->G == 1 ? h->stopflag : nullptr;
+    const int *skip = h->stopflag;
+    static_assert(S_P0PREV == S_STOP + 1, "the guard's two scalars are adjacent");
+    double *guard = h->dscal + S_STOP;
+    // the run-away test after the kick that ends step `step`: rank 0 owns momenta[0], a slab shares the verdict
+    auto test = [&](int step, int mode) {
+      if (h->rank == 0) launch_runaway_guard(d_p, guard, h->G == 1 ? h->stopflag : nullptr, step, mode, h->stream);
+      if (h->G > 1 && mode != 0) {
+        if (h->rank != 0) BGPU_CUDA(cudaMemsetAsync(guard, 0, sizeof(double), h->stream));
+        h->comm->all_reduce_max(guard, 1, h->stream);
+        launch_runaway_apply(guard, h->stopflag, h->stream);
+      }
+    };
     BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
+    BGPU_CUDA(cudaMemsetAsync(guard, 0, 2 * sizeof(double), h->stream));
     kick_device(h, d_s, d_p, -(0.5 * eps));
+    test(0, 0);
     for (uint64_t jj = 0; jj < Neps; ++jj) {
       if (h->mass_fs) {
         require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
@@ -714,8 +770,19 @@ void leapfrog_device(bgpu_handle *h, double *d_s, double *d_p, uint64_t Neps, do
         h->fft.c2r(h->work, h->work, d_s, lop, sop);
       }
       if (h->mass_rs) launch_axpy_div(d_s, d_p, h->mass_r, eps, h->n, h->stream, skip);
-      kick_device(h, d_s, d_p, jj + 1 == Neps ? -(0.5 * eps) : -eps);
-      if (h->G == 1) launch_runaway_guard(d_p, h->stopflag, h->stream);
+      const bool last = jj + 1 == Neps;
+      kick_device(h, d_s, d_p, last ? -(0.5 * eps) : -eps);
+      test((int)(jj + 1 < 0x7fffffff ? jj + 1 : 0x7fffffff), last ? 2 : 1);
+    }
+    // the one host round trip of the trajectory.  Stopped before the last step, the state is frozen at the
+    // reference's (s, p) plus the half kick the merged kick had already added for the step that never ran:
+    // take it back with one more gradient at the same s.
+    BGPU_CUDA(cudaMemcpyAsync(h->hflag2, h->stopflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    sync(h);
+    const int stopped = *h->hflag2;
+    if (stopped > 0 && (uint64_t)stopped < Neps) {
+      BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
+      kick_device(h, d_s, d_p, +(0.5 * eps));
     }
     return;
   }
@@ -810,7 +877,7 @@ const char *bgpu_profile_kind_name(int kind) {
   static const char *names[KK_COUNT] = {"fft_strided_pass_y", "fft_r2c_zpass", "fft_c2r_zpass", "scatter",
                                         "gather_adjoint", "overdens_residual", "reduce", "stream", "colour_momenta",
                                         "fft_strided_pass_x", "all_to_all", "halo_exchange", "fft_zy_fused_r2c",
-                                        "fft_zy_fused_c2r"};
+                                        "fft_zy_fused_c2r", "fft_z_roundtrip"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "?";
 }
 
@@ -1015,6 +1082,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   dalloc(h->partials, (size_t)kReduceBlocks); dalloc(h->dscal, (size_t)S_COUNT);
   BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->stopflag), sizeof(int)));
   BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
+  BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hflag2), sizeof(int)));
+  *h->hflag2 = 0;
   {
     const char *lf = std::getenv("BGPU_LEAPFROG_FUSED");
     h->fused_leapfrog = !(lf && lf[0] == '0');
@@ -1107,6 +1176,7 @@ void bgpu_destroy(bgpu_handle *h) {
   if (h->sph_kmax) cudaFree(h->sph_kmax);
   if (h->dflag) cudaFree(h->dflag);
   if (h->stopflag) cudaFree(h->stopflag);
+  if (h->hflag2) cudaFreeHost(h->hflag2);
   if (h->hflag) cudaFreeHost(h->hflag);
   if (h->hscal) cudaFreeHost(h->hscal);
   h->fft.destroy();

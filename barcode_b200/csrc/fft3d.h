@@ -49,6 +49,7 @@ struct Fft3d {
   // fused z+y kernel (fft_fused.cuh): per-plane completion counters, their running target, producer lead
   bool use_fused = false;  // BGPU_FFT_FUSED=1
   bool two_warp = false;   // BGPU_FFT_2WARP=1: 512-point strided pencils over two warps (fft_tma.cuh, ColAccessWide)
+  bool z_round = true;     // (BGPU_ZROUND=0 turns it off) calc_h = 0: the c2r / r2c z passes around r * d_c(delta) fused
   bool share_x = true;     // (BGPU_SHARE_X=0 turns it off) the y and z components of a K_DISP / K_GRAD / K_INVLAP triple share one x pass
   bool force_generic = false;  // BGPU_FFT_SLAB_GENERIC=1: slab passes through fft_slab_generic.cuh even where TMA fits
   unsigned long long *zy_ready = nullptr;
@@ -98,7 +99,13 @@ struct Fft3d {
   //   xpass   one x pass in -> out, dir = -1 forward / +1 inverse, load and store functors of RotCtxX
   //   c2r_yz  the rest of an inverse transform: y pass in -> work with load functor ylop (in is preserved), z pass -> out
   //   r2c_zy  the start of a forward transform: z pass in -> work, y pass work -> yout with store functor ysop
+  //   ypass   one y pass in -> out with the extended functors (K_MULK* included)
+  //   zround  z round trip in place on a y-passed array: c2r z pass, times sop.a * sop.aux (real array), r2c z pass
+  //           (fft_tma.cuh fft_zround_tma) -- the real-space product of likelihood_calc_h without its HBM round trip
   bool can_share_x() const;
+  bool can_zround() const;
+  void ypass(const double2 *in, double2 *out, int dir, KOp lop, KOp sop) const;
+  void zround(double2 *work, ROp sop) const;
   void xpass(const double2 *in, double2 *out, int dir, KOp lop, KOp sop) const;
   void c2r_yz(const double2 *in, double2 *work, double *out, KOp ylop, ROp sop) const;
   void r2c_zy(const double *in, double2 *work, double2 *yout, ROp lop, KOp ysop) const;

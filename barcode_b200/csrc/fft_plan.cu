@@ -666,6 +666,8 @@ void Fft3d::init(int n, cudaStream_t st) {
     force_generic = fg && fg[0] == '1';
     const char *sx = std::getenv("BGPU_SHARE_X");
     share_x = !(sx && sx[0] == '0');  // default since round 2 (measured +7 % at 256^3, parity-green); BGPU_SHARE_X=0 = three x passes
+    const char *zr = std::getenv("BGPU_ZROUND");
+    z_round = !(zr && zr[0] == '0');
     const char *tw2 = std::getenv("BGPU_FFT_2WARP");
     two_warp = tw2 && tw2[0] == '1';
     const char *fu = std::getenv("BGPU_FFT_FUSED");
@@ -737,6 +739,60 @@ static void r2c_zy_impl(const Fft3d &f, const double *in, double2 *work, double2
   } else {
     throw std::runtime_error("bgpu: the shared x pass needs the TMA-staged strided pass (N = 128, 256 or 512)");
   }
+}
+
+template <int N>
+static void ypass_impl(const Fft3d &f, const double2 *in, double2 *out, int dir, KOp lop, KOp sop) {
+  if constexpr (tma_has_size<N>()) {
+    if (dir > 0)
+      launch_strided_tma<N, +1, 1, -1>(f, in, out, lop, sop, PassIo{}, f.stream);
+    else
+      launch_strided_tma<N, -1, 1, -1>(f, in, out, lop, sop, PassIo{}, f.stream);
+  } else {
+    throw std::runtime_error("bgpu: single y passes need the TMA-staged strided pass (N = 128, 256 or 512)");
+  }
+}
+
+template <int N>
+static void zround_impl(const Fft3d &f, double2 *work, ROp op) {
+  if constexpr (tma_has_size<N>()) {
+    constexpr int E = ZShape<N>::E, TR = ZShape<N>::TR, NSTAGE = 3;
+    constexpr int threads = TR * (N / 2 / E);
+    using Z = ZTile<N, TR, NSTAGE, true>;
+    constexpr int smem = Z::smem_bytes;
+    static_assert(smem <= 227 * 1024, "z round-trip ring does not fit");
+    auto kern = fft_zround_tma<N, E, TR, NSTAGE, 1>;
+    static int blocks_per_sm_dev[kMaxDevices] = {};
+    int &blocks_per_sm = blocks_per_sm_dev[f.device % kMaxDevices];
+    if (!blocks_per_sm) {
+      BGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int occ = 0;
+      BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+      blocks_per_sm = occ > 0 ? occ : 1;
+    }
+    const int ntiles = (int)((size_t)f.Ns * N / TR);
+    int blocks = f.sm_count * blocks_per_sm;
+    if (blocks > ntiles) blocks = ntiles;
+    ProfScope prof(KK_FFT_ZROUND, f.stream);
+    kern<<<blocks, threads, smem, f.stream>>>(work, work, f.twN, f.twM, op, ntiles);
+    BGPU_LAUNCHED(1);
+  } else {
+    throw std::runtime_error("bgpu: the z round trip needs the bulk-copy z pass (N = 128, 256 or 512)");
+  }
+}
+
+bool Fft3d::can_zround() const { return z_round && can_share_x(); }
+
+void Fft3d::ypass(const double2 *in, double2 *out, int dir, KOp lop, KOp sop) const {
+#define CALL(n) ypass_impl<n>(*this, in, out, dir, lop, sop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
+
+void Fft3d::zround(double2 *work, ROp sop) const {
+#define CALL(n) zround_impl<n>(*this, work, sop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
 }
 
 void Fft3d::xpass(const double2 *in, double2 *out, int dir, KOp lop, KOp sop) const {

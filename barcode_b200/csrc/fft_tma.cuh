@@ -206,7 +206,8 @@ struct RowAccess {  // a contiguous row of double2 (z pass)
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
-template <int N, int E, int S, int DIR, int STG, class Acc>
+// CONJ: the register twiddles were loaded for the opposite direction (a kernel that transforms both ways keeps one set)
+template <int N, int E, int S, int DIR, int STG, class Acc, bool CONJ = false>
 __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc, const double2 (*twr)[E]) {
   constexpr int LP = N / E;
   constexpr int R = StageRadix<N, S>::value;
@@ -233,7 +234,7 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         double2 x = v[j + k * NB];
-        if (k > 0) x = cmul(x, twr[STG][j + k * NB]);
+        if (k > 0) x = cmul(x, CONJ ? cconj(twr[STG][j + k * NB]) : twr[STG][j + k * NB]);
         int e = q + R * base + k * S;
         if constexpr (S == 1) e ^= (e >> 3) & 7;  // conflict-free stride-8 scatter
         sts128(acc.at(e), x);
@@ -246,7 +247,7 @@ __device__ __forceinline__ void wp_stages(double2 (&v)[E], int t, const Acc &acc
       if constexpr (S == 1) e ^= (e >> 3) & 7;
       v[m] = lds128(acc.at(e));
     }
-    wp_stages<N, E, S * R, DIR, STG + 1, Acc>(v, t, acc, twr);
+    wp_stages<N, E, S * R, DIR, STG + 1, Acc, CONJ>(v, t, acc, twr);
   }
 }
 
@@ -596,7 +597,7 @@ __device__ __forceinline__ double2 root16(int m) {
 // One row of the z pass, in place in shared memory (rbase = the row, N/2 + 1 double2 of room): forward =
 // N/2-point complex FFT of z[j] = x[2j] + i x[2j+1] + Hermitian split; inverse = Hermitian merge + FFT.
 // Lane t of the LP = N/(2E) lanes that own the row; `auxrow` (AUX) = the row of the real multiplier.
-template <int N, int E, bool C2R, bool AUX>
+template <int N, int E, bool C2R, bool AUX, bool TWCONJ = false>
 __device__ __forceinline__ void zrow_transform(uint32_t rbase, uint32_t auxrow, int t,
                                                const double2 (*twr)[E], double2 wt,
                                                const double2 *__restrict__ twN, const ROp &op) {
@@ -616,7 +617,7 @@ __device__ __forceinline__ void zrow_transform(uint32_t rbase, uint32_t auxrow, 
 #pragma unroll
       for (int m = 0; m < E; ++m) v[m] = make_double2(v[m].x * op.a, v[m].y * op.a);
     }
-    wp_stages<M, E, 1, DIR, 0>(v, t, acc, twr);
+    wp_stages<M, E, 1, DIR, 0, RowAccess, TWCONJ>(v, t, acc, twr);
     // Hermitian split: X[k] = E + w^k O, E = (Z[k] + conj Z[M-k])/2, O = (Z[k] - conj Z[M-k])/(2i)
     __syncwarp();
 #pragma unroll
@@ -652,7 +653,7 @@ __device__ __forceinline__ void zrow_transform(uint32_t rbase, uint32_t auxrow, 
       const double2 o = cmul(d, cconj(split_twiddle(m)));
       v[m] = make_double2(e.x - o.y, e.y + o.x);
     }
-    wp_stages<M, E, 1, DIR, 0>(v, t, acc, twr);
+    wp_stages<M, E, 1, DIR, 0, RowAccess, TWCONJ>(v, t, acc, twr);
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < E; ++m) {
@@ -759,6 +760,95 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
       const int j = i + NSTAGE - 1;
       if (j < my_count) {
         bulk_wait_read<1>();  // my row of the stage used one iteration ago has drained
+        issue_load(j);
+      }
+    }
+  }
+  if (tid < 32) bulk_wait<0>();
+}
+
+// ---------------------------------------------------------------------------
+// z round trip: half-complex row -> real row, times a real array, -> half-complex row, in ONE pass.
+//
+// likelihood_calc_h (HMC_models_testing.cpp:25-50) forms g_c = r * d_c(delta) in real space between an inverse and a
+// forward transform (gradfft, gradient.cpp:38-74, then grad_inv_lap_FS, :157-211).  Only the z passes of the two
+// transforms meet real space, and the product is local, so the pair "c2r z pass (x r) -> r2c z pass" runs on
+// the row while it sits in shared memory: 24 B per cell cross HBM instead of 40, and three launches fewer per
+// evaluation.  Same row arithmetic as fft_zpass_tma (zrow_transform), one twiddle set for both directions.
+// ---------------------------------------------------------------------------
+template <int N, int E, int TR, int NSTAGE, int MINB>
+__global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
+    fft_zround_tma(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ twN,
+                   const double2 *__restrict__ twM, ROp op, int ntiles) {
+  constexpr int M = N / 2;
+  constexpr int LP = M / E;
+  constexpr int NSTG = StageCount<M>::value;
+  using Z = ZTile<N, TR, NSTAGE, true>;
+  constexpr uint32_t row_bytes = (M + 1) * 16;
+  static_assert(LP >= 8 && LP <= 32 && TR <= 32, "row must live inside one warp; warp 0 issues one copy per row");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t *smem_al = smem_raw + (smem0 - smem_u32(smem_raw));
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_al + NSTAGE * Z::stage_bytes);
+
+  const int tid = threadIdx.x;
+  const int row = tid / LP;
+  const int t = tid % LP;
+  const int my_count = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const char *gin = reinterpret_cast<const char *>(in);
+  char *gout = reinterpret_cast<char *>(out);
+
+  auto issue_load = [&](int i) {
+    const int s = i % NSTAGE;
+    const size_t grow = (size_t)(blockIdx.x + (size_t)i * gridDim.x) * TR + tid;
+    if (tid == 0) mbar_expect_tx(&full[s], TR * (row_bytes + N * 8));
+    __syncwarp();
+    if (tid < TR) {
+      bulk_load_1d(smem_al + s * Z::stage_bytes + tid * Z::pitch, gin + grow * row_bytes, row_bytes, &full[s]);
+      bulk_load_1d(smem_al + s * Z::stage_bytes + Z::main_bytes + tid * (N * 8),
+                   reinterpret_cast<const char *>(op.aux) + grow * (N * 8), N * 8, &full[s]);
+    }
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid < 32) {
+#pragma unroll
+    for (int i = 0; i < NSTAGE - 1; ++i)
+      if (i < my_count) issue_load(i);
+  }
+
+  double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
+  wp_load_twiddles<M, E, 1, +1, 0>(twr, t, twM);  // inverse-direction twiddles; the forward transform conjugates them
+  const double2 wt = __ldg(twN + t);
+  ROp fwd;
+  fwd.kind = R_LOAD;
+
+  for (int i = 0; i < my_count; ++i) {
+    const int s = i % NSTAGE;
+    const uint32_t rbase = smem0 + s * Z::stage_bytes + row * Z::pitch;
+    const uint32_t auxrow = smem0 + s * Z::stage_bytes + Z::main_bytes + row * (N * 8);
+    mbar_wait(&full[s], (i / NSTAGE) & 1);
+
+    zrow_transform<N, E, true, true>(rbase, auxrow, t, twr, wt, twN, op);      // -> a * x(z) * aux(z), N reals in place
+    __syncwarp();
+    zrow_transform<N, E, false, false, true>(rbase, auxrow, t, twr, wt, twN, fwd);  // -> N/2 + 1 complex in place
+    fence_proxy_async();
+    __syncthreads();
+    if (tid < 32) {
+      if (tid < TR) {
+        const size_t grow = (size_t)(blockIdx.x + (size_t)i * gridDim.x) * TR + tid;
+        bulk_store_1d(gout + grow * row_bytes, smem_al + s * Z::stage_bytes + tid * Z::pitch, row_bytes);
+      }
+      bulk_commit();
+      const int j = i + NSTAGE - 1;
+      if (j < my_count) {
+        bulk_wait_read<1>();
         issue_load(j);
       }
     }

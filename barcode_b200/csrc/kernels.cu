@@ -823,9 +823,28 @@ __global__ void axpy_kernel(double *__restrict__ y, const double *__restrict__ x
   if (i < n) y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));  // HMC.cc:294,339,352 (two roundings)
 }
 // HMC.cc:360-364: a trajectory whose momentum has run away is stopped -- on the device by raising a flag that
-// every later update of the trajectory honours (ROp::skip, launch_axpy's skip)
-__global__ void runaway_guard_kernel(const double *__restrict__ p, int *__restrict__ flag) {
-  if (fabs(p[0]) > 1e50) *flag = 1;
+// every later update of the trajectory honours (ROp::skip, launch_axpy's skip).  The reference tests momenta[0]
+// after the second half kick of every step.  With merged kicks that value is never stored, but it is the midpoint
+// of momenta[0] before and after the merged kick (p - eps/2 g between p and p - eps g), which this kernel keeps.
+//   mode 0: remember momenta[0] (after the trajectory's first half kick; the reference does not test there)
+//   mode 1: after a merged kick (both half kicks of a step boundary): test the midpoint
+//   mode 2: after a plain half kick (the last step): test momenta[0] itself
+// scal[0] = the step at which the trajectory stopped (0 = running), scal[1] = momenta[0] after the previous kick.
+__global__ void runaway_guard_kernel(const double *__restrict__ p, double *__restrict__ scal, int *__restrict__ flag,
+                                     int step, int mode) {
+  const double now = p[0];
+  if (mode != 0 && scal[0] == 0.0) {
+    const double seen = mode == 1 ? 0.5 * (scal[1] + now) : now;
+    if (fabs(seen) > 1e50) {
+      scal[0] = (double)step;
+      if (flag) *flag = step;
+    }
+  }
+  scal[1] = now;
+}
+// slab chains: rank 0 owns momenta[0]; its verdict reaches the others by an all-reduce of scal[0]
+__global__ void runaway_apply_kernel(const double *__restrict__ scal, int *__restrict__ flag) {
+  if (*flag == 0 && scal[0] > 0.0) *flag = (int)scal[0];
 }
 __global__ void scale_kernel(double *__restrict__ y, const double *__restrict__ x, double a, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -851,8 +870,12 @@ void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st
   axpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n, skip);
   BGPU_LAUNCHED(1);
 }
-void launch_runaway_guard(const double *p, int *flag, cudaStream_t st) {
-  runaway_guard_kernel<<<1, 1, 0, st>>>(p, flag);
+void launch_runaway_guard(const double *p, double *scal2, int *flag, int step, int mode, cudaStream_t st) {
+  runaway_guard_kernel<<<1, 1, 0, st>>>(p, scal2, flag, step, mode);
+  BGPU_LAUNCHED(1);
+}
+void launch_runaway_apply(const double *scal2, int *flag, cudaStream_t st) {
+  runaway_apply_kernel<<<1, 1, 0, st>>>(scal2, flag);
   BGPU_LAUNCHED(1);
 }
 void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t st) {

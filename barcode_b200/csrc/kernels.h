@@ -152,8 +152,10 @@ void launch_findif_product(const double *delta, const double *resid, double *out
 
 // y += a * x ; y = a * x ; y += a * x / m (m <= 0 -> 0)
 void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st, const int *skip = nullptr);
-// *flag = 1 if |p[0]| > 1e50 (the run-away test of Hamiltonian_EoM, HMC.cc:360-364)
-void launch_runaway_guard(const double *p, int *flag, cudaStream_t st);
+// the run-away test of Hamiltonian_EoM (HMC.cc:360-364) on the device, see kernels.cu: scal2 = {stopped at step,
+// momenta[0] after the previous kick}; flag (may be null) is raised with the step where the trajectory stopped
+void launch_runaway_guard(const double *p, double *scal2, int *flag, int step, int mode, cudaStream_t st);
+void launch_runaway_apply(const double *scal2, int *flag, cudaStream_t st);
 void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t st);
 void launch_axpy_div(double *y, const double *x, const double *m, double a, size_t n, cudaStream_t st,
                      const int *skip = nullptr);

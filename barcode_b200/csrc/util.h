@@ -47,7 +47,8 @@ enum KernelKind : int {
   KK_HALO = 11,
   KK_FFT_ZY_R2C = 12,  // fused z+y passes (fft_fused.cuh)
   KK_FFT_ZY_C2R = 13,
-  KK_COUNT = 14
+  KK_FFT_ZROUND = 14,  // c2r z pass x real array -> r2c z pass on the row in shared memory (fft_tma.cuh)
+  KK_COUNT = 15
 };
 
 struct Profiler {

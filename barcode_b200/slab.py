@@ -98,6 +98,13 @@ class SlabChain(Chain):
         communicator) and distributes it through the initialised torch.distributed group."""
         return cls(params, rank, world, broadcast_unique_id(rank, world) if world > 1 else None)
 
+    def fused_transpose(self) -> bool:
+        """True where the distributed FFT's transpose rides inside the strided pass (TMA stores into the peers'
+        receive buffers): the TMA-staged sizes, unless BGPU_SLAB_P2P=0 / BGPU_FFT_SLAB_GENERIC=1."""
+        import os
+        return (self.world > 1 and self.N1 in (128, 256, 512) and os.environ.get("BGPU_SLAB_P2P", "1") != "0"
+                and os.environ.get("BGPU_FFT_SLAB_GENERIC", "0") != "1")
+
     @property
     def shape(self):
         return (self.Ns, self.N1, self.N1)

@@ -51,6 +51,7 @@ def parse():
                     help="e2e_chains: chains (handles, host threads) on the GPU; 3 = one uploading, one computing, one "
                          "downloading (each phase takes about as long at PCIe 5 x16 rates)")
     ap.add_argument("--no-e2e-chains", action="store_true", help="skip the interleaved-chains e2e leg")
+    ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the slab-decomposed leg (512^3 / 1024^3)")
     return ap.parse_args()
 
 
@@ -316,9 +317,9 @@ def run_ours(args):
     nh = args.grid * args.grid * (args.grid // 2 + 1)
     # x pass: every launch reads and writes the half-complex array once (32 B / element); the last one of an
     # evaluation also reads its operands -- (V/N)/P (8 B) for calc_h = 1, plus the accumulated h^ (16 B) otherwise
-    x_launches = {0: 12, 1: 5, 4: 8}[args.calc_h]
-    if os.environ.get("BGPU_SHARE_X") == "1":   # opt-in shared x pass: two x passes per component triple
-        x_launches = {0: 9, 1: 5, 4: 6}[args.calc_h]
+    x_launches = {0: 9, 1: 5, 4: 6}[args.calc_h]   # shared x pass: two x passes per component triple
+    if os.environ.get("BGPU_SHARE_X") == "0":
+        x_launches = {0: 12, 1: 5, 4: 8}[args.calc_h]
     x_bytes = ((x_launches - 1) * 32 + (40 if args.calc_h == 1 else 56)) * nh / x_launches
     alg_bytes = {  # algorithmic bytes per launch of each kernel class ("Kernels")
         "fft_strided_pass_y": 2 * nh * 16, "fft_strided_pass_x": x_bytes,
@@ -327,6 +328,7 @@ def run_ours(args):
         # fused z+y passes: the real array and the half-complex array cross HBM once each; the
         # intermediate between the two passes stays in L2
         "fft_zy_fused_r2c": n * 8 + nh * 16, "fft_zy_fused_c2r": n * 8 + nh * 16,
+        "fft_z_roundtrip": n * 8 + 2 * nh * 16,   # half-complex row in and out, the real multiplier in
         "scatter": 4 * n * 8,                       # Psi_x,y,z in, rho out
         "gather_adjoint": 7 * n * 8,
         "overdens_residual": 5 * n * 8,
@@ -416,6 +418,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = cpu_baseline(args, cfg)
     ch.close()
+    slab = slab_leg(args, info) if (world > 1 and not args.no_slab) else None
     if rank == 0 and world == 1 and not args.no_e2e_chains:
         # independent chains interleaved on the GPU hide the PCIe transfers of one under the kernels of another;
         # measured in a child process with a timeout, reported beside (not instead of) the single-chain e2e.value
@@ -432,6 +435,7 @@ def run_ours(args):
                              "evaluation against 126 MB of L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches_timed),
             "clocks": clock_info,
+            "slab": slab,
             "also": {
                 f"gradient_evals_per_s_calc_h_{other_h}": world * args.steps / (ms_other * 1e-3),
                 "leapfrog_steps_per_s": world * leap_steps / (ms_leap * 1e-3),
@@ -553,20 +557,16 @@ def e2e_chains_leg(args, timeout_s=240):
         return {"error": repr(e)}
 
 
-def run_slab(args):
-    """ONE chain across all ranks (x-slab decomposition, barcode_b200/slab.py): strong scaling.
-    value = gradient evaluations of that one chain per second, device-timed, max over ranks."""
+def slab_measure(grid, calc_h, steps, warmup, info, with_clocks=True):
+    """ONE chain across all ranks (x-slab decomposition, barcode_b200/slab.py), gradient evaluations of that one
+    chain per second, device-timed, max over ranks.  The process group must be up.  Returns the result dict (same
+    on every rank up to the per-rank profile)."""
     import torch
     from barcode_b200 import chain as bc
     from barcode_b200 import inputs, multi, slab
 
-    info = multi.rank_info()
     world, rank, local_rank = info.world, info.rank, info.local_rank
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    multi.init("nccl", info, torch.device("cuda", local_rank))
-    cfg, name = workload(args.grid, args.calc_h)
+    cfg, name = workload(grid, calc_h)
     sc = slab.SlabChain.create(bc.Params(device=local_rank, **cfg), rank, world)
     prob = inputs.slab_problem(sc, seed=1)
     stream = torch.cuda.current_stream()
@@ -581,57 +581,145 @@ def run_slab(args):
     def step():
         sc.gradient_psi_dev(d_s.data_ptr(), d_g.data_ptr())
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = bc.kernel_launches()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
     launches = bc.kernel_launches() - l0
     barrier()
     ms = multi.max_over_ranks(e0.elapsed_time(e1), info, "cuda")
-    clock_info = clocks.stop() if rank == 0 else {}
+    clock_info = clocks.stop() if (rank == 0 and with_clocks) else {}
     bc.profile_begin()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     prof = bc.profile_end()
     n_loc = sc.N
     nh_loc = sc.Nhalf
     # bytes each rank sends per all-to-all (its whole k-space slab minus the block it keeps)
     a2a_bytes = nh_loc * 16 * (world - 1) / max(world, 1)
-    per_kernel = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+    per_kernel = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps}
                   for k, v in prof.items() if v[1]}
-    fused_transpose = os.environ.get("BGPU_SLAB_P2P", "1") != "0" and args.grid in (128, 256, 512)
+    fused_transpose = os.environ.get("BGPU_SLAB_P2P", "1") != "0" and sc.fused_transpose()
+    nvlink = {}
     if "all_to_all" in per_kernel and world > 1:
         t = prof["all_to_all"][0] * 1e-3 / prof["all_to_all"][1]
+        transposes = prof["all_to_all"][1] / steps
         if fused_transpose:
             # the NVLink traffic rides inside the strided pass (TMA stores into the peers' receive buffers);
             # what is timed under this name is only the cross-rank barrier that follows
             per_kernel["all_to_all"]["note"] = "fused transpose: this entry is the cross-rank barrier only"
             tp = (prof["fft_strided_pass_y"][0] + prof["fft_strided_pass_x"][0]) * 1e-3 / (2 * prof["all_to_all"][1])
-            per_kernel["all_to_all"]["GBps_sent_per_gpu_inside_pass"] = a2a_bytes / tp / 1e9
+            gbs = a2a_bytes / tp / 1e9
+            nvlink = {"GBps_sent_per_gpu": gbs, "frac_of_nvlink_900GBps": gbs / 900.0,
+                      "where": "inside the transposing strided pass (lower bound: the pass also transforms)",
+                      "transposes_per_eval": transposes}
         else:
-            per_kernel["all_to_all"]["GBps_sent_per_gpu"] = a2a_bytes / t / 1e9
-            per_kernel["all_to_all"]["frac_of_nvlink_900GBps"] = a2a_bytes / t / 1e9 / 900.0
+            gbs = a2a_bytes / t / 1e9
+            nvlink = {"GBps_sent_per_gpu": gbs, "frac_of_nvlink_900GBps": gbs / 900.0, "where": "NCCL grouped send/recv",
+                      "transposes_per_eval": transposes,
+                      "share_of_step": prof["all_to_all"][0] / max(1e-9, sum(v[0] for v in prof.values()))}
     sc.close()
-    if rank == 0:
+    return {
+        "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "grid": grid, "calc_h": calc_h,
+        "workload": name, "n_gpus": world, "steps": steps, "warmup": warmup, "scaling": "strong",
+        "parallelism": f"one chain, x-slab decomposed over {world} GPU(s): distributed FFT with "
+                       + ("the transpose fused into the strided pass (TMA stores over NVLink peer memory)"
+                          if fused_transpose else "NCCL all-to-all transposes") + ", halo-exchanged mass assignment",
+        "per_kernel": per_kernel, "nvlink": nvlink, "a2a_bytes_sent_per_gpu_per_transpose": a2a_bytes,
+        "local_cells": n_loc, "gpu_launches": int(launches), "clocks": clock_info,
+    }
+
+
+def slab_parity(grid, info):
+    """The slab-decomposed chain against the single-GPU chain (which the parity tests pin to the reference) on the
+    same inputs: forward density, both energies and the calc_h = 0 / 4 gradients.  Returns the worst relative L2."""
+    import torch
+    import torch.distributed as dist
+    from barcode_b200 import chain as bc
+    from barcode_b200 import inputs, slab
+    N = grid
+    L = inputs.box_length(N)
+    rng = np.random.default_rng(3)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L)
+    n = N ** 3
+    nobs = np.maximum(0.0, 1.0 + 0.3 * rng.standard_normal(n)).reshape(N, N, N)
+    one = np.ones((N, N, N))
+    w = rng.standard_normal((N, N, N))
+    s = 0.5 * np.fft.irfftn(np.fft.rfftn(w) * np.sqrt(np.maximum(P[:, :, :N // 2 + 1], 0) * n / L ** 3), s=(N, N, N),
+                            axes=(0, 1, 2))
+
+    def gather(local):
+        t = torch.from_numpy(np.ascontiguousarray(local)).cuda()
+        out = [torch.empty_like(t) for _ in range(info.world)]
+        dist.all_gather(out, t)
+        return torch.cat(out, 0).cpu().numpy()
+
+    worst = 0.0
+    for calc_h in (0, 4):
+        kw = dict(N1=N, L1=L, masskernel=1, likelihood=1, rsd_model=True, calc_h=calc_h, mass_type=1, sfmodel=2)
+        sc = slab.SlabChain.create(bc.Params(device=info.local_rank, **kw), info.rank, info.world)
+        sc.set_static(Power=sc.local(P), nobs=sc.local(nobs), noise=sc.local(one), window=sc.local(one))
+        g = gather(sc.gradient_psi(sc.local(s)))
+        pp, pl, dX = sc.psi(sc.local(s))
+        dX = gather(dX)
+        sc.close()
+        if info.rank == 0:
+            with bc.Chain(bc.Params(device=info.local_rank, **kw)) as ch:
+                ch.set_static(Power=P, nobs=nobs, noise=one, window=one)
+                g0 = ch.gradient_psi(s)
+                pp0, pl0, dX0 = ch.psi(s)
+            rel = lambda a, b: float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))  # noqa: E731
+            worst = max(worst, rel(g, g0), rel(dX, dX0), abs(pp - pp0) / abs(pp0), abs(pl - pl0) / abs(pl0))
+    t = torch.tensor([worst], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def slab_leg(args, info):
+    """N > 1 GPUs: besides the independent chains, ONE chain slab-decomposed over all ranks (BASELINE.json configs[3],
+    [4]): parity against the single-GPU chain at 128^3 and 256^3 first, then 512^3 -- and 1024^3 where it fits (8 GPUs)."""
+    out = {}
+    try:
+        out["parity_max_rel"] = {str(g): slab_parity(g, info) for g in (128, 256)}
+        steps = max(3, args.steps // 2)
+        out["512"] = slab_measure(512, args.calc_h, steps, 2, info, with_clocks=False)
+        if info.world >= 8:
+            out["1024"] = slab_measure(1024, args.calc_h, max(2, steps // 2), 1, info, with_clocks=False)
+        elif info.world >= 4:
+            out["1024"] = {"skipped": "1024^3 needs ~22 N^3 doubles = 190 GB over the ranks plus buffers: run on 8 GPUs"}
+    except Exception as e:  # noqa: BLE001 -- the chains leg's numbers must survive a failure here
+        out["error"] = repr(e)
+    return out
+
+
+def run_slab(args):
+    """`--mode slab`: only the slab-decomposed chain (strong scaling), one JSON line."""
+    import torch
+    from barcode_b200 import multi
+
+    info = multi.rank_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
+    torch.cuda.set_device(info.local_rank)
+    multi.init("nccl", info, torch.device("cuda", info.local_rank))
+    r = slab_measure(args.grid, args.calc_h, args.steps, args.warmup, info)
+    if info.rank == 0:
         line = {
-            "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": info.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "grid": args.grid, "calc_h": args.calc_h,
-                       "parallelism": f"one chain, x-slab decomposed over {world} GPU(s): distributed FFT with "
-                                      + ("the transpose fused into the strided pass (TMA stores over NVLink peer memory)"
-                                         if fused_transpose else "NCCL all-to-all transposes")
-                                      + ", halo-exchanged mass assignment",
+            "config": {"workload": r["workload"], "grid": args.grid, "calc_h": args.calc_h, "parallelism": r["parallelism"],
                        "l2": "inputs larger than L2; no explicit flush"},
-            "per_kernel": per_kernel, "local_cells": n_loc, "gpu_launches": int(launches), "clocks": clock_info,
+            "per_kernel": r["per_kernel"], "nvlink": r["nvlink"], "local_cells": r["local_cells"],
+            "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
         }
         print(json.dumps(line))
     multi.finalize()

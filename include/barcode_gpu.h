@@ -175,7 +175,7 @@ uint64_t bgpu_kernel_launches(void);
 /* per-kernel-class device timing (bench.py's roofline leg): CUDA events on the launching
  * stream around every launch between begin and end; a launch of the reduce / residual class
  * is a pair of kernels.  nkinds <= BGPU_PROFILE_KINDS. */
-#define BGPU_PROFILE_KINDS 14
+#define BGPU_PROFILE_KINDS 15
 int bgpu_profile_begin(void);
 int bgpu_profile_end(double *ms_per_kind, uint64_t *launches_per_kind, int nkinds);
 const char *bgpu_profile_kind_name(int kind);

@@ -95,9 +95,26 @@ int main(int argc, char **argv) {
     const int k = (int)(idx % N), j = (int)((idx / N) % N), i = (int)(idx / ((size_t)N * N));
     auto kv = [&](int a) { return a <= N / 2 ? kf * a : -kf * (N - a); };
     const double kk = std::sqrt(kv(i) * kv(i) + kv(j) * kv(j) + kv(k) * kv(k));
-    power[idx] = idx == 0 ? 0.0 : 2.0e4 * kk / (1.0 + std::pow(kk / 0.02, 3.0));  // a smooth CDM-like bump, P(0) = 0
+    power[idx] = idx == 0 ? 0.0 : 2.2e4 * (kk / 0.02) / (1.0 + std::pow(kk / 0.02, 2.5));  // CDM-like, P(0) = 0
     nobs[idx] = 1.0 + 0.3 * unit_noise(idx, 1);
-    sig[idx] = 0.3 * unit_noise(idx, 2);
+    sig[idx] = std::sqrt(3.0) * unit_noise(idx, 2);  // unit-variance white noise, coloured below
+  }
+  {
+    // the signal: half a Gaussian-ish random field with that spectrum (create_GARFIELD's normalisation,
+    // random.cpp:81-83: |s^|^2 = P N^2 / V), i.e. displacements of a few cells that vary smoothly -- what the
+    // chain sees in production and what bench.py's synthetic problem is; white noise would not be
+    const size_t nh = (size_t)N * N * (N / 2 + 1);
+    std::vector<double> hat(2 * nh);
+    CHECK(bgpu_fft_r2c(H[0], sig.data(), hat.data()));
+    const double vol = p.L1 * p.L1 * p.L1;
+#pragma omp parallel for schedule(static)
+    for (long m = 0; m < (long)nh; ++m) {
+      const int k = (int)(m % (N / 2 + 1)), j = (int)((m / (N / 2 + 1)) % N), i = (int)(m / ((size_t)(N / 2 + 1) * N));
+      const double a = 0.5 * std::sqrt(power[((size_t)i * N + j) * N + k] * (double)n / vol);
+      hat[2 * m] *= a;
+      hat[2 * m + 1] *= a;
+    }
+    CHECK(bgpu_fft_c2r(H[0], hat.data(), sig.data()));
   }
   double e[2][2];
   for (int v = 0; v < 2; ++v) {
