@@ -49,6 +49,7 @@ struct Fft3d {
   // fused z+y kernel (fft_fused.cuh): per-plane completion counters, their running target, producer lead
   bool use_fused = false;  // BGPU_FFT_FUSED=1
   bool two_warp = false;   // BGPU_FFT_2WARP=1: 512-point strided pencils over two warps (fft_tma.cuh, ColAccessWide)
+  bool use_pdl = true;     // (BGPU_PDL=0 turns it off) programmatic dependent launch of the TMA-staged passes
   bool z_round = true;     // (BGPU_ZROUND=0 turns it off) calc_h = 0: the c2r / r2c z passes around r * d_c(delta) fused
   bool share_x = true;     // (BGPU_SHARE_X=0 turns it off) the y and z components of a K_DISP / K_GRAD / K_INVLAP triple share one x pass
   bool force_generic = false;  // BGPU_FFT_SLAB_GENERIC=1: slab passes through fft_slab_generic.cuh even where TMA fits

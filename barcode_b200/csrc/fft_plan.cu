@@ -149,6 +149,23 @@ const CUtensorMap &Fft3d::tensor_map(const void *base, int axis, bool cplx, int 
   return maps_.back().map;
 }
 
+// launch with (or without) the programmatic-stream-serialization attribute, see fft_tma.cuh pdl_wait()
+template <class... KArgs, class... Args>
+static void launch_pass(void (*kern)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t st, bool pdl,
+                        Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  BGPU_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
 constexpr int kMaxDevices = 16;  // GPUs one process may drive (per-device launch configuration below)
 
 template <int N> struct TmaShape;
@@ -224,7 +241,7 @@ static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, 
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > tiles) blocks = tiles;
   ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, st);
-  kern<<<blocks, threads, smem, st>>>(maps, f.twN, lop, sop, geo);
+  launch_pass(kern, blocks, threads, smem, st, f.use_pdl, maps, f.twN, lop, sop, geo);
   BGPU_LAUNCHED(1);
 }
 
@@ -358,7 +375,7 @@ static void launch_zpass_tma(const Fft3d &f, const void *in, void *out, ROp op, 
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > ntiles) blocks = ntiles;
   ProfScope prof(C2R ? KK_FFT_C2R_Z : KK_FFT_R2C_Z, st);
-  kern<<<blocks, threads, smem, st>>>(pin, pout, f.twN, f.twM, op, ntiles);
+  launch_pass(kern, blocks, threads, smem, st, f.use_pdl, (const void *)pin, (void *)pout, f.twN, f.twM, op, ntiles);
   BGPU_LAUNCHED(1);
 }
 
@@ -666,6 +683,8 @@ void Fft3d::init(int n, cudaStream_t st) {
     force_generic = fg && fg[0] == '1';
     const char *sx = std::getenv("BGPU_SHARE_X");
     share_x = !(sx && sx[0] == '0');  // default since round 2 (measured +7 % at 256^3, parity-green); BGPU_SHARE_X=0 = three x passes
+    const char *pd = std::getenv("BGPU_PDL");
+    use_pdl = !(pd && pd[0] == '0');
     const char *zr = std::getenv("BGPU_ZROUND");
     z_round = !(zr && zr[0] == '0');
     const char *tw2 = std::getenv("BGPU_FFT_2WARP");
@@ -774,7 +793,7 @@ static void zround_impl(const Fft3d &f, double2 *work, ROp op) {
     int blocks = f.sm_count * blocks_per_sm;
     if (blocks > ntiles) blocks = ntiles;
     ProfScope prof(KK_FFT_ZROUND, f.stream);
-    kern<<<blocks, threads, smem, f.stream>>>(work, work, f.twN, f.twM, op, ntiles);
+    launch_pass(kern, blocks, threads, smem, f.stream, f.use_pdl, (const double2 *)work, work, f.twN, f.twM, op, ntiles);
     BGPU_LAUNCHED(1);
   } else {
     throw std::runtime_error("bgpu: the z round trip needs the bulk-copy z pass (N = 128, 256 or 512)");

@@ -104,6 +104,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, int c0, int
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// Programmatic dependent launch: a pass launched with the programmatic-stream-serialization attribute may become
+// resident while the previous kernel of the stream drains; everything up to pdl_wait() (barrier set-up, twiddle
+// loads -- nothing the previous kernel writes) overlaps that tail, everything after it sees the previous kernel's
+// results.  pdl_trigger() lets the NEXT kernel of the stream do the same with this one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 template <int K>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -452,15 +459,16 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
   // as the store issued a moment ago has finished reading its stage, so the load still overlaps
   // the whole transform.
   constexpr bool EARLY = (NSTAGE == 2);
+  // tile-invariant twiddles (a constant table: safe ahead of pdl_wait)
+  double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
+  wp_load_twiddles<N, E, 1, DIR, 0>(twr, t, tw);
+  pdl_trigger();
+  pdl_wait();
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < (EARLY ? 1 : NSTAGE - 1); ++i)
       if (i < my_count) issue_load(i);
   }
-
-  // tile-invariant twiddles
-  double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
-  wp_load_twiddles<N, E, 1, DIR, 0>(twr, t, tw);
 
   for (int i = 0; i < my_count; ++i) {
     const int s = i % NSTAGE;
@@ -693,7 +701,10 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
   constexpr uint32_t out_row_bytes = C2R ? N * 8 : (M + 1) * 16;
   static_assert(LP >= 8 && LP <= 32 && TR <= 32, "row must live inside one warp; warp 0 issues one copy per row");
   if constexpr (C2R) {
-    if (op.skip && *op.skip) return;  // uniform over the grid; nothing has been issued yet
+    if (op.skip) {
+      pdl_wait();  // the flag is an earlier kernel's result
+      if (*op.skip) return;  // uniform over the grid; nothing has been issued yet
+    }
   }
 
   extern __shared__ uint8_t smem_raw[];
@@ -728,16 +739,17 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
     fence_barrier_init();
   }
   __syncthreads();
+  double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
+  wp_load_twiddles<M, E, 1, DIR, 0>(twr, t, twM);
+  // split / merge twiddle w_N^k, k = t + m LP: for E == 8, LP = N/16 and w_N^(m LP) is a 16th root of unity
+  const double2 wt = __ldg(twN + t);
+  pdl_trigger();
+  pdl_wait();
   if (tid < 32) {
 #pragma unroll
     for (int i = 0; i < NSTAGE - 1; ++i)
       if (i < my_count) issue_load(i);
   }
-
-  double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
-  wp_load_twiddles<M, E, 1, DIR, 0>(twr, t, twM);
-  // split / merge twiddle w_N^k, k = t + m LP: for E == 8, LP = N/16 and w_N^(m LP) is a 16th root of unity
-  const double2 wt = __ldg(twN + t);
 
   for (int i = 0; i < my_count; ++i) {
     const int s = i % NSTAGE;
@@ -817,15 +829,16 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
     fence_barrier_init();
   }
   __syncthreads();
+  double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
+  wp_load_twiddles<M, E, 1, +1, 0>(twr, t, twM);  // inverse-direction twiddles; the forward transform conjugates them
+  const double2 wt = __ldg(twN + t);
+  pdl_trigger();
+  pdl_wait();
   if (tid < 32) {
 #pragma unroll
     for (int i = 0; i < NSTAGE - 1; ++i)
       if (i < my_count) issue_load(i);
   }
-
-  double2 twr[NSTG > 1 ? NSTG - 1 : 1][E];
-  wp_load_twiddles<M, E, 1, +1, 0>(twr, t, twM);  // inverse-direction twiddles; the forward transform conjugates them
-  const double2 wt = __ldg(twN + t);
   ROp fwd;
   fwd.kind = R_LOAD;
 

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PK_TABLE = os.path.join(os.path.dirname(_HERE), "tests", "golden", "pk_table.npz")
+PK_TABLE = os.path.join(_HERE, "data", "pk_table.npz")   # package data (written by tests/golden/make_golden.py)
 
 
 def calc_ki(N: int, L: float) -> np.ndarray:

@@ -9,7 +9,7 @@ Every output array below is produced by the UNMODIFIED reference sources
 restatement or the CUDA path.  The reference's own tests hold no golden vector
 for the hot path, so these files are the pin.
 
-  pk_table.npz        the tabulated linear P(k) the reference reads (data/WMAP7_CAMB.dat),
+  ../../barcode_b200/data/pk_table.npz  the tabulated linear P(k) the reference reads (data/WMAP7_CAMB.dat),
                       in the float32 precision of calc_power.cc:41-42
   case_<name>.npz     inputs + reference outputs of one configuration at 16^3
   garfield_n8.npz     white-noise stream, coloured field and momenta at 8^3
@@ -73,7 +73,7 @@ NEPS_U, EPS_U = 0.3, 0.01   # N_eps_fac = 8 -> Neps = floor(8*0.3)+1 = 3 ; eps_f
 
 def main():
     tab = np.loadtxt(CAMB)
-    np.savez_compressed(os.path.join(HERE, "pk_table.npz"), k=tab[:, 0].astype(np.float32),
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(HERE)), "barcode_b200", "data", "pk_table.npz"), k=tab[:, 0].astype(np.float32),
                         P=tab[:, 1].astype(np.float32))
 
     only = set(sys.argv[1:])

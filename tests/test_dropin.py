@@ -116,7 +116,7 @@ def run(exe, d, par):
 @pytest.mark.parametrize("masskernel,likelihood,rsd,mass_type", [(1, 1, "false", 1), (2, 1, "true", 1), (1, 0, "false", 0),
                                                                   (1, 1, "false", 2)])
 def test_unchanged_host_driver_runs_on_the_gpu_path(tmp_path, masskernel, likelihood, rsd, mass_type):
-    with np.load(os.path.join(GOLDEN, "pk_table.npz")) as f:
+    with np.load(os.path.join(ROOT, "barcode_b200", "data", "pk_table.npz")) as f:
         k, P = f["k"], f["P"]
     pk = tmp_path / "pk.dat"
     with open(pk, "w") as o:
@@ -151,7 +151,7 @@ def test_host_driver_with_the_device_momentum_generator(tmp_path, monkeypatch):
     """BARCODE_GPU_DEVICE_RNG=1: the momentum draw itself runs on the device (Philox; not GSL-seed-compatible),
     everything else of the reference's sampler unchanged.  The chain must run, accept candidates at a small step
     and conserve energy as the CPU-stream run does (dH of the same order)."""
-    with np.load(os.path.join(GOLDEN, "pk_table.npz")) as f:
+    with np.load(os.path.join(ROOT, "barcode_b200", "data", "pk_table.npz")) as f:
         k, P = f["k"], f["P"]
     pk = tmp_path / "pk.dat"
     with open(pk, "w") as o:
@@ -190,7 +190,7 @@ def test_the_reference_smoke_config_on_the_gpu_path(tmp_path):
     SPH kernel, calc_h = 2, adaptive step size (eps_fac_update_type 3), N_eps_fac 8, N_bin 200 -- at Nx = 8,
     Lx = 500, N_Gibbs = 5.  The reference only checks that the process exits; here the GPU drop-in must also
     write the same log and fields as the CPU build."""
-    with np.load(os.path.join(GOLDEN, "pk_table.npz")) as f:
+    with np.load(os.path.join(ROOT, "barcode_b200", "data", "pk_table.npz")) as f:
         k, P = f["k"], f["P"]
     pk = tmp_path / "pk.dat"
     with open(pk, "w") as o:

@@ -508,6 +508,7 @@ def test_measure_spectrum_matches_reference_and_oracle():
     (128, 2, 0, False, 0, 1, 1),    # configs[2] at its own size: 128^3 ZA + TSC, Poisson
     (256, 1, 1, True, 0, 1, 2),     # configs[1] at its own size: 256^3 (2LPT requested ->) ZA + CIC, Gaussian, RSD
     (128, 1, 1, False, 0, 1, 3),    # configs[3]'s physics at 128^3: ALPT + CIC (Lag2Eul_non_zeldovich)
+    (512, 1, 1, True, 0, 1, 2),     # the north star's own size: 512^3 ZA + CIC, Gaussian, RSD (no trajectory: CPU minutes)
     pytest.param(512, 1, 1, False, 0, 1, 3, marks=pytest.mark.skipif(
         not os.environ.get("BGPU_HEAVY_TESTS"), reason="configs[3] at its own size, 512^3 ALPT + CIC: minutes of "
         "reference CPU time; set BGPU_HEAVY_TESTS=1 (run once per round, log under profiles/)")),
