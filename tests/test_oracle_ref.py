@@ -90,7 +90,7 @@ def test_reference_smoke_config_runs(tmp_path):
     td = importlib.import_module("test_dropin")
     if not os.path.exists(td.CPU):
         pytest.skip("oracle/_ref/barcode_cpu not built")
-    with np.load(os.path.join(td.GOLDEN, "pk_table.npz")) as f:
+    with np.load(os.path.join(td.ROOT, "barcode_b200", "data", "pk_table.npz")) as f:
         k, P = f["k"], f["P"]
     pk = tmp_path / "pk.dat"
     with open(pk, "w") as o:
