@@ -12,6 +12,7 @@
 #include <vector>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 #include "fft3d.h"
 #include "kernels.h"
@@ -111,6 +112,7 @@ struct bgpu_handle {
   // SPH kernel hull (SPH_kernel_3D_cells_hull_1): k half-range per (i, j) column, on the device
   int *sph_kmax = nullptr;
   int sph_R = 0;
+  double *sph_hW = nullptr;  // calc_h = 3: h * SPH_kernel_F on the padded half grid (HMC_models_testing.cpp:88-105)
 };
 
 namespace {
@@ -170,12 +172,12 @@ void validate(const bgpu_params &p) {
             "bgpu: particle_kernel_h_rel must be in (0, N1/4] for the SPH kernel (init_par.cc:373-375)");
   require(p.likelihood >= 0 && p.likelihood <= 3,
           "bgpu: likelihood must be 0 (Poisson), 1 (Gaussian), 2 (log-normal) or 3 (Gaussian random field)");
-  require(p.calc_h == 0 || p.calc_h == 1 || p.calc_h == 2 || p.calc_h == BGPU_CALC_H_EXACT,
-          "bgpu: calc_h must be 0, 1, 2 (SPH adjoint) or 4 (NGP/CIC/TSC adjoint); 3 is not implemented");
-  require(p.calc_h == 0 || p.calc_h == 1 || (p.calc_h == 2 && p.masskernel == 3) ||
+  require(p.calc_h == 0 || p.calc_h == 1 || p.calc_h == 2 || p.calc_h == 3 || p.calc_h == BGPU_CALC_H_EXACT,
+          "bgpu: calc_h must be 0, 1, 2 (SPH adjoint), 3 (its Fourier / TSC variant) or 4 (NGP/CIC/TSC adjoint)");
+  require(p.calc_h == 0 || p.calc_h == 1 || ((p.calc_h == 2 || p.calc_h == 3) && p.masskernel == 3) ||
               (p.calc_h == BGPU_CALC_H_EXACT && p.masskernel != 3),
-          "Must use SPH mass kernel (masskernel = 3) when using likelihood_calc_h_SPH (calc_h = 2); the exact "
-          "adjoint of the SPH kernel is calc_h = 2, of NGP/CIC/TSC calc_h = 4");
+          "Must use SPH mass kernel (masskernel = 3) when using likelihood_calc_h_SPH (calc_h = 2 or 3)!  (The exact "
+          "adjoint of NGP/CIC/TSC is calc_h = 4.)");
   require(p.mass_type >= 0 && p.mass_type <= 4,
           "bgpu: mass_type must be 0 ... 4 on the GPU path (5/6/60, the first-order likelihood-force expansion, are O(N) FFTs of cold set-up)");
   if (p.mass_type == 2 || p.mass_type == 3)
@@ -185,7 +187,8 @@ void validate(const bgpu_params &p) {
     // for it (HMC_models.cc:458): its gradients are calc_h 0 / 1 on the forward density.
     // calc_h 0 / 1 are the reference's gradients on the forward density; calc_h = 4 is the exact adjoint (new)
     require(p.calc_h == 0 || p.calc_h == 1 || (p.calc_h == BGPU_CALC_H_EXACT && p.masskernel != 3),
-            "bgpu: sfmodel != 1 supports calc_h 0, 1 and 4 (NGP / CIC / TSC)");
+            "bgpu: sfmodel != 1 supports calc_h 0, 1 and 4 (NGP / CIC / TSC); the reference's SPH adjoints (calc_h 2, 3) "
+            "are Zel'dovich-only (HMC_models.cc:442-458)");
     if (p.calc_h == BGPU_CALC_H_EXACT)
       require(p.correct_delta != 0, "bgpu: the exact adjoint of the 2LPT/ALPT model needs correct_delta = true");
     require(p.slength > 0., "bgpu: sfmodel != 1 needs slength > 0 (the ALPT smoothing radius, input.par slength)");
@@ -608,6 +611,22 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     if (h->out_hooks && h->out_hooks->after)
       for (int c = 0; c < h->out_hooks->chunks; ++c) h->out_hooks->after(h->out_hooks->ctx, c);
     return;
+  } else if (p.calc_h == 3) {
+    // likelihood_calc_V_SPH_fourier_TSC (HMC_models_testing.cpp:54-188): V_c(p) = TSC-interpolation at the particle of
+    // IFFT[i k_c h W^(k) r^(k)], z times (1 + f) under RSD; then the back-projection of calc_h = 2.  The residual and
+    // the density are free once r^ exists and take V_x, V_y; V_z goes over Psi_z last (positions come from Psi).
+    r2c_plain(h, h->resid, h->dhat);
+    ROp unit;
+    unit.kind = R_SCALE;
+    unit.a = inv_n;
+    double *V[3] = {h->resid, h->delta, h->psi[2]};
+    for (int c = 0; c < 3; ++c) {
+      launch_sph_fourier_comp(h->dhat, h->sph_hW, h->acc, h->N, h->kfac, c, h->stream);
+      h->fft.c2r(h->acc, h->acc, h->tmp, KOp{}, unit);
+      const double fz = (c == 2 && p.rsd_model) ? h->geom.fgrow : 0.0;   // out_z += f1 * out_z (:176-186)
+      launch_interp_tsc(h->geom, h->psi[0], h->psi[1], h->psi[2], h->tmp, V[c], fz, h->stream);
+    }
+    backproject(h, V);
   } else {
     // exact adjoint: V = gather(r) in place over Psi, then the same back-projection
     if (p.calc_h == 2)
@@ -927,7 +946,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     require(!(p->calc_h == BGPU_CALC_H_EXACT && p->sfmodel != 1 && !p->rsd_model),
             "bgpu_slab_create: the exact adjoint of the 2LPT/ALPT model is not built for slabs yet");
     require(p->calc_h == 0 || p->calc_h == 1 || p->calc_h == BGPU_CALC_H_EXACT,
-            "bgpu_slab_create: calc_h must be 0, 1 or 4 (the SPH adjoint is not built for slabs yet)");
+            "bgpu_slab_create: calc_h must be 0, 1 or 4 (the SPH adjoints, calc_h 2 / 3, are not built for slabs yet)");
     require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
     require(p->sfmodel == 1 || p->rsd_model || p->N1 / nranks >= 8,
             "bgpu_slab_create: the 2LPT/ALPT model needs at least 8 planes per rank (4-plane stencil halo)");
@@ -1055,6 +1074,45 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->sph_kmax), kmax.size() * sizeof(int)));
     BGPU_CUDA(cudaMemcpy(h->sph_kmax, kmax.data(), kmax.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
+  if (p->calc_h == 3) {
+    // h * SPH_kernel_F (HMC_models_testing.cpp:62-105), evaluated on the HOST, operation by operation, with the C
+    // library the reference itself calls: the numerator 3 + cos 2k - k sin k + cos k (k sin k - 4) cancels to
+    // ~k^6 / 240, so at the grid's small k its value is rounding noise that depends on libm's last bits -- a
+    // table from the same libm is the only way to agree with the reference there.  Static: built once per handle.
+    const int N = h->N, nzh = N / 2 + 1;
+    const double hh = g.sph_h;
+    const double norm = (24. / (hh * hh * hh)) * (p->rho_c * p->L1 * p->L2 * p->L3 / h->ncells);
+    std::vector<double> tab((size_t)N * N * (nzh + 1), 0.0);
+    auto kv = [&](int m) { return (m <= N / 2) ? h->kfac * (double)m : -h->kfac * (double)(N - m); };
+    auto fill_planes = [&](int i0, int i1) {
+    for (int i = i0; i < i1; ++i)
+      for (int j = 0; j < N; ++j)
+        for (int k = 0; k < nzh; ++k) {
+          const double kx = kv(i), ky = kv(j), kz = kv(k);
+          const double k_sq = kx * kx + ky * ky + kz * kz;
+          double F;
+          if (k_sq == 0.) {
+            F = 1. / (hh * hh * hh);
+          } else {
+            const double kk = std::sqrt(k_sq);
+            const double ksink = kk * std::sin(kk);
+            F = norm * (3 + std::cos(2 * kk) - ksink + std::cos(kk) * (ksink - 4)) / (k_sq * k_sq * k_sq);
+          }
+          tab[((size_t)i * N + j) * (nzh + 1) + k] = hh * F;
+        }
+    };
+    {
+      unsigned nt = std::thread::hardware_concurrency();
+      if (nt < 1) nt = 1;
+      if (nt > 16) nt = 16;
+      if ((int)nt > N) nt = (unsigned)N;
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < nt; ++t) pool.emplace_back(fill_planes, (int)((size_t)N * t / nt), (int)((size_t)N * (t + 1) / nt));
+      for (auto &th : pool) th.join();
+    }
+    dalloc(h->sph_hW, tab.size());
+    BGPU_CUDA(cudaMemcpy(h->sph_hW, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   h->like.likelihood = p->likelihood;
   h->like.rho_c = p->rho_c;
   h->like.biasP = p->biasP;
@@ -1174,6 +1232,7 @@ void bgpu_destroy(bgpu_handle *h) {
     if (h->ev_dn[c]) cudaEventDestroy(h->ev_dn[c]);
   }
   if (h->sph_kmax) cudaFree(h->sph_kmax);
+  if (h->sph_hW) cudaFree(h->sph_hW);
   if (h->dflag) cudaFree(h->dflag);
   if (h->stopflag) cudaFree(h->stopflag);
   if (h->hflag2) cudaFreeHost(h->hflag2);

@@ -684,7 +684,9 @@ void Fft3d::init(int n, cudaStream_t st) {
     const char *sx = std::getenv("BGPU_SHARE_X");
     share_x = !(sx && sx[0] == '0');  // default since round 2 (measured +7 % at 256^3, parity-green); BGPU_SHARE_X=0 = three x passes
     const char *pd = std::getenv("BGPU_PDL");
-    use_pdl = !(pd && pd[0] == '0');
+    // measured (B200, round 2): +1.3 % per evaluation at 256^3, where a pass is ~55 us and the launch ramp shows;
+    // -2 % at 512^3 -- so on by default up to 256 only (BGPU_PDL=0 / 1 overrides)
+    use_pdl = pd ? pd[0] != '0' : n <= 256;
     const char *zr = std::getenv("BGPU_ZROUND");
     z_round = !(zr && zr[0] == '0');
     const char *tw2 = std::getenv("BGPU_FFT_2WARP");

@@ -1457,4 +1457,83 @@ void launch_gather_sph(const GridGeom &g, double *ax, double *ay, double *az, co
   BGPU_LAUNCHED(1);
 }
 
+// ---------------------------------------------------------------------------
+// calc_h = 3: likelihood_calc_V_SPH_fourier_TSC (HMC_models_testing.cpp:54-188) -- the SPH adjoint with the gather
+// replaced by a k-space convolution and a TSC interpolation to the particles.
+// ---------------------------------------------------------------------------
+// out = i k_c * hW(k) * r^(k), hW = h * SPH_kernel_F on the padded half grid (built on the host with the C library the
+// reference uses, api.cu); no Nyquist zeroing (:111-128).  Cube layout [x][y][z <= N/2].
+__global__ void sph_fourier_comp_kernel(const double2 *__restrict__ rhat, const double *__restrict__ hW,
+                                        double2 *__restrict__ out, int N, double kfac, int comp) {
+  const int nzh = N / 2 + 1;
+  const size_t n = (size_t)N * N * nzh;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const size_t row = idx / nzh;
+  const int z = (int)(idx - row * nzh);
+  const int y = (int)(row % N), x = (int)(row / N);
+  const int m = comp == 0 ? x : (comp == 1 ? y : z);
+  const double kc = (m <= N / 2) ? kfac * (double)m : -kfac * (double)(N - m);  // scale_space.cpp:41-51
+  const double f = kc * hW[row * (nzh + 1) + z];
+  const double2 v = rhat[idx];
+  out[idx] = make_double2(f * -v.y, f * v.x);
+}
+
+void launch_sph_fourier_comp(const double2 *rhat, const double *hW_half, double2 *out, int N, double kfac, int comp,
+                             cudaStream_t st) {
+  ProfScope prof(KK_STREAM, st);
+  const size_t n = (size_t)N * N * (N / 2 + 1);
+  sph_fourier_comp_kernel<<<blocks_for(n, 256), 256, 0, st>>>(rhat, hW_half, out, N, kfac, comp);
+  BGPU_LAUNCHED(1);
+}
+
+// interpolate_TSC (interpolate_grid.cpp:134-202) at the particle positions (recomputed from Psi), bug-compatible:
+// the upper weights of x and y are formed from dz (:166-167).  Safe in place over one of the Psi arrays: a thread
+// reads only its own element of them.
+__global__ void interp_tsc_kernel(GridGeom g, const double *psix, const double *psiy, const double *psiz,
+                                  const double *__restrict__ field, double *out, double fz) {
+  const int N = g.N;
+  const size_t n = (size_t)N * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int sh = 31 - __clz(N);
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
+  double px, py, pz;
+  particle_position(g, i, j, k, psix[idx], psiy[idx], psiz[idx], px, py, pz);
+  const double xk = __ddiv_rn(px, g.d), yk = __ddiv_rn(py, g.d), zk = __ddiv_rn(pz, g.d);
+  unsigned ix = (unsigned)xk, iy = (unsigned)yk, iz = (unsigned)zk;
+  const double dx = __dsub_rn(xk, (double)ix + 0.5), dy = __dsub_rn(yk, (double)iy + 0.5),
+               dz = __dsub_rn(zk, (double)iz + 0.5);
+  // (a position that rounds to exactly L would index one past the grid in the reference: fold it)
+  if (ix >= (unsigned)N) ix -= (unsigned)N;
+  if (iy >= (unsigned)N) iy -= (unsigned)N;
+  if (iz >= (unsigned)N) iz -= (unsigned)N;
+  auto sq = [](double a) { return __dmul_rn(a, a); };
+  const double up = __dmul_rn(0.5, sq(__dsub_rn(1.5, fabs(__dsub_rn(dz, 1.0)))));  // shared by x, y and z: the slip
+  const double wx[3] = {__dmul_rn(0.5, sq(__dsub_rn(1.5, fabs(__dadd_rn(dx, 1.0))))), __dsub_rn(0.75, sq(dx)), up};
+  const double wy[3] = {__dmul_rn(0.5, sq(__dsub_rn(1.5, fabs(__dadd_rn(dy, 1.0))))), __dsub_rn(0.75, sq(dy)), up};
+  const double wz[3] = {__dmul_rn(0.5, sq(__dsub_rn(1.5, fabs(__dadd_rn(dz, 1.0))))), __dsub_rn(0.75, sq(dz)), up};
+  const unsigned cx[3] = {(ix + N - 1) % N, ix, (ix + 1) % N}, cy[3] = {(iy + N - 1) % N, iy, (iy + 1) % N},
+                 cz[3] = {(iz + N - 1) % N, iz, (iz + 1) % N};
+  double acc = 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double *row = field + ((size_t)cx[a] * N + cy[b]) * N;
+      const double wab = __dmul_rn(wx[a], wy[b]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(wab, wz[c]), __ldg(row + cz[c])));
+    }
+  out[idx] = fz != 0.0 ? acc + fz * acc : acc;
+}
+
+void launch_interp_tsc(const GridGeom &g, const double *psix, const double *psiy, const double *psiz,
+                       const double *field, double *out, double fz, cudaStream_t st) {
+  ProfScope prof(KK_GATHER, st);
+  const size_t n = (size_t)g.N * g.N * g.N;
+  interp_tsc_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, psix, psiy, psiz, field, out, fz);
+  BGPU_LAUNCHED(1);
+}
+
 }  // namespace bgpu

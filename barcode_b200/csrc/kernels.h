@@ -171,4 +171,13 @@ void launch_colour_momenta(const double2 *white_full, const double *spec_full, d
 // p += sqrt(mass_r) * gauss (HMC_momenta.cc:76-92)
 void launch_add_real_momenta(double *p, const double *mass_r, const double *gauss, size_t n, cudaStream_t st);
 
+// calc_h = 3 (likelihood_calc_V_SPH_fourier_TSC, HMC_models_testing.cpp:54-188)
+//   out = i k_c hW(k) r^(k) on the cube's half grid, hW = h * SPH_kernel_F with the multipliers' padded pitch
+void launch_sph_fourier_comp(const double2 *rhat, const double *hW_half, double2 *out, int N, double kfac, int comp,
+                             cudaStream_t st);
+//   out[p] = v + fz * v, v = interpolate_TSC(field, x_p) at the particle positions recomputed from Psi
+//   (interpolate_grid.cpp:134-202; fz = the growth rate for the z component under RSD, else 0)
+void launch_interp_tsc(const GridGeom &g, const double *psix, const double *psiy, const double *psiz,
+                       const double *field, double *out, double fz, cudaStream_t st);
+
 }  // namespace bgpu

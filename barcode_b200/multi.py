@@ -71,6 +71,37 @@ def sum_over_ranks(value: float, info: RankInfo, device="cpu") -> float:
     return float(t.item())
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this process (and the pinned host buffers it allocates from now on: first touch) to the CPUs of the NUMA
+    node its GPU hangs off.  One process per GPU each staging N^3-cell arrays through host memory contend for one
+    node's memory controllers otherwise (round 1: end-to-end efficiency 0.44 at 8 GPUs with every rank on node 0).
+    Returns a dict describing what was done; never raises (containers may hide sysfs)."""
+    info = {"bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/numa_node") as f:
+            node = int(f.read().strip())
+        with open(f"{base}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        info.update({"pci": bdf, "numa_node": node, "cpus": len(cpus), "allowed": len(allowed)})
+        if cpus and node >= 0:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+    except Exception as e:  # noqa: BLE001
+        info["error"] = repr(e)
+    return info
+
+
 def gather_to_root(values, info: RankInfo, device="cpu"):
     """Per-chain scalars (energies, acceptance flags) to rank 0: [world, len(values)] or None."""
     t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)

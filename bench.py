@@ -51,6 +51,7 @@ def parse():
                     help="e2e_chains: chains (handles, host threads) on the GPU; 3 = one uploading, one computing, one "
                          "downloading (each phase takes about as long at PCIe 5 x16 rates)")
     ap.add_argument("--no-e2e-chains", action="store_true", help="skip the interleaved-chains e2e leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the slab-decomposed leg (512^3 / 1024^3)")
     return ap.parse_args()
 
@@ -223,6 +224,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GPU path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # each rank on the CPUs / memory of its GPU's NUMA node, before any pinned buffer is allocated
+    numa = {"bound": False, "note": "--no-numa-bind"} if args.no_numa_bind else multi.bind_to_gpu_numa(local_rank)
     multi.init("nccl", info, torch.device("cuda", local_rank))
 
     cfg, name = workload(args.grid, args.calc_h)
@@ -306,6 +309,7 @@ def run_ours(args):
     for i in range(n_cand):
         ch.candidate(1, 1 + i, NEPS, 1e-5)
     cand_ms = (time.perf_counter() - t0) * 1e3 / n_cand
+    cand_ms = multi.max_over_ranks(cand_ms, info, "cuda")
 
     # roofline leg: the same K steps again with CUDA events around every kernel launch
     bc.profile_begin()
@@ -413,6 +417,13 @@ def run_ours(args):
     e2e["trajectory"] = {"api": "bgpu_leapfrog(host s_i, p_i -> host s_f, p_f), Neps = 8", "gradient_evals_per_s":
                          world * ntraj * (neps + 1) / dt_traj, "leapfrog_steps_per_s": world * ntraj * neps / dt_traj,
                          "h2d_bytes_per_call": 2 * n * 8, "d2h_bytes_per_call": 2 * n * 8}
+    # the glue's device-resident sampler loop (BARCODE_GPU_DEVICE_RNG=1): one call per HMC candidate, scalars only
+    e2e["candidate"] = {"api": "bgpu_candidate(seed, draw, Neps = 8, eps) -> 6 energies; signal and momenta stay on the "
+                               "device (momentum draw, trajectory, kinetic + psi at both ends)",
+                        "ms_per_candidate": cand_ms, "gradient_evals_per_s": world * (NEPS + 1) / (cand_ms * 1e-3),
+                        "leapfrog_steps_per_s": world * NEPS / (cand_ms * 1e-3),
+                        "h2d_bytes_per_call": 0, "d2h_bytes_per_call": 6 * 8 + 8}
+    e2e["numa"] = numa
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

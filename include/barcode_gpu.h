@@ -55,8 +55,9 @@ typedef struct bgpu_params {
   int sfmodel;               /* 1 Zel'dovich; else Lag2Eul_non_zeldovich (2LPT + spherical collapse, ALPT);
                               * with rsd_model the reference runs Zel'dovich for any value */
   int rsd_model;
-  int calc_h;                /* 0, 1, 2 (SPH adjoint, needs masskernel 3) as the reference; BGPU_CALC_H_EXACT =
-                              * exact adjoint of NGP / CIC / TSC under the Zel'dovich or the 2LPT/ALPT model */
+  int calc_h;                /* 0, 1, 2 (SPH adjoint) and 3 (its Fourier / TSC variant, HMC_models_testing.cpp:54-188; both
+                              * need masskernel 3) as the reference; BGPU_CALC_H_EXACT = exact adjoint of NGP / CIC / TSC
+                              * under the Zel'dovich or the 2LPT/ALPT model */
   int mass_type;             /* 0 ones (R), 1 1/P (FS), 4 P (FS); 2 / 3: 1/P + likelihood-force spectrum / its mean (FS,
                               * HMC_mass.cc:39-160; bgpu_hamiltonian_mass_x) */
   double D1, D2, ascale, OM, OL;
@@ -91,7 +92,7 @@ void bgpu_destroy(bgpu_handle *h);
  * rank must make the same sequence of calls.  Supported: N1 in {128, 256, 512, 1024}; NGP / CIC / TSC;
  * Zel'dovich and 2LPT/ALPT forward models, RSD; all four likelihoods; calc_h 0, 1 and BGPU_CALC_H_EXACT
  * (Zel'dovich); mass types 0 - 4; bgpu_measure_spectrum; bgpu_draw_momenta_device.
- * Not on slabs yet: the SPH kernel (calc_h 2), the exact adjoint of the 2LPT/ALPT model, and the host-stream
+ * Not on slabs yet: the SPH kernel (calc_h 2 / 3), the exact adjoint of the 2LPT/ALPT model, and the host-stream
  * momentum draw (bgpu_color_momenta). */
 int bgpu_nccl_unique_id(void *out128);
 int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out);

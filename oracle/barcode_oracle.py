@@ -36,7 +36,7 @@ class Params:
     masskernel: int = 1        # 0 NGP, 1 CIC, 2 TSC (massFunctions.cc)
     likelihood: int = 1        # 0 Poisson, 1 Gaussian, 2 log-normal, 3 Gaussian random field (init_par.cc:534-559)
     rsd_model: bool = False
-    calc_h: int = 0            # 0, 1 reference; 4 = exact mass-assignment adjoint (new)
+    calc_h: int = 0            # 0, 1, 2 (SPH adjoint), 3 (its Fourier / TSC variant): reference; 4 = exact NGP/CIC/TSC adjoint (new)
     mass_type: int = 1         # 0 ones (R), 1 1/P (FS), 4 P (FS)  (HMC_mass.cc:315-368)
     D1: float = 1.0
     D2: float = -3.0 / 7.0 * 0.272 ** (-1.0 / 143.0)  # init_par.cc:526-528 at z = 0: -3/7 D1^2 Omega^(-1/143)
@@ -401,6 +401,75 @@ def calc_V_sph(p: Params, r, x, y, z):
     return [v.reshape(shp) for v in V]
 
 
+def sph_kernel_fourier(p: Params) -> np.ndarray:
+    """h * SPH_kernel_F on the half grid, as likelihood_calc_V_SPH_fourier_TSC writes it
+    (HMC_models_testing.cpp:62-105): norm = 24/h^3 * rho_c V/N, the kernel transform
+    (3 + cos 2k - k sin k + cos k (k sin k - 4)) / k^6 in the PHYSICAL k (not k h), 1/h^3 at k = 0.
+    The numerator cancels to ~k^6/240, so at the grid's small k its value is rounding noise that depends on the C
+    library's last bits: evaluated here with the same C library calls (math.sin / cos / sqrt), operation by
+    operation, so that the restatement and the compiled reference agree on one machine."""
+    import math
+    N, h = p.N1, p.kernel_h
+    norm = (24.0 / (h * h * h)) * (p.rho_c * p.vol / float(p.N))
+    k1 = calc_ki(N, p.L1)
+    out = np.empty((N, N, N // 2 + 1))
+    for i in range(N):
+        kx = float(k1[i])
+        for j in range(N):
+            ky = float(k1[j])
+            for k in range(N // 2 + 1):
+                kz = float(k1[k])
+                k_sq = kx * kx + ky * ky + kz * kz
+                if k_sq == 0.0:
+                    f = 1.0 / (h * h * h)
+                else:
+                    kk = math.sqrt(k_sq)
+                    ksink = kk * math.sin(kk)
+                    f = norm * (3 + math.cos(2 * kk) - ksink + math.cos(kk) * (ksink - 4)) / (k_sq * k_sq * k_sq)
+                out[i, j, k] = f
+    return out
+
+
+def interpolate_tsc_buggy(p: Params, x, y, z, field) -> np.ndarray:
+    """interpolate_TSC (interpolate_grid.cpp:134-190), bug-compatible: the upper weights of x and y are computed
+    from dz (:166-167).  Cell = (unsigned)(x/d), weights 3/4 - D^2 and 1/2 (3/2 - |D -+ 1|)^2."""
+    N, d = p.N1, p.d
+    x, y, z = (np.asarray(a, dtype=np.float64).ravel() for a in (x, y, z))
+    f = np.asarray(field, dtype=np.float64).reshape(N, N, N)
+    xk, yk, zk = x / d, y / d, z / d
+    ix, iy, iz = xk.astype(np.int64), yk.astype(np.int64), zk.astype(np.int64)
+    dx, dy, dz = xk - (ix + 0.5), yk - (iy + 0.5), zk - (iz + 0.5)
+    wx = [0.5 * (1.5 - np.abs(dx + 1)) ** 2, 0.75 - dx * dx, 0.5 * (1.5 - np.abs(dz - 1)) ** 2]
+    wy = [0.5 * (1.5 - np.abs(dy + 1)) ** 2, 0.75 - dy * dy, 0.5 * (1.5 - np.abs(dz - 1)) ** 2]
+    wz = [0.5 * (1.5 - np.abs(dz + 1)) ** 2, 0.75 - dz * dz, 0.5 * (1.5 - np.abs(dz - 1)) ** 2]
+    cx = [(ix - 1 + N) % N, ix % N, (ix + 1) % N]
+    cy = [(iy - 1 + N) % N, iy % N, (iy + 1) % N]
+    cz = [(iz - 1 + N) % N, iz % N, (iz + 1) % N]
+    out = np.zeros_like(x)
+    for a in range(3):
+        for b in range(3):
+            for c in range(3):
+                out += wx[a] * wy[b] * wz[c] * f[cx[a], cy[b], cz[c]]
+    return out
+
+
+def calc_V_sph_fourier_tsc(p: Params, r, x, y, z):
+    """likelihood_calc_V_SPH_fourier_TSC (HMC_models_testing.cpp:54-188; calc_h = 3): the residual convolved with
+    the gradient of the SPH kernel in k-space -- i k_c h W^(k) r^(k), no Nyquist zeroing -- and TSC-interpolated to
+    the particle positions; z component times (1 + f) under plane-parallel RSD."""
+    N = p.N1
+    kx, ky, kz = k_grids(N, p.L1)
+    rh = rfft(np.asarray(r, dtype=np.float64).reshape(N, N, N))
+    hW = p.kernel_h * sph_kernel_fourier(p)
+    V = []
+    for kc in (kx, ky, kz):
+        conv = irfft((kc * hW) * (-rh.imag + 1j * rh.real), N)
+        V.append(interpolate_tsc_buggy(p, x, y, z, conv))
+    if p.rsd_model:
+        V[2] = V[2] + fgrow(p.ascale, p.OM, p.OL) * V[2]
+    return [v.reshape(N, N, N) for v in V]
+
+
 def overdens(rho) -> np.ndarray:
     """massFunctions.cc:30-47: rho / mean - 1, mean accumulated in double."""
     mean = float(np.sum(rho, dtype=np.float64)) / float(rho.size)
@@ -675,6 +744,10 @@ def grad_log_like(p: Params, signal, nobs, noise, window):
         # likelihood_calc_h_SPH (HMC_models.cc:312-372): the reference's exact adjoint, SPH kernel only
         r = partial_f(p, dX, nobs, noise, window)
         h = grad_inv_lap_sum(p, calc_V_sph(p, r, x, y, z))
+    elif p.calc_h == 3:
+        # the Fourier / TSC variant of the same adjoint (HMC_models.cc:336-340)
+        r = partial_f(p, dX, nobs, noise, window)
+        h = grad_inv_lap_sum(p, calc_V_sph_fourier_tsc(p, r, x, y, z))
     elif p.calc_h == 4:
         r = partial_f(p, dX, nobs, noise, window, exact_sign=True)
         mean = 1.0  # rho/mean: mean == 1 analytically for NGP/CIC/TSC

@@ -12,7 +12,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 CASE_NAMES = ["za_cic_gauss", "za_cic_gauss_rsd", "za_tsc_poisson", "za_ngp_gauss_h1", "za_tsc_gauss_rsd_mass0",
               "za_cic_poisson_mass4_dq", "alpt_cic_gauss", "alpt_tsc_poisson_h1",
-              "za_sph_gauss_h2", "za_sph_gauss_rsd_h2", "za_sph_poisson_h2",
+              "za_sph_gauss_h2", "za_sph_gauss_rsd_h2", "za_sph_poisson_h2", "za_sph_gauss_h3", "za_sph_gauss_rsd_h3",
               "za_cic_lognormal_h1", "za_tsc_lognormal_rsd", "grf", "za_cic_gauss_mass2", "za_tsc_gauss_rsd_mass3"]
 
 

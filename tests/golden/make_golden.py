@@ -51,6 +51,11 @@ CASES = {
     "za_sph_gauss_rsd_h2": dict(masskernel=3, likelihood=1, rsd_model=True, calc_h=2, mass_type=1,
                                 particle_kernel_h_rel=1.3),
     "za_sph_poisson_h2": dict(masskernel=3, likelihood=0, rsd_model=False, calc_h=2, mass_type=4),
+    # calc_h = 3: the Fourier / TSC variant of the SPH adjoint (likelihood_calc_V_SPH_fourier_TSC,
+    # HMC_models_testing.cpp:54-188), interpolate_TSC's dz slip included
+    "za_sph_gauss_h3": dict(masskernel=3, likelihood=1, rsd_model=False, calc_h=3, mass_type=1),
+    "za_sph_gauss_rsd_h3": dict(masskernel=3, likelihood=1, rsd_model=True, calc_h=3, mass_type=1,
+                                particle_kernel_h_rel=1.3),
     # log-normal likelihood (lognormal_independent.cpp): h = r, and the gradfindif product form with RSD in the
     # gradient's forward model but not in log_like's; a gentle signal keeps every cell occupied (the reference takes
     # the log of the unclamped density in the residual)

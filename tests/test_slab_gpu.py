@@ -34,5 +34,5 @@ def test_slab_chain_matches_single_gpu_chain(p2p, generic, sfmodel, extra):
                         "--master-addr", "127.0.0.1", "--master-port", "29655",
                         os.path.join(ROOT, "tools", "slab_check.py"), "--grid", "128", "--sfmodel", str(sfmodel)] + extra,
                        env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0, r.stdout[-3000:] + "\n...\n" + r.stderr[-6000:]
     assert "OK" in r.stdout

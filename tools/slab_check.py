@@ -62,6 +62,8 @@ def main():
         return torch.cat(out, 0).cpu().numpy()
 
     for calc_h in (0, 1, 4):
+        if calc_h == 4 and a.sfmodel != 1:
+            continue   # the exact adjoint of the 2LPT/ALPT model is single-GPU only (bgpu_slab_create says so)
         kw = dict(N1=N, L1=L, masskernel=a.masskernel, likelihood=a.likelihood, rsd_model=(a.sfmodel == 1),
                   calc_h=calc_h, mass_type=a.mass_type, sfmodel=a.sfmodel, N_bin=40)
         sc = slab.SlabChain.create(bc.Params(device=info.local_rank, **kw), info.rank, info.world)
