@@ -230,6 +230,25 @@ class Chain:
         _lib.check(self.L.bgpu_measure_spectrum(self._h, _dp(s), int(n_bin), _dp(kmode), _dp(power)))
         return kmode, power
 
+    def mock_data(self, seed: int, window_type: int = 1, data_model: int = 0, sigma_min: float = 1.0,
+                  sigma_fac: float = 0.0, negative_obs: bool = False):
+        """setup_random_test (barcoderunner.cc:42-205) on the device: returns dict(delta_lag, delta_eul, nobs, noise,
+        window) and leaves nobs / noise / window as the chain's static inputs."""
+        class MP(C.Structure):
+            _fields_ = [("window_type", C.c_int), ("data_model", C.c_int), ("sigma_min", C.c_double),
+                        ("sigma_fac", C.c_double), ("negative_obs", C.c_int)]
+        mp = MP(int(window_type), int(data_model), float(sigma_min), float(sigma_fac), int(bool(negative_obs)))
+        out = {k: np.empty(self.N) for k in ("delta_lag", "delta_eul", "nobs", "noise", "window")}
+        _lib.check(self.L.bgpu_mock_data(self._h, int(seed), C.byref(mp), _dp(out["delta_lag"]), _dp(out["delta_eul"]),
+                                         _dp(out["nobs"]), _dp(out["noise"]), _dp(out["window"])))
+        return {k: v.reshape(self.shape) for k, v in out.items()}
+
+    def initial_guess(self, seed: int, kind: int = 2, smoothing_scale: float = 0.0):
+        """make_initial_guess (barcoderunner.cc:207-247) on the device: kind 0 zeros, 2 GRF, 3 smoothed GRF, 4 noise."""
+        s = np.empty(self.N)
+        _lib.check(self.L.bgpu_initial_guess(self._h, int(seed), int(kind), float(smoothing_scale), _dp(s)))
+        return s.reshape(self.shape)
+
     def forward(self, signal, want_pos=False):
         s = _f64(signal, self.N)
         dX = np.empty(self.N)

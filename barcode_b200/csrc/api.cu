@@ -1672,6 +1672,107 @@ int bgpu_accept(bgpu_handle *h, double *x_out, double *deltaX_out) {
   BGPU_CATCH
 }
 
+// ---------------------------------------------------------------------------
+// F4: the mock-data generator and the initial guess on the device (barcoderunner.cc:42-247) -- a production
+// run never draws 2 N^3 serial GSL Gaussians for them.  Counter-based Philox streams, not GSL's.
+// ---------------------------------------------------------------------------
+namespace {
+// a Gaussian random field with spectrum h->power (create_GARFIELD's normalisation, random.cpp:81-83), optionally
+// smoothed with the Gaussian filter of kernelcomp (filtertype 1, convolution.cpp:224-322): d_out, real space
+void grf_device(bgpu_handle *h, uint64_t seed, uint64_t draw, unsigned stream, double smoothing, double *d_out) {
+  require(h->have_power, "bgpu: Power must be set first (bgpu_set_static)");
+  require(h->G == 1, "bgpu: the device field generator is single-GPU (draw on a cube handle and distribute the slabs)");
+  launch_philox_normals(h->tmp, h->n, 0, seed, draw, stream, h->stream);
+  r2c_plain(h, h->tmp, h->work);
+  launch_colour_white(h->work, h->power, h->N, h->ncells / (h->p.L1 * h->p.L2 * h->p.L3), h->stream);
+  KOp lop;
+  if (smoothing > 0.) {
+    lop.kind = K_GAUSS;
+    lop.a = smoothing;
+    lop.kfac = h->kfac;
+  }
+  ROp sop;
+  sop.kind = R_SCALE;
+  sop.a = 1.0 / h->ncells;
+  h->fft.c2r(h->work, h->work, d_out, lop, sop);
+}
+}  // namespace
+
+int bgpu_mock_data(bgpu_handle *h, uint64_t seed, const bgpu_mock_params *mp, double *delta_lag, double *delta_eul,
+                   double *nobs, double *noise, double *window) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(mp != nullptr, "bgpu_mock_data: null parameters");
+  const bgpu_params &p = h->p;
+  require(mp->window_type == 1 || mp->window_type == 10 || mp->window_type == 23,
+          "in barcoderunner: window_type is not a valid choice! (1, 10 or 23)");
+  require(mp->data_model == 0 || mp->data_model == 1, "in barcoderunner: data_model is not a valid choice! (0 or 1)");
+  if (mp->data_model == 0)
+    require(p.likelihood == 0 || p.likelihood == 1 || p.likelihood == 3,
+            "in barcoderunner: linear data model was chosen (additive error), but incompatible likelihood!");
+  // the truth: delta_lag ~ GRF(Power) -> h->sig ; delta_eul = Lag2Eul(delta_lag) with the handle's own model -> h->delta
+  grf_device(h, seed, 0, 2, 0.0, h->sig);
+  if (p.likelihood == 3) {
+    // no structure formation in the Gaussian-random-field test: the "Eulerian" field is not used by its data model
+    BGPU_CUDA(cudaMemcpyAsync(h->delta, h->sig, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    r2c_plain(h, h->sig, h->shat);
+    forward_from_shat(h, h->sig, 1.0, p.rsd_model != 0, nullptr, nullptr, nullptr);
+    LikeParams lp = h->like;
+    lp.exact_sign = 0;
+    launch_fill(h->mom, 1.0, h->n, h->stream);
+    launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->mom, h->mom, h->mom, nullptr, h->n, h->ncells,
+                             h->partials, h->dscal + S_NLL, h->stream);
+  }
+  MockObs mo;
+  mo.likelihood = p.likelihood;
+  mo.data_model = mp->data_model;
+  mo.window_type = mp->window_type;
+  mo.negative_obs = mp->negative_obs;
+  mo.rho_c = p.rho_c;
+  mo.delta_min = p.delta_min;
+  mo.sigma_min = mp->sigma_min;
+  mo.sigma_fac = mp->sigma_fac;
+  launch_fill(h->noise, 0.0, h->n, h->stream);
+  launch_mock_obs(mo, h->delta, h->sig, h->window, h->nobs, h->noise, h->n, 0, h->n, seed, h->stream);
+  h->have_obs = true;
+  if (delta_lag) d2h(h, delta_lag, h->sig, h->n);
+  if (delta_eul) d2h(h, delta_eul, h->delta, h->n);
+  if (nobs) d2h(h, nobs, h->nobs, h->n);
+  if (noise) d2h(h, noise, h->noise, h->n);
+  if (window) d2h(h, window, h->window, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
+int bgpu_initial_guess(bgpu_handle *h, uint64_t seed, int initial_guess, double smoothing_scale, double *signal) {
+  BGPU_TRY
+  BGPU_CUDA(cudaSetDevice(h->p.device));
+  require(signal != nullptr, "bgpu_initial_guess: null output");
+  switch (initial_guess) {
+    case 0:  // zero initial guess
+      launch_fill(h->sig, 0.0, h->n, h->stream);
+      break;
+    case 2:  // GRF initial guess
+      grf_device(h, seed, 0, 3, 0.0, h->sig);
+      break;
+    case 3:  // smoothed GRF initial guess (Gaussian filter)
+      require(smoothing_scale > 0., "bgpu_initial_guess: initial_guess 3 needs a smoothing scale > 0");
+      grf_device(h, seed, 0, 3, smoothing_scale, h->sig);
+      break;
+    case 4:  // zero plus some random noise: sigma = 0.1
+      launch_philox_normals(h->tmp, h->n, (size_t)h->x0 * h->N * h->N, seed, 0, 4, h->stream);
+      launch_scale(h->sig, h->tmp, 1.e-1, h->n, h->stream);
+      break;
+    default:
+      throw std::runtime_error("In barcoderunner: invalid choice of initial_guess (" + std::to_string(initial_guess) +
+                               ")! (1, a file, is the host's job)");
+  }
+  d2h(h, signal, h->sig, h->n);
+  sync(h);
+  BGPU_CATCH
+}
+
 int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *posx, double *posy, double *posz) {
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));

@@ -1536,4 +1536,109 @@ void launch_interp_tsc(const GridGeom &g, const double *psix, const double *psiy
   BGPU_LAUNCHED(1);
 }
 
+// ---------------------------------------------------------------------------
+// F4: setup_random_test's observations (barcoderunner.cc:94-195) with the generator on the device.  One
+// thread per cell: window (window_type 1 / 10 / 23), then nobs and noise by data model and likelihood.
+// Counter-based stream: cell g of (seed, draw 1) always gets the same numbers, whatever the launch shape;
+// a Poisson rejection loop takes its k-th attempt from counter word 3 = k.  NOT GSL's stream (which is serial).
+// ---------------------------------------------------------------------------
+struct MockRng {
+  uint64_t g, seed;
+  uint32_t attempt;
+  __device__ __forceinline__ void next(double &u1, double &u2) {
+    uint32_t c[4] = {(uint32_t)g, (uint32_t)(g >> 32), 1u, (3u << 24) ^ attempt};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    ++attempt;
+    u1 = u53(c[0], c[1]);
+    u2 = u53(c[2], c[3]);
+  }
+  __device__ __forceinline__ double normal() {  // Box-Muller, as philox_normal_kernel
+    double u1, u2;
+    next(u1, u2);
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    return sqrt(-2.0 * log(u1)) * cs;
+  }
+  // Poisson(lam): CDF inversion below 30, Hoermann's transformed rejection (PTRS, 1993) above
+  __device__ double poisson(double lam) {
+    if (!(lam > 0.0)) return 0.0;  // gsl_ran_poisson returns 0 for mu <= 0
+    double u1, u2;
+    if (lam < 30.0) {
+      next(u1, u2);
+      double p = exp(-lam), F = p;
+      int k = 0;
+      while (u1 > F && k < 2000) {
+        ++k;
+        p *= lam / (double)k;
+        F += p;
+      }
+      return (double)k;
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (int it = 0; it < 1000; ++it) {
+      next(u1, u2);
+      const double U = u1 - 0.5, V = u2, us = 0.5 - fabs(U);
+      const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
+      if (us >= 0.07 && V <= vr) return k;
+      if (k < 0.0 || (us < 0.013 && V > us)) continue;
+      if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
+    }
+    return floor(lam);
+  }
+};
+
+__global__ void mock_obs_kernel(MockObs mp, const double *__restrict__ delta_eul, const double *__restrict__ delta_lag,
+                                double *__restrict__ window, double *__restrict__ nobs, double *__restrict__ noise,
+                                size_t n, size_t first, size_t n_global, uint64_t seed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t g = first + i;
+  const double de = delta_eul[i];
+  double w = 1.0;                                             // window_type 1
+  if (mp.window_type == 10) w = g < n_global / 2 ? 0.0 : 1.0;  // :105-108
+  else if (mp.window_type == 23) w = de > 3. ? 1.0 : 0.0;      // :109-117, as written there
+  window[i] = w;
+  MockRng rng{(uint64_t)g, seed, 0u};
+  if (mp.data_model == 0) {  // linear data model, :127-166
+    const double Lambda = mp.rho_c * (1.0 + de);
+    if (w > 0.) {
+      if (mp.likelihood == 0) {
+        nobs[i] = rng.poisson(Lambda);
+      } else if (mp.likelihood == 1) {
+        const double sigma = mp.sigma_min + mp.sigma_fac * Lambda;
+        noise[i] = sigma;
+        double v = Lambda + sigma * rng.normal();
+        if (!mp.negative_obs && v < 0) v = 0;
+        nobs[i] = v;
+      } else {  // 3: Gaussian random field, sigma quadratic in the Lagrangian field
+        const double dl = delta_lag[i];
+        const double sigma = mp.sigma_min + mp.sigma_fac * (dl * dl);
+        noise[i] = sigma;
+        nobs[i] = dl + sigma * rng.normal();
+      }
+    } else {
+      nobs[i] = 0.0;
+    }
+  } else {  // log-normal data model, :167-188
+    const double d = de < mp.delta_min ? mp.delta_min : de;
+    const double Lambda = log(mp.rho_c * (1.0 + d));
+    if (w > 0.) {
+      noise[i] = mp.sigma_fac;
+      nobs[i] = Lambda + mp.sigma_fac * rng.normal();
+    } else {
+      const double q = mp.rho_c * (1 + mp.delta_min);
+      nobs[i] = log(q * q);  // "huh, why squared?" (:186)
+    }
+  }
+}
+
+void launch_mock_obs(const MockObs &mp, const double *delta_eul, const double *delta_lag, double *window, double *nobs,
+                     double *noise, size_t n, size_t first, size_t n_global, uint64_t seed, cudaStream_t st) {
+  ProfScope prof(KK_COLOUR, st);
+  mock_obs_kernel<<<blocks_for(n, 256), 256, 0, st>>>(mp, delta_eul, delta_lag, window, nobs, noise, n, first, n_global, seed);
+  BGPU_LAUNCHED(1);
+}
+
 }  // namespace bgpu

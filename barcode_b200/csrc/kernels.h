@@ -180,4 +180,12 @@ void launch_sph_fourier_comp(const double2 *rhat, const double *hW_half, double2
 void launch_interp_tsc(const GridGeom &g, const double *psix, const double *psiy, const double *psiz,
                        const double *field, double *out, double fz, cudaStream_t st);
 
+// setup_random_test's window / nobs / noise (barcoderunner.cc:94-195) drawn on the device (Philox, not GSL's stream)
+struct MockObs {
+  int likelihood, data_model, window_type, negative_obs;
+  double rho_c, delta_min, sigma_min, sigma_fac;
+};
+void launch_mock_obs(const MockObs &mp, const double *delta_eul, const double *delta_lag, double *window, double *nobs,
+                     double *noise, size_t n, size_t first, size_t n_global, uint64_t seed, cudaStream_t st);
+
 }  // namespace bgpu

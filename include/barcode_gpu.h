@@ -146,6 +146,25 @@ int bgpu_set_signal(bgpu_handle *h, const double *x);
 int bgpu_candidate(bgpu_handle *h, uint64_t seed, uint64_t draw_index, uint64_t Neps, double epsilon, double *energies6,
                    double *p_f0);
 int bgpu_accept(bgpu_handle *h, double *x_out, double *deltaX_out);
+/* setup_random_test (barcoderunner.cc:42-205) and make_initial_guess (:207-247) with the generator on the device
+ * (SURVEY 8f F4): delta_lag ~ GRF(Power), delta_eul = Lag2Eul(delta_lag) with the handle's own forward model, the
+ * window by window_type (1 ones, 10 lower half masked, 23 as written there), nobs / noise_sf by data model and
+ * likelihood -- Poisson counts, Gaussian with sigma = sigma_min + sigma_fac * Lambda clamped at 0 unless
+ * negative_obs, the GRF test, or the log-normal data model.  nobs / noise / window become the handle's static
+ * inputs; any output pointer may be null.  Counter-based Philox streams keyed by `seed`: the same distribution as
+ * the reference's draw, NOT its GSL mt19937 stream (serial: 2 N^3 host Gaussians per field).  Single-GPU handles.
+ * bgpu_initial_guess: initial_guess 0 (zeros), 2 (GRF), 3 (GRF smoothed with the Gaussian filter of width
+ * smoothing_scale), 4 (0.1 * white noise); 1 (a file) stays with the host. */
+typedef struct bgpu_mock_params {
+  int window_type;   /* input.par window_type */
+  int data_model;    /* 0 linear, 1 log-normal */
+  double sigma_min, sigma_fac;
+  int negative_obs;
+} bgpu_mock_params;
+int bgpu_mock_data(bgpu_handle *h, uint64_t seed, const bgpu_mock_params *mp, double *delta_lag, double *delta_eul,
+                   double *nobs, double *noise, double *window);
+int bgpu_initial_guess(bgpu_handle *h, uint64_t seed, int initial_guess, double smoothing_scale, double *signal);
+
 /* Lag2Eul / Lag2Eul_rsd_zeldovich as likelihood_grad_log_like calls them (HMC_models.cc:383-406);
  * pos* may be NULL */
 int bgpu_forward(bgpu_handle *h, const double *signal, double *deltaX, double *posx, double *posy, double *posz);

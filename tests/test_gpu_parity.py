@@ -598,3 +598,87 @@ def test_device_resident_candidate_equals_the_separate_calls():
         # the accepted field is the new current signal: the next candidate starts from it
         E2 = ch.candidate(9, 5, 1, eps)
         assert abs(E2["psi_prior_i"] - ppf) <= 1e-12 * abs(ppf)
+
+
+# ---------------------------------------------------------------- F4: mock data and initial guess on the device
+@pytest.mark.parametrize("like,rho_c", [(1, 1.0), (0, 1.0), (0, 40.0), (3, 1.0)])
+def test_mock_data_on_the_device(like, rho_c):
+    """bgpu_mock_data = setup_random_test (barcoderunner.cc:42-205) with counter-based device streams: the truth has
+    the spectrum it was drawn from, delta_eul is the chain's own forward model of it, and the observations follow
+    their data model (Gaussian: unit-variance residuals; Poisson: counts with mean and variance Lambda, through both
+    the inversion and the rejection branch of the sampler); the same seed reproduces the draw."""
+    from barcode_b200.chain import Chain, Params
+    from barcode_b200 import inputs
+    N = 64
+    L = inputs.box_length(N)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L)
+    n = N ** 3
+    with Chain(Params(N1=N, L1=L, masskernel=1, likelihood=like, rho_c=rho_c)) as ch:
+        ch.set_static(Power=P)
+        m = ch.mock_data(7, window_type=1, data_model=0, sigma_min=0.5, sigma_fac=0.1, negative_obs=True)
+        m2 = ch.mock_data(7, window_type=1, data_model=0, sigma_min=0.5, sigma_fac=0.1, negative_obs=True)
+        assert all(np.array_equal(m[k], m2[k]) for k in ("delta_lag", "nobs"))   # (delta_eul: unordered atomics)
+        m3 = ch.mock_data(8, window_type=10, data_model=0, sigma_min=0.5, sigma_fac=0.1, negative_obs=False)
+        assert not np.array_equal(m["delta_lag"], m3["delta_lag"])
+        assert np.all(m3["window"].ravel()[: n // 2] == 0) and np.all(m3["window"].ravel()[n // 2:] == 1)
+        assert np.all(m3["nobs"].ravel()[: n // 2] == 0) and np.all(m3["nobs"] >= 0)
+        # the truth's spectrum: <|d^|^2> = N^2/V P per mode (random.cpp:81-83), averaged over many modes
+        dh = np.abs(np.fft.rfftn(m["delta_lag"])) ** 2
+        Ph = P.reshape(N, N, N)[:, :, : N // 2 + 1]
+        ok = Ph > 0
+        ratio = dh[ok] / (float(n) ** 2 / L ** 3 * Ph[ok])
+        assert abs(ratio.mean() - 1) < 0.02
+        if like != 3:
+            assert rel_l2(m["delta_eul"], ch.forward(m["delta_lag"])) < 1e-12
+            assert abs(m["delta_eul"].mean()) < 1e-10
+        lam = rho_c * (1 + m["delta_eul"]).ravel()
+        nobs = m["nobs"].ravel()
+        if like == 1:
+            sig = 0.5 + 0.1 * lam
+            assert rel_l2(m["noise"].ravel(), sig) < 1e-14
+            z = (nobs - lam) / sig
+            assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+        elif like == 0:
+            assert np.all(nobs == np.round(nobs)) and np.all(nobs >= 0)
+            lo, hi = lam < 30, lam >= 30            # CDF inversion / transformed rejection
+            for sel in (lo, hi):
+                if sel.sum() < 1000:
+                    continue
+                r = nobs[sel] - lam[sel]
+                assert abs(r.mean()) < 5 * np.sqrt(lam[sel].mean() / sel.sum())
+                assert abs(r.var() / lam[sel].mean() - 1) < 0.05
+            if rho_c > 1:
+                assert hi.sum() > 1000 and lo.sum() > 1000
+        else:
+            dl = m["delta_lag"].ravel()
+            sig = 0.5 + 0.1 * dl * dl
+            z = (nobs - dl) / sig
+            assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+
+
+def test_initial_guess_on_the_device():
+    """bgpu_initial_guess = make_initial_guess (barcoderunner.cc:207-247): zeros, a GRF with the prior's spectrum, the
+    same smoothed with the Gaussian filter, or 0.1 * white noise."""
+    from barcode_b200.chain import Chain, Params
+    from barcode_b200 import inputs
+    N = 64
+    L = inputs.box_length(N)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L)
+    n = N ** 3
+    with Chain(Params(N1=N, L1=L)) as ch:
+        ch.set_static(Power=P)
+        assert np.all(ch.initial_guess(1, 0) == 0)
+        w = ch.initial_guess(1, 4)
+        assert abs(w.std() - 0.1) < 0.1 * 5 / np.sqrt(2 * n) and abs(w.mean()) < 0.1 * 5 / np.sqrt(n)
+        g = ch.initial_guess(3, 2)
+        gs = ch.initial_guess(3, 3, smoothing_scale=10.0)
+        kx, ky, kz = (inputs.calc_ki(N, L)[:, None, None], inputs.calc_ki(N, L)[None, :, None],
+                      inputs.calc_ki(N, L)[None, None, : N // 2 + 1])
+        K = np.exp(-(kx ** 2 + ky ** 2 + kz ** 2) * 10.0 ** 2 / 2)
+        assert rel_l2(np.fft.rfftn(gs), K * np.fft.rfftn(g)) < 1e-12   # same stream, filtered in k-space
+        Ph = P.reshape(N, N, N)[:, :, : N // 2 + 1]
+        ok = Ph > 0
+        ratio = (np.abs(np.fft.rfftn(g)) ** 2)[ok] / (float(n) ** 2 / L ** 3 * Ph[ok])
+        assert abs(ratio.mean() - 1) < 0.02
+        with pytest.raises(Exception):
+            ch.initial_guess(1, 1)
