@@ -617,11 +617,17 @@ def test_mock_data_on_the_device(like, rho_c):
         ch.set_static(Power=P)
         m = ch.mock_data(7, window_type=1, data_model=0, sigma_min=0.5, sigma_fac=0.1, negative_obs=True)
         m2 = ch.mock_data(7, window_type=1, data_model=0, sigma_min=0.5, sigma_fac=0.1, negative_obs=True)
-        assert all(np.array_equal(m[k], m2[k]) for k in ("delta_lag", "nobs"))   # (delta_eul: unordered atomics)
+        assert np.array_equal(m["delta_lag"], m2["delta_lag"])
+        # (delta_eul comes out of unordered atomics: equal to rounding, and so are the observations drawn around it)
+        if like == 0:
+            assert np.mean(m["nobs"] != m2["nobs"]) < 1e-4
+        else:
+            assert rel_l2(m["nobs"], m2["nobs"]) < 1e-12
         m3 = ch.mock_data(8, window_type=10, data_model=0, sigma_min=0.5, sigma_fac=0.1, negative_obs=False)
         assert not np.array_equal(m["delta_lag"], m3["delta_lag"])
         assert np.all(m3["window"].ravel()[: n // 2] == 0) and np.all(m3["window"].ravel()[n // 2:] == 1)
-        assert np.all(m3["nobs"].ravel()[: n // 2] == 0) and np.all(m3["nobs"] >= 0)
+        assert np.all(m3["nobs"].ravel()[: n // 2] == 0)
+        assert like == 3 or np.all(m3["nobs"] >= 0)   # counts, or the Gaussian draw clamped at 0 (negative_obs off)
         # the truth's spectrum: <|d^|^2> = N^2/V P per mode (random.cpp:81-83), averaged over many modes
         dh = np.abs(np.fft.rfftn(m["delta_lag"])) ** 2
         Ph = P.reshape(N, N, N)[:, :, : N // 2 + 1]
