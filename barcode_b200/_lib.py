@@ -67,6 +67,9 @@ SIGNATURES = {
     "bgpu_candidate": (C.c_int, [_h, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, _dp, _dp]),
     "bgpu_accept": (C.c_int, [_h, _dp, _dp]),
     "bgpu_device_normals": (C.c_int, [_h, C.c_uint64, C.c_uint64, C.c_uint, C.c_size_t, C.c_size_t, _dp]),
+    "bgpu_local_group_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "bgpu_local_group_destroy": (None, [C.c_void_p]),
+    "bgpu_slab_create_local": (C.c_int, [C.POINTER(BgpuParams), C.c_int, C.c_int, C.c_void_p, C.POINTER(_h)]),
     "bgpu_mock_data": (C.c_int, [_h, C.c_uint64, C.c_void_p, _dp, _dp, _dp, _dp, _dp]),
     "bgpu_initial_guess": (C.c_int, [_h, C.c_uint64, C.c_int, C.c_double, _dp]),
     "bgpu_forward": (C.c_int, [_h, _dp, _dp, _dp, _dp, _dp]),

@@ -80,7 +80,7 @@ struct bgpu_handle {
   // n / nh / nhp are always the LOCAL element counts.
   int G = 1, rank = 0, Ns = 0, x0 = 0;
   double ncells = 0.0;          // N^3, the global cell count (FFT normalisation, mean density)
-  NcclComm *comm = nullptr;
+  ChainComm *comm = nullptr;      // NCCL (one process per GPU) or the in-process communicator (ranks = threads, tests)
   int Hmax = 0;                 // halo planes allocated each side of rho_ext
   double *rho_ext = nullptr;    // [(Ns + 2 Hmax)][N][N]; delta points at the owned planes inside it
   double *halo_recv = nullptr;  // 2 * Hmax * N^2
@@ -93,6 +93,7 @@ struct bgpu_handle {
   double kick_a = 0.0;
   int *stopflag = nullptr;       // device: the step after which |momenta[0]| > 1e50 stopped the trajectory, 0 = running
   int *hflag2 = nullptr;         // pinned copy
+  bool parseval = true;          // BGPU_PARSEVAL=0: kinetic energy and prior through the inverse transform, as the reference
   bool fused_leapfrog = true;    // BGPU_LEAPFROG_FUSED=0: the step-by-step form with separate kicks and a host test per step     // create_impl ran to completion (the destructor's collectives are safe)
   double *phi1 = nullptr, *xa = nullptr, *xb = nullptr, *xc = nullptr;  // exact 2LPT/ALPT adjoint: phi^(1) + 3 scratch arrays
   double *fext = nullptr;       // log-normal + calc_h 0 on a slab: f(delta_x) with 2 halo planes each side
@@ -688,14 +689,19 @@ void psi_device(bgpu_handle *h, const double *d_s) {
   const bgpu_params &p = h->p;
   const double inv_n = 1.0 / h->ncells;
   r2c_plain(h, d_s, h->shat);
-  KOp lop;
-  lop.kind = K_MULREAL;
-  lop.real0 = h->inv_power;
-  ROp sop;
-  sop.kind = R_SCALE;
-  sop.a = inv_n;
-  h->fft.c2r(h->shat, h->work, h->tmp, lop, sop);
-  launch_half_dot(d_s, h->tmp, h->n, h->partials, h->dscal + S_PRIOR, h->stream);
+  if (h->parseval) {
+    // 1/2 s . S^-1 s = (1/2N) sum_k w_k (V/N)/P_k |s^_k|^2: no inverse transform (kernels.cu HalfQuadF)
+    launch_half_quadratic(h->shat, h->inv_power, h->N, h->nh, h->ncells, h->partials, h->dscal + S_PRIOR, h->stream);
+  } else {
+    KOp lop;
+    lop.kind = K_MULREAL;
+    lop.real0 = h->inv_power;
+    ROp sop;
+    sop.kind = R_SCALE;
+    sop.a = inv_n;
+    h->fft.c2r(h->shat, h->work, h->tmp, lop, sop);
+    launch_half_dot(d_s, h->tmp, h->n, h->partials, h->dscal + S_PRIOR, h->stream);
+  }
   allreduce_scalar(h, S_PRIOR);
 
   if (p.likelihood == 3) {  // gaussian_random_field.cpp:40-52: -lnL on the Lagrangian field itself
@@ -728,6 +734,13 @@ void apply_inv_mass_fs(bgpu_handle *h, const double *d_p) {
 
 void kinetic_device(bgpu_handle *h, const double *d_p) {
   require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
+  if (h->mass_fs && !h->mass_rs && h->parseval) {
+    // 1/2 p . M^-1 p in k-space (Parseval): one forward transform and a half-grid reduction
+    r2c_plain(h, d_p, h->work);
+    launch_half_quadratic(h->work, h->inv_mass, h->N, h->nh, h->ncells, h->partials, h->dscal + S_KIN, h->stream);
+    allreduce_scalar(h, S_KIN);
+    return;
+  }
   if (h->mass_fs) apply_inv_mass_fs(h, d_p);
   launch_kinetic(d_p, h->mass_fs ? h->tmp : nullptr, h->mass_rs ? h->mass_r : nullptr, h->n, h->partials,
                  h->dscal + S_KIN, h->stream);
@@ -930,7 +943,8 @@ void bgpu_default_params(bgpu_params *p) {
   p->N_bin = 200;         // data/input.par:129
 }
 
-static int create_impl(const bgpu_params *p, int rank, int nranks, const void *nccl_id, bgpu_handle **out) {
+static int create_impl(const bgpu_params *p, int rank, int nranks, const void *nccl_id, bgpu_handle **out,
+                       LocalGroup *local = nullptr) {
   bgpu_handle *h = nullptr;
   BGPU_TRY
   require(p && out, "bgpu_create: null argument");
@@ -950,7 +964,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
     require(p->sfmodel == 1 || p->rsd_model || p->N1 / nranks >= 8,
             "bgpu_slab_create: the 2LPT/ALPT model needs at least 8 planes per rank (4-plane stencil halo)");
-    require(nccl_id != nullptr, "bgpu_slab_create: a NCCL unique id is required");
+    require(nccl_id != nullptr || local != nullptr, "bgpu_slab_create: a NCCL unique id is required");
   }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -978,7 +992,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     BGPU_CUDA(cudaEventCreateWithFlags(&h->ev_dn[c], cudaEventDisableTiming));
   }
   if (nranks > 1) {
-    h->comm = new NcclComm(nccl_id, rank, nranks);
+    if (local) h->comm = new LocalComm(local, rank, nranks);
+    else h->comm = new NcclComm(nccl_id, rank, nranks);
     dalloc(h->sendbuf, h->nh);
     dalloc(h->recvbuf, 2 * h->nh);   // two receive buffers, alternating between transforms
     h->Hmax = h->Ns < 24 ? h->Ns : 24;
@@ -996,7 +1011,17 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     h->fft.sendbuf = h->sendbuf;
     h->fft.recvbuf = h->recvbuf;
     const char *e2 = std::getenv("BGPU_SLAB_P2P");
-    if (!(e2 && e2[0] == '0')) {
+    if (!(e2 && e2[0] == '0') && local) {
+      // ranks of one process on one device: every rank's receive buffer is directly addressable
+      require(nranks <= 8, "bgpu_slab_create: at most 8 ranks");
+      void *all[8] = {};
+      local_group_exchange_ptr(local, rank, h->recvbuf, all);
+      for (int r = 0; r < nranks; ++r) {
+        h->fft.peer_recv[0][r] = static_cast<double2 *>(all[r]);
+        h->fft.peer_recv[1][r] = static_cast<double2 *>(all[r]) + h->nh;
+      }
+      h->fft.p2p = true;
+    } else if (!(e2 && e2[0] == '0')) {
       // fused transpose: map every rank's receive buffers into this process (CUDA IPC over NVLink peer
       // access); the 64-byte handles travel through the NCCL communicator itself
       static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1145,6 +1170,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   {
     const char *lf = std::getenv("BGPU_LEAPFROG_FUSED");
     h->fused_leapfrog = !(lf && lf[0] == '0');
+    const char *pv = std::getenv("BGPU_PARSEVAL");
+    h->parseval = !(pv && pv[0] == '0');
   }
   BGPU_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h->hscal), S_COUNT * sizeof(double)));
   BGPU_CUDA(cudaMemsetAsync(h->dscal, 0, S_COUNT * sizeof(double), h->stream));
@@ -1183,6 +1210,23 @@ int bgpu_nccl_unique_id(void *out128) {
 
 int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out) {
   return create_impl(p, rank, nranks, nccl_id128, out);
+}
+
+int bgpu_local_group_create(int nranks, bgpu_local_group **out) {
+  BGPU_TRY
+  require(out != nullptr, "bgpu_local_group_create: null argument");
+  *out = reinterpret_cast<bgpu_local_group *>(local_group_create(nranks));
+  BGPU_CATCH
+}
+
+void bgpu_local_group_destroy(bgpu_local_group *g) { local_group_destroy(reinterpret_cast<LocalGroup *>(g)); }
+
+int bgpu_slab_create_local(const bgpu_params *p, int rank, int nranks, bgpu_local_group *g, bgpu_handle **out) {
+  if (!g) {
+    g_last_error = "bgpu_slab_create_local: null group";
+    return 1;
+  }
+  return create_impl(p, rank, nranks, nullptr, out, reinterpret_cast<LocalGroup *>(g));
 }
 
 int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *nx_local) {

@@ -293,6 +293,24 @@ struct KineticF {  // HMC.cc:88-110
   }
 };
 
+// 1/2 sum_x a(x) (C^-1 a)(x) by Parseval on the half grid: (1/2N) sum_k w_k mult_k |a^_k|^2 with w = 1 on the planes
+// k_z = 0 and N/2 (their mirrors are stored) and 2 elsewhere; mult = the padded half-grid multiplier (V/N)/C of
+// convolveInvCorrFuncWithSignal (HMC_help.cc:41-58).  Saves the inverse transform of kinetic_term (HMC.cc:82-110)
+// and of the prior (gaussian.cpp:20-35); any row layout (cube, transposed slab): only z matters.
+struct HalfQuadF {
+  const double2 *v;
+  const double *mult;
+  int nzh;
+  double inv_2n;
+  __device__ double operator()(size_t i) const {
+    const size_t row = i / (size_t)nzh;
+    const int z = (int)(i - row * (size_t)nzh);
+    const double2 a = v[i];
+    const double w = (z == 0 || z == nzh - 1) ? 1.0 : 2.0;
+    return inv_2n * w * mult[row * (size_t)(nzh + 1) + z] * (a.x * a.x + a.y * a.y);
+  }
+};
+
 template <class F>
 static void reduce(F f, size_t n, double *scratch, double *out, cudaStream_t st, int kind = KK_REDUCE) {
   ProfScope prof(kind, st);
@@ -304,6 +322,10 @@ static void reduce(F f, size_t n, double *scratch, double *out, cudaStream_t st,
   BGPU_LAUNCHED(2);
 }
 
+void launch_half_quadratic(const double2 *vhat, const double *mult_half, int N, size_t n_half, double ncells,
+                           double *scratch, double *out, cudaStream_t st) {
+  reduce(HalfQuadF{vhat, mult_half, N / 2 + 1, 0.5 / ncells}, n_half, scratch, out, st);
+}
 void launch_sum(const double *a, size_t n, double *scratch, double *out, cudaStream_t st) {
   reduce(SumF{a}, n, scratch, out, st);
 }
@@ -1359,18 +1381,42 @@ __device__ void deposit_sph(const GridGeom &g, double x, double y, double z, dou
   const int ix = (int)(unsigned long long)(x / d), iy = (int)(unsigned long long)(y / d),
             iz = (int)(unsigned long long)(z / d);
   const double ccx = ((double)ix + 0.5) * d, ccy = ((double)iy + 0.5) * d, ccz = ((double)iz + 0.5) * d;
+  // The reference tests all (2 reach + 1)^3 cells with a square root and two divisions each
+  // (massFunctions.cc:423-476, :366-384).  Here:
+  //  * a cell whose distance along x alone, or in the (x, y) plane alone, already exceeds 2h cannot pass r/h <= 2:
+  //    those planes and rows are skipped on the squared distance (margin far wider than rounding) -- the set of
+  //    cells that receive mass is unchanged;
+  //  * q = r/h is formed as r^2 * rsqrt(r^2) / h with the reciprocal of h hoisted: one special-function call per
+  //    cell instead of a square root and two divisions.  q differs from the reference's by an ulp or two, W by as
+  //    much; a cell within that of the edge q = 2 carries (2 - q)^3 / 4 ~ 1e-45 either way.
+  const double lim = 4. * h * h * (1. + 1.e-9);
+  const double h_inv = 1. / h;
+  const double a = 1. / M_PI / (h * h * h);
   for (int i1 = -reach; i1 <= reach; ++i1) {
     const double dx = x - (ccx + (double)i1 * d);
+    if (dx * dx > lim) continue;
     const int kx = (N + i1 + ix) % N;
     for (int i2 = -reach; i2 <= reach; ++i2) {
       const double dy = y - (ccy + (double)i2 * d);
-      const int ky = (N + i2 + iy) % N;
       const double rxy = dx * dx + dy * dy;
+      if (rxy > lim) continue;
+      const int ky = (N + i2 + iy) % N;
       double *row = rho + ((size_t)kx * N + ky) * N;
       for (int i3 = -reach; i3 <= reach; ++i3) {
         const double dz = z - (ccz + (double)i3 * d);
-        const double r = sqrt(rxy + dz * dz);
-        if (r / h <= 2.) red_add(row + (N + i3 + iz) % N, sph_kernel(r, h));
+        const double r2 = rxy + dz * dz;
+        if (r2 > lim) continue;
+        const double q = r2 > 0. ? r2 * rsqrt(r2) * h_inv : 0.;
+        double w;
+        if (q <= 1.) {
+          w = a * (1 - 3. / 2 * q * q + 3. / 4 * q * q * q);
+        } else if (q <= 2.) {
+          const double t = 2. - q;
+          w = a * (1. / 4 * (t * t * t));
+        } else {
+          continue;
+        }
+        red_add(row + (N + i3 + iz) % N, w);
       }
     }
   }
@@ -1425,11 +1471,14 @@ __global__ void gather_sph_kernel(GridGeom g, double *__restrict__ ax, double *_
         const double dzh = dpcz - (double)i3 * d_h;
         const double q_sq = qxy + dzh * dzh;
         if (q_sq > 4.) continue;
-        const double q = sqrt(q_sq);
+        // q and 1/q from one reciprocal square root (the reference takes a square root and divides,
+        // SPH_kernel.cpp:148-208; an ulp of difference in q)
+        const double q_inv = q_sq > 0. ? rsqrt(q_sq) : 0.;
+        const double q = q_sq * q_inv;
         double partial;
         if (q_sq > 1.) {
           const double qm = q - 2.;
-          partial = -0.75 * qm * qm * norm / q;
+          partial = -0.75 * qm * qm * norm * q_inv;
         } else {
           partial = (2.25 * q - 3.) * norm;
         }

@@ -188,4 +188,8 @@ struct MockObs {
 void launch_mock_obs(const MockObs &mp, const double *delta_eul, const double *delta_lag, double *window, double *nobs,
                      double *noise, size_t n, size_t first, size_t n_global, uint64_t seed, cudaStream_t st);
 
+// out = 1/2 sum_x a (C^-1 a) from a^ on the half grid (Parseval; see kernels.cu HalfQuadF)
+void launch_half_quadratic(const double2 *vhat, const double *mult_half, int N, size_t n_half, double ncells,
+                           double *scratch, double *out, cudaStream_t st);
+
 }  // namespace bgpu

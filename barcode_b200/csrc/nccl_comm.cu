@@ -5,8 +5,11 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace bgpu {
 
@@ -64,7 +67,9 @@ void NcclComm::unique_id(void *out128) {
   check(api().GetUniqueId(static_cast<ncclUniqueId *>(out128)), "ncclGetUniqueId");
 }
 
-NcclComm::NcclComm(const void *id128, int rank_, int nranks_) : rank(rank_), nranks(nranks_) {
+NcclComm::NcclComm(const void *id128, int rank_, int nranks_) {
+  rank = rank_;
+  nranks = nranks_;
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   ncclComm_t c = nullptr;
@@ -123,6 +128,152 @@ void NcclComm::shift(const double *send, int to, double *recv, int from, size_t 
   check(a.Send(send, count, ncclDouble, to, c, st), "ncclSend");
   check(a.Recv(recv, count, ncclDouble, from, c, st), "ncclRecv");
   check(a.GroupEnd(), "ncclGroupEnd");
+}
+
+// ---------------------------------------------------------------------------
+// LocalComm: slab ranks as threads of one process on one device (see nccl_comm.h)
+// ---------------------------------------------------------------------------
+struct LocalGroup {
+  int n = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int waiting = 0;
+  unsigned long generation = 0;
+  struct Slot {
+    const void *p[2] = {nullptr, nullptr};
+    int to[2] = {-1, -1};
+  };
+  std::vector<Slot> slot;
+  // all ranks arrive, then all leave (a classic generation barrier)
+  void rendezvous() {
+    std::unique_lock<std::mutex> lk(mu);
+    const unsigned long gen = generation;
+    if (++waiting == n) {
+      waiting = 0;
+      ++generation;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return generation != gen; });
+    }
+  }
+};
+
+LocalGroup *local_group_create(int nranks) {
+  if (nranks < 1 || nranks > 8) throw std::runtime_error("bgpu: a local slab group has 1 to 8 ranks");
+  LocalGroup *g = new LocalGroup;
+  g->n = nranks;
+  g->slot.resize(nranks);
+  return g;
+}
+void local_group_destroy(LocalGroup *g) { delete g; }
+
+void local_group_exchange_ptr(LocalGroup *g, int rank, void *mine, void **all) {
+  g->slot[rank].p[0] = mine;
+  g->rendezvous();
+  for (int r = 0; r < g->n; ++r) all[r] = const_cast<void *>(g->slot[r].p[0]);
+  g->rendezvous();
+}
+
+namespace {
+__global__ void local_reduce_kernel(double *out, const double *const *in, int n, size_t count, int op) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double v = in[0][i];
+  for (int r = 1; r < n; ++r) {  // fixed rank order: every rank computes the same bits
+    const double w = in[r][i];
+    v = op == 0 ? v + w : (w > v ? w : v);
+  }
+  out[i] = v;
+}
+void cuda_ok(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in LocalComm ") + what + ": " + cudaGetErrorString(e));
+}
+}  // namespace
+
+LocalComm::LocalComm(LocalGroup *g, int rank_, int nranks_) : group(g) {
+  rank = rank_;
+  nranks = nranks_;
+  if (!g || g->n != nranks_) throw std::runtime_error("bgpu: local slab group of the wrong size");
+}
+LocalComm::~LocalComm() {
+  if (stage) cudaFree(stage);
+}
+
+void LocalComm::barrier(cudaStream_t st) {
+  cuda_ok(cudaStreamSynchronize(st), "barrier");
+  group->rendezvous();
+}
+
+void LocalComm::all_to_all(const void *send, void *recv, size_t count, cudaStream_t st) {
+  cuda_ok(cudaStreamSynchronize(st), "all_to_all");
+  group->slot[rank].p[0] = send;
+  group->rendezvous();
+  double *r = static_cast<double *>(recv);
+  for (int h = 0; h < nranks; ++h)  // block `rank` of rank h's send buffer is mine
+    cuda_ok(cudaMemcpyAsync(r + (size_t)h * count, static_cast<const double *>(group->slot[h].p[0]) + (size_t)rank * count,
+                            count * sizeof(double), cudaMemcpyDeviceToDevice, st), "all_to_all copy");
+  cuda_ok(cudaStreamSynchronize(st), "all_to_all");
+  group->rendezvous();
+}
+
+void LocalComm::reduce(double *buf, size_t count, int op, cudaStream_t st) {
+  if (count > stage_count) {
+    if (stage) cudaFree(stage);
+    stage_count = count < 8192 ? 8192 : count;
+    cuda_ok(cudaMalloc(reinterpret_cast<void **>(&stage), (stage_count + 16) * sizeof(double)), "stage");
+  }
+  cuda_ok(cudaStreamSynchronize(st), "all_reduce");
+  group->slot[rank].p[0] = buf;
+  group->rendezvous();
+  const double *host_ptrs[8];
+  for (int r = 0; r < nranks; ++r) host_ptrs[r] = static_cast<const double *>(group->slot[r].p[0]);
+  // the pointer table rides behind the staged result (16 spare doubles = 8 pointers + slack)
+  const double **d_ptrs = reinterpret_cast<const double **>(stage + stage_count);
+  cuda_ok(cudaMemcpyAsync(d_ptrs, host_ptrs, nranks * sizeof(double *), cudaMemcpyHostToDevice, st), "ptrs");
+  local_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(stage, d_ptrs, nranks, count, op);
+  cuda_ok(cudaStreamSynchronize(st), "all_reduce");
+  group->rendezvous();  // everyone has read everyone's input: overwrite mine
+  cuda_ok(cudaMemcpyAsync(buf, stage, count * sizeof(double), cudaMemcpyDeviceToDevice, st), "all_reduce store");
+}
+void LocalComm::all_reduce_sum(double *buf, size_t count, cudaStream_t st) { reduce(buf, count, 0, st); }
+void LocalComm::all_reduce_max(double *buf, size_t count, cudaStream_t st) { reduce(buf, count, 1, st); }
+
+void LocalComm::exchange2(const double *a_, int to_a, const double *b_, int to_b, double *ra, int from_a, double *rb,
+                          int from_b, size_t count, cudaStream_t st) {
+  cuda_ok(cudaStreamSynchronize(st), "exchange");
+  LocalGroup::Slot &mine = group->slot[rank];
+  mine.p[0] = a_;
+  mine.to[0] = to_a;
+  mine.p[1] = b_;
+  mine.to[1] = to_b;
+  group->rendezvous();
+  // NCCL pairs the k-th receive from a rank with that rank's k-th send to me (matters when both neighbours are
+  // the same rank, G = 2)
+  double *dst[2] = {ra, rb};
+  const int from[2] = {from_a, from_b};
+  for (int j = 0; j < 2; ++j) {
+    if (!dst[j] || from[j] < 0) continue;
+    int nth = 0;
+    for (int e = 0; e < j; ++e)
+      if (dst[e] && from[e] == from[j]) ++nth;
+    const LocalGroup::Slot &src = group->slot[from[j]];
+    const void *p = nullptr;
+    for (int e = 0, seen = 0; e < 2; ++e)
+      if (src.p[e] && src.to[e] == rank) {
+        if (seen == nth) p = src.p[e];
+        ++seen;
+      }
+    if (!p) throw std::runtime_error("bgpu: LocalComm exchange without a matching send");
+    cuda_ok(cudaMemcpyAsync(dst[j], p, count * sizeof(double), cudaMemcpyDeviceToDevice, st), "exchange copy");
+  }
+  cuda_ok(cudaStreamSynchronize(st), "exchange");
+  group->rendezvous();
+  mine.p[0] = mine.p[1] = nullptr;
+  mine.to[0] = mine.to[1] = -1;
+}
+
+void LocalComm::shift(const double *send, int to, double *recv, int from, size_t count, cudaStream_t st) {
+  exchange2(send, to, nullptr, -1, recv, from, nullptr, -1, count, st);
 }
 
 }  // namespace bgpu

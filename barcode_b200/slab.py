@@ -75,7 +75,7 @@ def broadcast_unique_id(rank: int, world: int) -> bytes:
 class SlabChain(Chain):
     """`Chain` whose arrays are this rank's slab [Ns][N][N]; every rank makes the same calls."""
 
-    def __init__(self, params: Params, rank: int, world: int, unique_id: bytes | None):
+    def __init__(self, params: Params, rank: int, world: int, unique_id: bytes | None, local_group=None):
         self.params = params
         self.L = _lib.load()
         self.N1 = int(params.N1)
@@ -86,6 +86,9 @@ class SlabChain(Chain):
         self._h = C.c_void_p()
         cp = params.to_c()
         idbuf = None
+        if local_group is not None:
+            _lib.check(self.L.bgpu_slab_create_local(C.byref(cp), self.rank, self.world, local_group.ptr, C.byref(self._h)))
+            return
         if world > 1:
             if unique_id is None or len(unique_id) != 128:
                 raise ValueError("a 128-byte NCCL unique id is required")
@@ -97,6 +100,12 @@ class SlabChain(Chain):
         """Collective constructor: draws a fresh NCCL unique id on rank 0 (an id bootstraps exactly one
         communicator) and distributes it through the initialised torch.distributed group."""
         return cls(params, rank, world, broadcast_unique_id(rank, world) if world > 1 else None)
+
+    @classmethod
+    def create_local(cls, params: Params, rank: int, group: "LocalGroup"):
+        """Rank `rank` of a chain whose ranks all live in this process on one device (bgpu_slab_create_local): call
+        from the host thread that will drive this rank; collective across the group's threads."""
+        return cls(params, rank, group.world, None, local_group=group)
 
     def fused_transpose(self) -> bool:
         """True where the distributed FFT's transpose rides inside the strided pass (TMA stores into the peers'
@@ -118,3 +127,42 @@ class SlabChain(Chain):
         """This rank's slab of a full (N, N, N) array."""
         a = np.asarray(full).reshape(self.N1, self.N1, self.N1)
         return np.ascontiguousarray(a[self.x0:self.x0 + self.Ns])
+
+
+class LocalGroup:
+    """The rendezvous object of an in-process slab chain (bgpu_local_group_*): one per chain, shared by its ranks."""
+
+    def __init__(self, world: int):
+        self.world = int(world)
+        self.ptr = C.c_void_p()
+        _lib.check(_lib.load().bgpu_local_group_create(self.world, C.byref(self.ptr)))
+
+    def close(self):
+        if self.ptr:
+            _lib.load().bgpu_local_group_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def run_local_ranks(world: int, fn):
+    """Run fn(rank, group) on `world` host threads sharing one LocalGroup (ctypes releases the GIL inside the library, so
+    the ranks' collective calls can meet); returns the list of results, re-raises the first exception."""
+    import threading
+    group = LocalGroup(world)
+    out, err = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            out[r] = fn(r, group)
+        except BaseException as e:  # noqa: BLE001
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    group.close()
+    for e in err:
+        if e is not None:
+            raise e
+    return out

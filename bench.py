@@ -51,6 +51,7 @@ def parse():
                     help="e2e_chains: chains (handles, host threads) on the GPU; 3 = one uploading, one computing, one "
                          "downloading (each phase takes about as long at PCIe 5 x16 rates)")
     ap.add_argument("--no-e2e-chains", action="store_true", help="skip the interleaved-chains e2e leg")
+    ap.add_argument("--no-sph", action="store_true", help="skip the SPH (masskernel 3, calc_h 2) line in `also`")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the slab-decomposed leg (512^3 / 1024^3)")
     return ap.parse_args()
@@ -278,6 +279,23 @@ def run_ours(args):
     ms_other = timed(lambda: ch2.gradient_psi_dev(d_s.data_ptr(), d_g.data_ptr()), args.steps, args.warmup)
     ch2.close()
 
+    # the reference's SHIPPED default (data/input.par:11-13,134): SPH spline mass assignment with its exact adjoint,
+    # calc_h = 2, real space -- same grid, same data, its own per-kernel split
+    sph = None
+    if not args.no_sph:
+        ch3 = bc.Chain(bc.Params(device=local_rank, **{**cfg, "masskernel": 3, "calc_h": 2, "rsd_model": False, "sfmodel": 1}))
+        ch3.set_static(Power=prob["Power"], nobs=prob["nobs"], noise=prob["noise"], window=prob["window"])
+        ch3.set_stream(stream.cuda_stream)
+        sph_steps = max(2, args.steps // 2)
+        ms_sph = timed(lambda: ch3.gradient_psi_dev(d_s.data_ptr(), d_g.data_ptr()), sph_steps, 1)
+        bc.profile_begin()
+        ch3.gradient_psi_dev(d_s.data_ptr(), d_g.data_ptr())
+        prof3 = bc.profile_end()
+        ch3.close()
+        sph = {"gradient_evals_per_s": world * sph_steps / (ms_sph * 1e-3), "ms_per_eval": ms_sph / sph_steps,
+               "config": "masskernel 3 (SPH spline, h = 1 cell), calc_h 2 (likelihood_calc_h_SPH), real space, same grid",
+               "per_kernel_ms": {k: v[0] for k, v in prof3.items() if v[1]}}
+
     # one leapfrog step = kick, M^-1 p, drift, gradient, kick (HMC.cc:289-352)
     ch.hamiltonian_mass()
     d_s2, d_p2 = d_s.clone(), d_p.clone()
@@ -452,6 +470,7 @@ def run_ours(args):
                 "leapfrog_steps_per_s": world * leap_steps / (ms_leap * 1e-3),
                 "device_momentum_draw_ms": ms_draw / draw_calls,
                 "hmc_candidate_ms_neps8_device_resident": cand_ms,
+                "sph_default_config": sph,
                 "kernel_launches_total": int(bc.kernel_launches() - launches0),
             },
         }

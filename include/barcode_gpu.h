@@ -97,6 +97,14 @@ void bgpu_destroy(bgpu_handle *h);
 int bgpu_nccl_unique_id(void *out128);
 int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out);
 int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *nx_local);
+/* The same slab-decomposed chain with all its ranks inside ONE process on ONE device: rank r is driven by its own host
+ * thread (every rank still makes the same sequence of calls, each from its thread), the collectives are host
+ * rendezvous + device copies.  NCCL refuses two ranks on one GPU; this is how a single-GPU box runs -- and tests --
+ * the slab code path (layouts, halos, fused transposes).  Not a performance configuration. */
+typedef struct bgpu_local_group bgpu_local_group;
+int bgpu_local_group_create(int nranks, bgpu_local_group **out);
+void bgpu_local_group_destroy(bgpu_local_group *g);
+int bgpu_slab_create_local(const bgpu_params *p, int rank, int nranks, bgpu_local_group *g, bgpu_handle **out);
 
 /* static inputs: data->observational->{Power, nobs, noise_sf, window} (main.cc:150-154).
  * NULL leaves an array unchanged. */
