@@ -176,7 +176,8 @@ class Chain:
     def color_momenta(self, white=None, real_gauss=None):
         w = None if white is None else np.ascontiguousarray(white, dtype=np.complex128).reshape(-1)
         g = None if real_gauss is None else _f64(real_gauss, self.N)
-        if w is not None and w.size != self.N:
+        n_full = int(self.params.N1) ** 3   # a slab rank passes the full grid too (barcode_gpu.h)
+        if w is not None and w.size != n_full:
             raise ValueError("white noise must be the full N1^3 complex grid")
         out = np.empty(self.N)
         _lib.check(self.L.bgpu_color_momenta(

@@ -304,9 +304,12 @@ void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, d
                               h->stream));
     BGPU_CUDA(cudaStreamSynchronize(h->stream));
     int H = (int)std::ceil(h->hscal[S_MAXPSI] / g.d) + 2;
+    // the SPH spline reaches sph_R cells around the particle's own cell (massFunctions.cc:420, SPH_kernel.cpp:62-139)
+    if (g.masskernel == 3) H = (int)std::ceil(h->hscal[S_MAXPSI] / g.d) + 1 + h->sph_R;
     if (!(h->hscal[S_MAXPSI] == h->hscal[S_MAXPSI]) || H > h->Hmax)
       throw std::runtime_error("bgpu: displacement of " + std::to_string(h->hscal[S_MAXPSI] / g.d) +
-                               " cells along x exceeds the slab halo (" + std::to_string(h->Hmax) + " planes)");
+                               " cells along x" + (g.masskernel == 3 ? " plus the SPH kernel's reach" : "") +
+                               " exceeds the slab halo (" + std::to_string(h->Hmax) + " planes)");
     g.H = H;
     h->H_cur = H;
     h->delta = h->rho_ext + (size_t)H * plane;
@@ -630,7 +633,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     backproject(h, V);
   } else {
     // exact adjoint: V = gather(r) in place over Psi, then the same back-projection
-    if (p.calc_h == 2)
+    if (p.calc_h == 2 && h->G == 1)
       launch_gather_sph(h->geom, h->psi[0], h->psi[1], h->psi[2], h->resid, h->sph_kmax, h->sph_R,
                         p.rho_c * (p.L1 * p.L2 * p.L3) / h->ncells, h->stream);
     else if (h->G == 1)
@@ -650,7 +653,11 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
       }
       GridGeom g = h->geom;
       g.H = H;
-      launch_gather_adjoint(g, h->psi[0], h->psi[1], h->psi[2], h->resid_ext, h->stream);
+      if (p.calc_h == 2)
+        launch_gather_sph(g, h->psi[0], h->psi[1], h->psi[2], h->resid_ext, h->sph_kmax, h->sph_R,
+                          p.rho_c * (p.L1 * p.L2 * p.L3) / h->ncells, h->stream);
+      else
+        launch_gather_adjoint(g, h->psi[0], h->psi[1], h->psi[2], h->resid_ext, h->stream);
     }
     backproject(h, h->psi);
   }
@@ -959,9 +966,9 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
             "bgpu_slab_create: N1 must be a multiple of the number of ranks, at least 8 planes per rank");
     require(!(p->calc_h == BGPU_CALC_H_EXACT && p->sfmodel != 1 && !p->rsd_model),
             "bgpu_slab_create: the exact adjoint of the 2LPT/ALPT model is not built for slabs yet");
-    require(p->calc_h == 0 || p->calc_h == 1 || p->calc_h == BGPU_CALC_H_EXACT,
-            "bgpu_slab_create: calc_h must be 0, 1 or 4 (the SPH adjoints, calc_h 2 / 3, are not built for slabs yet)");
-    require(p->masskernel != 3, "bgpu_slab_create: the SPH kernel is not built for slabs yet");
+    require(p->calc_h == 0 || p->calc_h == 1 || p->calc_h == 2 || p->calc_h == BGPU_CALC_H_EXACT,
+            "bgpu_slab_create: calc_h must be 0, 1, 2 or 4 (the Fourier / TSC variant of the SPH adjoint, calc_h 3, is "
+            "not built for slabs)");
     require(p->sfmodel == 1 || p->rsd_model || p->N1 / nranks >= 8,
             "bgpu_slab_create: the 2LPT/ALPT model needs at least 8 planes per rank (4-plane stencil halo)");
     require(nccl_id != nullptr || local != nullptr, "bgpu_slab_create: a NCCL unique id is required");
@@ -998,7 +1005,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     dalloc(h->recvbuf, 2 * h->nh);   // two receive buffers, alternating between transforms
     h->Hmax = h->Ns < 24 ? h->Ns : 24;
     dalloc(h->halo_recv, (size_t)2 * h->Hmax * h->N * h->N);
-    if (p->calc_h == BGPU_CALC_H_EXACT) dalloc(h->resid_ext, (size_t)(h->Ns + 2 * h->Hmax) * h->N * h->N);
+    if (p->calc_h == BGPU_CALC_H_EXACT || p->calc_h == 2)
+      dalloc(h->resid_ext, (size_t)(h->Ns + 2 * h->Hmax) * h->N * h->N);
     if (p->calc_h == 0 && p->likelihood == 2) dalloc(h->fext, (size_t)(h->Ns + 4) * h->N * h->N);
     BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->dflag), sizeof(int)));
     BGPU_CUDA(cudaMemsetAsync(h->dflag, 0, sizeof(int), h->stream));
@@ -1079,6 +1087,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   {
     const char *sw = std::getenv("BGPU_SWEEP");  // 0 = first-generation particle-per-thread kernels; n > 1 = segment length
     g.sweep = sw ? std::atoi(sw) : 1;
+    const char *ln = std::getenv("BGPU_LEAN");
+    g.lean = !(ln && ln[0] == '0');
   }
   if (p->masskernel == 3) {
     // SPH_kernel_3D_cells + _hull_1 (SPH_kernel.cpp:62-139)
@@ -1554,16 +1564,19 @@ int bgpu_color_momenta(bgpu_handle *h, const double *white, const double *real_g
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
   require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
-  require(h->G == 1, "bgpu_color_momenta: not available on a slab-decomposed chain yet (colour on the host or a cube handle)");
   if (h->mass_fs) {
     require(white != nullptr, "bgpu_color_momenta: white noise is required for a Fourier-space mass");
-    // the full complex white-noise grid (2 N^3 doubles) does not fit any resident scratch array: own temporary
+    // the full complex white-noise grid (2 N^3 doubles) does not fit any resident scratch array: own temporary.
+    // A slab rank takes the FULL grid too (a mode's source entry or its mirror partner's can sit anywhere in it:
+    // the host stream is serial anyway, random.cpp:57-60) and colours its own k-space rows.
     double2 *d_white = nullptr;
-    dalloc(d_white, h->n);
+    const size_t n_white = (size_t)h->N * h->N * h->N;
+    dalloc(d_white, n_white);
     try {
-      BGPU_CUDA(cudaMemcpyAsync(d_white, white, h->n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+      BGPU_CUDA(cudaMemcpyAsync(d_white, white, n_white * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
       const double amp = h->ncells * h->ncells / (h->p.L1 * h->p.L2 * h->p.L3);  // random.cpp:81-83
-      launch_colour_momenta(d_white, h->mass_f, h->work, h->N, amp, h->stream);
+      if (h->G == 1) launch_colour_momenta(d_white, h->mass_f, h->work, h->N, amp, h->stream);
+      else launch_colour_momenta_rows(d_white, h->inv_mass, h->work, h->N, h->Ns, h->rank * h->Ns, h->ncells, h->stream);
       ROp sop;
       sop.kind = R_SCALE;
       sop.a = 1.0 / h->ncells;

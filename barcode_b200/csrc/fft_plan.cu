@@ -236,7 +236,7 @@ static void launch_strided_tma(const Fft3d &f, const double2 *in, double2 *out, 
   if (io.peer_out)
     for (int h = 0; h < io.G; ++h) maps.peer[h] = f.tensor_map(io.peer_out[h], AXIS, true, 1, io.G, io.Ns);
   PassGeom geo{n_other, io.other0, io.in_packed ? io.Ns : 0, io.out_packed ? io.Ns : 0, io.peer_out ? io.Ns : 0,
-               io.my_rank};
+               io.my_rank, f.next_rev()};
   const int tiles = n_other * ((N / 2 + 1 + 7) / 8);
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > tiles) blocks = tiles;
@@ -375,7 +375,9 @@ static void launch_zpass_tma(const Fft3d &f, const void *in, void *out, ROp op, 
   int blocks = f.sm_count * blocks_per_sm;
   if (blocks > ntiles) blocks = ntiles;
   ProfScope prof(C2R ? KK_FFT_C2R_Z : KK_FFT_R2C_Z, st);
-  launch_pass(kern, blocks, threads, smem, st, f.use_pdl, (const void *)pin, (void *)pout, f.twN, f.twM, op, ntiles);
+  // a pass over a row range (the streaming host API) keeps the plain order
+  const int rev = (row0 == 0 && nrows == (size_t)f.Ns * N) ? f.next_rev() : 0;
+  launch_pass(kern, blocks, threads, smem, st, f.use_pdl, (const void *)pin, (void *)pout, f.twN, f.twM, op, ntiles, rev);
   BGPU_LAUNCHED(1);
 }
 
@@ -687,6 +689,8 @@ void Fft3d::init(int n, cudaStream_t st) {
     // measured (B200, round 2): +1.3 % per evaluation at 256^3, where a pass is ~55 us and the launch ramp shows;
     // -2 % at 512^3 -- so on by default up to 256 only (BGPU_PDL=0 / 1 overrides)
     use_pdl = pd ? pd[0] != '0' : n <= 256;
+    const char *pp = std::getenv("BGPU_PINGPONG");
+    pingpong = pp && pp[0] == '1';
     const char *zr = std::getenv("BGPU_ZROUND");
     z_round = !(zr && zr[0] == '0');
     const char *tw2 = std::getenv("BGPU_FFT_2WARP");
@@ -795,7 +799,8 @@ static void zround_impl(const Fft3d &f, double2 *work, ROp op) {
     int blocks = f.sm_count * blocks_per_sm;
     if (blocks > ntiles) blocks = ntiles;
     ProfScope prof(KK_FFT_ZROUND, f.stream);
-    launch_pass(kern, blocks, threads, smem, f.stream, f.use_pdl, (const double2 *)work, work, f.twN, f.twM, op, ntiles);
+    launch_pass(kern, blocks, threads, smem, f.stream, f.use_pdl, (const double2 *)work, work, f.twN, f.twM, op, ntiles,
+                f.next_rev());
     BGPU_LAUNCHED(1);
   } else {
     throw std::runtime_error("bgpu: the z round trip needs the bulk-copy z pass (N = 128, 256 or 512)");

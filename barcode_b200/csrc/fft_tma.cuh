@@ -293,6 +293,9 @@ struct PassGeom {
   // pass axes -- the all-to-all of the distributed transform happens inside the pass kernel
   int out_peers;
   int my_rank;
+  // walk the tiles from the last to the first: consecutive passes that alternate direction start on the part of
+  // their input the previous pass wrote last, which is still in L2 (Fft3d::pingpong)
+  int reverse;
 };
 
 // shared-memory address of (row, pencil p) in a 64-byte-swizzled tile of doubles (T = 8 per row)
@@ -425,8 +428,12 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
 
   const int my_count = (NTILES - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+  auto tile_of = [&](int i) {
+    const int tl = blockIdx.x + i * gridDim.x;
+    return geo.reverse ? NTILES - 1 - tl : tl;
+  };
   auto issue_load = [&](int i) {
-    const int tile = blockIdx.x + i * gridDim.x;
+    const int tile = tile_of(i);
     const int s = i % NSTAGE;
     const int other = tile / ZT, zt = tile % ZT;
     uint8_t *dst = smem_al + s * Tile::stage_bytes;
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(8 * (N / E), MINB)
 
   for (int i = 0; i < my_count; ++i) {
     const int s = i % NSTAGE;
-    const int tile = blockIdx.x + i * gridDim.x;
+    const int tile = tile_of(i);
     const int other = tile / ZT, zt = tile % ZT;
     const int iz = zt * T + p;
     const uint32_t tbase = smem0 + s * Tile::stage_bytes;
@@ -691,7 +698,7 @@ struct ZTile {
 template <int N, int E, int TR, int NSTAGE, bool C2R, bool AUX, int MINB>
 __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
     fft_zpass_tma(const void *__restrict__ in, void *__restrict__ out, const double2 *__restrict__ twN,
-                  const double2 *__restrict__ twM, ROp op, int ntiles) {
+                  const double2 *__restrict__ twM, ROp op, int ntiles, int rev) {
   constexpr int M = N / 2;
   constexpr int LP = M / E;
   constexpr int DIR = C2R ? +1 : -1;
@@ -716,13 +723,17 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
   const int row = tid / LP;
   const int t = tid % LP;
   const int my_count = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int i) {  // rev: last tile first (see PassGeom::reverse)
+    const int tl = (int)blockIdx.x + i * (int)gridDim.x;
+    return rev ? ntiles - 1 - tl : tl;
+  };
   const char *gin = static_cast<const char *>(in);
   char *gout = static_cast<char *>(out);
 
   // warp 0, lane r: load row r of my i-th tile
   auto issue_load = [&](int i) {
     const int s = i % NSTAGE;
-    const size_t grow = (size_t)(blockIdx.x + (size_t)i * gridDim.x) * TR + tid;
+    const size_t grow = (size_t)tile_of(i) * TR + tid;
     if (tid == 0) mbar_expect_tx(&full[s], TR * (in_row_bytes + (AUX ? N * 8 : 0)));
     __syncwarp();
     if (tid < TR) {
@@ -761,7 +772,7 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
     __syncthreads();
     if (tid < 32) {
       if (tid < TR) {
-        const size_t grow = (size_t)(blockIdx.x + (size_t)i * gridDim.x) * TR + tid;
+        const size_t grow = (size_t)tile_of(i) * TR + tid;
         const void *src = smem_al + s * Z::stage_bytes + tid * Z::pitch;
         if (C2R && op.kind == R_AXPY)
           bulk_reduce_add_f64_1d(gout + grow * out_row_bytes, src, out_row_bytes);
@@ -791,7 +802,7 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
 template <int N, int E, int TR, int NSTAGE, int MINB>
 __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
     fft_zround_tma(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ twN,
-                   const double2 *__restrict__ twM, ROp op, int ntiles) {
+                   const double2 *__restrict__ twM, ROp op, int ntiles, int rev) {
   constexpr int M = N / 2;
   constexpr int LP = M / E;
   constexpr int NSTG = StageCount<M>::value;
@@ -808,12 +819,16 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
   const int row = tid / LP;
   const int t = tid % LP;
   const int my_count = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int i) {
+    const int tl = (int)blockIdx.x + i * (int)gridDim.x;
+    return rev ? ntiles - 1 - tl : tl;
+  };
   const char *gin = reinterpret_cast<const char *>(in);
   char *gout = reinterpret_cast<char *>(out);
 
   auto issue_load = [&](int i) {
     const int s = i % NSTAGE;
-    const size_t grow = (size_t)(blockIdx.x + (size_t)i * gridDim.x) * TR + tid;
+    const size_t grow = (size_t)tile_of(i) * TR + tid;
     if (tid == 0) mbar_expect_tx(&full[s], TR * (row_bytes + N * 8));
     __syncwarp();
     if (tid < TR) {
@@ -855,7 +870,7 @@ __global__ void __launch_bounds__(TR *(N / 2 / E), MINB)
     __syncthreads();
     if (tid < 32) {
       if (tid < TR) {
-        const size_t grow = (size_t)(blockIdx.x + (size_t)i * gridDim.x) * TR + tid;
+        const size_t grow = (size_t)tile_of(i) * TR + tid;
         bulk_store_1d(gout + grow * row_bytes, smem_al + s * Z::stage_bytes + tid * Z::pitch, row_bytes);
       }
       bulk_commit();

@@ -177,7 +177,24 @@ __global__ void cell_indices_kernel(GridGeom g, const double *__restrict__ x, co
                                     const double *__restrict__ z, int *ci, int *cj, int *ck, size_t n) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  if (g.masskernel == 1) {
+  if (g.masskernel == 1 && g.lean) {
+    // the arithmetic of the lean sweep kernels (particles_sweep.cu), so that the bit-exact index tests pin it
+    const LeanConst lc = lean_const(g);
+    const double pos[3] = {x[idx], y[idx], z[idx]};
+    int *const out[3] = {ci, cj, ck};
+    for (int c = 0; c < 3; ++c) {
+      unsigned c0, c1;
+      double w0, w1;
+      bool slow = !(pos[c] >= 0. && pos[c] < g.L);
+      lean_axis(pos[c], lc, c0, c1, w0, w1, slow);
+      if (slow) {
+        int a, b;
+        cic_axis(pos[c], g.d, g.L, g.N, a, b, w0, w1);
+        c0 = (unsigned)a;
+      }
+      out[c][idx] = (int)c0;
+    }
+  } else if (g.masskernel == 1) {
     int a, b;
     double t, dx;
     cic_axis(x[idx], g.d, g.L, g.N, a, b, t, dx);
@@ -1030,6 +1047,56 @@ void launch_colour_momenta(const double2 *white_full, const double *spec_full, d
   BGPU_LAUNCHED(1);
 }
 
+// The same draw on a slab-decomposed chain: this rank colours its rows of the transposed k-space layout
+// [x][y_local][z <= N/2] (y = y0 + y_local) from the FULL white-noise grid -- a mode's source entry, or its mirror
+// partner's, can sit anywhere in it -- with sigma^2 = (N^2/V) M / 2 = N / (2 inv), inv = (V/N)/M being the padded
+// half-grid multiplier of the kinetic term (the full spectrum M is x-slab decomposed and not addressable here).
+__global__ void colour_momenta_rows_kernel(const double2 *__restrict__ W, const double *__restrict__ inv,
+                                           double2 *__restrict__ half, int N, int Ns, int y0, double ncells) {
+  const int h = N / 2, nzh = h + 1;
+  const size_t n = (size_t)N * Ns * nzh;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const size_t row = idx / nzh;
+  const int c = (int)(idx - row * nzh);
+  const int b = y0 + (int)(row % Ns);
+  const int a = (int)(row / Ns);
+  const double m = inv[row * (nzh + 1) + c];
+  const double sigma = m > 0.0 ? sqrt(ncells / (2.0 * m)) : 0.0;
+  const bool a_fix = (a == 0 || a == h), b_fix = (b == 0 || b == h), c_fix = (c == 0 || c == h);
+  const int ma = (N - a) % N, mb = (N - b) % N;
+  double2 out;
+  if (a_fix && b_fix && c_fix) {
+    if (a == 0 && b == 0 && c == 0) {
+      out = make_double2(0.0, 0.0);                                 // random.cpp:347-351
+    } else {
+      const double2 w = W[((size_t)a * N + b) * N + c];
+      out = make_double2(w.x * (sqrt(2.0) * sigma), 0.0);           // :243-247, 439-483
+    }
+  } else {
+    bool mirror;
+    int sa = a, sb = b, sc = c;
+    if (!c_fix) {
+      mirror = (!a_fix && !b_fix && a > h && b > h);                // :136-140
+      if (mirror) { sa = ma; sb = mb; sc = N - c; }
+    } else {
+      mirror = (!b_fix && b > h) || (b_fix && !a_fix && a > h);     // :144-162, 251-268, 308-345, 355-409
+      if (mirror) { sa = ma; sb = mb; }
+    }
+    const double2 w = W[((size_t)sa * N + sb) * N + sc];
+    out = make_double2(w.x * sigma, mirror ? -(w.y * sigma) : w.y * sigma);
+  }
+  half[idx] = out;
+}
+
+void launch_colour_momenta_rows(const double2 *white_full, const double *inv_half, double2 *half, int N, int Ns, int y0,
+                                double ncells, cudaStream_t st) {
+  ProfScope prof(KK_COLOUR, st);
+  const size_t n = (size_t)N * Ns * (N / 2 + 1);
+  colour_momenta_rows_kernel<<<blocks_for(n, 256), 256, 0, st>>>(white_full, inv_half, half, N, Ns, y0, ncells);
+  BGPU_LAUNCHED(1);
+}
+
 __global__ void add_real_momenta_kernel(double *__restrict__ p, const double *__restrict__ mass_r,
                                         const double *__restrict__ gauss, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1358,11 +1425,12 @@ __global__ void scatter_sph_kernel(GridGeom g, const double *__restrict__ psix, 
                                    const double *__restrict__ psiz, double *__restrict__ rho, double *__restrict__ posx,
                                    double *__restrict__ posy, double *__restrict__ posz) {
   const int N = g.N;
-  const size_t n = (size_t)N * N * N;
+  const size_t n = (size_t)g.Ns * N * N;  // the Lagrangian planes this rank owns (a cube: all of them)
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int sh = 31 - __clz(N);  // N is a power of two
-  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)),
+            i = g.x0 + (int)(idx >> (2 * sh));
   double x, y, z;
   particle_position(g, i, j, k, psix[idx], psiy[idx], psiz[idx], x, y, z);
   if (posx) {
@@ -1392,10 +1460,18 @@ __device__ void deposit_sph(const GridGeom &g, double x, double y, double z, dou
   const double lim = 4. * h * h * (1. + 1.e-9);
   const double h_inv = 1. / h;
   const double a = 1. / M_PI / (h * h * h);
+  // plane of the (halo-extended, slab-local) density tile that global cell plane c maps to (a cube: c itself)
+  const int lo = g.x0 - g.H, np = g.Ns + 2 * g.H;
   for (int i1 = -reach; i1 <= reach; ++i1) {
     const double dx = x - (ccx + (double)i1 * d);
     if (dx * dx > lim) continue;
-    const int kx = (N + i1 + ix) % N;
+    int kx = (N + i1 + ix) % N - lo;
+    if (kx < 0) kx += N;
+    if (kx >= N) kx -= N;
+    if (kx >= np) {  // beyond the halo: drop the deposit and raise the flag (the host turns it into an error)
+      if (g.flag) *g.flag = 1;
+      continue;
+    }
     for (int i2 = -reach; i2 <= reach; ++i2) {
       const double dy = y - (ccy + (double)i2 * d);
       const double rxy = dx * dx + dy * dy;
@@ -1432,8 +1508,8 @@ __global__ void scatter_sph_positions_kernel(GridGeom g, const double *__restric
 void launch_scatter_sph(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
                         double *posx, double *posy, double *posz, cudaStream_t st) {
   ProfScope prof(KK_SCATTER, st);
-  const size_t n = (size_t)g.N * g.N * g.N;
-  BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
+  const size_t n = (size_t)g.Ns * g.N * g.N;
+  BGPU_CUDA(cudaMemsetAsync(rho, 0, (size_t)(g.Ns + 2 * g.H) * g.N * g.N * sizeof(double), st));
   scatter_sph_kernel<<<blocks_for(n, 128), 128, 0, st>>>(g, psix, psiy, psiz, rho, posx, posy, posz);
   BGPU_LAUNCHED(1);
 }
@@ -1445,11 +1521,14 @@ __global__ void gather_sph_kernel(GridGeom g, double *__restrict__ ax, double *_
                                   const double *__restrict__ resid, const int *__restrict__ kmax, int R,
                                   double normalize) {
   const int N = g.N;
-  const size_t n = (size_t)N * N * N;
+  const size_t n = (size_t)g.Ns * N * N;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int sh = 31 - __clz(N);  // N is a power of two
-  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)), i = (int)(idx >> (2 * sh));
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)),
+            i = g.x0 + (int)(idx >> (2 * sh));
+  // the residual is [(Ns + 2H)][N][N] with plane 0 = global x0 - H (a cube: the whole grid)
+  const int lo = g.x0 - g.H, np = g.Ns + 2 * g.H;
   double px, py, pz;
   particle_position(g, i, j, k, ax[idx], ay[idx], az[idx], px, py, pz);
   const double d = g.d, h = g.sph_h, h_inv = 1. / h, d_h = d * h_inv;
@@ -1460,7 +1539,10 @@ __global__ void gather_sph_kernel(GridGeom g, double *__restrict__ ax, double *_
   double vx = 0., vy = 0., vz = 0.;
   for (int i1 = -R; i1 <= R; ++i1) {
     const double dxh = dpcx - (double)i1 * d_h;
-    const int kx = (ix + i1 + N) % N;
+    int kx = (ix + i1 + N) % N - lo;
+    if (kx < 0) kx += N;
+    if (kx >= N) kx -= N;
+    if (kx >= np) continue;  // beyond the halo: the scatter of the same evaluation has raised the flag already
     for (int i2 = -R; i2 <= R; ++i2) {
       const int K = kmax[(i1 + R) * (2 * R + 1) + (i2 + R)];
       if (K < 0) continue;
@@ -1501,7 +1583,7 @@ __global__ void gather_sph_kernel(GridGeom g, double *__restrict__ ax, double *_
 void launch_gather_sph(const GridGeom &g, double *ax, double *ay, double *az, const double *resid, const int *kmax,
                        int R, double normalize, cudaStream_t st) {
   ProfScope prof(KK_GATHER, st);
-  const size_t n = (size_t)g.N * g.N * g.N;
+  const size_t n = (size_t)g.Ns * g.N * g.N;
   gather_sph_kernel<<<blocks_for(n, 128), 128, 0, st>>>(g, ax, ay, az, resid, kmax, R, normalize);
   BGPU_LAUNCHED(1);
 }

@@ -25,6 +25,7 @@ struct GridGeom {
   int cellbound;   // displacements are cell-boundary averaged on read (cellboundcomp; non-Zel'dovich model)
   const double *cb_lo;  // slab: plane x0-1 of Psi_x, Psi_y, Psi_z ([3][N][N], from the lower neighbour); null on a cube
   int sweep;       // x-sweep scatter / gather (particles_sweep.cu): 0 off, 1 on, > 1 = planes per sweep segment
+  int lean;        // lean per-particle arithmetic in the sweep kernels where it applies (BGPU_LEAN=0 turns it off)
   double sph_h;    // SPH scale length particle_kernel_h = h_rel * d (init_par.cc:379), masskernel 3
 };
 
@@ -168,6 +169,9 @@ void launch_mass(const double *power, double *mass_f, double *mass_r, int mass_t
 // create_GARFIELD colouring + Hermitian symmetrisation into the half array (random.cpp:102-507)
 void launch_colour_momenta(const double2 *white_full, const double *spec_full, double2 *half, int N, double amp,
                            cudaStream_t st);
+// the same on the rows [x][y0 + y_local][z <= N/2] of a slab-decomposed chain, sigma from the kinetic term's multiplier
+void launch_colour_momenta_rows(const double2 *white_full, const double *inv_half, double2 *half, int N, int Ns, int y0,
+                                double ncells, cudaStream_t st);
 // p += sqrt(mass_r) * gauss (HMC_momenta.cc:76-92)
 void launch_add_real_momenta(double *p, const double *mass_r, const double *gauss, size_t n, cudaStream_t st);
 

@@ -93,6 +93,52 @@ __device__ __forceinline__ void tsc_axis(double x, double xmin, double d, int N,
   w[0] = __dmul_rn(__dmul_rn(0.5, b), b);
 }
 
+// ---------------------------------------------------------------------------
+// lean variants for the sweep kernels (particles_sweep.cu, which explains them): same bits as pacman / cic_axis for
+// a coordinate within 3/4 of a box length of the box; anything else raises `slow` and the caller takes the general path
+// ---------------------------------------------------------------------------
+struct LeanConst {
+  double d, L, half, rd, Lmid, far;
+  unsigned N;
+};
+
+// pacman() for a coordinate in [-L, 2L): identical to its branch-free part; `slow` if the coordinate is not safely there
+__device__ __forceinline__ double lean_wrap(double x, const LeanConst &c, bool &slow) {
+  slow |= fabs(__dsub_rn(x, c.Lmid)) > c.far;
+  if (x < 0.) x = __dadd_rn(x, c.L);
+  if (x >= c.L) x = __dsub_rn(x, c.L);
+  return x;
+}
+
+// cic_axis() (particle_math.cuh) for x in [0, L): cells c0, c1 and weights w0 = 1 - dx, w1 = dx
+__device__ __forceinline__ void lean_axis(double x, const LeanConst &c, unsigned &c0, unsigned &c1, double &w0,
+                                          double &w1, bool &slow) {
+  double xpos = __dsub_rn(x, c.half);          // in [-d/2, L): pacman's in-range part
+  if (xpos < 0.) xpos = __dadd_rn(xpos, c.L);
+  if (xpos >= c.L) xpos = __dsub_rn(xpos, c.L);
+  const double q0 = __dmul_rn(xpos, c.rd);     // RN(xpos / d), see above
+  const double r = __fma_rn(-q0, c.d, xpos);
+  const double q = __fma_rn(r, c.rd, q0);
+  const double t = __dadd_rz(q, 4503599627370496.0);  // 2^52 + trunc(q): the cell index sits in the low word
+  c0 = (unsigned)__double2loint(t);
+  slow |= c0 >= c.N;                            // q rounded up to N: the reference wraps the cell and keeps q (dx = N)
+  w1 = __dsub_rn(q, __dsub_rn(t, 4503599627370496.0));
+  w0 = __dsub_rn(1.0, w1);
+  c1 = (c0 + 1u) & (c.N - 1u);
+}
+
+__device__ __forceinline__ LeanConst lean_const(const GridGeom &g) {
+  LeanConst lc;
+  lc.d = g.d;
+  lc.L = g.L;
+  lc.half = __dmul_rn(0.5, g.d);
+  lc.rd = __ddiv_rn(1.0, g.d);
+  lc.Lmid = 0.5 * g.L;
+  lc.far = 1.25 * g.L;
+  lc.N = (unsigned)g.N;
+  return lc;
+}
+
 __device__ __forceinline__ bool in_domain(const GridGeom &g, double x, double y, double z) {
   if (g.masskernel == 2)  // massFunctions.cc:195 (closed upper bound)
     return (x >= g.min1 && x <= g.min1 + g.L) && (y >= g.min2 && y <= g.min2 + g.L) &&

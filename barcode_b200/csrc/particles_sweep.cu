@@ -376,6 +376,296 @@ __global__ void __launch_bounds__(256) gather_cic_sweep_kernel(GridGeom g, doubl
   }
 }
 
+// ---------------------------------------------------------------------------
+// Lean CIC scatter: the same sweep with the per-particle arithmetic cut to what the common case needs.
+//
+// ncu's source page of the kernel above (profiles/ncu_source_r01_scatter_instruction_mix.txt) shows a scatter bound by
+// instruction issue, not by its reductions: seven pacman() calls with their range tests and inlined fmod loops, three
+// IEEE divisions, F2I / I2F conversions, validity predicates around every reduction, 64-bit index arithmetic.  Here
+//   * positions, cells and weights come from lean_axis(): branch-free wraps valid for a coordinate within 3/4 of a box
+//     length of the box, a correctly rounded quotient by Markstein's correction (q0 = x rd, r = fma(-q0, d, x),
+//     q = fma(r, rd, q0) with rd = RN(1/d): three FP64 instructions, same bits as the division), truncation by the
+//     2^52 trick.  Same operations in the same order as particle_math.cuh otherwise, so the same bits.  A coordinate
+//     outside that range, or a quotient that rounds up to N, raises `slow`: the whole warp then recomputes the particle
+//     with the general functions (never in practice: a displacement of 3/4 of the box);
+//   * the box starts at the origin (min = 0; the launcher checks), so every wrapped position is inside the domain and
+//     the validity predicates disappear;
+//   * one address comparison decides the z hand-over of both (x, y) rows of a plane (equal lower-row base addresses
+//     imply equal upper rows), and the decision travels to the lane below by ballot instead of a second shuffle;
+//   * row offsets by shifts (N is a power of two), 32-bit throughout.
+// ---------------------------------------------------------------------------
+// the general path for one particle (any displacement), out of line: eight plain reductions, nothing carried
+template <bool RSD>
+__device__ __noinline__ void lean_slow_deposit(GridGeom g, int i, double half, double qy, double qz, double px, double py,
+                                               double pz, double *__restrict__ rho) {
+  double x, y, z;
+  sweep_position<RSD>(g, i, half, qy, qz, px, py, pz, x, y, z);
+  if (!in_domain(g, x, y, z)) return;
+  int ci[2], cj[2], ck[2];
+  double wi[2], wj[2], wk[2];
+  cic_axis(x, g.d, g.L, g.N, ci[0], ci[1], wi[0], wi[1]);
+  cic_axis(y, g.d, g.L, g.N, cj[0], cj[1], wj[0], wj[1]);
+  cic_axis(z, g.d, g.L, g.N, ck[0], ck[1], wk[0], wk[1]);
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const double wab = __dmul_rn(wi[a], wj[b]);
+      double *row = rho + ((size_t)ci[a] * g.N + cj[b]) * g.N;
+      atomicAdd(row + ck[0], __dmul_rn(wab, wk[0]));
+      atomicAdd(row + ck[1], __dmul_rn(wab, wk[1]));
+    }
+}
+
+template <bool RSD>
+__global__ void __launch_bounds__(256, 2) scatter_cic_lean_kernel(GridGeom g, const double *__restrict__ psix,
+                                                                  const double *__restrict__ psiy,
+                                                                  const double *__restrict__ psiz,
+                                                                  double *__restrict__ rho, int seg) {
+  const int N = g.N;
+  const SweepIdx s = sweep_index(N, seg);
+  if (!s.live) return;  // whole warps only
+  const int lane = s.lane;
+  const int sh = 31 - __clz(N);
+  const size_t pl = (size_t)N * N;
+  const LeanConst lc = lean_const(g);
+  const double qy = __dadd_rn(__dmul_rn(g.d, (double)s.j), lc.half), qz = __dadd_rn(__dmul_rn(g.d, (double)s.k), lc.half);
+  const double rsd_a = g.cpecvel, rsd_b = g.v_norm;
+  size_t idx = s.idx;
+  // carried: the particle's upper x plane, 2 x 2 (y, z) cells, and the address of its (cj0, ck0) cell
+  double c00 = 0., c01 = 0., c10 = 0., c11 = 0.;
+  unsigned cbase = kNoAddr, cj1s_c = 0, ck1_c = 0;
+  double px = psix[idx], py = psiy[idx], pz = psiz[idx];
+  double fi = (double)s.i_begin;
+  const int i_end = s.i_begin + seg;
+  for (int i = s.i_begin; i < i_end; ++i, idx += pl, fi += 1.0) {
+    double nx = 0., ny = 0., nz = 0.;
+    if (i + 1 < i_end) {  // the next plane's displacement is in flight while this one is deposited
+      nx = psix[idx + pl];
+      ny = psiy[idx + pl];
+      nz = psiz[idx + pl];
+    }
+    unsigned ci0, ci1, cj0, cj1, ck0, ck1;
+    double wi0, wi1, wj0, wj1, wk0, wk1;
+    bool slow = false;
+    {
+      // disp_part.cc:55-126, rsd.cc:30-64 (particle_math.cuh particle_position / sweep_position)
+      const double x = lean_wrap(__dadd_rn(__dadd_rn(__dmul_rn(lc.d, fi), lc.half), px), lc, slow);
+      const double y = lean_wrap(__dadd_rn(qy, py), lc, slow);
+      double z = lean_wrap(__dadd_rn(qz, pz), lc, slow);
+      if constexpr (RSD) z = lean_wrap(__dadd_rn(z, __dmul_rn(__dmul_rn(rsd_a, pz), rsd_b)), lc, slow);
+      lean_axis(x, lc, ci0, ci1, wi0, wi1, slow);
+      lean_axis(y, lc, cj0, cj1, wj0, wj1, slow);
+      lean_axis(z, lc, ck0, ck1, wk0, wk1, slow);
+    }
+    if (__any_sync(FULL, slow)) {
+      // never in practice (a displacement of 3/4 of the box): the warp reduces what it carries, deposits this
+      // particle the general way and carries nothing into the next plane
+      const unsigned crow0 = cbase & ~(lc.N - 1u), ck0_c = cbase & (lc.N - 1u);
+      const unsigned crow1 = (crow0 & ~((lc.N << sh) - lc.N)) + cj1s_c;
+      const bool have = cbase != kNoAddr;
+      red_zpair(rho, cbase, crow0 + ck1_c, c00, c01, have, lane);
+      red_zpair(rho, crow1 + ck0_c, crow1 + ck1_c, c10, c11, have, lane);
+      lean_slow_deposit<RSD>(g, i, lc.half, qy, qz, px, py, pz, rho);
+      cbase = kNoAddr;
+      px = nx;
+      py = ny;
+      pz = nz;
+      continue;
+    }
+    const unsigned r0 = ci0 << (2 * sh), r1 = ci1 << (2 * sh), j0 = cj0 << sh, j1 = cj1 << sh;
+    const unsigned a_lo = r0 + j0 + ck0, a_hi = r0 + j0 + ck1;
+    // mass * w_x * w_y * w_z evaluated left to right, massFunctions.cc:129-157
+    const double w00 = __dmul_rn(wi0, wj0), w01 = __dmul_rn(wi0, wj1), w10 = __dmul_rn(wi1, wj0),
+                 w11 = __dmul_rn(wi1, wj1);
+    double v00 = __dmul_rn(w00, wk0), v01 = __dmul_rn(w00, wk1), v10 = __dmul_rn(w01, wk0),
+           v11 = __dmul_rn(w01, wk1);
+    // my lower x plane is the carried upper plane of the previous particle when the base cells agree
+    const bool match = a_lo == cbase;
+    if (match) {
+      v00 += c00;
+      v01 += c01;
+      v10 += c10;
+      v11 += c11;
+    }
+    const bool orphan = cbase != kNoAddr && !match;
+    if (__any_sync(FULL, orphan)) {  // carried values nobody continues: reduce them where they belong
+      const unsigned crow0 = cbase & ~(lc.N - 1u), ck0_c = cbase & (lc.N - 1u);
+      const unsigned crow1 = (crow0 & ~((lc.N << sh) - lc.N)) + cj1s_c;
+      red_zpair(rho, cbase, crow0 + ck1_c, c00, c01, orphan, lane);
+      red_zpair(rho, crow1 + ck0_c, crow1 + ck1_c, c10, c11, orphan, lane);
+    }
+    // z hand-over: the lane below hands me its upper z cells when they are my lower ones (both rows at once)
+    const unsigned p_ahi = __shfl_up_sync(FULL, a_hi, 1);
+    const double p_v01 = __shfl_up_sync(FULL, v01, 1), p_v11 = __shfl_up_sync(FULL, v11, 1);
+    const bool take = lane > 0 && p_ahi == a_lo;
+    const unsigned takers = __ballot_sync(FULL, take);
+    const bool handed_up = ((takers >> 1) >> lane) & 1u;  // lane + 1 takes mine
+    if (take) {
+      v00 += p_v01;
+      v10 += p_v11;
+    }
+    atomicAdd(rho + a_lo, v00);
+    atomicAdd(rho + (r0 + j1 + ck0), v10);
+    if (!handed_up) {
+      atomicAdd(rho + a_hi, v01);
+      atomicAdd(rho + (r0 + j1 + ck1), v11);
+    }
+    c00 = __dmul_rn(w10, wk0);
+    c01 = __dmul_rn(w10, wk1);
+    c10 = __dmul_rn(w11, wk0);
+    c11 = __dmul_rn(w11, wk1);
+    cbase = r1 + j0 + ck0;
+    cj1s_c = j1;
+    ck1_c = ck1;
+    px = nx;
+    py = ny;
+    pz = nz;
+  }
+  {
+    const unsigned crow0 = cbase & ~(lc.N - 1u), ck0_c = cbase & (lc.N - 1u);
+    const unsigned crow1 = (crow0 & ~((lc.N << sh) - lc.N)) + cj1s_c;
+    const bool have = cbase != kNoAddr;
+    red_zpair(rho, cbase, crow0 + ck1_c, c00, c01, have, lane);
+    red_zpair(rho, crow1 + ck0_c, crow1 + ck1_c, c10, c11, have, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Lean CIC gather (exact adjoint): the sweep of gather_cic_sweep_kernel with the lean per-particle arithmetic above
+// ---------------------------------------------------------------------------
+// the general path for one particle, out of line: eight loads, nothing carried
+template <bool RSD>
+__device__ __noinline__ void lean_slow_gather(GridGeom g, int i, double half, double qy, double qz, double px, double py,
+                                              double pz, const double *__restrict__ resid, double *vout) {
+  double x, y, z;
+  sweep_position<RSD>(g, i, half, qy, qz, px, py, pz, x, y, z);
+  double vx = 0., vy = 0., vz = 0.;
+  if (in_domain(g, x, y, z)) {
+    int ci[2], cj[2], ck[2];
+    double wi[2], wj[2], wk[2];
+    cic_axis(x, g.d, g.L, g.N, ci[0], ci[1], wi[0], wi[1]);
+    cic_axis(y, g.d, g.L, g.N, cj[0], cj[1], wj[0], wj[1]);
+    cic_axis(z, g.d, g.L, g.N, ck[0], ck[1], wk[0], wk[1]);
+    const double inv_d = 1.0 / g.d;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c) {
+          const double rc = __ldg(resid + ((size_t)ci[a] * g.N + cj[b]) * g.N + ck[c]);
+          const double gx = a ? inv_d : -inv_d, gy = b ? inv_d : -inv_d, gz = c ? inv_d : -inv_d;
+          vx += rc * gx * wj[b] * wk[c];
+          vy += rc * wi[a] * gy * wk[c];
+          vz += rc * wi[a] * wj[b] * gz;
+        }
+  }
+  vout[0] = vx;
+  vout[1] = vy;
+  vout[2] = vz;
+}
+
+template <bool RSD>
+__global__ void __launch_bounds__(256, 2) gather_cic_lean_kernel(GridGeom g, double *ax, double *ay, double *az,
+                                                                 const double *__restrict__ resid, int seg) {
+  const int N = g.N;
+  const SweepIdx s = sweep_index(N, seg);
+  if (!s.live) return;
+  const int lane = s.lane;
+  const int sh = 31 - __clz(N);
+  const size_t pl = (size_t)N * N;
+  const LeanConst lc = lean_const(g);
+  const double qy = __dadd_rn(__dmul_rn(g.d, (double)s.j), lc.half), qz = __dadd_rn(__dmul_rn(g.d, (double)s.k), lc.half);
+  const double rsd_a = g.cpecvel, rsd_b = g.v_norm;
+  const double inv_d = 1.0 / g.d;
+  size_t idx = s.idx;
+  // carried: residual at the particle's upper x plane
+  double c00 = 0., c01 = 0., c10 = 0., c11 = 0.;
+  unsigned cbase = kNoAddr;
+  double px = ax[idx], py = ay[idx], pz = az[idx];
+  double fi = (double)s.i_begin;
+  const int i_end = s.i_begin + seg;
+  for (int i = s.i_begin; i < i_end; ++i, idx += pl, fi += 1.0) {
+    double nx = 0., ny = 0., nz = 0.;
+    if (i + 1 < i_end) {
+      nx = ax[idx + pl];
+      ny = ay[idx + pl];
+      nz = az[idx + pl];
+    }
+    unsigned ci0, ci1, cj0, cj1, ck0, ck1;
+    double wi0, wi1, wj0, wj1, wk0, wk1;
+    bool slow = false;
+    {
+      const double x = lean_wrap(__dadd_rn(__dadd_rn(__dmul_rn(lc.d, fi), lc.half), px), lc, slow);
+      const double y = lean_wrap(__dadd_rn(qy, py), lc, slow);
+      double z = lean_wrap(__dadd_rn(qz, pz), lc, slow);
+      if constexpr (RSD) z = lean_wrap(__dadd_rn(z, __dmul_rn(__dmul_rn(rsd_a, pz), rsd_b)), lc, slow);
+      lean_axis(x, lc, ci0, ci1, wi0, wi1, slow);
+      lean_axis(y, lc, cj0, cj1, wj0, wj1, slow);
+      lean_axis(z, lc, ck0, ck1, wk0, wk1, slow);
+    }
+    if (__any_sync(FULL, slow)) {  // never in practice: the general functions, nothing carried
+      double v[3];
+      lean_slow_gather<RSD>(g, i, lc.half, qy, qz, px, py, pz, resid, v);
+      if constexpr (RSD) v[2] += g.fgrow * v[2];
+      ax[idx] = v[0];
+      ay[idx] = v[1];
+      az[idx] = v[2];
+      cbase = kNoAddr;
+      px = nx;
+      py = ny;
+      pz = nz;
+      continue;
+    }
+    const unsigned r0 = ci0 << (2 * sh), r1 = ci1 << (2 * sh), j0 = cj0 << sh, j1 = cj1 << sh;
+    // lower x plane: carried from the previous particle of the sweep, or loaded
+    double a00, a01, a10, a11;
+    if (r0 + j0 + ck0 == cbase) {
+      a00 = c00;
+      a01 = c01;
+      a10 = c10;
+      a11 = c11;
+    } else {
+      a00 = __ldg(resid + (r0 + j0 + ck0));
+      a01 = __ldg(resid + (r0 + j0 + ck1));
+      a10 = __ldg(resid + (r0 + j1 + ck0));
+      a11 = __ldg(resid + (r0 + j1 + ck1));
+    }
+    // upper x plane: the lower z cells are loaded, the upper ones are the lane above's lower cells where they are
+    const unsigned b_lo = r1 + j0 + ck0, b_hi = r1 + j0 + ck1;
+    const double b00 = __ldg(resid + b_lo), b10 = __ldg(resid + (r1 + j1 + ck0));
+    const unsigned n_lo = __shfl_down_sync(FULL, b_lo, 1);
+    double b01 = __shfl_down_sync(FULL, b00, 1), b11 = __shfl_down_sync(FULL, b10, 1);
+    if (!(lane < 31 && n_lo == b_hi)) {  // equal row bases imply the same second row (see the scatter)
+      b01 = __ldg(resid + b_hi);
+      b11 = __ldg(resid + (r1 + j1 + ck1));
+    }
+    // V = sum r dW/dx: the cells in the order of gather_adjoint_kernel (a, b, c)
+    double vx = 0., vy = 0., vz = 0.;
+    auto acc = [&](double rc, double gx, double wx, double gy, double wy, double gz, double wz) {
+      vx += rc * gx * wy * wz;
+      vy += rc * wx * gy * wz;
+      vz += rc * wx * wy * gz;
+    };
+    acc(a00, -inv_d, wi0, -inv_d, wj0, -inv_d, wk0);
+    acc(a01, -inv_d, wi0, -inv_d, wj0, inv_d, wk1);
+    acc(a10, -inv_d, wi0, inv_d, wj1, -inv_d, wk0);
+    acc(a11, -inv_d, wi0, inv_d, wj1, inv_d, wk1);
+    acc(b00, inv_d, wi1, -inv_d, wj0, -inv_d, wk0);
+    acc(b01, inv_d, wi1, -inv_d, wj0, inv_d, wk1);
+    acc(b10, inv_d, wi1, inv_d, wj1, -inv_d, wk0);
+    acc(b11, inv_d, wi1, inv_d, wj1, inv_d, wk1);
+    if constexpr (RSD) vz += g.fgrow * vz;  // d z_s / d Psi_z = 1 + f (cf. HMC_models.cc:295-301)
+    ax[idx] = vx;
+    ay[idx] = vy;
+    az[idx] = vz;
+    c00 = b00;
+    c01 = b01;
+    c10 = b10;
+    c11 = b11;
+    cbase = b_lo;
+    px = nx;
+    py = ny;
+    pz = nz;
+  }
+}
+
 int sweep_seg(const GridGeom &g) {
   const int N = g.N;
   // short segments keep enough threads in flight (N^2 * N/seg of them); each one ends with a flush of the carried plane
@@ -407,7 +697,10 @@ void launch_scatter_sweep(const GridGeom &g, const double *psix, const double *p
   const int seg = sweep_seg(g);
   BGPU_CUDA(cudaMemsetAsync(rho, 0, (size_t)g.N * g.N * g.N * sizeof(double), st));
   const unsigned blocks = sweep_blocks(g.N, seg);
-  if (g.masskernel == 1) {
+  if (g.masskernel == 1 && g.lean && g.min1 == 0. && g.min2 == 0. && g.min3 == 0.) {
+    if (g.rsd) scatter_cic_lean_kernel<true><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
+    else scatter_cic_lean_kernel<false><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
+  } else if (g.masskernel == 1) {
     if (g.rsd) scatter_cic_sweep_kernel<true><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
     else scatter_cic_sweep_kernel<false><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
   } else {
@@ -423,7 +716,10 @@ void launch_gather_sweep(const GridGeom &g, double *ax, double *ay, double *az, 
   ProfScope prof(KK_GATHER, st);
   const int seg = sweep_seg(g);
   const unsigned blocks = sweep_blocks(g.N, seg);
-  if (g.rsd) gather_cic_sweep_kernel<true><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
+  if (g.lean && g.min1 == 0. && g.min2 == 0. && g.min3 == 0.) {
+    if (g.rsd) gather_cic_lean_kernel<true><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
+    else gather_cic_lean_kernel<false><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
+  } else if (g.rsd) gather_cic_sweep_kernel<true><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
   else gather_cic_sweep_kernel<false><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
   BGPU_LAUNCHED(1);
 }

@@ -89,11 +89,11 @@ void bgpu_destroy(bgpu_handle *h);
  * rank 0 calls bgpu_nccl_unique_id and the host program hands the 128 bytes to the other ranks
  * (MPI_Bcast, a file, torch.distributed ...).  The distributed FFT transposes with NCCL
  * all-to-all, the mass-assignment halo goes to the two x neighbours, scalars are all-reduced; every
- * rank must make the same sequence of calls.  Supported: N1 in {128, 256, 512, 1024}; NGP / CIC / TSC;
- * Zel'dovich and 2LPT/ALPT forward models, RSD; all four likelihoods; calc_h 0, 1 and BGPU_CALC_H_EXACT
- * (Zel'dovich); mass types 0 - 4; bgpu_measure_spectrum; bgpu_draw_momenta_device.
- * Not on slabs yet: the SPH kernel (calc_h 2 / 3), the exact adjoint of the 2LPT/ALPT model, and the host-stream
- * momentum draw (bgpu_color_momenta). */
+ * rank must make the same sequence of calls.  Supported: N1 in {128, 256, 512, 1024}; NGP / CIC / TSC / SPH;
+ * Zel'dovich and 2LPT/ALPT forward models, RSD; all four likelihoods; calc_h 0, 1, 2 (SPH adjoint) and
+ * BGPU_CALC_H_EXACT (Zel'dovich); mass types 0 - 4; bgpu_measure_spectrum; bgpu_draw_momenta_device;
+ * bgpu_color_momenta (every rank passes the FULL white-noise grid, real_gauss and momenta are slabs).
+ * Not on slabs: calc_h 3 and the exact adjoint of the 2LPT/ALPT model. */
 int bgpu_nccl_unique_id(void *out128);
 int bgpu_slab_create(const bgpu_params *p, int rank, int nranks, const void *nccl_id128, bgpu_handle **out);
 int bgpu_slab_info(const bgpu_handle *h, int *rank, int *nranks, int *x0, int *nx_local);

@@ -333,6 +333,30 @@ def test_gradient_128_matches_oracle(calc_h, masskernel, rsd, sfmodel):
     assert rel_l2(dX, dXo) < TOL
 
 
+@pytest.mark.parametrize("rsd,amp", [(True, 1.0), (False, 1.0), (True, 40.0), (False, 4000.0)])
+def test_particle_kernel_generations_agree(rsd, amp, monkeypatch):
+    """The three generations of the CIC scatter / gather -- particle per thread (kernels.cu), x sweep, lean x sweep
+    (particles_sweep.cu) -- deposit the same products into the same cells: density and exact-adjoint gradient agree to
+    summation order.  amp = 40 wraps particles around the box; amp = 4000 throws them several box lengths away, which
+    is the lean kernels' out-of-line general path (coordinates beyond 3/4 of a box length from the box)."""
+    from barcode_b200.chain import Chain, Params
+    N, L, P, nobs, noise, window, s = _problem_128()
+    s = amp * s
+    out = {}
+    for tag, env in (("lean", {}), ("sweep", {"BGPU_LEAN": "0"}), ("thread", {"BGPU_SWEEP": "0"})):
+        for k in ("BGPU_LEAN", "BGPU_SWEEP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Chain(Params(N1=N, L1=L, masskernel=1, likelihood=1, rsd_model=rsd, calc_h=4, mass_type=1)) as ch:
+            ch.set_static(Power=P, nobs=nobs, noise=noise, window=window)
+            out[tag] = (ch.forward(s), ch.gradient_psi(s))
+    for tag in ("sweep", "thread"):
+        assert rel_l2(out["lean"][0], out[tag][0]) < 1e-13, tag
+        assert rel_l2(out["lean"][1], out[tag][1]) < 1e-12, tag
+    assert abs(out["lean"][0].sum()) < 1e-6 * N ** 3   # delta_x sums to zero: every particle was deposited
+
+
 @pytest.mark.parametrize("N", [128, 256])
 def test_tma_pass_matches_cp_async_pass(N, monkeypatch):
     """Two independent implementations of the strided pass (TMA ring vs cp.async) agree to rounding."""
