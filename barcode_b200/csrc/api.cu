@@ -412,8 +412,10 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   forward_from_shat(h, d_s, p.deltaQ_factor, p.rsd_model != 0, nullptr, nullptr, nullptr);
   LikeParams lp = h->like;
   lp.exact_sign = (p.calc_h == BGPU_CALC_H_EXACT) ? 1 : 0;
+  // a gradient evaluation uses the residual only (-lnL belongs to psi()); delta_x itself is read again by
+  // likelihood_calc_h alone (HMC_models_testing.cpp:25-50: gradfft / gradfindif of delta_x)
   launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->nobs, h->noise, h->window, h->resid, h->n,
-                           h->ncells, h->partials, h->dscal + S_NLL, h->stream);
+                           h->ncells, h->partials, nullptr, h->stream, /*keep_delta=*/p.calc_h == 0);
 
   // norm = -1 * deltaQ_factor * (D1 if correct_delta)   (HMC_models.cc:460-469)
   double norm = -1.0;
@@ -1088,7 +1090,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     const char *sw = std::getenv("BGPU_SWEEP");  // 0 = first-generation particle-per-thread kernels; n > 1 = segment length
     g.sweep = sw ? std::atoi(sw) : 1;
     const char *ln = std::getenv("BGPU_LEAN");
-    g.lean = !(ln && ln[0] == '0');
+    g.lean = ln ? std::atoi(ln) : 1;   // > 1: occupancy / read-ahead variants (particles_sweep.cu)
   }
   if (p->masskernel == 3) {
     // SPH_kernel_3D_cells + _hull_1 (SPH_kernel.cpp:62-139)

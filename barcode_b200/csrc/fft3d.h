@@ -52,8 +52,8 @@ struct Fft3d {
   bool use_pdl = true;     // (BGPU_PDL=0 turns it off) programmatic dependent launch of the TMA-staged passes
   bool z_round = true;     // (BGPU_ZROUND=0 turns it off) calc_h = 0: the c2r / r2c z passes around r * d_c(delta) fused
   bool share_x = true;     // (BGPU_SHARE_X=0 turns it off) the y and z components of a K_DISP / K_GRAD / K_INVLAP triple share one x pass
-  // BGPU_PINGPONG=1 (single GPU): consecutive passes walk their tiles in alternating directions, so a pass starts on
-  // the end of the array the previous pass wrote last (still in the 126 MB L2 at 256^3)
+  // (BGPU_PINGPONG=0 turns it off; single GPU, N <= 256) consecutive passes walk their tiles in alternating directions,
+  // so a pass starts on the end of the array the previous pass wrote last (still in the 126 MB L2 at 256^3)
   bool pingpong = false;
   mutable int rev_state = 0;
   int next_rev() const {

@@ -366,7 +366,8 @@ __device__ __forceinline__ double pow_bias(double x, double e) {
   else return pow(x, e);
 }
 
-template <bool UNIT>
+// VALUE = false: the residual only (gradient evaluations do not use -lnL; its divisions and logs are compiled out)
+template <bool UNIT, bool VALUE = true>
 struct ResidualEval {
   LikeParams lp;
   double nmean;
@@ -381,8 +382,10 @@ struct ResidualEval {
       const double Lambda = __dmul_rn(__dmul_rn(w, lp.rho_c), pow_bias<UNIT>(base, lp.biasE));
       if (w > 0. && Lambda > 0.0) {
         r = __ddiv_rn(__dsub_rn(n, Lambda), __dmul_rn(sg, sg));
-        const double q = __ddiv_rn(__dsub_rn(Lambda, n), sg);
-        val = __dmul_rn(0.5, __dmul_rn(q, q));
+        if constexpr (VALUE) {
+          const double q = __ddiv_rn(__dsub_rn(Lambda, n), sg);
+          val = __dmul_rn(0.5, __dmul_rn(q, q));
+        }
       }
     } else if (lp.likelihood == 2) {
       // log-normal (lognormal_independent.cpp:41-55, 57-62, 112-122): the residual takes the log of the
@@ -395,8 +398,10 @@ struct ResidualEval {
         r = __ddiv_rn(__dsub_rn(n, Lr), __dmul_rn(sg, sg));
         if (lp.exact_sign)  // exact adjoint: -d(-lnL)/d delta of the clamped value, chain factor 1/(1 + delta) included
           r = delta < lp.delta_min ? 0.0 : __ddiv_rn(__ddiv_rn(__dsub_rn(n, Lv), __dmul_rn(sg, sg)), __dadd_rn(1.0, delta));
-        const double q = __dsub_rn(Lv, n);
-        val = __ddiv_rn(__dmul_rn(__dmul_rn(0.5, q), q), __dmul_rn(sg, sg));
+        if constexpr (VALUE) {
+          const double q = __dsub_rn(Lv, n);
+          val = __ddiv_rn(__dmul_rn(__dmul_rn(0.5, q), q), __dmul_rn(sg, sg));
+        }
       }
     } else {
       const double dens = __dadd_rn(1.0, __dmul_rn(lp.biasP, delta));
@@ -405,20 +410,24 @@ struct ResidualEval {
         r = (1 - n / Lambda) * lp.rho_c * lp.biasE * lp.biasP * (UNIT ? 1.0 : pow_bias<false>(dens, lp.biasE - 1));
         if (lp.exact_sign) r = -r;
       }
-      if (w > 0. && Lambda > 0.0) val = __dsub_rn(Lambda, __dmul_rn(n, log(Lambda)));
+      if constexpr (VALUE) {
+        if (w > 0. && Lambda > 0.0) val = __dsub_rn(Lambda, __dmul_rn(n, log(Lambda)));
+      }
     }
     return val;
   }
 };
 
-// two elements per thread per trip (16-byte loads), two trips in flight
-template <bool UNIT>
+// two elements per thread per trip (16-byte loads), two trips in flight.  VALUE = false (gradient evaluations):
+// no -lnL partial sums; `keep_delta` = false additionally leaves the density array alone (only calc_h = 0 reads
+// delta_x again after the residual), one array less to write.
+template <bool UNIT, bool VALUE>
 __global__ void __launch_bounds__(kReduceThreads, 4)
     overdens_residual_kernel(LikeParams lp, double2 *__restrict__ rho_delta, const double *__restrict__ sum_rho,
                              const double2 *__restrict__ nobs, const double2 *__restrict__ noise,
                              const double2 *__restrict__ window, double2 *__restrict__ resid, size_t n2, double count,
-                             double *__restrict__ part) {
-  ResidualEval<UNIT> ev{lp, __ddiv_rn(*sum_rho, count)};
+                             double *__restrict__ part, int keep_delta) {
+  ResidualEval<UNIT, VALUE> ev{lp, __ddiv_rn(*sum_rho, count)};
   double acc = 0.0;
   const size_t stride = (size_t)gridDim.x * kReduceThreads;
   size_t i = (size_t)blockIdx.x * kReduceThreads + threadIdx.x;
@@ -433,8 +442,10 @@ __global__ void __launch_bounds__(kReduceThreads, 4)
     acc += ev(ra.y, na.y, sa.y, wa.y, da.y, qa.y);
     acc += ev(rb.x, nb.x, sb.x, wb.x, db.x, qb.x);
     acc += ev(rb.y, nb.y, sb.y, wb.y, db.y, qb.y);
-    rho_delta[i] = da;
-    rho_delta[j] = db;
+    if (keep_delta) {
+      rho_delta[i] = da;
+      rho_delta[j] = db;
+    }
     if (resid) {
       resid[i] = qa;
       resid[j] = qb;
@@ -445,28 +456,32 @@ __global__ void __launch_bounds__(kReduceThreads, 4)
     double2 da, qa;
     acc += ev(ra.x, na.x, sa.x, wa.x, da.x, qa.x);
     acc += ev(ra.y, na.y, sa.y, wa.y, da.y, qa.y);
-    rho_delta[i] = da;
+    if (keep_delta) rho_delta[i] = da;
     if (resid) resid[i] = qa;
   }
-  const double r = block_sum(acc);
-  if (threadIdx.x == 0) part[blockIdx.x] = r;
+  if constexpr (VALUE) {
+    const double r = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = r;
+  }
 }
 
 void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const double *sum_rho, const double *nobs,
                               const double *noise, const double *window, double *resid, size_t n,
-                              double ncells_global, double *scratch, double *nll, cudaStream_t st) {
+                              double ncells_global, double *scratch, double *nll, cudaStream_t st, bool keep_delta) {
   ProfScope prof(KK_RESIDUAL, st);
   const size_t n2 = n / 2;  // n = N^3 with N a power of two >= 8
   const int blocks = (int)((n2 + kReduceThreads - 1) / kReduceThreads < (size_t)kReduceBlocks
                                ? (n2 + kReduceThreads - 1) / kReduceThreads
                                : (size_t)kReduceBlocks);
-  auto kern = lp.biasE == 1.0 ? overdens_residual_kernel<true> : overdens_residual_kernel<false>;
+  const bool unit = lp.biasE == 1.0;
+  auto kern = nll ? (unit ? overdens_residual_kernel<true, true> : overdens_residual_kernel<false, true>)
+                  : (unit ? overdens_residual_kernel<true, false> : overdens_residual_kernel<false, false>);
   kern<<<blocks, kReduceThreads, 0, st>>>(
       lp, reinterpret_cast<double2 *>(rho_delta), sum_rho, reinterpret_cast<const double2 *>(nobs),
       reinterpret_cast<const double2 *>(noise), reinterpret_cast<const double2 *>(window),
-      reinterpret_cast<double2 *>(resid), n2, ncells_global, scratch);
-  final_sum_kernel<<<1, kReduceThreads, 0, st>>>(scratch, blocks, nll);
-  BGPU_LAUNCHED(2);
+      reinterpret_cast<double2 *>(resid), n2, ncells_global, scratch, keep_delta ? 1 : 0);
+  if (nll) final_sum_kernel<<<1, kReduceThreads, 0, st>>>(scratch, blocks, nll);
+  BGPU_LAUNCHED(nll ? 2 : 1);
 }
 
 __global__ void lognormal_f_kernel(const double *__restrict__ delta, double *__restrict__ out, size_t n, double rho_c,

@@ -127,10 +127,11 @@ void launch_kinetic(const double *p, const double *conv, const double *mass_r, s
                     double *out, cudaStream_t st);
 
 // delta = rho / mean - 1 (in place), residual r, and -lnL partial sum -> *nll (device scalar).
-// mean is read from the device scalar `sum_rho` (/N).  resid may be null (value only).
+// mean is read from the device scalar `sum_rho` (/N).  resid may be null (value only); nll may be null (residual
+// only: a gradient evaluation), and then keep_delta = false leaves rho_delta untouched as well.
 void launch_overdens_residual(const LikeParams &lp, double *rho_delta, const double *sum_rho, const double *nobs,
                               const double *noise, const double *window, double *resid, size_t n, double ncells_global,
-                              double *scratch, double *nll, cudaStream_t st);
+                              double *scratch, double *nll, cudaStream_t st, bool keep_delta = true);
 
 // x-sweep variants (particles_sweep.cu): full cube, Lagrangian lattice without cell-boundary averaging, N >= 32.
 // launch_scatter / launch_gather_adjoint dispatch to them where they apply (BGPU_SWEEP=0 keeps the first-generation kernels).

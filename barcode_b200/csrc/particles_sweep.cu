@@ -415,8 +415,10 @@ __device__ __noinline__ void lean_slow_deposit(GridGeom g, int i, double half, d
     }
 }
 
-template <bool RSD>
-__global__ void __launch_bounds__(256, 2) scatter_cic_lean_kernel(GridGeom g, const double *__restrict__ psix,
+// MINB: resident CTAs per SM the register allocation is bounded for; PF: planes of displacement in flight ahead of
+// the one being deposited (the sweep is a dependent chain per thread: what keeps HBM busy is loads in flight)
+template <bool RSD, int MINB, int PF>
+__global__ void __launch_bounds__(256, MINB) scatter_cic_lean_kernel(GridGeom g, const double *__restrict__ psix,
                                                                   const double *__restrict__ psiy,
                                                                   const double *__restrict__ psiz,
                                                                   double *__restrict__ rho, int seg) {
@@ -433,16 +435,33 @@ __global__ void __launch_bounds__(256, 2) scatter_cic_lean_kernel(GridGeom g, co
   // carried: the particle's upper x plane, 2 x 2 (y, z) cells, and the address of its (cj0, ck0) cell
   double c00 = 0., c01 = 0., c10 = 0., c11 = 0.;
   unsigned cbase = kNoAddr, cj1s_c = 0, ck1_c = 0;
-  double px = psix[idx], py = psiy[idx], pz = psiz[idx];
-  double fi = (double)s.i_begin;
   const int i_end = s.i_begin + seg;
+  double fx[PF], fy[PF], fz[PF];  // displacements of planes i .. i + PF - 1
+#pragma unroll
+  for (int f = 0; f < PF; ++f) {
+    const bool in = s.i_begin + f < i_end;
+    fx[f] = in ? psix[idx + (size_t)f * pl] : 0.;
+    fy[f] = in ? psiy[idx + (size_t)f * pl] : 0.;
+    fz[f] = in ? psiz[idx + (size_t)f * pl] : 0.;
+  }
+  double fi = (double)s.i_begin;
   for (int i = s.i_begin; i < i_end; ++i, idx += pl, fi += 1.0) {
+    const double px = fx[0], py = fy[0], pz = fz[0];
     double nx = 0., ny = 0., nz = 0.;
-    if (i + 1 < i_end) {  // the next plane's displacement is in flight while this one is deposited
-      nx = psix[idx + pl];
-      ny = psiy[idx + pl];
-      nz = psiz[idx + pl];
+    if (i + PF < i_end) {  // the displacement PF planes ahead goes in flight while this one is deposited
+      nx = psix[idx + (size_t)PF * pl];
+      ny = psiy[idx + (size_t)PF * pl];
+      nz = psiz[idx + (size_t)PF * pl];
     }
+#pragma unroll
+    for (int f = 0; f + 1 < PF; ++f) {
+      fx[f] = fx[f + 1];
+      fy[f] = fy[f + 1];
+      fz[f] = fz[f + 1];
+    }
+    fx[PF - 1] = nx;
+    fy[PF - 1] = ny;
+    fz[PF - 1] = nz;
     unsigned ci0, ci1, cj0, cj1, ck0, ck1;
     double wi0, wi1, wj0, wj1, wk0, wk1;
     bool slow = false;
@@ -466,9 +485,6 @@ __global__ void __launch_bounds__(256, 2) scatter_cic_lean_kernel(GridGeom g, co
       red_zpair(rho, crow1 + ck0_c, crow1 + ck1_c, c10, c11, have, lane);
       lean_slow_deposit<RSD>(g, i, lc.half, qy, qz, px, py, pz, rho);
       cbase = kNoAddr;
-      px = nx;
-      py = ny;
-      pz = nz;
       continue;
     }
     const unsigned r0 = ci0 << (2 * sh), r1 = ci1 << (2 * sh), j0 = cj0 << sh, j1 = cj1 << sh;
@@ -516,9 +532,6 @@ __global__ void __launch_bounds__(256, 2) scatter_cic_lean_kernel(GridGeom g, co
     cbase = r1 + j0 + ck0;
     cj1s_c = j1;
     ck1_c = ck1;
-    px = nx;
-    py = ny;
-    pz = nz;
   }
   {
     const unsigned crow0 = cbase & ~(lc.N - 1u), ck0_c = cbase & (lc.N - 1u);
@@ -561,8 +574,8 @@ __device__ __noinline__ void lean_slow_gather(GridGeom g, int i, double half, do
   vout[2] = vz;
 }
 
-template <bool RSD>
-__global__ void __launch_bounds__(256, 2) gather_cic_lean_kernel(GridGeom g, double *ax, double *ay, double *az,
+template <bool RSD, int MINB, int PF>
+__global__ void __launch_bounds__(256, MINB) gather_cic_lean_kernel(GridGeom g, double *ax, double *ay, double *az,
                                                                  const double *__restrict__ resid, int seg) {
   const int N = g.N;
   const SweepIdx s = sweep_index(N, seg);
@@ -578,16 +591,33 @@ __global__ void __launch_bounds__(256, 2) gather_cic_lean_kernel(GridGeom g, dou
   // carried: residual at the particle's upper x plane
   double c00 = 0., c01 = 0., c10 = 0., c11 = 0.;
   unsigned cbase = kNoAddr;
-  double px = ax[idx], py = ay[idx], pz = az[idx];
-  double fi = (double)s.i_begin;
   const int i_end = s.i_begin + seg;
+  double fx[PF], fy[PF], fz[PF];  // displacements of planes i .. i + PF - 1 (read ahead of the in-place stores)
+#pragma unroll
+  for (int f = 0; f < PF; ++f) {
+    const bool in = s.i_begin + f < i_end;
+    fx[f] = in ? ax[idx + (size_t)f * pl] : 0.;
+    fy[f] = in ? ay[idx + (size_t)f * pl] : 0.;
+    fz[f] = in ? az[idx + (size_t)f * pl] : 0.;
+  }
+  double fi = (double)s.i_begin;
   for (int i = s.i_begin; i < i_end; ++i, idx += pl, fi += 1.0) {
+    const double px = fx[0], py = fy[0], pz = fz[0];
     double nx = 0., ny = 0., nz = 0.;
-    if (i + 1 < i_end) {
-      nx = ax[idx + pl];
-      ny = ay[idx + pl];
-      nz = az[idx + pl];
+    if (i + PF < i_end) {
+      nx = ax[idx + (size_t)PF * pl];
+      ny = ay[idx + (size_t)PF * pl];
+      nz = az[idx + (size_t)PF * pl];
     }
+#pragma unroll
+    for (int f = 0; f + 1 < PF; ++f) {
+      fx[f] = fx[f + 1];
+      fy[f] = fy[f + 1];
+      fz[f] = fz[f + 1];
+    }
+    fx[PF - 1] = nx;
+    fy[PF - 1] = ny;
+    fz[PF - 1] = nz;
     unsigned ci0, ci1, cj0, cj1, ck0, ck1;
     double wi0, wi1, wj0, wj1, wk0, wk1;
     bool slow = false;
@@ -608,9 +638,6 @@ __global__ void __launch_bounds__(256, 2) gather_cic_lean_kernel(GridGeom g, dou
       ay[idx] = v[1];
       az[idx] = v[2];
       cbase = kNoAddr;
-      px = nx;
-      py = ny;
-      pz = nz;
       continue;
     }
     const unsigned r0 = ci0 << (2 * sh), r1 = ci1 << (2 * sh), j0 = cj0 << sh, j1 = cj1 << sh;
@@ -660,9 +687,6 @@ __global__ void __launch_bounds__(256, 2) gather_cic_lean_kernel(GridGeom g, dou
     c10 = b10;
     c11 = b11;
     cbase = b_lo;
-    px = nx;
-    py = ny;
-    pz = nz;
   }
 }
 
@@ -698,8 +722,20 @@ void launch_scatter_sweep(const GridGeom &g, const double *psix, const double *p
   BGPU_CUDA(cudaMemsetAsync(rho, 0, (size_t)g.N * g.N * g.N * sizeof(double), st));
   const unsigned blocks = sweep_blocks(g.N, seg);
   if (g.masskernel == 1 && g.lean && g.min1 == 0. && g.min2 == 0. && g.min3 == 0.) {
-    if (g.rsd) scatter_cic_lean_kernel<true><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
-    else scatter_cic_lean_kernel<false><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
+    // BGPU_LEAN = 1 (default) / 22 / 32 / 33 / 43: resident CTAs per SM x planes in flight
+#define BGPU_LEAN_SCATTER(MINB, PF)                                                                       \
+  do {                                                                                                    \
+    if (g.rsd) scatter_cic_lean_kernel<true, MINB, PF><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg); \
+    else scatter_cic_lean_kernel<false, MINB, PF><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);      \
+  } while (0)
+    switch (g.lean) {
+      case 22: BGPU_LEAN_SCATTER(2, 2); break;
+      case 32: BGPU_LEAN_SCATTER(3, 2); break;
+      case 33: BGPU_LEAN_SCATTER(3, 3); break;
+      case 43: BGPU_LEAN_SCATTER(4, 3); break;
+      default: BGPU_LEAN_SCATTER(2, 1); break;
+    }
+#undef BGPU_LEAN_SCATTER
   } else if (g.masskernel == 1) {
     if (g.rsd) scatter_cic_sweep_kernel<true><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
     else scatter_cic_sweep_kernel<false><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
@@ -717,8 +753,19 @@ void launch_gather_sweep(const GridGeom &g, double *ax, double *ay, double *az, 
   const int seg = sweep_seg(g);
   const unsigned blocks = sweep_blocks(g.N, seg);
   if (g.lean && g.min1 == 0. && g.min2 == 0. && g.min3 == 0.) {
-    if (g.rsd) gather_cic_lean_kernel<true><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
-    else gather_cic_lean_kernel<false><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
+#define BGPU_LEAN_GATHER(MINB, PF)                                                                    \
+  do {                                                                                                \
+    if (g.rsd) gather_cic_lean_kernel<true, MINB, PF><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg); \
+    else gather_cic_lean_kernel<false, MINB, PF><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);      \
+  } while (0)
+    switch (g.lean) {
+      case 22: BGPU_LEAN_GATHER(2, 2); break;
+      case 32: BGPU_LEAN_GATHER(3, 2); break;
+      case 33: BGPU_LEAN_GATHER(3, 3); break;
+      case 43: BGPU_LEAN_GATHER(4, 3); break;
+      default: BGPU_LEAN_GATHER(2, 1); break;
+    }
+#undef BGPU_LEAN_GATHER
   } else if (g.rsd) gather_cic_sweep_kernel<true><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
   else gather_cic_sweep_kernel<false><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
   BGPU_LAUNCHED(1);

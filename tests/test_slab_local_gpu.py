@@ -102,9 +102,10 @@ def test_local_slab_chain_matches_single_gpu_chain(world, p2p, generic, sfmodel,
             ref["gradient"] = ch.gradient_psi(s)
         for k, want in ref.items():
             assert rel_l2(got[k], want) < 1e-11, (k, calc_h)
-        if calc_h == 0 and generic == "0":
+        if calc_h == 0 and generic == "0" and mass_type == 1:
             # the device draw does not depend on the decomposition at all (same stream, same colouring arithmetic, and
-            # -- on the TMA-staged passes both chains run -- the same transform arithmetic)
+            # -- on the TMA-staged passes both chains run -- the same transform arithmetic); with a mass that is itself
+            # all-reduced (types 2 / 3: the binned likelihood-force spectrum) the agreement is to rounding, checked above
             assert np.array_equal(got["device_draw"].ravel(), ref["device_draw"].ravel())
 
 
