@@ -1090,7 +1090,7 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     const char *sw = std::getenv("BGPU_SWEEP");  // 0 = first-generation particle-per-thread kernels; n > 1 = segment length
     g.sweep = sw ? std::atoi(sw) : 1;
     const char *ln = std::getenv("BGPU_LEAN");
-    g.lean = ln ? std::atoi(ln) : 1;   // > 1: occupancy / read-ahead variants (particles_sweep.cu)
+    g.lean = ln ? std::atoi(ln) : 1;   // 21: the gather with 2 CTAs per SM and no read-ahead (particles_sweep.cu)
   }
   if (p->masskernel == 3) {
     // SPH_kernel_3D_cells + _hull_1 (SPH_kernel.cpp:62-139)

@@ -722,20 +722,11 @@ void launch_scatter_sweep(const GridGeom &g, const double *psix, const double *p
   BGPU_CUDA(cudaMemsetAsync(rho, 0, (size_t)g.N * g.N * g.N * sizeof(double), st));
   const unsigned blocks = sweep_blocks(g.N, seg);
   if (g.masskernel == 1 && g.lean && g.min1 == 0. && g.min2 == 0. && g.min3 == 0.) {
-    // BGPU_LEAN = 1 (default) / 22 / 32 / 33 / 43: resident CTAs per SM x planes in flight
-#define BGPU_LEAN_SCATTER(MINB, PF)                                                                       \
-  do {                                                                                                    \
-    if (g.rsd) scatter_cic_lean_kernel<true, MINB, PF><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg); \
-    else scatter_cic_lean_kernel<false, MINB, PF><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);      \
-  } while (0)
-    switch (g.lean) {
-      case 22: BGPU_LEAN_SCATTER(2, 2); break;
-      case 32: BGPU_LEAN_SCATTER(3, 2); break;
-      case 33: BGPU_LEAN_SCATTER(3, 3); break;
-      case 43: BGPU_LEAN_SCATTER(4, 3); break;
-      default: BGPU_LEAN_SCATTER(2, 1); break;
-    }
-#undef BGPU_LEAN_SCATTER
+    // measured (B200, 256^3, round 2): more resident CTAs (3 per SM) or deeper read-ahead (2-3 planes) leave the
+    // scatter where it is or slow it down (0.341 -> 0.344 / 0.361 / 0.414 / 0.545 ms for (2,2) / (3,2) / (3,3) / (4,3)):
+    // it is bound by the L2 reduction units, not by loads in flight
+    if (g.rsd) scatter_cic_lean_kernel<true, 2, 1><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
+    else scatter_cic_lean_kernel<false, 2, 1><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
   } else if (g.masskernel == 1) {
     if (g.rsd) scatter_cic_sweep_kernel<true><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
     else scatter_cic_sweep_kernel<false><<<blocks, 256, 0, st>>>(g, psix, psiy, psiz, rho, seg);
@@ -753,19 +744,13 @@ void launch_gather_sweep(const GridGeom &g, double *ax, double *ay, double *az, 
   const int seg = sweep_seg(g);
   const unsigned blocks = sweep_blocks(g.N, seg);
   if (g.lean && g.min1 == 0. && g.min2 == 0. && g.min3 == 0.) {
-#define BGPU_LEAN_GATHER(MINB, PF)                                                                    \
-  do {                                                                                                \
-    if (g.rsd) gather_cic_lean_kernel<true, MINB, PF><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg); \
-    else gather_cic_lean_kernel<false, MINB, PF><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);      \
-  } while (0)
-    switch (g.lean) {
-      case 22: BGPU_LEAN_GATHER(2, 2); break;
-      case 32: BGPU_LEAN_GATHER(3, 2); break;
-      case 33: BGPU_LEAN_GATHER(3, 3); break;
-      case 43: BGPU_LEAN_GATHER(4, 3); break;
-      default: BGPU_LEAN_GATHER(2, 1); break;
-    }
-#undef BGPU_LEAN_GATHER
+    // measured (B200, 256^3, round 2): 3 resident CTAs per SM with the displacement read 2 planes ahead:
+    // 0.287 -> 0.252 ms ((2,2): 0.287, (3,3): 0.281, (4,3): 0.373 -- spills); BGPU_LEAN=21 keeps the (2,1) form
+    if (g.lean == 21) {
+      if (g.rsd) gather_cic_lean_kernel<true, 2, 1><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
+      else gather_cic_lean_kernel<false, 2, 1><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
+    } else if (g.rsd) gather_cic_lean_kernel<true, 3, 2><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
+    else gather_cic_lean_kernel<false, 3, 2><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
   } else if (g.rsd) gather_cic_sweep_kernel<true><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
   else gather_cic_sweep_kernel<false><<<blocks, 256, 0, st>>>(g, ax, ay, az, resid, seg);
   BGPU_LAUNCHED(1);
