@@ -40,6 +40,7 @@ class BgpuParams(C.Structure):
 # every symbol include/barcode_gpu.h declares: (restype, argtypes)
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
 _h = C.c_void_p
 SIGNATURES = {
     "bgpu_default_params": (None, [C.POINTER(BgpuParams)]),
@@ -84,6 +85,21 @@ SIGNATURES = {
     "bgpu_psi_dev": (C.c_int, [_h, C.c_void_p, _dp, _dp, C.c_void_p]),
     "bgpu_kinetic_dev": (C.c_int, [_h, C.c_void_p, _dp]),
     "bgpu_leapfrog_dev": (C.c_int, [_h, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double]),
+    # single-precision mode (reference build option SINGLE_PREC)
+    "bgpu_f32_create": (C.c_int, [C.POINTER(BgpuParams), C.POINTER(_h)]),
+    "bgpu_f32_destroy": (None, [_h]),
+    "bgpu_f32_set_static": (C.c_int, [_h, _fp, _fp, _fp, _fp]),
+    "bgpu_f32_set_mass": (C.c_int, [_h, _fp, _fp]),
+    "bgpu_f32_hamiltonian_mass": (C.c_int, [_h, _fp, _fp]),
+    "bgpu_f32_gradient_psi": (C.c_int, [_h, _fp, _fp]),
+    "bgpu_f32_psi": (C.c_int, [_h, _fp, _dp, _dp, _fp]),
+    "bgpu_f32_kinetic": (C.c_int, [_h, _fp, _dp]),
+    "bgpu_f32_leapfrog": (C.c_int, [_h, _fp, _fp, C.c_uint64, C.c_double, _fp, _fp]),
+    "bgpu_f32_set_stream": (C.c_int, [_h, C.c_void_p]),
+    "bgpu_f32_synchronize": (C.c_int, [_h]),
+    "bgpu_f32_gradient_psi_dev": (C.c_int, [_h, C.c_void_p, C.c_void_p]),
+    "bgpu_f32_psi_dev": (C.c_int, [_h, C.c_void_p, _dp, _dp, C.c_void_p]),
+    "bgpu_f32_leapfrog_dev": (C.c_int, [_h, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double]),
     "bgpu_kernel_launches": (C.c_uint64, []),
     "bgpu_profile_begin": (C.c_int, []),
     "bgpu_profile_end": (C.c_int, [_dp, C.POINTER(C.c_uint64), C.c_int]),

@@ -15,6 +15,7 @@
 #include <thread>
 
 #include "fft3d.h"
+#include "host_math.h"
 #include "kernels.h"
 #include "nccl_comm.h"
 #include "util.h"
@@ -42,6 +43,9 @@ void Profiler::record_stop(cudaStream_t st) {
 using namespace bgpu;
 
 static thread_local std::string g_last_error;
+namespace bgpu {
+void set_last_error(const std::string &msg) { g_last_error = msg; }  // f32_path.cu reports through the same string
+}
 
 struct bgpu_handle {
   bgpu_params p{};
@@ -152,16 +156,9 @@ void require(bool ok, const char *msg) {
   if (!ok) throw std::runtime_error(msg);
 }
 
-// E_Hubble_a, fgrow, c_pecvel: cosmo.cc:26-31,182-235
-double E_Hubble_a(double a, double OM, double OL) {
-  const double OK = 1. - OM - OL;
-  return std::sqrt(OM / (a * a * a) + OK / (a * a) + OL);
-}
-double fgrow1(double a, double OM, double OL) {
-  const double E = E_Hubble_a(a, OM, OL);
-  const double Omega = OM / ((E * E) * (a * a * a));
-  return std::pow(Omega, 5. / 9.);
-}
+// E_Hubble_a, fgrow, c_pecvel: cosmo.cc:26-31,182-235 (host_math.h, shared with the single-precision mode)
+double E_Hubble_a(double a, double OM, double OL) { return host_E_Hubble_a(a, OM, OL); }
+double fgrow1(double a, double OM, double OL) { return host_fgrow(a, OM, OL); }
 
 void validate(const bgpu_params &p) {
   require(p.N1 == p.N2 && p.N2 == p.N3, "bgpu: only cubic grids are supported (the reference sets N2=N3=N1, init_par.cc:116-122)");

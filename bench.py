@@ -52,6 +52,7 @@ def parse():
                          "downloading (each phase takes about as long at PCIe 5 x16 rates)")
     ap.add_argument("--no-e2e-chains", action="store_true", help="skip the interleaved-chains e2e leg")
     ap.add_argument("--no-sph", action="store_true", help="skip the SPH (masskernel 3, calc_h 2) line in `also`")
+    ap.add_argument("--no-f32", action="store_true", help="skip the single-precision (bgpu_f32_*) line in `also`")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the slab-decomposed leg (512^3 / 1024^3)")
     return ap.parse_args()
@@ -296,6 +297,39 @@ def run_ours(args):
                "config": "masskernel 3 (SPH spline, h = 1 cell), calc_h 2 (likelihood_calc_h_SPH), real space, same grid",
                "per_kernel_ms": {k: v[0] for k, v in prof3.items() if v[1]}}
 
+    # the single-precision mode (reference build option SINGLE_PREC, bgpu_f32_*): the same workload and the same
+    # (float-rounded) data, reported BESIDE the FP64 headline, with its distance from the FP64 gradient
+    f32 = None
+    if not args.no_f32 and args.grid <= 512:
+        from barcode_b200.chain_f32 import ChainF32
+        c32 = ChainF32(bc.Params(device=local_rank, **cfg))
+        c32.set_static(Power=prob["Power"], nobs=prob["nobs"], noise=prob["noise"], window=prob["window"])
+        c32.set_stream(stream.cuda_stream)
+        d_s32 = d_s.float()
+        d_g32 = torch.empty_like(d_s32)
+        ms_f32 = timed(lambda: c32.gradient_psi_dev(d_s32.data_ptr(), d_g32.data_ptr()), args.steps, args.warmup)
+        bc.profile_begin()
+        c32.gradient_psi_dev(d_s32.data_ptr(), d_g32.data_ptr())
+        prof32 = bc.profile_end()
+        ch.gradient_psi_dev(d_s32.double().data_ptr(), d_g.data_ptr())   # FP64 on the same rounded signal
+        torch.cuda.synchronize()
+        rel32 = float((d_g32.double() - d_g).norm() / d_g.norm())
+        c32.hamiltonian_mass()
+        d_s32b, d_p32, d_p32b = d_s32.clone(), d_p.float(), d_p.float()
+        def traj32():
+            d_s32b.copy_(d_s32)
+            d_p32b.copy_(d_p32)
+            c32.leapfrog_dev(d_s32b.data_ptr(), d_p32b.data_ptr(), 8, 1e-3)
+        calls32 = max(2, args.steps // 4)
+        ms_leap32 = timed(traj32, calls32, 1)
+        c32.close()
+        f32 = {"gradient_evals_per_s": world * args.steps / (ms_f32 * 1e-3), "ms_per_eval": ms_f32 / args.steps,
+               "leapfrog_steps_per_s": world * calls32 * 8 / (ms_leap32 * 1e-3),
+               "rel_l2_vs_fp64_gradient": rel32, "dtype": "f32 arrays and transforms, f64 reductions",
+               "whole_path_frac": 130 * n * (world * args.steps / (ms_f32 * 1e-3)) / world / 1e9 / 6550.1,
+               "whole_path_note": "SURVEY 8(d)'s 260 N bytes halve with 4-byte reals: 130 N bytes per evaluation",
+               "per_kernel_ms": {k: v[0] for k, v in prof32.items() if v[1]}}
+
     # one leapfrog step = kick, M^-1 p, drift, gradient, kick (HMC.cc:289-352)
     ch.hamiltonian_mass()
     d_s2, d_p2 = d_s.clone(), d_p.clone()
@@ -471,6 +505,7 @@ def run_ours(args):
                 "device_momentum_draw_ms": ms_draw / draw_calls,
                 "hmc_candidate_ms_neps8_device_resident": cand_ms,
                 "sph_default_config": sph,
+                "single_precision_mode": f32,
                 "kernel_launches_total": int(bc.kernel_launches() - launches0),
             },
         }

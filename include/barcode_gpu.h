@@ -197,6 +197,36 @@ int bgpu_kinetic_dev(bgpu_handle *h, const double *d_momenta, double *K);
 int bgpu_leapfrog_dev(bgpu_handle *h, double *d_signal, double *d_momenta, uint64_t Neps, double epsilon);
 int bgpu_draw_momenta_device_dev(bgpu_handle *h, uint64_t seed, uint64_t draw_index, double *d_momenta);
 
+/* ---------------------------------------------------------------------------
+ * Single-precision mode.  The reference chooses its arithmetic at build time: SINGLE_PREC makes
+ * real_prec = float and routes the transforms through fftwf (barlib/include/define_opt.h:50-59,
+ * cmake/Modules/Options.cmake:65-66, barlib/src/fftwrapper.cc:32-36,62-66).  A SINGLE_PREC build binds
+ * the entry points below where a DOUBLE_PREC build binds their bgpu_* namesakes (same seams S1-S4,
+ * same argument meaning, real_prec arrays as float; energies stay double).
+ * Built for the north-star path: Zel'dovich model (sfmodel 1 or rsd_model), CIC, plane-parallel RSD,
+ * Poisson / Gaussian likelihood, calc_h 0 / 1 / 4, mass_type 0 / 1 / 4, N1 = 32 ... 512, one GPU, box at
+ * the origin; bgpu_f32_create refuses anything else with a message.  Arrays and transforms are float,
+ * reductions accumulate in double.  Tolerance against the FP64 path: 1e-5 relative (BASELINE.json).
+ * --------------------------------------------------------------------------- */
+typedef struct bgpu_f32_handle bgpu_f32_handle;
+int bgpu_f32_create(const bgpu_params *p, bgpu_f32_handle **out);
+void bgpu_f32_destroy(bgpu_f32_handle *h);
+int bgpu_f32_set_static(bgpu_f32_handle *h, const float *Power, const float *nobs, const float *noise,
+                        const float *window);
+int bgpu_f32_set_mass(bgpu_f32_handle *h, const float *mass_f, const float *mass_r);
+int bgpu_f32_hamiltonian_mass(bgpu_f32_handle *h, float *mass_f_out, float *mass_r_out);  /* HMC_mass.cc:315-368, types 0/1/4 */
+int bgpu_f32_gradient_psi(bgpu_f32_handle *h, const float *signal, float *gradpsi);         /* S1: HMC.cc:146-206 */
+int bgpu_f32_psi(bgpu_f32_handle *h, const float *signal, double *psi_prior, double *psi_likeli,
+                 float *deltaX_out);                                                         /* S2: HMC.cc:124-143 */
+int bgpu_f32_kinetic(bgpu_f32_handle *h, const float *momenta, double *K);                   /* S3: HMC.cc:64-121 */
+int bgpu_f32_leapfrog(bgpu_f32_handle *h, const float *s_i, const float *p_i, uint64_t Neps, double epsilon,
+                      float *s_f, float *p_f);                                               /* S4: HMC.cc:251-369 */
+int bgpu_f32_set_stream(bgpu_f32_handle *h, void *cuda_stream);
+int bgpu_f32_synchronize(bgpu_f32_handle *h);
+int bgpu_f32_gradient_psi_dev(bgpu_f32_handle *h, const float *d_signal, float *d_gradpsi);
+int bgpu_f32_psi_dev(bgpu_f32_handle *h, const float *d_signal, double *psi_prior, double *psi_likeli, float *d_deltaX);
+int bgpu_f32_leapfrog_dev(bgpu_f32_handle *h, float *d_signal, float *d_momenta, uint64_t Neps, double epsilon);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t bgpu_kernel_launches(void);
 

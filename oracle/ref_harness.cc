@@ -52,6 +52,10 @@ real_prec delta_Hamiltonian(struct HAMIL_DATA *hd, real_prec *signali, real_prec
 void Hamiltonian_EoM(struct HAMIL_DATA *hd, real_prec *signali, real_prec *momentai, real_prec *signalf,
                      real_prec *momentaf, gsl_rng *seed, struct DATA *data);
 
+/* arrays are real_prec (double in the default build, float under SINGLE_PREC -- oracle/Makefile target
+ * libbarcode_ref_sp.so); scalars are double in both */
+typedef real_prec rp_t;
+
 extern "C" {
 
 struct ref_params {
@@ -250,7 +254,7 @@ void ref_destroy(void *hv) {
 }
 
 /* pointers to the reference's own arrays (length N doubles) */
-double *ref_array(void *hv, const char *name) {
+rp_t *ref_array(void *hv, const char *name) {
   auto *h = static_cast<ref_handle *>(hv);
   OBSERVATIONAL *o = h->data->observational;
   std::string s(name);
@@ -314,71 +318,71 @@ int ref_readtab(void *hv, const char *fname) {
 }
 
 /* S1: HMC.cc:146-206 */
-int ref_gradient_psi(void *hv, const double *signal, double *out) {
+int ref_gradient_psi(void *hv, const rp_t *signal, rp_t *out) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  gradient_psi(h->hd, const_cast<double *>(signal), h->data);
-  std::memcpy(out, h->hd->gradpsi, h->hd->numerical->N * sizeof(double));
+  gradient_psi(h->hd, const_cast<rp_t *>(signal), h->data);
+  std::memcpy(out, h->hd->gradpsi, h->hd->numerical->N * sizeof(rp_t));
   REF_CATCH
 }
 
 /* the likelihood half alone: HMC_models.cc:377-471 */
-int ref_grad_log_like(void *hv, const double *signal, double *out) {
+int ref_grad_log_like(void *hv, const rp_t *signal, rp_t *out) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  likelihood_grad_log_like(h->hd, const_cast<double *>(signal), out);
+  likelihood_grad_log_like(h->hd, const_cast<rp_t *>(signal), out);
   REF_CATCH
 }
 
 /* the prior half alone: hmc/prior/gaussian.cpp:15-18 */
-int ref_grad_log_prior(void *hv, const double *signal, double *out) {
+int ref_grad_log_prior(void *hv, const rp_t *signal, rp_t *out) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  h->hd->grad_log_prior(h->hd, const_cast<double *>(signal), out);
+  h->hd->grad_log_prior(h->hd, const_cast<rp_t *>(signal), out);
   REF_CATCH
 }
 
 /* S2: HMC.cc:124-143 (deltaX side effect readable through ref_array("deltaX")) */
-int ref_psi(void *hv, const double *signal, double *psi_prior, double *psi_like) {
+int ref_psi(void *hv, const rp_t *signal, double *psi_prior, double *psi_like) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  psi(h->hd, const_cast<double *>(signal), h->data);
+  psi(h->hd, const_cast<rp_t *>(signal), h->data);
   *psi_prior = h->hd->numerical->psi_prior;
   *psi_like = h->hd->numerical->psi_likeli;
   REF_CATCH
 }
 
 /* S3: HMC.cc:64-121 */
-int ref_kinetic(void *hv, const double *momenta, double *K) {
+int ref_kinetic(void *hv, const rp_t *momenta, double *K) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  *K = kinetic_term(h->hd, const_cast<double *>(momenta), h->data);
+  *K = kinetic_term(h->hd, const_cast<rp_t *>(momenta), h->data);
   REF_CATCH
 }
 
 /* S4: HMC.cc:251-369.  u_Neps, u_eps are the two uniforms the reference draws
  * first (Neps = floor(N_eps_fac*u)+1, eps = eps_fac*u). */
-int ref_EoM(void *hv, const double *si, const double *pi, double *sf, double *pf, double u_Neps, double u_eps) {
+int ref_EoM(void *hv, const rp_t *si, const rp_t *pi, rp_t *sf, rp_t *pf, double u_Neps, double u_eps) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
   shim_gsl_rng_force_uniform(h->rng, u_Neps);
   shim_gsl_rng_force_uniform(h->rng, u_eps);
-  Hamiltonian_EoM(h->hd, const_cast<double *>(si), const_cast<double *>(pi), sf, pf, h->rng, h->data);
+  Hamiltonian_EoM(h->hd, const_cast<rp_t *>(si), const_cast<rp_t *>(pi), sf, pf, h->rng, h->data);
   REF_CATCH
 }
 
 /* HMC.cc:209-248; scalars readable through ref_scalar */
-int ref_delta_hamiltonian(void *hv, const double *si, const double *pi, const double *sf, const double *pf,
+int ref_delta_hamiltonian(void *hv, const rp_t *si, const rp_t *pi, const rp_t *sf, const rp_t *pf,
                           double *dH) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  *dH = delta_Hamiltonian(h->hd, const_cast<double *>(si), const_cast<double *>(pi), const_cast<double *>(sf),
-                          const_cast<double *>(pf), h->data);
+  *dH = delta_Hamiltonian(h->hd, const_cast<rp_t *>(si), const_cast<rp_t *>(pi), const_cast<rp_t *>(sf),
+                          const_cast<rp_t *>(pf), h->data);
   REF_CATCH
 }
 
 /* S5: HMC_momenta.cc:42-74 with a fresh mt19937 stream of the given seed */
-int ref_draw_momenta(void *hv, unsigned long seed, double *momenta) {
+int ref_draw_momenta(void *hv, unsigned long seed, rp_t *momenta) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
   gsl_rng_set(h->rng, seed);
@@ -387,7 +391,7 @@ int ref_draw_momenta(void *hv, unsigned long seed, double *momenta) {
 }
 
 /* random.cpp:48-511 */
-int ref_create_garfield(void *hv, unsigned long seed, const double *power, double *out) {
+int ref_create_garfield(void *hv, unsigned long seed, const rp_t *power, rp_t *out) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
   HAMIL_NUMERICAL *n = h->hd->numerical;
@@ -397,7 +401,7 @@ int ref_create_garfield(void *hv, unsigned long seed, const double *power, doubl
 }
 
 /* random.hpp:36-120, full grid: 2*N1^3 doubles (re, im interleaved) */
-int ref_white_noise(int N1, unsigned long seed, double *out) {
+int ref_white_noise(int N1, unsigned long seed, rp_t *out) {
   REF_TRY
   gsl_rng *r = gsl_rng_alloc(gsl_rng_mt19937);
   gsl_rng_set(r, seed);
@@ -427,7 +431,7 @@ int ref_hamiltonian_mass(void *hv) {
 }
 
 /* forward model as the gradient / likelihood call it (HMC_models.cc:389-406) */
-int ref_forward(void *hv, const double *signal, double *deltaX, double *posx, double *posy, double *posz) {
+int ref_forward(void *hv, const rp_t *signal, rp_t *deltaX, rp_t *posx, rp_t *posy, rp_t *posz) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
   HAMIL_DATA *hd = h->hd;
@@ -444,10 +448,10 @@ int ref_forward(void *hv, const double *signal, double *deltaX, double *posx, do
     Lag2Eul(in, hd->deltaX, hd->posx, hd->posy, hd->posz, n->N1, n->N2, n->N3, n->L1, n->L2, n->L3, n->d1, n->d2,
             n->d3, n->min1, n->min2, n->min3, hd->D1, hd->D2, hd->ascale, hd->OM, hd->OL, hd->sfmodel, n->mk, n->kth, 1,
             true, nullptr, "", kernel_scale, n->R2Cplan, n->C2Rplan);
-  std::memcpy(deltaX, hd->deltaX, n->N * sizeof(double));
-  if (posx) std::memcpy(posx, hd->posx, n->N * sizeof(double));
-  if (posy) std::memcpy(posy, hd->posy, n->N * sizeof(double));
-  if (posz) std::memcpy(posz, hd->posz, n->N * sizeof(double));
+  std::memcpy(deltaX, hd->deltaX, n->N * sizeof(rp_t));
+  if (posx) std::memcpy(posx, hd->posx, n->N * sizeof(rp_t));
+  if (posy) std::memcpy(posy, hd->posy, n->N * sizeof(rp_t));
+  if (posz) std::memcpy(posz, hd->posz, n->N * sizeof(rp_t));
   REF_CATCH
 }
 
@@ -468,7 +472,7 @@ int ref_kernelcomp(void *hv) {
 }
 
 /* mass assignment alone on given positions (massFunctions.cc:49-495), no overdens */
-int ref_density(void *hv, const double *x, const double *y, const double *z, double *rho) {
+int ref_density(void *hv, const rp_t *x, const rp_t *y, const rp_t *z, rp_t *rho) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
   HAMIL_NUMERICAL *n = h->hd->numerical;
@@ -498,31 +502,31 @@ int ref_density(void *hv, const double *x, const double *y, const double *z, dou
 }
 
 /* residual alone: hd->partial_f_delta_x_log_like (gaussian_independent.cpp:24-42 etc.) */
-int ref_partial_f(void *hv, const double *deltaX, double *out) {
+int ref_partial_f(void *hv, const rp_t *deltaX, rp_t *out) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  h->hd->partial_f_delta_x_log_like(h->hd, const_cast<double *>(deltaX), out);
+  h->hd->partial_f_delta_x_log_like(h->hd, const_cast<rp_t *>(deltaX), out);
   REF_CATCH
 }
 
 /* A5: HMC_help.cc:16-64 */
-int ref_convolve_inv_corr(void *hv, const double *signal, const double *corr, double *out) {
+int ref_convolve_inv_corr(void *hv, const rp_t *signal, const rp_t *corr, rp_t *out) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  convolveInvCorrFuncWithSignal(h->hd, const_cast<double *>(signal), out, corr);
+  convolveInvCorrFuncWithSignal(h->hd, const_cast<rp_t *>(signal), out, corr);
   REF_CATCH
 }
 
 /* fftwrapper.cc:26-84 through the shim: r2c then c2r */
-int ref_fft_r2c(int N1, const double *in, double *out_complex) {
+int ref_fft_r2c(int N1, const rp_t *in, rp_t *out_complex) {
   REF_TRY
   ULONG N = (ULONG)N1 * N1 * N1;
   fftw_array<real_prec> tmp(N);
-  std::memcpy(tmp.data, in, N * sizeof(double));
+  std::memcpy(tmp.data, in, N * sizeof(rp_t));
   fftR2C(N1, N1, N1, tmp, reinterpret_cast<complex_prec *>(out_complex));
   REF_CATCH
 }
-int ref_fft_c2r(int N1, const double *in_complex, double *out) {
+int ref_fft_c2r(int N1, const rp_t *in_complex, rp_t *out) {
   REF_TRY
   ULONG Nh = (ULONG)N1 * N1 * (N1 / 2 + 1);
   fftw_array<complex_prec> tmp(Nh);
@@ -532,31 +536,31 @@ int ref_fft_c2r(int N1, const double *in_complex, double *out) {
 }
 
 /* spectral / finite-difference gradient components (gradient.cpp:22-153) */
-int ref_gradfft(int N1, double L1, const double *in, double *out, unsigned dim) {
+int ref_gradfft(int N1, double L1, const rp_t *in, rp_t *out, unsigned dim) {
   REF_TRY
-  gradfft(N1, N1, N1, L1, L1, L1, const_cast<double *>(in), out, dim);
+  gradfft(N1, N1, N1, L1, L1, L1, const_cast<rp_t *>(in), out, dim);
   REF_CATCH
 }
-int ref_gradfindif(int N1, double L1, const double *in, double *out, unsigned dim) {
+int ref_gradfindif(int N1, double L1, const rp_t *in, rp_t *out, unsigned dim) {
   REF_TRY
   gradfindif(N1, L1, in, out, dim);
   REF_CATCH
 }
 
 /* measure_spectrum, field_statistics.cpp:20-90 (per-sample diagnostics) */
-int ref_measure_spectrum(int N1, double L1, const double *signal, unsigned long N_bin, double *kmode, double *power) {
+int ref_measure_spectrum(int N1, double L1, const rp_t *signal, unsigned long N_bin, rp_t *kmode, rp_t *power) {
   REF_TRY
-  measure_spectrum(N1, N1, N1, L1, L1, L1, const_cast<double *>(signal), kmode, power, N_bin);
+  measure_spectrum(N1, N1, N1, L1, L1, L1, const_cast<rp_t *>(signal), kmode, power, N_bin);
   REF_CATCH
 }
 
 /* CPU baseline timing: seconds per gradient_psi call, 1 warm-up + reps timed (omp_get_wtime) */
-int ref_time_gradient_psi(void *hv, const double *signal, int reps, double *seconds_per_call) {
+int ref_time_gradient_psi(void *hv, const rp_t *signal, int reps, double *seconds_per_call) {
   auto *h = static_cast<ref_handle *>(hv);
   REF_TRY
-  gradient_psi(h->hd, const_cast<double *>(signal), h->data);
+  gradient_psi(h->hd, const_cast<rp_t *>(signal), h->data);
   const double t0 = omp_get_wtime();
-  for (int r = 0; r < reps; ++r) gradient_psi(h->hd, const_cast<double *>(signal), h->data);
+  for (int r = 0; r < reps; ++r) gradient_psi(h->hd, const_cast<rp_t *>(signal), h->data);
   *seconds_per_call = (omp_get_wtime() - t0) / reps;
   REF_CATCH
 }

@@ -45,6 +45,22 @@ int fftw_init_threads(void);
 void fftw_plan_with_nthreads(int nthreads);
 void fftw_cleanup_threads(void);
 
+/* single-precision API (the reference's SINGLE_PREC build, fftwrapper.cc:32-36,62-66): each execute widens the
+ * input to double, runs the double transform and rounds the result to float once -- a correctly rounded
+ * single-precision DFT, at least as accurate as any float FFT */
+typedef float fftwf_complex[2];
+typedef struct shim_fftwf_plan_s *fftwf_plan;
+void *fftwf_malloc(size_t n);
+void fftwf_free(void *p);
+fftwf_plan fftwf_plan_dft_r2c_3d(int n0, int n1, int n2, float *in, fftwf_complex *out, unsigned flags);
+fftwf_plan fftwf_plan_dft_c2r_3d(int n0, int n1, int n2, fftwf_complex *in, float *out, unsigned flags);
+fftwf_plan fftwf_plan_dft_3d(int n0, int n1, int n2, fftwf_complex *in, fftwf_complex *out, int sign, unsigned flags);
+void fftwf_execute(const fftwf_plan p);
+void fftwf_destroy_plan(fftwf_plan p);
+int fftwf_init_threads(void);
+void fftwf_plan_with_nthreads(int nthreads);
+void fftwf_cleanup_threads(void);
+
 /* shim-only: which backend is linked (reported by bench.py's cpu_baseline) */
 const char *shim_fftw_backend(void);
 

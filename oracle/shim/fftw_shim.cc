@@ -400,6 +400,81 @@ int fftw_init_threads(void) { return 1; }
 void fftw_plan_with_nthreads(int) {}
 void fftw_cleanup_threads(void) {}
 
+/* ---- single precision: widen, transform in double, round once ---- */
+struct shim_fftwf_plan_s {
+  Kind kind;
+  int n0, n1, n2, sign;
+  void *in, *out;
+  fftw_plan dplan;
+  double *dreal;          /* n0*n1*n2 (r2c / c2r) */
+  double (*dcplx)[2];     /* n0*n1*(n2/2+1) (r2c / c2r) or n0*n1*n2 (c2c) */
+};
+
+static fftwf_plan make_plan_f(Kind kind, int n0, int n1, int n2, void *in, void *out, int sign) {
+  auto *p = new shim_fftwf_plan_s;
+  p->kind = kind;
+  p->n0 = n0; p->n1 = n1; p->n2 = n2; p->sign = sign;
+  p->in = in; p->out = out;
+  const size_t nr = (size_t)n0 * n1 * n2, nc = (size_t)n0 * n1 * (n2 / 2 + 1);
+  p->dreal = nullptr;
+  if (kind == C2C) {
+    p->dcplx = static_cast<double (*)[2]>(fftw_malloc(nr * sizeof(double[2])));
+    p->dplan = make_plan(C2C, n0, n1, n2, p->dcplx, p->dcplx, sign);
+  } else {
+    p->dreal = static_cast<double *>(fftw_malloc(nr * sizeof(double)));
+    p->dcplx = static_cast<double (*)[2]>(fftw_malloc(nc * sizeof(double[2])));
+    p->dplan = kind == R2C ? make_plan(R2C, n0, n1, n2, p->dreal, p->dcplx, -1)
+                           : make_plan(C2R, n0, n1, n2, p->dcplx, p->dreal, +1);
+  }
+  return p;
+}
+
+void *fftwf_malloc(size_t n) { return fftw_malloc(n); }
+void fftwf_free(void *p) { std::free(p); }
+fftwf_plan fftwf_plan_dft_r2c_3d(int n0, int n1, int n2, float *in, fftwf_complex *out, unsigned) {
+  return make_plan_f(R2C, n0, n1, n2, in, out, -1);
+}
+fftwf_plan fftwf_plan_dft_c2r_3d(int n0, int n1, int n2, fftwf_complex *in, float *out, unsigned) {
+  return make_plan_f(C2R, n0, n1, n2, in, out, +1);
+}
+fftwf_plan fftwf_plan_dft_3d(int n0, int n1, int n2, fftwf_complex *in, fftwf_complex *out, int sign, unsigned) {
+  return make_plan_f(C2C, n0, n1, n2, in, out, sign);
+}
+void fftwf_execute(const fftwf_plan p) {
+  const size_t nr = (size_t)p->n0 * p->n1 * p->n2, nc = (size_t)p->n0 * p->n1 * (p->n2 / 2 + 1);
+  const float *in = static_cast<const float *>(p->in);
+  float *out = static_cast<float *>(p->out);
+  double *dc = &p->dcplx[0][0];
+  if (p->kind == R2C) {
+#pragma omp parallel for
+    for (long i = 0; i < (long)nr; ++i) p->dreal[i] = (double)in[i];
+    fftw_execute(p->dplan);
+#pragma omp parallel for
+    for (long i = 0; i < (long)(2 * nc); ++i) out[i] = (float)dc[i];
+  } else if (p->kind == C2R) {
+#pragma omp parallel for
+    for (long i = 0; i < (long)(2 * nc); ++i) dc[i] = (double)in[i];
+    fftw_execute(p->dplan);
+#pragma omp parallel for
+    for (long i = 0; i < (long)nr; ++i) out[i] = (float)p->dreal[i];
+  } else {
+#pragma omp parallel for
+    for (long i = 0; i < (long)(2 * nr); ++i) dc[i] = (double)in[i];
+    fftw_execute(p->dplan);
+#pragma omp parallel for
+    for (long i = 0; i < (long)(2 * nr); ++i) out[i] = (float)dc[i];
+  }
+}
+void fftwf_destroy_plan(fftwf_plan p) {
+  fftw_destroy_plan(p->dplan);
+  std::free(p->dreal);
+  std::free(p->dcplx);
+  delete p;
+}
+int fftwf_init_threads(void) { return 1; }
+void fftwf_plan_with_nthreads(int) {}
+void fftwf_cleanup_threads(void) {}
+
 const char *shim_fftw_backend(void) {
   return "oracle/shim/fftw_shim.cc (own OpenMP Stockham radix-4 pencil FFT, not FFTW)";
 }

@@ -1,0 +1,141 @@
+"""Single-precision mode (bgpu_f32_*; the reference's SINGLE_PREC build option, define_opt.h:50-59) on the GPU.
+
+Three references, all on the same float-rounded inputs:
+  * the FP64 CUDA path (`Chain`) -- the accuracy yardstick at every size;
+  * the unmodified reference compiled DOUBLE_PREC (oracle/_ref/libbarcode_ref.so) and
+  * compiled SINGLE_PREC (oracle/_ref/libbarcode_ref_sp.so) -- live, at the sizes the CPU finishes in seconds.
+Tolerance: 1e-5 relative (BASELINE.json north_star: "1e-5 in FP32") for the Gaussian likelihood; where the
+reference's own SINGLE_PREC build is further than that from its DOUBLE_PREC build (the Poisson residual
+1 - n / Lambda is ill-conditioned in float), the bar is the reference's own single-precision error.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = np.ravel(a).astype(np.float64), np.ravel(b).astype(np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _problem(N, like, rsd, calc_h, mass_type=1):
+    """Inputs from the FP64 chain's synthetic recipe, rounded to float32 once; FP64 results on those inputs."""
+    from barcode_b200 import inputs
+    from barcode_b200.chain import Chain, Params
+    L = inputs.box_length(N)
+    kw = dict(N1=N, L1=L, masskernel=1, likelihood=like, rsd_model=rsd, calc_h=calc_h, mass_type=mass_type, sfmodel=1)
+    with Chain(Params(**kw)) as ch:
+        prob = inputs.synthetic_problem(ch, seed=5)
+        rng = np.random.default_rng(11)
+        noise = (1.0 + 0.5 * rng.random(ch.N)).astype(np.float32)
+        f = {k: np.asarray(prob[k], dtype=np.float32) for k in ("Power", "nobs", "window", "signal", "momenta")}
+        f["noise"] = noise
+        d = {k: v.astype(np.float64) for k, v in f.items()}
+        ch.set_static(Power=d["Power"], nobs=d["nobs"], noise=d["noise"], window=d["window"])
+        ch.hamiltonian_mass()
+        out = dict(grad=ch.gradient_psi(d["signal"]), psi=ch.psi(d["signal"]), K=ch.kinetic_term(d["momenta"]),
+                   traj=ch.leapfrog(d["signal"], d["momenta"], 3, 1e-5))
+    return kw, f, out
+
+
+@pytest.mark.parametrize("N,like,rsd,calc_h", [
+    (32, 1, True, 0), (32, 1, False, 4), (32, 0, False, 4), (32, 1, True, 1),
+    (64, 1, True, 0), (64, 1, True, 4), (64, 1, False, 0),
+    (128, 1, True, 0), (128, 1, True, 4),
+    (256, 1, True, 0),          # BASELINE.json configs[1]
+    (256, 1, True, 4),
+])
+def test_f32_mode_matches_the_fp64_path(N, like, rsd, calc_h):
+    from barcode_b200.chain import Params
+    from barcode_b200.chain_f32 import ChainF32
+    kw, f, want = _problem(N, like, rsd, calc_h)
+    with ChainF32(Params(**kw)) as c32:
+        c32.set_static(Power=f["Power"], nobs=f["nobs"], noise=f["noise"], window=f["window"])
+        c32.hamiltonian_mass()
+        g = c32.gradient_psi(f["signal"])
+        pp, pl, dX = c32.psi(f["signal"])
+        K = c32.kinetic_term(f["momenta"])
+        sf, pf = c32.leapfrog(f["signal"], f["momenta"], 3, 1e-5)
+    assert g.dtype == np.float32 and np.all(np.isfinite(g))
+    errs = dict(grad=rel_l2(g, want["grad"]), prior=abs(pp - want["psi"][0]) / abs(want["psi"][0]),
+                like=abs(pl - want["psi"][1]) / abs(want["psi"][1]), deltaX=rel_l2(dX, want["psi"][2]),
+                K=abs(K - want["K"]) / abs(want["K"]), s_f=rel_l2(sf, want["traj"][0]), p_f=rel_l2(pf, want["traj"][1]))
+    print("f32 vs fp64", N, like, rsd, calc_h, {k: "%.2e" % v for k, v in errs.items()})
+    tol = 1e-5 if like == 1 else 1e-3   # Poisson: see the module docstring and the reference-pinned test below
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("N,like,rsd,calc_h,mass_type", [
+    (32, 1, True, 0, 1), (64, 1, True, 0, 1), (64, 1, False, 0, 4), (32, 0, False, 0, 1), (64, 0, False, 0, 1),
+    (64, 1, True, 1, 0),
+])
+def test_f32_mode_against_the_reference_compiled_single_and_double(N, like, rsd, calc_h, mass_type):
+    """bgpu_f32_* against the unmodified reference, compiled with its own SINGLE_PREC option and DOUBLE_PREC, live:
+    the GPU's single-precision results are as close to the reference's double-precision ones as the reference's own
+    single-precision build is (within a factor 2), and within 1e-5 for the Gaussian likelihood."""
+    from oracle import ref, ref_sp
+    if not (ref.available() and ref_sp.available()):
+        pytest.skip("oracle/_ref/libbarcode_ref.so / libbarcode_ref_sp.so not built")
+    from barcode_b200 import inputs
+    from barcode_b200.chain import Params
+    from barcode_b200.chain_f32 import ChainF32
+    L = inputs.box_length(N)
+    cfg = ref.Config(N1=N, L1=L, masskernel=1, likelihood=like, sfmodel=1, rsd_model=rsd, calc_h=calc_h,
+                     mass_type=mass_type, N_eps_fac=8.0, eps_fac=1.0)
+    R, S = ref.Reference(cfg), ref_sp.ReferenceSP(cfg)
+    P = inputs.power_on_grid(*inputs.load_pk_table(), N, L).ravel()
+    rng = np.random.default_rng(65)
+    one = np.ones(R.N)
+    R.set_inputs(Power=P, window=one, noise=one, nobs=one)
+    truth = R.create_garfield(21, P)
+    dX_truth = R.forward(truth, want_pos=False)
+    nobs = np.maximum(0, 1 + dX_truth + rng.standard_normal(R.N)) if like == 1 else \
+        rng.poisson(np.maximum(1 + dX_truth, 0)) * 1.0
+    noise = 1.0 + 0.5 * rng.random(R.N)
+    s = 0.5 * R.create_garfield(22, P)
+    P32, nobs32, noise32, s32 = [a.astype(np.float32) for a in (P, nobs, noise, s)]
+    R.set_inputs(Power=P32, nobs=nobs32, noise=noise32, signal=s32)
+    S.set_inputs(Power=P32, nobs=nobs32, noise=noise32, window=one, signal=s32)
+    R.hamiltonian_mass()
+    mfs, mrs = S.hamiltonian_mass()
+    mom32 = R.draw_momenta(23).astype(np.float32)
+    s64, mom64 = s32.astype(np.float64), mom32.astype(np.float64)
+    want = dict(grad=R.gradient_psi(s64), psi=R.psi(s64), K=R.kinetic(mom64), traj=R.EoM(s64, mom64, 0.3, 1e-5))
+    neps, eps = int(R.scalar("Neps")), R.scalar("epsilon")
+    sp = dict(grad=S.gradient_psi(s32), psi=S.psi(s32), K=S.kinetic(mom32), traj=S.EoM(s32, mom32, 0.3, 1e-5))
+    R.close()
+    S.close()
+    with ChainF32(Params(N1=N, L1=L, masskernel=1, likelihood=like, rsd_model=rsd, calc_h=calc_h, mass_type=mass_type,
+                         sfmodel=1)) as c32:
+        c32.set_static(Power=P32, nobs=nobs32, noise=noise32, window=one)
+        mf_g, mr_g = c32.hamiltonian_mass()
+        got = dict(grad=c32.gradient_psi(s32), psi=c32.psi(s32)[:2], K=c32.kinetic_term(mom32),
+                   traj=c32.leapfrog(s32, mom32, neps, eps))
+    if mass_type == 0:
+        assert np.array_equal(mr_g.ravel(), mrs)
+    else:
+        assert rel_l2(mf_g, mfs) < 1e-6
+
+    def errors(x):
+        return dict(grad=rel_l2(x["grad"], want["grad"]), prior=abs(x["psi"][0] - want["psi"][0]) / abs(want["psi"][0]),
+                    like=abs(x["psi"][1] - want["psi"][1]) / abs(want["psi"][1]), K=abs(x["K"] - want["K"]) / abs(want["K"]),
+                    s_f=rel_l2(x["traj"][0], want["traj"][0]), p_f=rel_l2(x["traj"][1], want["traj"][1]))
+    e_gpu, e_ref = errors(got), errors(sp)
+    print("f32 GPU vs reference DOUBLE_PREC:", {k: "%.2e" % v for k, v in e_gpu.items()})
+    print("reference SINGLE_PREC vs DOUBLE_PREC:", {k: "%.2e" % v for k, v in e_ref.items()})
+    for k in e_gpu:
+        assert e_gpu[k] < max(1e-5, 2.0 * e_ref[k]), (k, e_gpu[k], e_ref[k])
+        if like == 1:
+            assert e_gpu[k] < 1e-5, (k, e_gpu[k])
+
+
+def test_f32_mode_refuses_what_it_is_not_built_for():
+    from barcode_b200._lib import BgpuError
+    from barcode_b200.chain import Params
+    from barcode_b200.chain_f32 import ChainF32
+    for bad in (dict(masskernel=2), dict(likelihood=2), dict(sfmodel=2), dict(calc_h=2, masskernel=3), dict(N1=16),
+                dict(mass_type=2)):
+        with pytest.raises(BgpuError):
+            ChainF32(Params(**{**dict(N1=32, L1=100.0), **bad}))
