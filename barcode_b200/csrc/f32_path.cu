@@ -82,9 +82,12 @@ static void reduce(F f, size_t n, double *scratch, double *out, cudaStream_t st)
   BGPU_LAUNCHED(2);
 }
 
-struct SumF {
-  const float *a;
-  __device__ double operator()(size_t i) const { return (double)a[i]; }
+struct SumF {  // four cells per index (16-byte loads)
+  const float4 *a;
+  __device__ double operator()(size_t i) const {
+    const float4 v = a[i];
+    return ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+  }
 };
 // 1/2 sum_x a (C^-1 a) by Parseval on the half grid (kernels.cu HalfQuadF; gaussian.cpp:20-35, HMC.cc:82-110)
 struct HalfQuadF {
@@ -203,37 +206,48 @@ struct LikeF {
   int exact_sign;
 };
 
+__device__ __forceinline__ float residual_one(const LikeF &lp, bool unit, float rho, float inv_mean, float nn, float sg,
+                                              float w, float &delta, float &r) {
+  delta = rho * inv_mean - 1.f;
+  const float dens = 1.f + lp.biasP * delta;
+  const float Lambda = w * lp.rho_c * (unit ? dens : powf(dens, lp.biasE));
+  float val = 0.f;
+  r = 0.f;
+  if (lp.likelihood == 1) {
+    if (w > 0.f && Lambda > 0.f) {
+      r = (nn - Lambda) / (sg * sg);
+      const float q = (Lambda - nn) / sg;
+      val = 0.5f * q * q;
+    }
+  } else {
+    if (w > 0.f && dens > 0.f) {
+      r = (1.f - nn / Lambda) * lp.rho_c * lp.biasE * lp.biasP * (unit ? 1.f : powf(dens, lp.biasE - 1.f));
+      if (lp.exact_sign) r = -r;
+    }
+    if (w > 0.f && Lambda > 0.f) val = Lambda - nn * logf(Lambda);
+  }
+  return val;
+}
+
+// four cells per thread per trip (16-byte loads); n4 = n / 4 (N^3 is a multiple of 4)
 __global__ void __launch_bounds__(kThreads)
-    residual_kernel(LikeF lp, float *__restrict__ rho_delta, const double *__restrict__ sum_rho, double count,
-                    const float *__restrict__ nobs, const float *__restrict__ noise, const float *__restrict__ window,
-                    float *__restrict__ resid, size_t n, double *__restrict__ part) {
+    residual_kernel(LikeF lp, float4 *__restrict__ rho_delta, const double *__restrict__ sum_rho, double count,
+                    const float4 *__restrict__ nobs, const float4 *__restrict__ noise, const float4 *__restrict__ window,
+                    float4 *__restrict__ resid, size_t n4, double *__restrict__ part) {
   const float inv_mean = (float)(count / *sum_rho);
   const bool unit = lp.biasE == 1.f;
   double acc = 0.0;
   const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    const float delta = rho_delta[i] * inv_mean - 1.f;
-    const float w = window[i], nn = nobs[i];
-    const float dens = 1.f + lp.biasP * delta;
-    const float Lambda = w * lp.rho_c * (unit ? dens : powf(dens, lp.biasE));
-    float r = 0.f, val = 0.f;
-    if (lp.likelihood == 1) {
-      if (w > 0.f && Lambda > 0.f) {
-        const float sg = noise[i];
-        r = (nn - Lambda) / (sg * sg);
-        const float q = (Lambda - nn) / sg;
-        val = 0.5f * q * q;
-      }
-    } else {
-      if (w > 0.f && dens > 0.f) {
-        r = (1.f - nn / Lambda) * lp.rho_c * lp.biasE * lp.biasP * (unit ? 1.f : powf(dens, lp.biasE - 1.f));
-        if (lp.exact_sign) r = -r;
-      }
-      if (w > 0.f && Lambda > 0.f) val = Lambda - nn * logf(Lambda);
-    }
-    rho_delta[i] = delta;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+    const float4 ro = rho_delta[i], nn = nobs[i], sg = noise[i], w = window[i];
+    float4 d, r;
+    float v = residual_one(lp, unit, ro.x, inv_mean, nn.x, sg.x, w.x, d.x, r.x);
+    v += residual_one(lp, unit, ro.y, inv_mean, nn.y, sg.y, w.y, d.y, r.y);
+    v += residual_one(lp, unit, ro.z, inv_mean, nn.z, sg.z, w.z, d.z, r.z);
+    v += residual_one(lp, unit, ro.w, inv_mean, nn.w, sg.w, w.w, d.w, r.w);
+    rho_delta[i] = d;
     if (resid) resid[i] = r;
-    acc += (double)val;
+    acc += (double)v;
   }
   const double r = block_sum(acc);
   if (threadIdx.x == 0) part[blockIdx.x] = r;
@@ -310,11 +324,40 @@ struct Fft {
     static constexpr int TR = (N_ / 16 >= 256) ? 1 : 256 / (N_ / 16);  // rows per z-pass CTA: 256 threads
     static constexpr size_t smem_strided = (size_t)2 * N_ * T * sizeof(float2);
     static constexpr size_t smem_z = (size_t)TR * (N_ / 2 + N_ / 16 + 1) * sizeof(float2);
+    static constexpr size_t smem_warp = (size_t)2 * (N_ + N_ / 8) * (T + 1) * sizeof(float2);
   };
+
+  bool warp_pass = true;  // BGPU_F32_WARP=0: the CTA-barrier strided pass at every size (cross-check)
+  int grid_warp = 0;
+
+  template <int N_>
+  void init_warp() {
+    if constexpr (N_ <= 256) {
+      using C = Cfg<N_>;
+      BGPU_CUDA(cudaFuncSetAttribute(strided_pass_warp<N_, C::T, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_warp));
+      BGPU_CUDA(cudaFuncSetAttribute(strided_pass_warp<N_, C::T, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_warp));
+      BGPU_CUDA(cudaFuncSetAttribute(strided_pass_warp<N_, C::T, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_warp));
+      BGPU_CUDA(cudaFuncSetAttribute(strided_pass_warp<N_, C::T, +1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_warp));
+      int occ = 0, dev = 0, sms = 0;
+      BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, strided_pass_warp<N_, C::T, +1, 0>, C::T * N_ / 8, C::smem_warp));
+      BGPU_CUDA(cudaGetDevice(&dev));
+      BGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      if (occ < 1) throw std::runtime_error("bgpu_f32: the warp-synchronous strided pass does not fit an SM at this size");
+      constexpr int tiles = N_ * ((N_ / 2) / C::T) + N_ / C::T;
+      grid_warp = occ * sms < tiles ? occ * sms : tiles;
+    } else {
+      warp_pass = false;
+    }
+  }
 
   template <int N_>
   void init_n() {
     using C = Cfg<N_>;
+    {
+      const char *e = std::getenv("BGPU_F32_WARP");
+      warp_pass = !(e && e[0] == '0');
+    }
+    if (warp_pass) init_warp<N_>();
     BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, C::T, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_strided));
     BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, C::T, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_strided));
     BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, C::T, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_strided));
@@ -366,6 +409,13 @@ struct Fft {
   void strided_n(const float2 *in, float2 *out, const KOpF &lop, const KOpF &sop) {
     using C = Cfg<N_>;
     ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, stream);
+    if constexpr (N_ <= 256) {
+      if (warp_pass) {
+        strided_pass_warp<N_, C::T, DIR, AXIS><<<grid_warp, C::T * N_ / 8, C::smem_warp, stream>>>(in, out, twN, lop, sop);
+        BGPU_LAUNCHED(1);
+        return;
+      }
+    }
     strided_pass<N_, C::T, DIR, AXIS><<<grid_strided, C::T * N_ / 8, C::smem_strided, stream>>>(in, out, twN, lop, sop);
     BGPU_LAUNCHED(1);
   }
@@ -489,16 +539,18 @@ void forward_from_shat(bgpu_f32_handle *h, float dQ, bool rsd) {
     scatter_cic_kernel<<<blocks_for(h->n, kThreads), kThreads, 0, h->stream>>>(g, h->psi[0], h->psi[1], h->psi[2], h->delta);
     BGPU_LAUNCHED(1);
   }
-  reduce(SumF{h->delta}, h->n, h->partials, h->dscal + S_SUMRHO, h->stream);
+  reduce(SumF{reinterpret_cast<const float4 *>(h->delta)}, h->n / 4, h->partials, h->dscal + S_SUMRHO, h->stream);
 }
 
 void residual(bgpu_f32_handle *h, bool exact_sign, float *resid) {
   ProfScope prof(KK_RESIDUAL, h->stream);
   LikeF lp = h->like;
   lp.exact_sign = exact_sign ? 1 : 0;
-  const int blocks = grid_for(h->n);
-  residual_kernel<<<blocks, kThreads, 0, h->stream>>>(lp, h->delta, h->dscal + S_SUMRHO, h->ncells, h->nobs, h->noise,
-                                                      h->window, resid, h->n, h->partials);
+  const int blocks = grid_for(h->n / 4);
+  residual_kernel<<<blocks, kThreads, 0, h->stream>>>(
+      lp, reinterpret_cast<float4 *>(h->delta), h->dscal + S_SUMRHO, h->ncells, reinterpret_cast<const float4 *>(h->nobs),
+      reinterpret_cast<const float4 *>(h->noise), reinterpret_cast<const float4 *>(h->window),
+      reinterpret_cast<float4 *>(resid), h->n / 4, h->partials);
   final_sum_kernel<<<1, kThreads, 0, h->stream>>>(h->partials, blocks, h->dscal + S_NLL);
   BGPU_LAUNCHED(2);
 }

@@ -403,11 +403,14 @@ def run_ours(args):
     dom_name, (dom_ms, dom_cnt) = dom
     achieved = alg_bytes[dom_name] / (dom_ms * 1e-3 / dom_cnt) / 1e9
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture, if one exists
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-            traffic = json.load(f).get(str(args.grid), {}).get(dom_name)
-    except (OSError, ValueError):
-        pass
+    for tf in ("traffic_r02.json", "traffic_r01.json"):   # the newest capture that has this grid and kernel class
+        try:
+            with open(os.path.join(ROOT, "profiles", tf)) as f:
+                traffic = json.load(f).get(str(args.grid), {}).get(dom_name)
+        except (OSError, ValueError):
+            traffic = None
+        if traffic is not None:
+            break
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes[dom_name],

@@ -62,8 +62,15 @@ def test_f32_mode_matches_the_fp64_path(N, like, rsd, calc_h):
                 like=abs(pl - want["psi"][1]) / abs(want["psi"][1]), deltaX=rel_l2(dX, want["psi"][2]),
                 K=abs(K - want["K"]) / abs(want["K"]), s_f=rel_l2(sf, want["traj"][0]), p_f=rel_l2(pf, want["traj"][1]))
     print("f32 vs fp64", N, like, rsd, calc_h, {k: "%.2e" % v for k, v in errs.items()})
-    tol = 1e-5 if like == 1 else 1e-3   # Poisson: see the module docstring and the reference-pinned test below
-    bad = {k: v for k, v in errs.items() if not v < tol}
+    tol = {k: (1e-5 if like == 1 else 1e-3) for k in errs}   # Poisson: module docstring, reference-pinned test below
+    if calc_h == 4:
+        # the exact CIC adjoint differentiates a piecewise-linear weight: its slope jumps at cell faces, so a particle
+        # that float and double arithmetic put on different sides of a face (probability ~1e-7 per particle and axis)
+        # gets an O(1) different V.  One such particle moves the relative L2 of the gradient by ~0.25 / N^1.5
+        # (measured: 1.6e-4 at 128^3, everything else at 1e-6); allow two of them.
+        for k in ("grad", "p_f"):
+            tol[k] = float(np.hypot(tol[k], 2 ** 0.5 * 0.5 / N ** 1.5))
+    bad = {k: v for k, v in errs.items() if not v < tol[k]}
     assert not bad, bad
 
 
