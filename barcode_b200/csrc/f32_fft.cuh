@@ -99,9 +99,6 @@ struct StageRadix {
 // One Stockham stage on the eight register elements of thread t (v[m] = element t + m N/8 on entry and on exit).
 // WARP: the N/8 threads of a transform sit in one warp (the z passes: a row is M/8 <= 32 lanes), so the exchange
 // needs __syncwarp only and a CTA never waits on a barrier; otherwise __syncthreads.
-// Twiddles: one table load per stage (w = tw[base]); the powers w^2 ... w^7 are formed by at most three dependent
-// multiplications (w^2 = w w, w^3 = w^2 w, w^4 = w^2 w^2, w^5 = w^4 w, w^6 = w^4 w^2, w^7 = w^4 w^3): six fewer loads
-// per stage on the critical path for ~3 float roundings in the last powers.
 template <bool WARP>
 __device__ __forceinline__ void stage_sync() {
   if constexpr (WARP) __syncwarp();
@@ -126,20 +123,10 @@ __device__ __forceinline__ void fft_stages(float2 (&v)[8], int t, const float2 *
       const int b = t + j * (N / 8);
       const int q = b & (S - 1);
       const int base = b - q;
-      float2 w[R];
-      w[1] = twiddle<DIR>(tw, base);
-      if constexpr (R > 2) {
-        w[2] = cmul(w[1], w[1]);
-        w[3] = cmul(w[2], w[1]);
-      }
-      if constexpr (R > 4) {
-        w[4] = cmul(w[2], w[2]);
-        w[5] = cmul(w[4], w[1]);
-        w[6] = cmul(w[4], w[2]);
-        w[7] = cmul(w[4], w[3]);
-      }
+      // (powers w^2 ... w^7 formed by multiplication instead of six more table loads were measured: no faster, and the
+      // gradient's distance from FP64 doubled, 1.1e-6 -> 2.4e-6 at 256^3)
 #pragma unroll
-      for (int k = 1; k < R; ++k) v[j + k * NB] = cmul(v[j + k * NB], w[k]);
+      for (int k = 1; k < R; ++k) v[j + k * NB] = cmul(v[j + k * NB], twiddle<DIR>(tw, base * k));
 #pragma unroll
       for (int k = 0; k < R; ++k) sm.store(q + R * base + k * S, v[j + k * NB]);
     }
@@ -328,109 +315,11 @@ __global__ void __launch_bounds__(T *N / 8, (T * N / 8 >= 1024) ? 1 : ((1024 / (
   }
 }
 
-// ---------------------------------------------------------------------------
-// strided pass, warp-synchronous form (N <= 256: the N/8 threads of a pencil are lanes of one warp).
-//
-// The kernel above pays CTA-wide barriers inside every Stockham exchange.  Here a tile of T = 16 pencils goes through
-// shared memory twice instead: the whole CTA copies it in with coalesced cp.async rows (128 bytes per row; every
-// thread applies the load functor to the elements IT copied, so operand arrays are read coalesced too), then each
-// warp transforms ITS pencil column in place with __syncwarp only, then the whole CTA stores the tile out with
-// coalesced rows, the store functor applied on the way.  Two tile buffers: the copy of the next tile is in flight
-// while this one is transformed.  Rows are padded (one pad row every 8, pitch T + 1) so that both the row-wise and
-// the column-wise accesses spread over the banks.  in == out is allowed.
-// ---------------------------------------------------------------------------
-struct SmCol {  // one pencil column of a tile buffer
-  float2 *col;  // &buf[pencil]
-  int pitch;
-  __device__ __forceinline__ void store(int e, float2 x) const { col[(e + (e >> 3)) * pitch] = x; }
-  __device__ __forceinline__ float2 load(int e) const { return col[(e + (e >> 3)) * pitch]; }
-};
-
-template <int N>
-__device__ __forceinline__ float2 kop_load_operands(const KOpF &lop, float2 v, size_t off) {
-  // K_MULREAL: v * real0 (HMC_help.cc:41-58, multiplier precomputed); K_FINAL: + a * cplx0 (prior + norm * h, HMC.cc:205)
-  const float f = __ldg(lop.real0 + off);
-  if (lop.kind == K_FINAL) {
-    const float2 hh = __ldg(lop.cplx0 + off);
-    return make_float2(v.x * f + lop.a * hh.x, v.y * f + lop.a * hh.y);
-  }
-  return make_float2(v.x * f, v.y * f);
-}
-
-template <int N, int T, int DIR, int AXIS>
-__global__ void __launch_bounds__(T *N / 8, (T * N / 8 >= 512) ? 2 : 4)
-    strided_pass_warp(const float2 *in, float2 *out, const float2 *__restrict__ tw, KOpF lop, KOpF sop) {
-  static_assert(N / 8 <= 32, "a pencil must fit one warp");
-  extern __shared__ float2 smem_f32[];
-  constexpr int NZH = N / 2 + 1;
-  constexpr int NTILES = N * ((N / 2) / T) + N / T;
-  constexpr int LP = N / 8;                  // lanes per pencil = rows per cooperative sweep
-  constexpr int PITCH = T + 1;
-  constexpr int TILE = (N + N / 8) * PITCH;  // float2 per tile buffer
-  constexpr size_t stride = (AXIS == 0) ? (size_t)N * NZH : (size_t)NZH;
-  // cooperative (row-wise) role: pencil cp, rows cr + m LP;  transform (column-wise) role: pencil wp, elements t + m LP
-  const int cp = threadIdx.x % T, cr = threadIdx.x / T;
-  const int wp = threadIdx.x / LP, t = threadIdx.x % LP;
-
-  auto issue_copy = [&](int tile, float2 *buf) {
-    int o, z;
-    size_t b;
-    strided_tile_coords<N, T, AXIS>(tile, cp, o, z, b);
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int r = cr + m * LP;
-      cp_async8(buf + (r + (r >> 3)) * PITCH + cp, in + b + (size_t)r * stride);
-    }
-  };
-
-  int tile = blockIdx.x, stage = 0;
-  if (tile < NTILES) issue_copy(tile, smem_f32);
-  cp_async_commit();
-  while (tile < NTILES) {
-    const int next = tile + gridDim.x;
-    float2 *cur = smem_f32 + stage * TILE;
-    if (next < NTILES) issue_copy(next, smem_f32 + (stage ^ 1) * TILE);
-    cp_async_commit();
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // everything but the copy just issued: `cur` has landed
-    int other, iz;
-    size_t base;
-    strided_tile_coords<N, T, AXIS>(tile, cp, other, iz, base);
-    if (lop.kind != K_NONE) {
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int r = cr + m * LP;
-        float2 *e = cur + (r + (r >> 3)) * PITCH + cp;
-        if (lop.kind == K_MULREAL || lop.kind == K_FINAL) *e = kop_load_operands<N>(lop, *e, base + (size_t)r * stride);
-        else *e = kop_load<N>(lop, *e, (AXIS == 0) ? r : other, (AXIS == 0) ? other : r, iz);
-      }
-    }
-    __syncthreads();  // the tile is complete in shared memory
-
-    {
-      SmCol sm{cur + wp, PITCH};
-      float2 v[8];
-#pragma unroll
-      for (int m = 0; m < 8; ++m) v[m] = sm.load(t + m * LP);
-      __syncwarp();
-      fft_stages<N, 1, DIR, true, SmCol>(v, t, tw, sm);
-#pragma unroll
-      for (int m = 0; m < 8; ++m) sm.store(t + m * LP, v[m]);
-    }
-    __syncthreads();  // every pencil of the tile is transformed
-
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int r = cr + m * LP;
-      const float2 x = cur[(r + (r >> 3)) * PITCH + cp];
-      const size_t off = base + (size_t)r * stride;
-      if (sop.kind != K_NONE) kop_store<N>(sop, out, x, off, (AXIS == 0) ? r : other, (AXIS == 0) ? other : r, iz);
-      else out[off] = x;
-    }
-    __syncthreads();  // `cur` is free: the next iteration copies the tile after next into it
-    tile = next;
-    stage ^= 1;
-  }
-}
+// Measured and dropped (B200, 256^3, round 2): a warp-synchronous form of the strided pass -- the CTA copies a tile in
+// with coalesced cp.async rows, each warp transforms its own pencil column in place with __syncwarp only, the CTA
+// stores the tile out with coalesced rows -- took 47.7 us per y pass against 40.1 us for the kernel above (x: 65 against
+// 53 us): three CTA barriers per tile and nine trips through shared memory per element cost more than the barriers
+// inside the exchanges it removes.
 
 // ---------------------------------------------------------------------------
 // z pass, real -> half-complex: N reals as M = N/2 complex z[j] = x[2j] + i x[2j+1], then

@@ -324,53 +324,36 @@ struct Fft {
     static constexpr int TR = (N_ / 16 >= 256) ? 1 : 256 / (N_ / 16);  // rows per z-pass CTA: 256 threads
     static constexpr size_t smem_strided = (size_t)2 * N_ * T * sizeof(float2);
     static constexpr size_t smem_z = (size_t)TR * (N_ / 2 + N_ / 16 + 1) * sizeof(float2);
-    static constexpr size_t smem_warp = (size_t)2 * (N_ + N_ / 8) * (T + 1) * sizeof(float2);
   };
 
-  bool warp_pass = true;  // BGPU_F32_WARP=0: the CTA-barrier strided pass at every size (cross-check)
-  int grid_warp = 0;
+  int tile8 = 0;  // BGPU_F32_T=8: tiles of 8 pencils (64-byte rows, CTAs of N threads) instead of 16
+  int grid_strided8 = 0;
 
-  template <int N_>
-  void init_warp() {
-    if constexpr (N_ <= 256) {
-      using C = Cfg<N_>;
-      BGPU_CUDA(cudaFuncSetAttribute(strided_pass_warp<N_, C::T, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_warp));
-      BGPU_CUDA(cudaFuncSetAttribute(strided_pass_warp<N_, C::T, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_warp));
-      BGPU_CUDA(cudaFuncSetAttribute(strided_pass_warp<N_, C::T, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_warp));
-      BGPU_CUDA(cudaFuncSetAttribute(strided_pass_warp<N_, C::T, +1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_warp));
-      int occ = 0, dev = 0, sms = 0;
-      BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, strided_pass_warp<N_, C::T, +1, 0>, C::T * N_ / 8, C::smem_warp));
-      BGPU_CUDA(cudaGetDevice(&dev));
-      BGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      if (occ < 1) throw std::runtime_error("bgpu_f32: the warp-synchronous strided pass does not fit an SM at this size");
-      constexpr int tiles = N_ * ((N_ / 2) / C::T) + N_ / C::T;
-      grid_warp = occ * sms < tiles ? occ * sms : tiles;
-    } else {
-      warp_pass = false;
-    }
+  template <int N_, int T_>
+  int init_strided() {
+    constexpr size_t smem = (size_t)2 * N_ * T_ * sizeof(float2);
+    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, +1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0, dev = 0, sms = 0;
+    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, strided_pass<N_, T_, +1, 0>, T_ * N_ / 8, smem));
+    BGPU_CUDA(cudaGetDevice(&dev));
+    BGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (occ < 1) throw std::runtime_error("bgpu_f32: the strided pass does not fit an SM at this size");
+    constexpr int tiles = N_ * ((N_ / 2) / T_) + N_ / T_;
+    return occ * sms < tiles ? occ * sms : tiles;
   }
 
   template <int N_>
   void init_n() {
     using C = Cfg<N_>;
-    {
-      const char *e = std::getenv("BGPU_F32_WARP");
-      warp_pass = !(e && e[0] == '0');
-    }
-    if (warp_pass) init_warp<N_>();
-    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, C::T, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_strided));
-    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, C::T, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_strided));
-    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, C::T, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_strided));
-    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, C::T, +1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_strided));
+    grid_strided = init_strided<N_, C::T>();
+    grid_strided8 = init_strided<N_, 8>();
+    const char *e = std::getenv("BGPU_F32_T");
+    tile8 = e && std::atoi(e) == 8;
     BGPU_CUDA(cudaFuncSetAttribute(r2c_zpass<N_, C::TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_z));
     BGPU_CUDA(cudaFuncSetAttribute(c2r_zpass<N_, C::TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_z));
-    int occ = 0, dev = 0, sms = 0;
-    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, strided_pass<N_, C::T, +1, 0>, C::T * N_ / 8, C::smem_strided));
-    BGPU_CUDA(cudaGetDevice(&dev));
-    BGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (occ < 1) throw std::runtime_error("bgpu_f32: the strided pass does not fit an SM at this size");
-    constexpr int tiles = N_ * ((N_ / 2) / C::T) + N_ / C::T;
-    grid_strided = occ * sms < tiles ? occ * sms : tiles;
   }
 
   void init(int n, cudaStream_t st) {
@@ -409,14 +392,10 @@ struct Fft {
   void strided_n(const float2 *in, float2 *out, const KOpF &lop, const KOpF &sop) {
     using C = Cfg<N_>;
     ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, stream);
-    if constexpr (N_ <= 256) {
-      if (warp_pass) {
-        strided_pass_warp<N_, C::T, DIR, AXIS><<<grid_warp, C::T * N_ / 8, C::smem_warp, stream>>>(in, out, twN, lop, sop);
-        BGPU_LAUNCHED(1);
-        return;
-      }
-    }
-    strided_pass<N_, C::T, DIR, AXIS><<<grid_strided, C::T * N_ / 8, C::smem_strided, stream>>>(in, out, twN, lop, sop);
+    if (tile8)
+      strided_pass<N_, 8, DIR, AXIS><<<grid_strided8, N_, (size_t)2 * N_ * 8 * sizeof(float2), stream>>>(in, out, twN, lop, sop);
+    else
+      strided_pass<N_, C::T, DIR, AXIS><<<grid_strided, C::T * N_ / 8, C::smem_strided, stream>>>(in, out, twN, lop, sop);
     BGPU_LAUNCHED(1);
   }
   template <int N_>

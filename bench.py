@@ -322,10 +322,29 @@ def run_ours(args):
             c32.leapfrog_dev(d_s32b.data_ptr(), d_p32b.data_ptr(), 8, 1e-3)
         calls32 = max(2, args.steps // 4)
         ms_leap32 = timed(traj32, calls32, 1)
+        # end to end through bgpu_f32_gradient_psi with pinned host buffers: half the PCIe bytes of the FP64 call
+        import ctypes as C32
+        fp = C32.POINTER(C32.c_float)
+        h_s32 = d_s32.cpu().pin_memory()
+        h_g32 = torch.empty(n, dtype=torch.float32).pin_memory()
+        def e2e32():
+            if c32.L.bgpu_f32_gradient_psi(c32._h, C32.cast(h_s32.data_ptr(), fp), C32.cast(h_g32.data_ptr(), fp)) != 0:
+                raise RuntimeError(c32.L.bgpu_last_error().decode())
+        for _ in range(2):
+            e2e32()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e32()
+        torch.cuda.synchronize()
+        dt32 = multi.max_over_ranks(time.perf_counter() - t0, info, "cuda")
         c32.close()
         f32 = {"gradient_evals_per_s": world * args.steps / (ms_f32 * 1e-3), "ms_per_eval": ms_f32 / args.steps,
                "leapfrog_steps_per_s": world * calls32 * 8 / (ms_leap32 * 1e-3),
                "rel_l2_vs_fp64_gradient": rel32, "dtype": "f32 arrays and transforms, f64 reductions",
+               "e2e": {"value": world * args.steps / dt32, "unit": UNIT, "h2d_bytes_per_step": n * 4,
+                       "d2h_bytes_per_step": n * 4, "ms_per_step": 1e3 * dt32 / args.steps,
+                       "api": "bgpu_f32_gradient_psi(host signal -> host gradpsi), pinned host buffers"},
                "whole_path_frac": 130 * n * (world * args.steps / (ms_f32 * 1e-3)) / world / 1e9 / 6550.1,
                "whole_path_note": "SURVEY 8(d)'s 260 N bytes halve with 4-byte reals: 130 N bytes per evaluation",
                "per_kernel_ms": {k: v[0] for k, v in prof32.items() if v[1]}}
