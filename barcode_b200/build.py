@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libbarcode_b200.so")
 
-CU_SOURCES = ["api.cu", "kernels.cu", "particles_sweep.cu", "fft_plan.cu", "nccl_comm.cu", "f32_path.cu"]
+CU_SOURCES = ["api.cu", "kernels.cu", "particles_sweep.cu", "particles_sph.cu", "fft_plan.cu", "nccl_comm.cu", "f32_path.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",

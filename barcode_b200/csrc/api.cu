@@ -1107,6 +1107,9 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
     h->sph_R = R;
     BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->sph_kmax), kmax.size() * sizeof(int)));
     BGPU_CUDA(cudaMemcpy(h->sph_kmax, kmax.data(), kmax.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // the static column lists both SPH kernels walk (particles_sph.cu); BGPU_SPH_COLS=0: the general kernels
+    const char *sc = std::getenv("BGPU_SPH_COLS");
+    if (!(sc && sc[0] == '0')) g.sph_cols = sph_columns_create(g, kmax.data(), R);
   }
   if (p->calc_h == 3) {
     // h * SPH_kernel_F (HMC_models_testing.cpp:62-105), evaluated on the HOST, operation by operation, with the C
@@ -1285,6 +1288,7 @@ void bgpu_destroy(bgpu_handle *h) {
     if (h->ev_dn[c]) cudaEventDestroy(h->ev_dn[c]);
   }
   if (h->sph_kmax) cudaFree(h->sph_kmax);
+  sph_columns_destroy(const_cast<SphColumns *>(h->geom.sph_cols));
   if (h->sph_hW) cudaFree(h->sph_hW);
   if (h->dflag) cudaFree(h->dflag);
   if (h->stopflag) cudaFree(h->stopflag);

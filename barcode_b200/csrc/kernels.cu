@@ -233,7 +233,10 @@ void launch_scatter_positions(const GridGeom &g, const double *x, const double *
   ProfScope prof(KK_SCATTER, st);
   const size_t n = (size_t)g.N * g.N * g.N;
   BGPU_CUDA(cudaMemsetAsync(rho, 0, n * sizeof(double), st));
-  if (g.masskernel == 3)
+  if (g.masskernel == 3 && g.sph_cols) {
+    launch_scatter_sph_cols_positions(g, g.sph_cols, x, y, z, rho, st);
+    return;
+  } else if (g.masskernel == 3)
     scatter_sph_positions_kernel<<<blocks_for(n, 128), 128, 0, st>>>(g, x, y, z, rho);
   else
     scatter_positions_kernel<<<blocks_for(n, 256), 256, 0, st>>>(g, x, y, z, rho);
@@ -1522,6 +1525,10 @@ __global__ void scatter_sph_positions_kernel(GridGeom g, const double *__restric
 
 void launch_scatter_sph(const GridGeom &g, const double *psix, const double *psiy, const double *psiz, double *rho,
                         double *posx, double *posy, double *posz, cudaStream_t st) {
+  if (g.sph_cols) {  // static column lists (particles_sph.cu); this file's kernels are the general path
+    launch_scatter_sph_cols(g, g.sph_cols, psix, psiy, psiz, rho, posx, posy, posz, st);
+    return;
+  }
   ProfScope prof(KK_SCATTER, st);
   const size_t n = (size_t)g.Ns * g.N * g.N;
   BGPU_CUDA(cudaMemsetAsync(rho, 0, (size_t)(g.Ns + 2 * g.H) * g.N * g.N * sizeof(double), st));
@@ -1597,6 +1604,10 @@ __global__ void gather_sph_kernel(GridGeom g, double *__restrict__ ax, double *_
 
 void launch_gather_sph(const GridGeom &g, double *ax, double *ay, double *az, const double *resid, const int *kmax,
                        int R, double normalize, cudaStream_t st) {
+  if (g.sph_cols) {
+    launch_gather_sph_cols(g, g.sph_cols, ax, ay, az, resid, normalize, st);
+    return;
+  }
   ProfScope prof(KK_GATHER, st);
   const size_t n = (size_t)g.Ns * g.N * g.N;
   gather_sph_kernel<<<blocks_for(n, 128), 128, 0, st>>>(g, ax, ay, az, resid, kmax, R, normalize);

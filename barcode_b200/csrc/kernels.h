@@ -27,7 +27,22 @@ struct GridGeom {
   int sweep;       // x-sweep scatter / gather (particles_sweep.cu): 0 off, 1 on, > 1 = planes per sweep segment
   int lean;        // lean per-particle arithmetic in the sweep kernels where it applies (BGPU_LEAN=0 turns it off)
   double sph_h;    // SPH scale length particle_kernel_h = h_rel * d (init_par.cc:379), masskernel 3
+  const struct SphColumns *sph_cols;  // HOST pointer: the static column lists of particles_sph.cu (null: general SPH kernels)
 };
+
+// masskernel 3: the columns (i1, i2, half-range K) the scatter / the adjoint gather walk (particles_sph.cu)
+struct SphColumns {
+  int n_scatter = 0, n_gather = 0;
+  void *dev = nullptr;  // int4[n_scatter + n_gather]
+};
+SphColumns *sph_columns_create(const GridGeom &g, const int *kmax_host, int R);  // null if the hull is too wide for them
+void sph_columns_destroy(SphColumns *c);
+void launch_scatter_sph_cols(const GridGeom &g, const SphColumns *c, const double *psix, const double *psiy,
+                             const double *psiz, double *rho, double *posx, double *posy, double *posz, cudaStream_t st);
+void launch_scatter_sph_cols_positions(const GridGeom &g, const SphColumns *c, const double *x, const double *y,
+                                       const double *z, double *rho, cudaStream_t st);
+void launch_gather_sph_cols(const GridGeom &g, const SphColumns *c, double *ax, double *ay, double *az,
+                            const double *resid, double normalize, cudaStream_t st);
 
 struct LikeParams {
   int likelihood;  // 0 Poisson, 1 Gaussian, 2 log-normal (3, Gaussian random field, never reaches the residual kernel)
