@@ -34,6 +34,7 @@ struct GridGeom {
 struct SphColumns {
   int n_scatter = 0, n_gather = 0;
   void *dev = nullptr;  // int4[n_scatter + n_gather]
+  bool z5 = false;      // every half-range K <= 2: the kernels with the unrolled z loop run
 };
 SphColumns *sph_columns_create(const GridGeom &g, const int *kmax_host, int R);  // null if the hull is too wide for them
 void sph_columns_destroy(SphColumns *c);

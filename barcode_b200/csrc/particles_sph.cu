@@ -16,6 +16,7 @@
 // The set of cells that receive mass is the reference's (the test q <= 2 is still made per cell); W differs by an
 // ulp or two in q.  The sum a cell receives is order-free in the reference as well (OpenMP atomics).
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.h"
@@ -198,6 +199,205 @@ __global__ void __launch_bounds__(256) gather_sph_cols_kernel(GridGeom g, double
   az_[idx] = vz;
 }
 
+
+// ---------------------------------------------------------------------------
+// Half-ranges K <= 2 (h up to 1.25 cells; the shipped default h = d has 21 columns, 81 cells): the z loop unrolled.
+//
+// ncu of the list kernels above (profiles/ncu_full_r02_sph_256.txt): instruction issue 75-83 % busy, FP64 pipe
+// 53-57 %; of 4684 warp instructions per 32 particles, 110 go to every COLUMN (two-stage wraps, 64-bit row
+// addresses, int -> double offsets) and 35 to every cell (of which the z step, its wrap and the loop are 8).  Here
+//   * everything along z is formed once per particle: five wrapped cell indices, five offsets, five squares;
+//     the column's cells are five unrolled bodies behind uniform tests of K, no stepping;
+//   * the column list in shared memory carries the offsets as doubles; the x wrap and dx^2 are redone only when
+//     i1 changes (the list is sorted by i1; a uniform branch); row offsets are 32-bit (N^3 <= 2^30 per tile);
+//   * q^2 >= 1 and q^2 >= 4 are tested on the high word of q^2 -- they differ from q > 1, q > 2 only AT q = 1 and
+//     q = 2, where the spline's two branches agree in value and slope / the kernel is zero -- and q^2 = 0 is kept
+//     finite by raising the high word fed to the rsqrt seed to the smallest normal (q = 0 * y = 0).
+// (A fully unrolled 5 x 5 x 5 variant was measured: scatter 2.59 ms, gather 4.43 ms against 2.86 / 2.84 for the
+// list kernels at 256^3 -- 104 registers and ~4000 instructions of straight-line code; dropped.)
+// ---------------------------------------------------------------------------
+struct ColD {
+  double ox, oy;  // i1 d / h, i2 d / h
+  int i1, i2, K, pad;
+};
+
+__device__ __forceinline__ void load_cols5(ColD *s, const Cols &c, double d_h) {
+  for (int t = threadIdx.x + threadIdx.y * blockDim.x; t < c.n; t += blockDim.x * blockDim.y) {
+    const int4 v = c.tab[t];
+    s[t] = ColD{(double)v.x * d_h, (double)v.y * d_h, v.x, v.y, v.z, 0};
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double rsqrt_seeded(double x, int hi) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(max(hi, 0x00100000), 0)));
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+
+struct ZAxis {
+  unsigned kz[5];
+  double dz[5], dz2[5];
+};
+
+__device__ __forceinline__ void z_axis(int iz, double az, double d_h, int N, ZAxis &zz) {
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    zz.kz[c] = (unsigned)wrap(iz + c - 2, N);
+    zz.dz[c] = az - (double)(c - 2) * d_h;
+    zz.dz2[c] = zz.dz[c] * zz.dz[c];
+  }
+}
+
+__device__ __forceinline__ void deposit_cols5(const GridGeom &g, const ColD *cols, int ncol, double x, double y, double z,
+                                              double *__restrict__ rho) {
+  const int N = g.N;
+  if (!in_domain(g, x, y, z)) return;
+  const double d = g.d, h = g.sph_h, h_inv = 1. / h, d_h = d * h_inv;
+  const double a0 = 1. / M_PI / (h * h * h);
+  const int ix = (int)(unsigned long long)(x / d), iy = (int)(unsigned long long)(y / d),
+            iz = (int)(unsigned long long)(z / d);
+  const double ax = (x - ((double)ix + 0.5) * d) * h_inv, ay = (y - ((double)iy + 0.5) * d) * h_inv,
+               az = (z - ((double)iz + 0.5) * d) * h_inv;
+  const int lo = g.x0 - g.H, np = g.Ns + 2 * g.H;
+  ZAxis zz;
+  z_axis(iz, az, d_h, N, zz);
+  int cur = 0x7fffffff, kx = 0;
+  double dx2 = 0.;
+  for (int c = 0; c < ncol; ++c) {
+    const ColD col = cols[c];
+    if (col.i1 != cur) {  // uniform: all lanes walk the same list
+      cur = col.i1;
+      kx = tile_plane(ix + cur, N, lo);
+      const double dx = ax - col.ox;
+      dx2 = dx * dx;
+    }
+    if (kx >= np) {  // beyond the halo: drop the deposit and raise the flag (the host turns it into an error)
+      if (g.flag) *g.flag = 1;
+      continue;
+    }
+    const double dy = ay - col.oy;
+    const double qxy = fma(dy, dy, dx2);
+    double *row = rho + ((unsigned)kx * (unsigned)N + (unsigned)wrap(iy + col.i2, N)) * (unsigned)N;
+#pragma unroll
+    for (int cz = 0; cz < 5; ++cz) {
+      if (col.K < (cz < 2 ? 2 - cz : cz - 2)) continue;
+      const double q2 = qxy + zz.dz2[cz];
+      const int hi = __double2hiint(q2);
+      const double q = q2 * rsqrt_seeded(q2, hi);
+      // Monaghan W_4 spline, SPH_kernel_3D (massFunctions.cc:366-384): a (1 - 3/2 q^2 + 3/4 q^3) inside q = 1,
+      // a (2 - q)^3 / 4 outside
+      const double t = 2. - q;
+      double w = fma(q2, fma(0.75 * a0, q, -1.5 * a0), a0);
+      if (hi >= 0x3ff00000) w = (0.25 * a0 * t) * (t * t);
+      if (hi < 0x40100000) atomicAdd(row + zz.kz[cz], w);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) scatter_sph_cols5_kernel(GridGeom g, const double *__restrict__ psix,
+                                                                const double *__restrict__ psiy,
+                                                                const double *__restrict__ psiz, double *__restrict__ rho,
+                                                                double *__restrict__ posx, double *__restrict__ posy,
+                                                                double *__restrict__ posz, Cols cols) {
+  __shared__ ColD s_cols[25];
+  load_cols5(s_cols, cols, g.d / g.sph_h);
+  const int N = g.N;
+  const size_t n = (size_t)g.Ns * N * N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int sh = 31 - __clz(N);  // N is a power of two
+  const int k = (int)(idx & (size_t)(N - 1)), j = (int)((idx >> sh) & (size_t)(N - 1)),
+            i = g.x0 + (int)(idx >> (2 * sh));
+  double x, y, z;
+  particle_position(g, i, j, k, psix[idx], psiy[idx], psiz[idx], x, y, z);
+  if (posx) {
+    posx[idx] = x;
+    posy[idx] = y;
+    posz[idx] = z;
+  }
+  deposit_cols5(g, s_cols, cols.n, x, y, z, rho);
+}
+
+__global__ void __launch_bounds__(128) scatter_sph_cols5_positions_kernel(GridGeom g, const double *__restrict__ x,
+                                                                          const double *__restrict__ y,
+                                                                          const double *__restrict__ z,
+                                                                          double *__restrict__ rho, Cols cols) {
+  __shared__ ColD s_cols[25];
+  load_cols5(s_cols, cols, g.d / g.sph_h);
+  const size_t n = (size_t)g.N * g.N * g.N;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) deposit_cols5(g, s_cols, cols.n, x[idx], y[idx], z[idx], rho);
+}
+
+__global__ void __launch_bounds__(256) gather_sph_cols5_kernel(GridGeom g, double *__restrict__ ax_, double *__restrict__ ay_,
+                                                               double *__restrict__ az_, const double *__restrict__ resid,
+                                                               Cols cols, double normalize) {
+  __shared__ ColD s_cols[25];
+  const double d = g.d, h = g.sph_h, h_inv = 1. / h, d_h = d * h_inv;
+  load_cols5(s_cols, cols, d_h);
+  const int N = g.N;
+  const int k = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y, il = blockIdx.z;
+  if (k >= N || j >= N) return;
+  const size_t idx = ((size_t)il * N + j) * N + k;
+  const int lo = g.x0 - g.H, np = g.Ns + 2 * g.H;
+  double px, py, pz;
+  particle_position(g, g.x0 + il, j, k, ax_[idx], ay_[idx], az_[idx], px, py, pz);
+  const int ix = (int)(px / d), iy = (int)(py / d), iz = (int)(pz / d);
+  const double dpcx = px * h_inv - ((double)ix + 0.5) * d_h, dpcy = py * h_inv - ((double)iy + 0.5) * d_h,
+               dpcz = pz * h_inv - ((double)iz + 0.5) * d_h;
+  ZAxis zz;
+  z_axis(iz, dpcz, d_h, N, zz);
+  double vx = 0., vy = 0., vz = 0.;
+  int cur = 0x7fffffff, kx = 0;
+  double dxh = 0., dx2 = 0.;
+  const int ncol = cols.n;
+  for (int c = 0; c < ncol; ++c) {
+    const ColD col = s_cols[c];
+    if (col.i1 != cur) {  // uniform
+      cur = col.i1;
+      kx = tile_plane(ix + cur, N, lo);
+      dxh = dpcx - col.ox;
+      dx2 = dxh * dxh;
+    }
+    if (kx >= np) continue;  // beyond the halo: the scatter of the same evaluation has raised the flag already
+    const double dyh = dpcy - col.oy;
+    const double qxy = fma(dyh, dyh, dx2);
+    const double *row = resid + ((unsigned)kx * (unsigned)N + (unsigned)wrap(iy + col.i2, N)) * (unsigned)N;
+    double sx = 0., sz = 0.;  // sum of r partial over the column, and of r partial dz: dx, dy are constant along it
+#pragma unroll
+    for (int cz = 0; cz < 5; ++cz) {
+      if (col.K < (cz < 2 ? 2 - cz : cz - 2)) continue;
+      const double r = __ldg(row + zz.kz[cz]);
+      const double q2 = qxy + zz.dz2[cz];
+      const int hi = __double2hiint(q2);
+      const double y = rsqrt_seeded(q2, hi);
+      const double q = q2 * y;
+      // partial(q) of SPH_kernel.cpp:148-208 without its 1 / (pi h^4): 9/4 q - 3 inside q = 1, -3/4 (q - 2)^2 / q outside
+      const double qm = q - 2.;
+      double partial = fma(2.25, q, -3.);
+      if (hi >= 0x3ff00000) partial = (-0.75 * y) * (qm * qm);
+      const double cc = hi < 0x40100000 ? r * partial : 0.;
+      sx += cc;
+      sz = fma(cc, zz.dz[cz], sz);
+    }
+    vx = fma(sx, dxh, vx);
+    vy = fma(sx, dyh, vy);
+    vz += sz;
+  }
+  const double f = normalize / (M_PI * (h * h) * (h * h));
+  vx *= f;
+  vy *= f;
+  vz *= f;
+  if (g.rsd) vz += g.fgrow * vz;  // HMC_models.cc:295-301
+  ax_[idx] = vx;
+  ay_[idx] = vy;
+  az_[idx] = vz;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -224,6 +424,14 @@ SphColumns *sph_columns_create(const GridGeom &g, const int *kmax_host, int R) {
     }
   if ((int)sc.size() > kMaxCols || (int)ga.size() > kMaxCols) return nullptr;  // the general kernels take over
   auto *out = new SphColumns;
+  // every half-range <= 2 and at most 25 columns: the kernels with the unrolled z loop (BGPU_SPH_Z5=0: the list kernels)
+  {
+    bool fits = sc.size() <= 25 && ga.size() <= 25;
+    for (const int4 &c : sc) fits = fits && c.z <= 2;
+    for (const int4 &c : ga) fits = fits && c.z <= 2;
+    const char *e = std::getenv("BGPU_SPH_Z5");
+    out->z5 = fits && !(e && e[0] == '0');
+  }
   out->n_scatter = (int)sc.size();
   out->n_gather = (int)ga.size();
   BGPU_CUDA(cudaMalloc(&out->dev, (sc.size() + ga.size()) * sizeof(int4)));
@@ -244,6 +452,11 @@ void launch_scatter_sph_cols(const GridGeom &g, const SphColumns *c, const doubl
   const size_t n = (size_t)g.Ns * g.N * g.N;
   BGPU_CUDA(cudaMemsetAsync(rho, 0, (size_t)(g.Ns + 2 * g.H) * g.N * g.N * sizeof(double), st));
   Cols cols{c->n_scatter, static_cast<const int4 *>(c->dev)};
+  if (c->z5) {
+    scatter_sph_cols5_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g, psix, psiy, psiz, rho, posx, posy, posz, cols);
+    BGPU_LAUNCHED(1);
+    return;
+  }
   scatter_sph_cols_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g, psix, psiy, psiz, rho, posx, posy, posz, cols);
   BGPU_LAUNCHED(1);
 }
@@ -252,6 +465,11 @@ void launch_scatter_sph_cols_positions(const GridGeom &g, const SphColumns *c, c
                                        const double *z, double *rho, cudaStream_t st) {
   const size_t n = (size_t)g.N * g.N * g.N;
   Cols cols{c->n_scatter, static_cast<const int4 *>(c->dev)};
+  if (c->z5) {
+    scatter_sph_cols5_positions_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g, x, y, z, rho, cols);
+    BGPU_LAUNCHED(1);
+    return;
+  }
   scatter_sph_cols_positions_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g, x, y, z, rho, cols);
   BGPU_LAUNCHED(1);
 }
@@ -261,6 +479,11 @@ void launch_gather_sph_cols(const GridGeom &g, const SphColumns *c, double *ax, 
   ProfScope prof(KK_GATHER, st);
   Cols cols{c->n_gather, static_cast<const int4 *>(c->dev) + c->n_scatter};
   const dim3 grid((unsigned)((g.N + 31) / 32), (unsigned)((g.N + 7) / 8), (unsigned)g.Ns), block(32, 8);
+  if (c->z5) {
+    gather_sph_cols5_kernel<<<grid, block, 0, st>>>(g, ax, ay, az, resid, cols, normalize);
+    BGPU_LAUNCHED(1);
+    return;
+  }
   gather_sph_cols_kernel<<<grid, block, 0, st>>>(g, ax, ay, az, resid, cols, normalize);
   BGPU_LAUNCHED(1);
 }
