@@ -233,9 +233,12 @@ __device__ __forceinline__ void strided_tile_coords(int tile, int p, int &other,
 // issues the cp.async copies of the eight elements IT will own in tile i + gridDim.x.  in == out is allowed (a tile
 // is read completely before it is written, and tiles are disjoint).
 // ---------------------------------------------------------------------------
-template <int N, int T, int DIR, int AXIS>
+template <int N, int T, int DIR, int AXIS, int PD = 1>
 __global__ void __launch_bounds__(T *N / 8, (T * N / 8 >= 1024) ? 1 : ((1024 / (T * N / 8) > 8) ? 8 : 1024 / (T * N / 8)))
     strided_pass(const float2 *in, float2 *out, const float2 *__restrict__ tw, KOpF lop, KOpF sop) {
+  // PD = tiles in flight ahead of the one being transformed (1 or 2): shared memory holds the exchange tile and PD
+  // prefetch tiles.  A thread reads back only the elements it copied itself, so cp.async.wait_group is all the
+  // ordering the ring needs.
   extern __shared__ float2 smem_f32[];
   constexpr int NZH = N / 2 + 1;
   constexpr int NTILES = N * ((N / 2) / T) + N / T;
@@ -245,36 +248,37 @@ __global__ void __launch_bounds__(T *N / 8, (T * N / 8 >= 1024) ? 1 : ((1024 / (
   const int t = threadIdx.x / T;
   constexpr size_t stride = (AXIS == 0) ? (size_t)N * NZH : (size_t)NZH;
 
-  int tile = blockIdx.x;
-  int other = 0, iz = 0;
-  size_t base = 0;
-  if (tile < NTILES) {
-    strided_tile_coords<N, T, AXIS>(tile, p, other, iz, base);
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int r = t + m * (N / 8);
-      cp_async8(pre + r * T + p, in + base + (size_t)r * stride);
-    }
-  }
-  cp_async_commit();
-
-  while (tile < NTILES) {
-    cp_async_wait_all();
-    float2 v[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) v[m] = pre[(t + m * (N / 8)) * T + p];
-    const int next = tile + gridDim.x;
-    if (next < NTILES) {
+  auto prefetch = [&](int tl, float2 *buf) {
+    if (tl < NTILES) {
       int o2, z2;
       size_t b2;
-      strided_tile_coords<N, T, AXIS>(next, p, o2, z2, b2);
+      strided_tile_coords<N, T, AXIS>(tl, p, o2, z2, b2);
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
         const int r = t + m * (N / 8);
-        cp_async8(pre + r * T + p, in + b2 + (size_t)r * stride);
+        cp_async8(buf + r * T + p, in + b2 + (size_t)r * stride);
       }
     }
     cp_async_commit();
+  };
+
+  int tile = blockIdx.x;
+  int other = 0, iz = 0, slot = 0;
+  size_t base = 0;
+  if (tile < NTILES) strided_tile_coords<N, T, AXIS>(tile, p, other, iz, base);
+#pragma unroll
+  for (int a = 0; a < PD; ++a) prefetch(tile + a * (int)gridDim.x, pre + a * N * T);
+
+  while (tile < NTILES) {
+    if constexpr (PD == 1) cp_async_wait_all();
+    else asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    float2 *cur = pre + slot * N * T;
+    float2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = cur[(t + m * (N / 8)) * T + p];
+    const int next = tile + gridDim.x;
+    prefetch(tile + PD * (int)gridDim.x, cur);
+    if constexpr (PD == 2) slot ^= 1;
 
     if (lop.kind == K_MULREAL || lop.kind == K_FINAL) {
       // v * real0 (HMC_help.cc:41-58, the multiplier precomputed) [+ a * cplx0: prior + norm * h, HMC.cc:205]

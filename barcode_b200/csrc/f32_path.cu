@@ -322,22 +322,25 @@ struct Fft {
   struct Cfg {
     static constexpr int T = 16;                                  // pencils per tile: 128-byte rows
     static constexpr int TR = (N_ / 16 >= 256) ? 1 : 256 / (N_ / 16);  // rows per z-pass CTA: 256 threads
-    static constexpr size_t smem_strided = (size_t)2 * N_ * T * sizeof(float2);
+    static constexpr size_t smem_strided = (size_t)3 * N_ * T * sizeof(float2);
     static constexpr size_t smem_z = (size_t)TR * (N_ / 2 + N_ / 16 + 1) * sizeof(float2);
   };
 
-  int tile8 = 0;  // BGPU_F32_T=8: tiles of 8 pencils (64-byte rows, CTAs of N threads) instead of 16
-  int grid_strided8 = 0;
+  // tiles in flight ahead of the one being transformed: 1.  Two (three tile buffers, BGPU_F32_PD=2) measured slower on
+  // B200 -- y pass 43.9 against 40.3 us at 256^3, 328 against 311 us at 512^3: the pass waits on its CTA barriers and
+  // on shared memory, not on the copies
+  int pd = 1;
+  int grid_strided_pd1 = 0;
 
-  template <int N_, int T_>
+  template <int N_, int T_, int PD>
   int init_strided() {
-    constexpr size_t smem = (size_t)2 * N_ * T_ * sizeof(float2);
-    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, -1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, -1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, +1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, +1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr size_t smem = (size_t)(1 + PD) * N_ * T_ * sizeof(float2);
+    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, -1, 0, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, -1, 1, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, +1, 0, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BGPU_CUDA(cudaFuncSetAttribute(strided_pass<N_, T_, +1, 1, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0, dev = 0, sms = 0;
-    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, strided_pass<N_, T_, +1, 0>, T_ * N_ / 8, smem));
+    BGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, strided_pass<N_, T_, +1, 0, PD>, T_ * N_ / 8, smem));
     BGPU_CUDA(cudaGetDevice(&dev));
     BGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (occ < 1) throw std::runtime_error("bgpu_f32: the strided pass does not fit an SM at this size");
@@ -348,10 +351,10 @@ struct Fft {
   template <int N_>
   void init_n() {
     using C = Cfg<N_>;
-    grid_strided = init_strided<N_, C::T>();
-    grid_strided8 = init_strided<N_, 8>();
-    const char *e = std::getenv("BGPU_F32_T");
-    tile8 = e && std::atoi(e) == 8;
+    grid_strided = init_strided<N_, C::T, 2>();
+    grid_strided_pd1 = init_strided<N_, C::T, 1>();
+    const char *e = std::getenv("BGPU_F32_PD");
+    pd = (e && std::atoi(e) == 2) ? 2 : 1;
     BGPU_CUDA(cudaFuncSetAttribute(r2c_zpass<N_, C::TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_z));
     BGPU_CUDA(cudaFuncSetAttribute(c2r_zpass<N_, C::TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_z));
   }
@@ -392,10 +395,10 @@ struct Fft {
   void strided_n(const float2 *in, float2 *out, const KOpF &lop, const KOpF &sop) {
     using C = Cfg<N_>;
     ProfScope prof(AXIS == 0 ? KK_FFT_STRIDED_X : KK_FFT_STRIDED, stream);
-    if (tile8)
-      strided_pass<N_, 8, DIR, AXIS><<<grid_strided8, N_, (size_t)2 * N_ * 8 * sizeof(float2), stream>>>(in, out, twN, lop, sop);
+    if (pd == 1)
+      strided_pass<N_, C::T, DIR, AXIS, 1><<<grid_strided_pd1, C::T * N_ / 8, (size_t)2 * N_ * C::T * sizeof(float2), stream>>>(in, out, twN, lop, sop);
     else
-      strided_pass<N_, C::T, DIR, AXIS><<<grid_strided, C::T * N_ / 8, C::smem_strided, stream>>>(in, out, twN, lop, sop);
+      strided_pass<N_, C::T, DIR, AXIS, 2><<<grid_strided, C::T * N_ / 8, C::smem_strided, stream>>>(in, out, twN, lop, sop);
     BGPU_LAUNCHED(1);
   }
   template <int N_>
