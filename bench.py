@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-e2e-chains", action="store_true", help="skip the interleaved-chains e2e leg")
     ap.add_argument("--no-sph", action="store_true", help="skip the SPH (masskernel 3, calc_h 2) line in `also`")
     ap.add_argument("--no-f32", action="store_true", help="skip the single-precision (bgpu_f32_*) line in `also`")
+    ap.add_argument("--no-512", action="store_true", help="N = 1, default grid: skip the 512^3 line in `also`")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the slab-decomposed leg (512^3 / 1024^3)")
     return ap.parse_args()
@@ -443,6 +444,12 @@ def run_ours(args):
                        "frac": 260 * n * value / world / 1e9 / peak_gbs,
                        "note": "SURVEY 8(d): 260 N bytes per exact-adjoint evaluation; calc_h=0 does 12 FFTs instead of 8"},
     }
+    exact_rate = value if args.calc_h == 4 else (world * args.steps / (ms_other * 1e-3) if other_h == 4 else None)
+    if exact_rate is not None:
+        # the evaluation SURVEY 8(d)'s 260 N bytes describe: the exact adjoint (8 FFTs, scatter, gather)
+        roofline["whole_path_exact_adjoint"] = {"gradient_evals_per_s": exact_rate,
+                                                "achieved_GBps": 260 * n * exact_rate / world / 1e9,
+                                                "frac": 260 * n * exact_rate / world / 1e9 / peak_gbs}
 
     # end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
     h_s = torch.from_numpy(np.ascontiguousarray(prob["signal"]).reshape(-1)).pin_memory()
@@ -509,6 +516,10 @@ def run_ours(args):
         # measured in a child process with a timeout, reported beside (not instead of) the single-chain e2e.value
         e2e["interleaved_chains"] = e2e_chains_leg(args)
 
+    grid512 = None
+    if rank == 0 and world == 1 and args.grid == 256 and not args.no_512:
+        grid512 = grid512_leg(args)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -527,6 +538,7 @@ def run_ours(args):
                 "device_momentum_draw_ms": ms_draw / draw_calls,
                 "hmc_candidate_ms_neps8_device_resident": cand_ms,
                 "sph_default_config": sph,
+                "grid_512": grid512,
                 "single_precision_mode": f32,
                 "kernel_launches_total": int(bc.kernel_launches() - launches0),
             },
@@ -638,6 +650,34 @@ def e2e_chains_leg(args, timeout_s=240):
         if r.returncode != 0:
             out["error"] = f"exit {r.returncode}"
         return out
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout_s} s"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def grid512_leg(args, timeout_s=300):
+    """The same bench at 512^3 (BASELINE.json's target size: >= 1 evaluation / s on one B200) in a child process, condensed
+    to the numbers `also` carries; returns {"error": ...} instead of raising or hanging."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--grid", "512", "--calc-h", str(args.calc_h), "--steps", "5",
+           "--warmup", "3", "--no-cpu-baseline", "--no-e2e-chains", "--no-sph", "--no-f32", "--no-512"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if not lines:
+            return {"error": f"exit {r.returncode}: {r.stderr.strip()[-300:]}"}
+        d = json.loads(lines[-1])
+        rf = d["roofline"]
+        return {"gradient_evals_per_s": d["value"], "ms_per_eval": d["ms_per_step"], "workload": d["config"]["workload"],
+                "whole_path_frac": rf["whole_path"]["frac"],
+                "exact_adjoint": rf.get("whole_path_exact_adjoint"),
+                "e2e_evals_per_s": d["e2e"]["value"], "leapfrog_steps_per_s": d["also"]["leapfrog_steps_per_s"],
+                "dominant_kernel": {"kernel": rf["kernel"], "frac": rf["frac"], "share_of_step": rf["share_of_step"]},
+                "per_kernel": {k: {"ms_per_step": round(v["ms_per_step"], 4), "GBps": round(v["GBps"], 1)}
+                               for k, v in rf["per_kernel"].items()},
+                "clocks": d.get("clocks")}
     except subprocess.TimeoutExpired:
         return {"error": f"timed out after {timeout_s} s"}
     except Exception as e:  # noqa: BLE001
