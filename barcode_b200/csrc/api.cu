@@ -95,6 +95,11 @@ struct bgpu_handle {
   // (bulk f64 reduce-add), the drift on the store of M^-1 p's; a device flag stops a run-away trajectory
   bool kick_on = false;          // gradient_device: apply kick_a * gradpsi to d_out (+=) instead of storing gradpsi
   double kick_a = 0.0;
+  // leapfrog in k-space (leapfrog_device): s^ lives in shat, p^ in phat for the whole trajectory; gradient_device then
+  // neither transforms s nor inverse-transforms gradpsi: its last sum goes straight into p^ (kernels.cu launch_kspace_kick)
+  bool kspace_lf = true;         // BGPU_LEAPFROG_KSPACE=0: the fused real-space form
+  bool kspace_on = false;        // gradient_device: shat is current, finish with the k-space kick
+  double2 *phat = nullptr;
   int *stopflag = nullptr;       // device: the step after which |momenta[0]| > 1e50 stopped the trajectory, 0 = running
   int *hflag2 = nullptr;         // pinned copy
   bool parseval = true;          // BGPU_PARSEVAL=0: kinetic energy and prior through the inverse transform, as the reference
@@ -388,9 +393,11 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   }
   // the prior's multiplier (V/N)/P -- or zeros when only the likelihood force is wanted (mass types 2 / 3)
   const double *prior_mult = h->like_only ? h->zero_half : h->inv_power;
-  h->fft.hooks = h->in_hooks;   // rows of the signal may still be arriving from the host
-  r2c_plain(h, d_s, h->shat);
-  h->fft.hooks = nullptr;
+  if (!h->kspace_on) {
+    h->fft.hooks = h->in_hooks;   // rows of the signal may still be arriving from the host
+    r2c_plain(h, d_s, h->shat);
+    h->fft.hooks = nullptr;
+  }
   if (p.likelihood == 3) {
     // Gaussian random field (HMC.cc:159-160, gaussian_random_field.cpp:25-38): no structure formation at all,
     // gradpsi = IFFT[(V/N)/P s^] + (s - nobs)/sigma^2
@@ -660,6 +667,11 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     }
     backproject(h, h->psi);
   }
+  if (h->kspace_on) {  // p^ += kick_a ((V/N)/P s^ + norm h^): the kick without gradpsi's inverse transform
+    launch_kspace_kick(h->phat, h->shat, h->acc, prior_mult, h->kick_a, norm, h->N, h->nh, h->ncells, h->partials,
+                       h->dscal + S_P0, h->stream, h->stopflag);
+    return;
+  }
   // gradpsi = IFFT[(V/N)/P s^ + norm * h^]
   ROp sop;
   sop.kind = R_SCALE;
@@ -776,7 +788,68 @@ void kick_device(bgpu_handle *h, const double *d_s, double *d_p, double a) {
 // honours; a slab chain shares rank 0's verdict with a one-element all-reduce per step.  The host reads the flag
 // once, after the trajectory.  The merged kick rounds p - eps g once where the reference rounds two half kicks: a
 // relative 1e-16 per step.
+// The trajectory in k-space: possible when both updates are diagonal there (Fourier-space mass only) and the
+// evaluation reads s^ alone and ends in the k-space sum (Zel'dovich model; not the GRF likelihood, calc_h = 1 or the
+// likelihood-only force) -- BASELINE.json's ZA + CIC configurations.  Per step it saves the forward transform of s,
+// the inverse transform of gradpsi and the transform pair around M^-1 p: 12 of 36 passes at calc_h = 0.  s and p
+// are transformed once at each end of the trajectory (a round trip through the FFT: ~1e-16 relative).
+static bool kspace_leapfrog_applies(const bgpu_handle *h) {
+  const bgpu_params &p = h->p;
+  const bool zeldovich = (p.sfmodel == 1 || p.rsd_model);
+  return h->kspace_lf && h->fused_leapfrog && h->G == 1 && h->mass_fs && !h->mass_rs && zeldovich && !h->like_only &&
+         !(p.likelihood == 3 || p.calc_h == 1);
+}
+
+static void kspace_kick(bgpu_handle *h, double a) {
+  h->kspace_on = true;
+  h->kick_a = a;
+  try {
+    gradient_device(h, nullptr, nullptr);
+  } catch (...) {
+    h->kspace_on = false;
+    throw;
+  }
+  h->kspace_on = false;
+}
+
+static void leapfrog_kspace(bgpu_handle *h, double *d_s, double *d_p, uint64_t Neps, double eps) {
+  require(h->have_mass, "bgpu: bgpu_set_mass or bgpu_hamiltonian_mass must be called first");
+  if (!h->phat) dalloc(h->phat, h->nh);
+  double *guard = h->dscal + S_STOP;
+  // kernels.cu runaway_guard_kernel on momenta[0] = the sum the kick returns in dscal[S_P0]
+  auto test = [&](int step, int mode) { launch_runaway_guard(h->dscal + S_P0, guard, h->stopflag, step, mode, h->stream); };
+  BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
+  BGPU_CUDA(cudaMemsetAsync(guard, 0, 2 * sizeof(double), h->stream));
+  r2c_plain(h, d_s, h->shat);
+  r2c_plain(h, d_p, h->phat);
+  kspace_kick(h, -(0.5 * eps));                                           // HMC.cc:293-294
+  test(0, 0);
+  for (uint64_t jj = 0; jj < Neps; ++jj) {
+    launch_kspace_drift(h->shat, h->phat, h->inv_mass, eps, h->N, h->nh, h->stream, h->stopflag);   // :298-339
+    const bool last = jj + 1 == Neps;
+    kspace_kick(h, last ? -(0.5 * eps) : -eps);                           // :343-352 (+ :293-294 of the next step)
+    test((int)(jj + 1 < 0x7fffffff ? jj + 1 : 0x7fffffff), last ? 2 : 1);
+  }
+  // the one host round trip of the trajectory (see the fused real-space form below for the undo)
+  BGPU_CUDA(cudaMemcpyAsync(h->hflag2, h->stopflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  sync(h);
+  const int stopped = *h->hflag2;
+  if (stopped > 0 && (uint64_t)stopped < Neps) {
+    BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
+    kspace_kick(h, +(0.5 * eps));
+  }
+  ROp back;
+  back.kind = R_SCALE;
+  back.a = 1.0 / h->ncells;
+  h->fft.c2r(h->shat, h->work, d_s, KOp{}, back);
+  h->fft.c2r(h->phat, h->work, d_p, KOp{}, back);
+}
+
 void leapfrog_device(bgpu_handle *h, double *d_s, double *d_p, uint64_t Neps, double eps) {
+  if (kspace_leapfrog_applies(h)) {
+    leapfrog_kspace(h, d_s, d_p, Neps, eps);
+    return;
+  }
   if (h->fused_leapfrog) {
     const int *skip = h->stopflag;
     static_assert(S_P0PREV == S_STOP + 1, "the guard's two scalars are adjacent");
@@ -1182,6 +1255,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   {
     const char *lf = std::getenv("BGPU_LEAPFROG_FUSED");
     h->fused_leapfrog = !(lf && lf[0] == '0');
+    const char *kl = std::getenv("BGPU_LEAPFROG_KSPACE");
+    h->kspace_lf = !(kl && kl[0] == '0');
     const char *pv = std::getenv("BGPU_PARSEVAL");
     h->parseval = !(pv && pv[0] == '0');
   }
@@ -1276,7 +1351,7 @@ void bgpu_destroy(bgpu_handle *h) {
                      h->partials, h->dscal, h->halo_recv};
   for (double *q : reals)
     if (q) cudaFree(q);
-  double2 *cplx[] = {h->shat, h->dhat, h->work, h->acc, h->ubuf, h->sendbuf, h->recvbuf};
+  double2 *cplx[] = {h->shat, h->dhat, h->work, h->acc, h->ubuf, h->sendbuf, h->recvbuf, h->phat};
   for (double2 *q : cplx)
     if (q) cudaFree(q);
   if (h->copy_stream) {

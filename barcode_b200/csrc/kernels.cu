@@ -342,6 +342,65 @@ static void reduce(F f, size_t n, double *scratch, double *out, cudaStream_t st,
   BGPU_LAUNCHED(2);
 }
 
+// ---------------------------------------------------------------------------
+// Leapfrog in k-space (api.cu leapfrog_device): with a Fourier-space mass and a forward model that reads s^ only,
+// both updates of Hamiltonian_EoM (HMC.cc:293-352) are diagonal on the half grid --
+//   drift  s^ += eps (V/N)/M p^                       (the transform pair of :298-339 without the transforms)
+//   kick   p^ += a ((V/N)/P s^ + norm h^)             (gradpsi's last sum, HMC.cc:205, before ITS inverse transform)
+// -- so a step needs neither the forward transform of s, nor the inverse transform of gradpsi, nor the pair around
+// M^-1 p.  The kick also returns momenta[0] = (1/N) sum_k w_k Re p^_k (w = 1 on the planes k_z = 0 and N/2, whose
+// mirrors are stored, 2 elsewhere) for the run-away test of :360-364, in the fixed order of the two-stage sum.
+// Multipliers use the padded row pitch N/2 + 2 (launch_inverse_spectrum).
+// ---------------------------------------------------------------------------
+__global__ void kspace_drift_kernel(double2 *__restrict__ shat, const double2 *__restrict__ phat,
+                                    const double *__restrict__ inv_mass, double eps, int nzh, size_t nh,
+                                    const int *__restrict__ skip) {
+  if (skip && *skip) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const size_t row = i / (size_t)nzh;
+  const double f = eps * inv_mass[row * (size_t)(nzh + 1) + (i - row * (size_t)nzh)];
+  const double2 pk = phat[i];
+  double2 sk = shat[i];
+  sk.x = fma(f, pk.x, sk.x);
+  sk.y = fma(f, pk.y, sk.y);
+  shat[i] = sk;
+}
+
+struct KspaceKickF {
+  double2 *phat;
+  const double2 *shat, *hhat;
+  const double *prior;
+  double a, norm, inv_n;
+  int nzh;
+  const int *skip;
+  __device__ double operator()(size_t i) const {
+    const size_t row = i / (size_t)nzh;
+    const int z = (int)(i - row * (size_t)nzh);
+    double2 pk = phat[i];
+    if (!(skip && *skip)) {
+      const double f = prior[row * (size_t)(nzh + 1) + z];
+      const double2 sk = shat[i], hk = hhat[i];
+      pk.x = fma(a, fma(sk.x, f, norm * hk.x), pk.x);
+      pk.y = fma(a, fma(sk.y, f, norm * hk.y), pk.y);
+      phat[i] = pk;
+    }
+    return ((z == 0 || z == nzh - 1) ? inv_n : 2.0 * inv_n) * pk.x;
+  }
+};
+
+void launch_kspace_drift(double2 *shat, const double2 *phat, const double *inv_mass, double eps, int N, size_t nh,
+                         cudaStream_t st, const int *skip) {
+  ProfScope prof(KK_STREAM, st);
+  kspace_drift_kernel<<<blocks_for(nh, 256), 256, 0, st>>>(shat, phat, inv_mass, eps, N / 2 + 1, nh, skip);
+  BGPU_LAUNCHED(1);
+}
+void launch_kspace_kick(double2 *phat, const double2 *shat, const double2 *hhat, const double *prior, double a,
+                        double norm, int N, size_t nh, double ncells, double *scratch, double *p0_out, cudaStream_t st,
+                        const int *skip) {
+  reduce(KspaceKickF{phat, shat, hhat, prior, a, norm, 1.0 / ncells, N / 2 + 1, skip}, nh, scratch, p0_out, st, KK_STREAM);
+}
+
 void launch_half_quadratic(const double2 *vhat, const double *mult_half, int N, size_t n_half, double ncells,
                            double *scratch, double *out, cudaStream_t st) {
   reduce(HalfQuadF{vhat, mult_half, N / 2 + 1, 0.5 / ncells}, n_half, scratch, out, st);

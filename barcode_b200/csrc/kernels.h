@@ -172,6 +172,13 @@ void launch_findif_product(const double *delta, const double *resid, double *out
 void launch_axpy(double *y, const double *x, double a, size_t n, cudaStream_t st, const int *skip = nullptr);
 // the run-away test of Hamiltonian_EoM (HMC.cc:360-364) on the device, see kernels.cu: scal2 = {stopped at step,
 // momenta[0] after the previous kick}; flag (may be null) is raised with the step where the trajectory stopped
+// leapfrog in k-space (kernels.cu): drift s^ += eps (V/N)/M p^ ; kick p^ += a ((V/N)/P s^ + norm h^), which also returns
+// momenta[0] = (1/N) sum_k p^_k in *p0_out
+void launch_kspace_drift(double2 *shat, const double2 *phat, const double *inv_mass, double eps, int N, size_t nh,
+                         cudaStream_t st, const int *skip);
+void launch_kspace_kick(double2 *phat, const double2 *shat, const double2 *hhat, const double *prior, double a,
+                        double norm, int N, size_t nh, double ncells, double *scratch, double *p0_out, cudaStream_t st,
+                        const int *skip);
 void launch_runaway_guard(const double *p, double *scal2, int *flag, int step, int mode, cudaStream_t st);
 void launch_runaway_apply(const double *scal2, int *flag, cudaStream_t st);
 void launch_scale(double *y, const double *x, double a, size_t n, cudaStream_t st);
