@@ -127,7 +127,11 @@ int bgpu_gradient_psi(bgpu_handle *h, const double *signal, double *gradpsi);
 int bgpu_psi(bgpu_handle *h, const double *signal, double *psi_prior, double *psi_likeli, double *deltaX_out);
 /* S3 kinetic_term (HMC.cc:64-121) */
 int bgpu_kinetic(bgpu_handle *h, const double *momenta, double *K);
-/* S4 Hamiltonian_EoM (HMC.cc:251-369) after its two RNG draws (Neps, epsilon stay with the host RNG) */
+/* S4 Hamiltonian_EoM (HMC.cc:251-369) after its two RNG draws (Neps, epsilon stay with the host RNG): the whole
+ * Neps-step trajectory on the device, stopped where the reference stops it (|momenta[0]| > 1e50, :360-364).  With a
+ * Fourier-space mass and the Zel'dovich model the trajectory runs in k-space (s^ and p^ updated on the half grid, s
+ * and p transformed once at each end); otherwise in real space with the kicks merged into the gradient's last store.
+ * Either form agrees with the reference's step-by-step form to rounding (1e-12 relative; tests/test_leapfrog_forms_gpu.py). */
 int bgpu_leapfrog(bgpu_handle *h, const double *s_i, const double *p_i, uint64_t Neps, double epsilon,
                   double *s_f, double *p_f);
 /* S5 draw_momenta (HMC_momenta.cc:42-92) after the RNG: white = the 2*N doubles of
