@@ -90,6 +90,12 @@ struct bgpu_handle {
   double *halo_recv = nullptr;  // 2 * Hmax * N^2
   double *cand_s = nullptr, *cand_p = nullptr, *cur_s = nullptr;  // device-resident HMC candidate and current signal (bgpu_candidate)
   bool have_signal = false;
+  // psi() of the current signal (prior, -lnL): valid until the signal or the static inputs change.  A candidate's
+  // initial energies are the final ones of the candidate that was accepted last (or its own predecessor's initial
+  // ones after a rejection); the reference recomputes them every time (HMC.cc:214-215)
+  bool cur_psi_valid = false;
+  double cur_psi[2] = {0., 0.}, cand_psi[2] = {0., 0.};
+  bool cache_psi = true;         // BGPU_CANDIDATE_CACHE=0: recompute, as the reference does
   bool constructed = false;
   // fused leapfrog (HMC.cc:251-369): the kick p += kick_a * gradpsi rides on the store of the gradient's last z pass
   // (bulk f64 reduce-add), the drift on the store of M^-1 p's; a device flag stops a run-away trajectory
@@ -1255,6 +1261,8 @@ static int create_impl(const bgpu_params *p, int rank, int nranks, const void *n
   {
     const char *lf = std::getenv("BGPU_LEAPFROG_FUSED");
     h->fused_leapfrog = !(lf && lf[0] == '0');
+    const char *cc = std::getenv("BGPU_CANDIDATE_CACHE");
+    h->cache_psi = !(cc && cc[0] == '0');
     const char *kl = std::getenv("BGPU_LEAPFROG_KSPACE");
     h->kspace_lf = !(kl && kl[0] == '0');
     const char *pv = std::getenv("BGPU_PARSEVAL");
@@ -1396,6 +1404,7 @@ int bgpu_set_static(bgpu_handle *h, const double *Power, const double *nobs, con
                     const double *window) {
   BGPU_TRY
   BGPU_CUDA(cudaSetDevice(h->p.device));
+  h->cur_psi_valid = false;  // psi() depends on every one of these
   if (Power) {
     h2d(h, h->power, Power, h->n);
     update_inverse(h, h->power, h->inv_power);
@@ -1764,6 +1773,7 @@ int bgpu_set_signal(bgpu_handle *h, const double *x) {
   }
   h2d(h, h->cur_s, x, h->n);
   h->have_signal = true;
+  h->cur_psi_valid = false;
   sync(h);
   BGPU_CATCH
 }
@@ -1777,13 +1787,19 @@ int bgpu_candidate(bgpu_handle *h, uint64_t seed, uint64_t draw_index, uint64_t 
   draw_momenta_device(h, seed, draw_index, h->cand_p);                       // HMC.cc:449
   // delta_Hamiltonian's initial energies (HMC.cc:214-215): the ends of the trajectory do not change them
   kinetic_device(h, h->cand_p);
-  psi_device(h, h->cur_s);
+  const bool cached = h->cache_psi && h->cur_psi_valid;
+  if (!cached) psi_device(h, h->cur_s);
   BGPU_CUDA(cudaMemcpyAsync(h->hscal, h->dscal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   BGPU_CUDA(cudaMemcpyAsync(h->cand_s, h->cur_s, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   sync(h);
+  if (!cached) {
+    h->cur_psi[0] = h->hscal[S_PRIOR];
+    h->cur_psi[1] = h->hscal[S_NLL];
+    h->cur_psi_valid = true;
+  }
   energies6[0] = h->hscal[S_KIN];
-  energies6[1] = h->hscal[S_PRIOR];
-  energies6[2] = h->hscal[S_NLL];
+  energies6[1] = h->cur_psi[0];
+  energies6[2] = h->cur_psi[1];
   leapfrog_device(h, h->cand_s, h->cand_p, Neps, epsilon);                   // HMC.cc:455
   kinetic_device(h, h->cand_p);                                              // :224-225; deltaX is left at s_f's
   psi_device(h, h->cand_s);
@@ -1791,8 +1807,8 @@ int bgpu_candidate(bgpu_handle *h, uint64_t seed, uint64_t draw_index, uint64_t 
   if (p_f0) BGPU_CUDA(cudaMemcpyAsync(p_f0, h->cand_p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   sync(h);
   energies6[3] = h->hscal[S_KIN];
-  energies6[4] = h->hscal[S_PRIOR];
-  energies6[5] = h->hscal[S_NLL];
+  energies6[4] = h->cand_psi[0] = h->hscal[S_PRIOR];
+  energies6[5] = h->cand_psi[1] = h->hscal[S_NLL];
   BGPU_CATCH
 }
 
@@ -1801,6 +1817,8 @@ int bgpu_accept(bgpu_handle *h, double *x_out, double *deltaX_out) {
   BGPU_CUDA(cudaSetDevice(h->p.device));
   require(h->have_signal && h->cand_s, "bgpu_accept: no candidate");
   BGPU_CUDA(cudaMemcpyAsync(h->cur_s, h->cand_s, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->cur_psi[0] = h->cand_psi[0];   // psi of the new current signal = the accepted candidate's final energies
+  h->cur_psi[1] = h->cand_psi[1];
   if (x_out) d2h(h, x_out, h->cur_s, h->n);
   if (deltaX_out) d2h(h, deltaX_out, h->delta, h->n);
   sync(h);
@@ -1871,6 +1889,7 @@ int bgpu_mock_data(bgpu_handle *h, uint64_t seed, const bgpu_mock_params *mp, do
   launch_fill(h->noise, 0.0, h->n, h->stream);
   launch_mock_obs(mo, h->delta, h->sig, h->window, h->nobs, h->noise, h->n, 0, h->n, seed, h->stream);
   h->have_obs = true;
+  h->cur_psi_valid = false;
   if (delta_lag) d2h(h, delta_lag, h->sig, h->n);
   if (delta_eul) d2h(h, delta_eul, h->delta, h->n);
   if (nobs) d2h(h, nobs, h->nobs, h->n);

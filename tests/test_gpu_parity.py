@@ -622,6 +622,14 @@ def test_device_resident_candidate_equals_the_separate_calls():
         # the accepted field is the new current signal: the next candidate starts from it
         E2 = ch.candidate(9, 5, 1, eps)
         assert abs(E2["psi_prior_i"] - ppf) <= 1e-12 * abs(ppf)
+        assert abs(E2["psi_likeli_i"] - plf) <= 1e-12 * abs(plf)
+        # not accepted: the current signal and its energies stay (the library keeps psi of the current signal
+        # instead of recomputing it per candidate as HMC.cc:214-215 does); a new signal drops them
+        E3 = ch.candidate(9, 6, 1, eps)
+        assert E3["psi_prior_i"] == E2["psi_prior_i"] and E3["psi_likeli_i"] == E2["psi_likeli_i"]
+        ch.set_signal(s)
+        E4 = ch.candidate(9, 7, 1, eps)
+        assert abs(E4["psi_prior_i"] - ppi) <= 1e-12 * abs(ppi) and abs(E4["psi_likeli_i"] - pli) <= 1e-12 * abs(pli)
 
 
 # ---------------------------------------------------------------- F4: mock data and initial guess on the device

@@ -49,10 +49,13 @@ def test_the_three_forms_walk_the_same_trajectory(monkeypatch, like, rsd, calc_h
     out = {f: run(monkeypatch, f, kw, prob, prob["momenta"], 5, 2e-3) for f in FORMS}
     moved = rel_l2(out["reference"][0], prob["signal"])
     assert moved > 1e-6, "the trajectory must go somewhere for the comparison to mean anything"
-    # rounding only (1e-12) -- except under the exact CIC / TSC adjoint (calc_h = 4), which differentiates a
-    # piecewise weight: a particle that two roundings of the same s put on different sides of a cell face changes
-    # its gradient by O(1) and the trajectory by ~1e-10; the golden trajectories use 1e-8 for the same reason
-    tol = 1e-12 if calc_h == 0 else 1e-8
+    # Rounding only.  The forms sum the same terms in different orders, and the scatter's reductions land in a
+    # different order every run, so the floor is a few 1e-13 for the Gaussian likelihood; the Poisson residual
+    # 1 - n / Lambda amplifies the density's rounding in nearly empty cells (1e-9); the exact CIC / TSC adjoint
+    # (calc_h = 4) differentiates a piecewise weight: a particle that two roundings of the same s put on different
+    # sides of a cell face changes its gradient by O(1) and the trajectory by ~1e-10 -- the golden trajectories use
+    # 1e-8 for the same reason.  A wrong factor or a missing update would show at 1e-3.
+    tol = 1e-8 if calc_h == 4 else (1e-9 if like == 0 else 1e-11)
     for f in ("fused", "kspace"):
         assert rel_l2(out[f][0], out["reference"][0]) < tol, f
         assert rel_l2(out[f][1], out["reference"][1]) < tol, f
