@@ -96,6 +96,12 @@ struct bgpu_handle {
   bool cur_psi_valid = false;
   double cur_psi[2] = {0., 0.}, cand_psi[2] = {0., 0.};
   bool cache_psi = true;         // BGPU_CANDIDATE_CACHE=0: recompute, as the reference does
+  // The last kick of a k-space trajectory evaluates the forward model at s_f: with the Gaussian likelihood (whose
+  // psi() and gradient share deltaQ_factor and the RSD switch) it can return psi(s_f) -- prior by Parseval from s^,
+  // -lnL from the residual kernel's value variant, deltaX left in h->delta -- and bgpu_candidate skips psi(s_f).
+  bool psi_at_end = false;       // request (bgpu_candidate -> leapfrog_kspace)
+  bool want_psi = false;         // gradient_device: this evaluation also fills dscal[S_PRIOR], dscal[S_NLL], delta
+  bool psi_from_kick = false;    // answer: dscal holds psi(s_f)
   bool constructed = false;
   // fused leapfrog (HMC.cc:251-369): the kick p += kick_a * gradpsi rides on the store of the gradient's last z pass
   // (bulk f64 reduce-add), the drift on the store of M^-1 p's; a device flag stops a run-away trajectory
@@ -404,6 +410,8 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
     r2c_plain(h, d_s, h->shat);
     h->fft.hooks = nullptr;
   }
+  if (h->want_psi)  // as psi_device: 1/2 s . S^-1 s by Parseval
+    launch_half_quadratic(h->shat, h->inv_power, h->N, h->nh, h->ncells, h->partials, h->dscal + S_PRIOR, h->stream);
   if (p.likelihood == 3) {
     // Gaussian random field (HMC.cc:159-160, gaussian_random_field.cpp:25-38): no structure formation at all,
     // gradpsi = IFFT[(V/N)/P s^] + (s - nobs)/sigma^2
@@ -425,7 +433,8 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   // a gradient evaluation uses the residual only (-lnL belongs to psi()); delta_x itself is read again by
   // likelihood_calc_h alone (HMC_models_testing.cpp:25-50: gradfft / gradfindif of delta_x)
   launch_overdens_residual(lp, h->delta, h->dscal + S_SUMRHO, h->nobs, h->noise, h->window, h->resid, h->n,
-                           h->ncells, h->partials, nullptr, h->stream, /*keep_delta=*/p.calc_h == 0);
+                           h->ncells, h->partials, h->want_psi ? h->dscal + S_NLL : nullptr, h->stream,
+                           /*keep_delta=*/p.calc_h == 0 || h->want_psi);
 
   // norm = -1 * deltaQ_factor * (D1 if correct_delta)   (HMC_models.cc:460-469)
   double norm = -1.0;
@@ -826,6 +835,9 @@ static void leapfrog_kspace(bgpu_handle *h, double *d_s, double *d_p, uint64_t N
   auto test = [&](int step, int mode) { launch_runaway_guard(h->dscal + S_P0, guard, h->stopflag, step, mode, h->stream); };
   BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
   BGPU_CUDA(cudaMemsetAsync(guard, 0, 2 * sizeof(double), h->stream));
+  const bool psi_wanted = h->psi_at_end && Neps > 0 && h->p.likelihood == 1 && h->parseval;
+  h->psi_at_end = false;
+  h->psi_from_kick = false;
   r2c_plain(h, d_s, h->shat);
   r2c_plain(h, d_p, h->phat);
   kspace_kick(h, -(0.5 * eps));                                           // HMC.cc:293-294
@@ -833,7 +845,9 @@ static void leapfrog_kspace(bgpu_handle *h, double *d_s, double *d_p, uint64_t N
   for (uint64_t jj = 0; jj < Neps; ++jj) {
     launch_kspace_drift(h->shat, h->phat, h->inv_mass, eps, h->N, h->nh, h->stream, h->stopflag);   // :298-339
     const bool last = jj + 1 == Neps;
+    h->want_psi = last && psi_wanted;
     kspace_kick(h, last ? -(0.5 * eps) : -eps);                           // :343-352 (+ :293-294 of the next step)
+    h->want_psi = false;
     test((int)(jj + 1 < 0x7fffffff ? jj + 1 : 0x7fffffff), last ? 2 : 1);
   }
   // the one host round trip of the trajectory (see the fused real-space form below for the undo)
@@ -844,6 +858,7 @@ static void leapfrog_kspace(bgpu_handle *h, double *d_s, double *d_p, uint64_t N
     BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
     kspace_kick(h, +(0.5 * eps));
   }
+  h->psi_from_kick = psi_wanted && stopped == 0;   // the last kick's evaluation was at the state being returned
   ROp back;
   back.kind = R_SCALE;
   back.a = 1.0 / h->ncells;
@@ -1800,9 +1815,13 @@ int bgpu_candidate(bgpu_handle *h, uint64_t seed, uint64_t draw_index, uint64_t 
   energies6[0] = h->hscal[S_KIN];
   energies6[1] = h->cur_psi[0];
   energies6[2] = h->cur_psi[1];
+  h->psi_from_kick = false;
+  h->psi_at_end = h->cache_psi;
   leapfrog_device(h, h->cand_s, h->cand_p, Neps, epsilon);                   // HMC.cc:455
+  h->psi_at_end = false;
   kinetic_device(h, h->cand_p);                                              // :224-225; deltaX is left at s_f's
-  psi_device(h, h->cand_s);
+  if (!h->psi_from_kick) psi_device(h, h->cand_s);                           // else the last kick has left psi(s_f) in dscal
+  h->psi_from_kick = false;
   BGPU_CUDA(cudaMemcpyAsync(h->hscal, h->dscal, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (p_f0) BGPU_CUDA(cudaMemcpyAsync(p_f0, h->cand_p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   sync(h);

@@ -50,15 +50,17 @@ def test_the_three_forms_walk_the_same_trajectory(monkeypatch, like, rsd, calc_h
     moved = rel_l2(out["reference"][0], prob["signal"])
     assert moved > 1e-6, "the trajectory must go somewhere for the comparison to mean anything"
     # Rounding only.  The forms sum the same terms in different orders, and the scatter's reductions land in a
-    # different order every run, so the floor is a few 1e-13 for the Gaussian likelihood; the Poisson residual
-    # 1 - n / Lambda amplifies the density's rounding in nearly empty cells (1e-9); the exact CIC / TSC adjoint
-    # (calc_h = 4) differentiates a piecewise weight: a particle that two roundings of the same s put on different
-    # sides of a cell face changes its gradient by O(1) and the trajectory by ~1e-10 -- the golden trajectories use
-    # 1e-8 for the same reason.  A wrong factor or a missing update would show at 1e-3.
-    tol = 1e-8 if calc_h == 4 else (1e-9 if like == 0 else 1e-11)
-    for f in ("fused", "kspace"):
-        assert rel_l2(out[f][0], out["reference"][0]) < tol, f
-        assert rel_l2(out[f][1], out["reference"][1]) < tol, f
+    # different order every run.  Measured on B200 over repeated runs: Gaussian 4e-15 ... 1e-14, Poisson (whose
+    # residual 1 - n / Lambda amplifies the density's rounding in nearly empty cells) 1e-13 ... 4e-12, exact TSC
+    # adjoint 1e-14; the exact CIC adjoint (calc_h = 4 with masskernel 1) differentiates a piecewise-LINEAR weight
+    # whose slope jumps at cell faces, so a particle that two roundings of the same s put on different sides of a
+    # face changes its gradient by O(1): 2e-10 in s_f and 6e-9 ... 2e-8 in p_f, between two runs of the SAME form
+    # as much as between forms.  A wrong factor or a missing update would show at 1e-3.
+    tol = 1e-6 if (calc_h == 4 and masskernel == 1) else (1e-9 if like == 0 else 1e-11)
+    errs = {f: (rel_l2(out[f][0], out["reference"][0]), rel_l2(out[f][1], out["reference"][1])) for f in ("fused", "kspace")}
+    print("leapfrog forms", like, rsd, calc_h, masskernel, {f: "%.2e %.2e" % e for f, e in errs.items()}, "tol %.0e" % tol)
+    for f, e in errs.items():
+        assert e[0] < tol and e[1] < tol, (f, e)
 
 
 def test_a_runaway_trajectory_stops_after_the_same_step_in_every_form(monkeypatch):
