@@ -24,6 +24,9 @@
 #include "struct_hamil.h"
 
 #include <cassert>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <complex>
 #include <fstream>
@@ -58,6 +61,38 @@ namespace {
 void check(int rc, const char *where) {
   if (rc != 0) throw std::runtime_error(std::string(where) + ": " + bgpu_last_error());
 }
+
+// BARCODE_GPU_TIMING=1: wall time spent inside every C-ABI call site, printed to stderr when the process ends
+struct CallTimes {
+  struct Row { const char *name; unsigned long calls; double ms; };
+  std::vector<Row> rows;
+  bool on = std::getenv("BARCODE_GPU_TIMING") != nullptr;
+  void add(const char *name, double ms) {
+    for (Row &r : rows)
+      if (r.name == name) { r.calls++; r.ms += ms; return; }
+    rows.push_back(Row{name, 1, ms});
+  }
+  ~CallTimes() {
+    if (!on) return;
+    for (const Row &r : rows) std::fprintf(stderr, "[barcode_gpu] %-28s %8lu calls %12.3f ms\n", r.name, r.calls, r.ms);
+  }
+};
+CallTimes g_times;
+struct CallTimer {
+  const char *name;
+  std::chrono::steady_clock::time_point t0;
+  explicit CallTimer(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~CallTimer() {
+    if (g_times.on)
+      g_times.add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+// BGPU_CALL(bgpu_x(...), "bgpu_x") with the call timed
+#define BGPU_CALL(expr, where) \
+  do {                         \
+    CallTimer timer__(where);  \
+    check((expr), where);      \
+  } while (0)
 
 // One device-resident chain per process, rebuilt only if the run parameters change.  The
 // reference allocates HAMIL_DATA afresh for every sample (call_hamil.cc:38-44); the device
@@ -122,7 +157,7 @@ bgpu_handle *session(struct HAMIL_DATA *hd, struct DATA *data) {
     if (g_session.h) bgpu_destroy(g_session.h);
     g_session.h = nullptr;
     g_session.valid = false;
-    check(bgpu_create(&p, &g_session.h), "bgpu_create");
+    BGPU_CALL(bgpu_create(&p, &g_session.h), "bgpu_create");
     g_session.p = p;
     g_session.valid = true;
   }
@@ -147,7 +182,7 @@ void write_to_performance_log(struct DATA *data, struct HAMIL_DATA *hd) {
 // ---------------------------------------------------------------------------
 real_prec kinetic_term(struct HAMIL_DATA *hd, real_prec *momenta, struct DATA *data) {
   double K = 0.;
-  check(bgpu_kinetic(session(hd, data), momenta, &K), "bgpu_kinetic");
+  BGPU_CALL(bgpu_kinetic(session(hd, data), momenta, &K), "bgpu_kinetic");
   wprintw(data->curses->table, "%5.0e ", K);
   return K;
 }
@@ -158,7 +193,7 @@ real_prec kinetic_term(struct HAMIL_DATA *hd, real_prec *momenta, struct DATA *d
 real_prec psi(struct HAMIL_DATA *hd, real_prec *signal, struct DATA *data) {
   HAMIL_NUMERICAL *n = hd->numerical;
   double prior = 0., like = 0.;
-  check(bgpu_psi(session(hd, data), signal, &prior, &like, hd->deltaX), "bgpu_psi");
+  BGPU_CALL(bgpu_psi(session(hd, data), signal, &prior, &like, hd->deltaX), "bgpu_psi");
   wprintw(data->curses->table, "%5.0e ", prior);
   wprintw(data->curses->table, "%5.0e ", like);
   n->psi_prior = prior;
@@ -170,7 +205,7 @@ real_prec psi(struct HAMIL_DATA *hd, real_prec *signal, struct DATA *data) {
 // S1  gradient_psi, HMC.cc:146-206
 // ---------------------------------------------------------------------------
 void gradient_psi(struct HAMIL_DATA *hd, real_prec *signal, struct DATA *data) {
-  check(bgpu_gradient_psi(session(hd, data), signal, hd->gradpsi), "bgpu_gradient_psi");
+  BGPU_CALL(bgpu_gradient_psi(session(hd, data), signal, hd->gradpsi), "bgpu_gradient_psi");
 }
 
 // ---------------------------------------------------------------------------
@@ -220,7 +255,7 @@ void Hamiltonian_EoM(struct HAMIL_DATA *hd, real_prec *signali, real_prec *momen
   wprintw(data->curses->status, "\nLeap-frogging on the GPU ... %lu steps", n->Neps);
   wrefresh(data->curses->status);
 
-  check(bgpu_leapfrog(session(hd, data), signali, momentai, n->Neps, n->epsilon, signalf, momentaf),
+  BGPU_CALL(bgpu_leapfrog(session(hd, data), signali, momentai, n->Neps, n->epsilon, signalf, momentaf),
         "bgpu_leapfrog");
   if (std::abs(momentaf[0]) > 1e50) {
     wprintw(data->curses->message, "\nLeap-frogging ... stopped, momentum too high (momenta[0] = %e)", momentaf[0]);
@@ -250,7 +285,7 @@ void draw_momenta(struct HAMIL_DATA *hd, gsl_rng *seed, real_prec *momenta, stru
   HAMIL_NUMERICAL *n = hd->numerical;
   if (device_rng_enabled()) {
     const uint64_t key = gsl_rng_get(seed);
-    check(bgpu_draw_momenta_device(session(hd, data), key, g_draw_index++, momenta), "bgpu_draw_momenta_device");
+    BGPU_CALL(bgpu_draw_momenta_device(session(hd, data), key, g_draw_index++, momenta), "bgpu_draw_momenta_device");
     return;
   }
   std::vector<std::complex<real_prec> > white;
@@ -260,7 +295,7 @@ void draw_momenta(struct HAMIL_DATA *hd, gsl_rng *seed, real_prec *momenta, stru
     gauss.resize(n->N);
     for (ULONG i = 0; i < n->N; ++i) gauss[i] = static_cast<real_prec>(GR_NUM(seed, 1., 0));
   }
-  check(bgpu_color_momenta(session(hd, data), n->mass_fs ? reinterpret_cast<const double *>(white.data()) : nullptr,
+  BGPU_CALL(bgpu_color_momenta(session(hd, data), n->mass_fs ? reinterpret_cast<const double *>(white.data()) : nullptr,
                            n->mass_rs ? gauss.data() : nullptr, momenta),
         "bgpu_color_momenta");
 }
@@ -269,12 +304,13 @@ void draw_momenta(struct HAMIL_DATA *hd, gsl_rng *seed, real_prec *momenta, stru
 // A1  HamiltonianMC, HMC.cc:372-548: candidate loop, Metropolis step, logs
 // ---------------------------------------------------------------------------
 void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
+  CallTimer whole__("HamiltonianMC (whole)");
   HAMIL_NUMERICAL *n = hd->numerical;
   NUMERICAL *dn = data->numerical;
   bgpu_handle *h = session(hd, data);
 
   // static inputs of this sample (main.cc:150-154; the mock data are made before the loop)
-  check(bgpu_set_static(h, hd->signal_PS, hd->nobs, hd->noise, hd->window), "bgpu_set_static");
+  BGPU_CALL(bgpu_set_static(h, hd->signal_PS, hd->nobs, hd->noise, hd->window), "bgpu_set_static");
 
   // Hamiltonian masses: recomputed every massnum samples, otherwise re-read from disk (HMC.cc:386-423)
   const ULONG massnum = (n->iGibbs > n->massnum_burn) ? n->massnum_burn : n->massnum_init;
@@ -284,9 +320,9 @@ void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
       // the likelihood-force masses (HMC_mass.cc:39-160) need likelihood_grad_log_like + measure_spectrum: on the
       // device, with the forcespec.dat dump the reference writes (likeli_force_power, :48-50)
       std::vector<real_prec> kmode(n->N_bin), fpower(n->N_bin);
-      check(bgpu_likeli_force_power(h, hd->x, kmode.data(), fpower.data()), "bgpu_likeli_force_power");
+      BGPU_CALL(bgpu_likeli_force_power(h, hd->x, kmode.data(), fpower.data()), "bgpu_likeli_force_power");
       dump_measured_spec(kmode.data(), fpower.data(), dn->dir + std::string("forcespec.dat"), n->N_bin);
-      check(bgpu_hamiltonian_mass_x(h, hd->x, hd->mass_f, nullptr), "bgpu_hamiltonian_mass_x");
+      BGPU_CALL(bgpu_hamiltonian_mass_x(h, hd->x, hd->mass_f, nullptr), "bgpu_hamiltonian_mass_x");
     } else {
       Hamiltonian_mass(hd, hd->x, data);   // host, unchanged (types 0/1/4 are one pass over Power)
     }
@@ -299,7 +335,7 @@ void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
     if (n->mass_rs) read_array(name_r, hd->mass_r, n->N1, n->N2, n->N3);
     if (n->mass_fs) read_array(name_f, hd->mass_f, n->N1, n->N2, n->N3);
   }
-  check(bgpu_set_mass(h, n->mass_fs ? hd->mass_f : nullptr, n->mass_rs ? hd->mass_r : nullptr), "bgpu_set_mass");
+  BGPU_CALL(bgpu_set_mass(h, n->mass_fs ? hd->mass_f : nullptr, n->mass_rs ? hd->mass_r : nullptr), "bgpu_set_mass");
 
   wprintw(data->curses->status, "starting Hamiltonian sampling (GPU path)");
   wrefresh(data->curses->status);
@@ -315,7 +351,7 @@ void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
   const bool fused = device_rng_enabled() && !fused_off;
   fftw_array<real_prec> momentai(fused ? 1 : n->N), momentaf(fused ? 1 : n->N), signali(fused ? 1 : n->N),
       signalf(fused ? 1 : n->N);
-  if (fused) check(bgpu_set_signal(h, hd->x), "bgpu_set_signal");
+  if (fused) BGPU_CALL(bgpu_set_signal(h, hd->x), "bgpu_set_signal");
   bool accepted = false;
   for (ULONG iter = 1; iter <= n->itmax && !accepted; ++iter) {
     wprintw(data->curses->table, "%6lu ", n->iGibbs);
@@ -333,7 +369,7 @@ void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
       wprintw(data->curses->table, "%4lu ", n->Neps);
       wrefresh(data->curses->table);
       double E[6], pf0 = 0.;
-      check(bgpu_candidate(h, key, g_draw_index++, n->Neps, n->epsilon, E, &pf0), "bgpu_candidate");
+      BGPU_CALL(bgpu_candidate(h, key, g_draw_index++, n->Neps, n->epsilon, E, &pf0), "bgpu_candidate");
       if (std::abs(pf0) > 1e50) {
         wprintw(data->curses->message, "\nLeap-frogging ... stopped, momentum too high (momenta[0] = %e)", pf0);
         wrefresh(data->curses->message);
@@ -377,7 +413,7 @@ void HamiltonianMC(struct HAMIL_DATA *hd, gsl_rng *seed, struct DATA *data) {
     wrefresh(data->curses->table);
 
     if (accepted) {
-      if (fused) check(bgpu_accept(h, hd->x, hd->deltaX), "bgpu_accept");
+      if (fused) BGPU_CALL(bgpu_accept(h, hd->x, hd->deltaX), "bgpu_accept");
       else copyArray(signalf, hd->x, n->N);
     } else {
       n->rejections++;

@@ -19,17 +19,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from test_dropin import CPU, GPU, INPUT_PAR  # noqa: E402
+from test_dropin import CPU, GPU, make_par  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--grid", type=int, default=64)
 ap.add_argument("--samples", type=int, default=6)
 ap.add_argument("--skip", nargs="*", default=[], help="variants to leave out: cpu, host_rng, separate")
+ap.add_argument("--verbose", action="store_true", help="print the glue's per-call wall times of every run")
 a = ap.parse_args()
 N = a.grid
 L = N * 200.0 / 64
 tmp = tempfile.mkdtemp(prefix="dropin_timing_")
-with np.load(os.path.join(ROOT, "tests", "golden", "pk_table.npz")) as f:
+with np.load(os.path.join(ROOT, "barcode_b200", "data", "pk_table.npz")) as f:
     k, P = f["k"], f["P"]
 pk = os.path.join(tmp, "pk.dat")
 with open(pk, "w") as o:
@@ -40,17 +41,31 @@ with open(pk, "w") as o:
 def run(exe, tag, n_gibbs, env=None):
     d = os.path.join(tmp, f"{tag}_{n_gibbs}")
     os.makedirs(os.path.join(d, "data"))
-    par = INPUT_PAR.format(calc_h=0, rsd="true", likelihood=1, eps_fac=0.004, mass_type=1, pk=pk, N=N, L=L,
+    par = make_par(calc_h=0, rsd="true", likelihood=1, eps_fac=0.004, mass_type=1, pk=pk, N=N, L=L,
                            n_gibbs=n_gibbs, masskernel=1)
     open(os.path.join(d, "input.par"), "w").write(par)
     t0 = time.time()
-    r = subprocess.run([exe], cwd=d, capture_output=True, text=True, env=dict(os.environ, **(env or {})))
+    r = subprocess.run([exe], cwd=d, capture_output=True, text=True,
+                       env=dict(os.environ, BARCODE_GPU_TIMING="1", **(env or {})))
     dt = time.time() - t0
     if r.returncode != 0:
         raise SystemExit(r.stdout[-2000:] + r.stderr[-2000:])
+    # the glue's own wall times per C-ABI call site (BARCODE_GPU_TIMING): bgpu_create is the CUDA context + plan
+    # set-up, 2.3 ... 2.9 s from run to run -- it is taken out of the run's wall time before the two runs are differenced
+    for ln in r.stderr.splitlines():
+        if ln.startswith("[barcode_gpu]"):
+            if a.verbose:
+                print(f"      {tag} N_Gibbs={n_gibbs}: {ln}")
+            f = ln.split()
+            if f[1] == "bgpu_create":
+                dt -= float(f[-2]) * 1e-3
     rows = open(os.path.join(d, "performance_log.txt")).read().strip().splitlines()[1:]
     neps = [float(x.split("\t")[2]) for x in rows]
-    return dt, len(rows), sum(neps)
+    inside = None   # wall time inside HamiltonianMC without bgpu_create, from the glue's timers
+    tm = {ln.split()[1]: float(ln.split()[-2]) for ln in r.stderr.splitlines() if ln.startswith("[barcode_gpu]")}
+    if "HamiltonianMC" in tm:
+        inside = (tm["HamiltonianMC"] - tm.get("bgpu_create", 0.0)) * 1e-3
+    return dt, len(rows), sum(neps), inside
 
 
 print(f"grid {N}^3, ZA + CIC, Gaussian likelihood, RSD; host cores: {os.cpu_count()}")
@@ -62,8 +77,9 @@ variants = [("cpu", CPU, "reference CPU build", None),
 for key, exe, tag, env in variants:
     if key in a.skip:
         continue
-    t1, c1, e1 = run(exe, key, 1, env)
-    tn, cn, en = run(exe, key, a.samples, env)
+    t1, c1, e1, _ = run(exe, key, 1, env)
+    tn, cn, en, inside = run(exe, key, a.samples, env)
     per = (tn - t1) / max(1, (a.samples - 1))
+    hmc = "" if inside is None else f"; inside HamiltonianMC {inside / a.samples * 1e3:.1f} ms / sample"
     print(f"  {tag:52s} {per * 1e3:10.1f} ms / sample   ({cn - c1} candidates, {en - e1:.0f} leapfrog steps in "
-          f"{tn - t1:.2f} s; set-up + first sample {t1:.2f} s)")
+          f"{tn - t1:.2f} s; set-up without bgpu_create + first sample {t1:.2f} s{hmc})")
