@@ -307,6 +307,32 @@ __global__ void axpy_div_kernel(float *__restrict__ y, const float *__restrict__
   }
 }
 
+// leapfrog in k-space (kernels.cu kspace_drift_kernel / KspaceKickF): s^ += eps (V/N)/M p^ ;
+// p^ += a ((V/N)/P s^ + norm h^) -- both diagonal on the half grid
+__global__ void kspace_drift_kernel(float2 *__restrict__ shat, const float2 *__restrict__ phat,
+                                    const float *__restrict__ inv_mass, float eps, size_t nh) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const float f = eps * inv_mass[i];
+  const float2 pk = phat[i];
+  float2 sk = shat[i];
+  sk.x = fmaf(f, pk.x, sk.x);
+  sk.y = fmaf(f, pk.y, sk.y);
+  shat[i] = sk;
+}
+__global__ void kspace_kick_kernel(float2 *__restrict__ phat, const float2 *__restrict__ shat,
+                                   const float2 *__restrict__ hhat, const float *__restrict__ prior, float a, float norm,
+                                   size_t nh) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nh) return;
+  const float f = prior[i];
+  const float2 sk = shat[i], hk = hhat[i];
+  float2 pk = phat[i];
+  pk.x = fmaf(a, fmaf(sk.x, f, norm * hk.x), pk.x);
+  pk.y = fmaf(a, fmaf(sk.y, f, norm * hk.y), pk.y);
+  phat[i] = pk;
+}
+
 static unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 // ---------------------------------------------------------------------------
@@ -469,6 +495,10 @@ struct bgpu_f32_handle {
   float *psi[3] = {nullptr, nullptr, nullptr};
   float *delta = nullptr, *resid = nullptr, *tmp = nullptr;
   float2 *shat = nullptr, *dhat = nullptr, *work = nullptr, *acc = nullptr;
+  // leapfrog in k-space (as the FP64 path, api.cu leapfrog_kspace): s^ in shat and p^ in phat for the whole trajectory
+  float2 *phat = nullptr;
+  bool kspace_on = false;   // gradient_device: shat is current, finish with the k-space kick
+  bool kspace_lf = true;    // BGPU_LEAPFROG_KSPACE=0: the real-space form
   double *partials = nullptr, *dscal = nullptr, *hscal = nullptr;
   bool kick_on = false;
   float kick_a = 0.f;
@@ -543,7 +573,7 @@ void gradient_device(bgpu_f32_handle *h, const float *d_s, float *d_out) {
   require(h->have_power && h->have_obs, "bgpu_f32: bgpu_f32_set_static (Power, nobs, noise, window) must be called first");
   const bgpu_params &p = h->p;
   const float inv_n = (float)(1.0 / h->ncells);
-  r2c_plain(h, d_s, h->shat);
+  if (!h->kspace_on) r2c_plain(h, d_s, h->shat);
   forward_from_shat(h, (float)p.deltaQ_factor, p.rsd_model != 0);
   residual(h, p.calc_h == BGPU_CALC_H_EXACT, h->resid);
   double norm = -1.0 * p.deltaQ_factor;  // HMC_models.cc:460-469
@@ -613,6 +643,13 @@ void gradient_device(bgpu_f32_handle *h, const float *d_s, float *d_out) {
       h->fft.r2c(h->psi[c], h->work, h->acc, ld, inv);
     }
   }
+  if (h->kspace_on) {  // p^ += kick_a ((V/N)/P s^ + norm h^): the kick without gradpsi's inverse transform
+    ProfScope prof(KK_STREAM, h->stream);
+    kspace_kick_kernel<<<blocks_for(h->nh, 256), 256, 0, h->stream>>>(h->phat, h->shat, h->acc, h->inv_power, h->kick_a,
+                                                                     (float)norm, h->nh);
+    BGPU_LAUNCHED(1);
+    return;
+  }
   // gradpsi = IFFT[(V/N)/P s^ + norm * h^]
   KOpF lop;
   lop.kind = K_FINAL;
@@ -660,8 +697,42 @@ void kick_device(bgpu_f32_handle *h, const float *d_s, float *d_p, float a) {
 // gradient's last z pass, the drift s += eps * M^-1 p (:338-339) by the store of M^-1 p's last z pass.  The
 // reference's run-away test |momenta[0]| > 1e50 (:360-364) cannot fire on a finite float; a trajectory that
 // overflows ends in inf / nan, which the caller's Metropolis step rejects.
+void kspace_kick(bgpu_f32_handle *h, float a) {
+  h->kspace_on = true;
+  h->kick_a = a;
+  try {
+    gradient_device(h, nullptr, nullptr);
+  } catch (...) {
+    h->kspace_on = false;
+    throw;
+  }
+  h->kspace_on = false;
+}
+
 void leapfrog_device(bgpu_f32_handle *h, float *d_s, float *d_p, uint64_t Neps, float eps) {
   require(h->have_mass, "bgpu_f32: bgpu_f32_set_mass or bgpu_f32_hamiltonian_mass must be called first");
+  if (h->kspace_lf && h->mass_fs && h->p.calc_h != 1) {
+    // in k-space, as the FP64 path (api.cu leapfrog_kspace): the mode's forward model is Zel'dovich and reads s^ only;
+    // a step drops the transform of s, the inverse transform of gradpsi and the pair around M^-1 p
+    if (!h->phat) BGPU_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->phat), h->nh * sizeof(float2)));
+    r2c_plain(h, d_s, h->shat);
+    r2c_plain(h, d_p, h->phat);
+    kspace_kick(h, -(0.5f * eps));
+    for (uint64_t jj = 0; jj < Neps; ++jj) {
+      {
+        ProfScope prof(KK_STREAM, h->stream);
+        kspace_drift_kernel<<<blocks_for(h->nh, 256), 256, 0, h->stream>>>(h->shat, h->phat, h->inv_mass, eps, h->nh);
+        BGPU_LAUNCHED(1);
+      }
+      kspace_kick(h, jj + 1 == Neps ? -(0.5f * eps) : -eps);
+    }
+    ROpF back;
+    back.kind = R_SCALE;
+    back.a = (float)(1.0 / h->ncells);
+    h->fft.c2r(h->shat, h->work, d_s, KOpF{}, back);
+    h->fft.c2r(h->phat, h->work, d_p, KOpF{}, back);
+    return;
+  }
   kick_device(h, d_s, d_p, -(0.5f * eps));
   for (uint64_t jj = 0; jj < Neps; ++jj) {
     if (h->mass_fs) {
@@ -744,6 +815,10 @@ int bgpu_f32_create(const bgpu_params *p, bgpu_f32_handle **out) {
   h->normFS = (float)((p->L1 * p->L2 * p->L3) / h->ncells);              // HMC_help.cc:26
   h->mass_fs = p->mass_type != 0;                                        // struct_hamil.h:276-296
   h->mass_rs = p->mass_type == 0;
+  {
+    const char *kl = std::getenv("BGPU_LEAPFROG_KSPACE");
+    h->kspace_lf = !(kl && kl[0] == '0');
+  }
   GeomF &g = h->geom;
   g.N = h->N;
   g.sh = 0;
@@ -802,7 +877,7 @@ void bgpu_f32_destroy(bgpu_f32_handle *h) {
   for (float *a : {h->power, h->nobs, h->noise, h->window, h->inv_power, h->mass_f, h->mass_r, h->inv_mass, h->sig, h->mom,
                    h->grad, h->psi[0], h->psi[1], h->psi[2], h->delta, h->resid, h->tmp})
     cudaFree(a);
-  for (float2 *a : {h->shat, h->dhat, h->work, h->acc}) cudaFree(a);
+  for (float2 *a : {h->shat, h->dhat, h->work, h->acc, h->phat}) cudaFree(a);
   cudaFree(h->partials);
   cudaFree(h->dscal);
   if (h->hscal) cudaFreeHost(h->hscal);

@@ -37,7 +37,7 @@ UNIT = "evals/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--calc-h", type=int, default=0, choices=[0, 1, 4])
