@@ -685,6 +685,7 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
   if (h->kspace_on) {  // p^ += kick_a ((V/N)/P s^ + norm h^): the kick without gradpsi's inverse transform
     launch_kspace_kick(h->phat, h->shat, h->acc, prior_mult, h->kick_a, norm, h->N, h->nh, h->ncells, h->partials,
                        h->dscal + S_P0, h->stream, h->stopflag);
+    allreduce_scalar(h, S_P0);   // a slab holds its modes' share of momenta[0]; every rank then tests the same number
     return;
   }
   // gradpsi = IFFT[(V/N)/P s^ + norm * h^]
@@ -811,7 +812,8 @@ void kick_device(bgpu_handle *h, const double *d_s, double *d_p, double a) {
 static bool kspace_leapfrog_applies(const bgpu_handle *h) {
   const bgpu_params &p = h->p;
   const bool zeldovich = (p.sfmodel == 1 || p.rsd_model);
-  return h->kspace_lf && h->fused_leapfrog && h->G == 1 && h->mass_fs && !h->mass_rs && zeldovich && !h->like_only &&
+  // (a slab chain as well: the updates are local to a rank's k-space slab, momenta[0] is one all-reduced scalar)
+  return h->kspace_lf && h->fused_leapfrog && h->mass_fs && !h->mass_rs && zeldovich && !h->like_only &&
          !(p.likelihood == 3 || p.calc_h == 1);
 }
 
@@ -835,7 +837,7 @@ static void leapfrog_kspace(bgpu_handle *h, double *d_s, double *d_p, uint64_t N
   auto test = [&](int step, int mode) { launch_runaway_guard(h->dscal + S_P0, guard, h->stopflag, step, mode, h->stream); };
   BGPU_CUDA(cudaMemsetAsync(h->stopflag, 0, sizeof(int), h->stream));
   BGPU_CUDA(cudaMemsetAsync(guard, 0, 2 * sizeof(double), h->stream));
-  const bool psi_wanted = h->psi_at_end && Neps > 0 && h->p.likelihood == 1 && h->parseval;
+  const bool psi_wanted = h->psi_at_end && Neps > 0 && h->p.likelihood == 1 && h->parseval && h->G == 1;
   h->psi_at_end = false;
   h->psi_from_kick = false;
   r2c_plain(h, d_s, h->shat);

@@ -753,9 +753,35 @@ def slab_measure(grid, calc_h, steps, warmup, info, with_clocks=True):
             nvlink = {"GBps_sent_per_gpu": gbs, "frac_of_nvlink_900GBps": gbs / 900.0, "where": "NCCL grouped send/recv",
                       "transposes_per_eval": transposes,
                       "share_of_step": prof["all_to_all"][0] / max(1e-9, sum(v[0] for v in prof.values()))}
+    # leapfrog steps / s of the slab chain (k-space form: the trajectory's s^ and p^ stay in the transposed k-space
+    # slabs; a step costs 10 transposes instead of 14): 2 trajectories of 4 steps from a device-drawn momentum
+    leap = None
+    try:
+        d_p = torch.empty_like(d_s)
+        sc.draw_momenta_device_dev(11, 1, d_p.data_ptr())
+        d_s2, d_p2 = d_s.clone(), d_p.clone()
+
+        def traj():
+            d_s2.copy_(d_s)
+            d_p2.copy_(d_p)
+            sc.leapfrog_dev(d_s2.data_ptr(), d_p2.data_ptr(), 4, 1e-3)
+
+        traj()
+        barrier()
+        e0.record(stream)
+        for _ in range(2):
+            traj()
+        e1.record(stream)
+        barrier()
+        ms_leap = multi.max_over_ranks(e0.elapsed_time(e1), info, "cuda")
+        leap = {"leapfrog_steps_per_s": 8 / (ms_leap * 1e-3), "ms_per_step": ms_leap / 8,
+                "trajectory": "Neps = 4: 5 kicks, 4 drifts, 4 end transforms", "finite": bool(torch.isfinite(d_p2).all().item())}
+    except Exception as e:  # noqa: BLE001
+        leap = {"error": repr(e)[:300]}
     sc.close()
     return {
         "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "grid": grid, "calc_h": calc_h,
+        "leapfrog": leap,
         "workload": name, "n_gpus": world, "steps": steps, "warmup": warmup, "scaling": "strong",
         "parallelism": f"one chain, x-slab decomposed over {world} GPU(s): distributed FFT with "
                        + ("the transpose fused into the strided pass (TMA stores over NVLink peer memory)"
