@@ -286,6 +286,24 @@ void forward_from_shat(bgpu_handle *h, const double *d_s, double dQ, bool rsd, d
     }
     lop.comp = 0;
     h->fft.c2r(disp_src, h->work, h->psi[0], lop, scale_n);
+  } else if (h->fft.can_share_x_slab()) {
+    // the same on a slab chain: ONE transposing x pass whose result stays in the receive buffer, read by the y passes
+    // of Psi_z and Psi_y -- 2 transposes for the three displacement components instead of 3
+    KOp lop;
+    lop.kind = K_DISP;
+    lop.comp = K_COMP_UNIT;
+    lop.a = disp_a;
+    lop.kfac = h->kfac;
+    h->fft.xpass_shared_inverse(disp_src, lop);
+    for (int c = 2; c >= 1; --c) {
+      KOp yl;
+      yl.kind = K_MULK;
+      yl.comp = c;
+      yl.kfac = h->kfac;
+      h->fft.c2r_yz_shared(h->work, h->psi[c], yl, scale_n);
+    }
+    lop.comp = 0;
+    h->fft.c2r(disp_src, h->work, h->psi[0], lop, scale_n);
   } else
   for (int c = 2; c >= 0; --c) {
     KOp lop;
@@ -562,6 +580,40 @@ void gradient_device(bgpu_handle *h, const double *d_s, double *d_out) {
       sop2.kind = K_INVLAP_ADD;
       sop2.comp = K_COMP_UNIT;
       h->fft.xpass(h->ubuf, h->acc, -1, KOp{}, sop2);
+    } else if (p.likelihood == 1 && h->fft.can_share_x_slab()) {
+      // slab chain: d_y(delta) and d_z(delta) share one transposing x pass (as the displacement components do);
+      // both products are formed before their forward transforms, so that the receive buffer the shared pass
+      // left its result in is read twice before any transpose writes it again.  Psi_y / Psi_z are free by now.
+      KOp lop;
+      lop.kind = K_GRAD;
+      lop.comp = 0;
+      lop.kfac = h->kfac;
+      ROp sop;
+      sop.kind = R_SCALE_MUL;
+      sop.a = inv_n;
+      sop.aux = h->resid;
+      h->fft.c2r(h->dhat, h->work, h->tmp, lop, sop);
+      ROp lop2;
+      lop2.kind = R_LOAD;
+      KOp sop2;
+      sop2.kfac = h->kfac;
+      sop2.kind = K_INVLAP_SET;
+      sop2.comp = 0;
+      h->fft.r2c(h->tmp, h->work, h->acc, lop2, sop2);
+      lop.comp = K_COMP_UNIT;
+      h->fft.xpass_shared_inverse(h->dhat, lop);
+      for (int c = 1; c < 3; ++c) {
+        KOp yl;
+        yl.kind = K_MULK;
+        yl.comp = c;
+        yl.kfac = h->kfac;
+        h->fft.c2r_yz_shared(h->work, h->psi[c], yl, sop);
+      }
+      for (int c = 1; c < 3; ++c) {
+        sop2.kind = K_INVLAP_ADD;
+        sop2.comp = c;
+        h->fft.r2c(h->psi[c], h->work, h->acc, lop2, sop2);
+      }
     } else
     for (int c = 0; c < 3; ++c) {
       if (p.likelihood == 1) {

@@ -119,6 +119,16 @@ struct Fft3d {
   void xpass(const double2 *in, double2 *out, int dir, KOp lop, KOp sop) const;
   void c2r_yz(const double2 *in, double2 *work, double *out, KOp ylop, ROp sop) const;
   void r2c_zy(const double *in, double2 *work, double2 *yout, ROp lop, KOp ysop) const;
+
+  // The same sharing on a slab-decomposed chain, inverse direction (a triple of inverse transforms whose y and z
+  // components differ only by k_y / k_z): ONE transposing x pass (k_c := 1) whose result stays in the receive
+  // buffer, then per component a y pass that reads that buffer with K_MULK and the z pass -- 2 transposes per triple
+  // instead of 3.  (BGPU_SHARE_X_SLAB=0 turns it off; the TMA-staged sizes.)
+  bool share_x_slab = true;
+  bool can_share_x_slab() const;
+  void xpass_shared_inverse(const double2 *in, KOp lop) const;
+  void c2r_yz_shared(double2 *work, double *out, KOp ylop, ROp sop) const;
+  mutable const double2 *shared_recv = nullptr;  // where xpass_shared_inverse left its result (packed [src][x_l][y_l][z])
 };
 
 }  // namespace bgpu

@@ -693,6 +693,8 @@ void Fft3d::init(int n, cudaStream_t st) {
     // measured (B200, round 2, 256^3): +1.1 % per evaluation (y passes -2 %); nothing to gain once the arrays are many
     // times the L2 (512^3: 1.07 GB against 126 MB) -- on by default up to 256 (BGPU_PINGPONG=0 / 1 overrides)
     pingpong = pp ? pp[0] != '0' : n <= 256;
+    const char *sxs = std::getenv("BGPU_SHARE_X_SLAB");
+    share_x_slab = !(sxs && sxs[0] == '0');
     const char *zr = std::getenv("BGPU_ZROUND");
     z_round = !(zr && zr[0] == '0');
     const char *tw2 = std::getenv("BGPU_FFT_2WARP");
@@ -810,6 +812,71 @@ static void zround_impl(const Fft3d &f, double2 *work, ROp op) {
 }
 
 bool Fft3d::can_zround() const { return z_round && can_share_x(); }
+
+// ---------------------------------------------------------------------------
+// shared x pass on slabs, inverse direction (fft3d.h)
+// ---------------------------------------------------------------------------
+bool Fft3d::can_share_x_slab() const {
+  return share_x && share_x_slab && G > 1 && use_tma && !force_generic && (N == 128 || N == 256 || N == 512);
+}
+
+template <int N>
+static void xpass_shared_inverse_impl(const Fft3d &f, const double2 *in, KOp lop) {
+  if constexpr (tma_has_size<N>()) {
+    // as the x pass of c2r_impl: pencils along x on the transposed layout [x][y_local][z], block h of the output =
+    // the x planes of rank h
+    PassIo x_io;
+    x_io.n_other = f.Ns;
+    x_io.other0 = f.rank * f.Ns;
+    x_io.G = f.G;
+    x_io.Ns = f.Ns;
+    if (f.p2p) {
+      double2 *const *peers = f.peer_recv[f.parity];
+      x_io.peer_out = peers;
+      x_io.my_rank = f.rank;
+      launch_strided_tma<N, +1, 0, -1>(f, in, nullptr, lop, KOp{}, x_io, f.stream);
+      f.barrier();
+      f.shared_recv = peers[f.rank];
+      // the buffers alternate per transpose: the transform after the component passes writes the other one, and the
+      // one after that writes this one again only behind a barrier every rank enters after its component passes
+      f.parity ^= 1;
+    } else {
+      launch_strided_tma<N, +1, 0, -1>(f, in, f.sendbuf, lop, KOp{}, x_io, f.stream);
+      slab_all_to_all(f, f.sendbuf, f.recvbuf);
+      f.shared_recv = f.recvbuf;
+    }
+  } else {
+    throw std::runtime_error("bgpu: the shared x pass needs the TMA-staged strided pass (N = 128, 256 or 512)");
+  }
+}
+
+template <int N>
+static void c2r_yz_shared_impl(const Fft3d &f, double2 *work, double *out, KOp ylop, ROp sop) {
+  if constexpr (tma_has_size<N>()) {
+    if (!f.shared_recv) throw std::runtime_error("bgpu: c2r_yz_shared without xpass_shared_inverse");
+    PassIo y_io;
+    y_io.n_other = f.Ns;
+    y_io.in_packed = true;
+    y_io.G = f.G;
+    y_io.Ns = f.Ns;
+    launch_strided_tma<N, +1, 1, -1>(f, f.shared_recv, work, ylop, KOp{}, y_io, f.stream);
+    if (!try_c2r_zpass_tma<N>(f, work, out, sop)) throw std::runtime_error("bgpu: shared x pass: no bulk-copy z pass");
+  } else {
+    throw std::runtime_error("bgpu: the shared x pass needs the TMA-staged strided pass (N = 128, 256 or 512)");
+  }
+}
+
+void Fft3d::xpass_shared_inverse(const double2 *in, KOp lop) const {
+#define CALL(n) xpass_shared_inverse_impl<n>(*this, in, lop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
+
+void Fft3d::c2r_yz_shared(double2 *work, double *out, KOp ylop, ROp sop) const {
+#define CALL(n) c2r_yz_shared_impl<n>(*this, work, out, ylop, sop)
+  BGPU_DISPATCH_N(CALL)
+#undef CALL
+}
 
 void Fft3d::ypass(const double2 *in, double2 *out, int dir, KOp lop, KOp sop) const {
 #define CALL(n) ypass_impl<n>(*this, in, out, dir, lop, sop)

@@ -872,7 +872,7 @@ def run_slab(args):
             "config": {"workload": r["workload"], "grid": args.grid, "calc_h": args.calc_h, "parallelism": r["parallelism"],
                        "l2": "inputs larger than L2; no explicit flush"},
             "per_kernel": r["per_kernel"], "nvlink": r["nvlink"], "local_cells": r["local_cells"],
-            "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
+            "leapfrog": r.get("leapfrog"), "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
         }
         print(json.dumps(line))
     multi.finalize()
