@@ -8,6 +8,8 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | 
 echo "bench default rc=$?"; tail -3 $OUT/bench_default.time
 ( time timeout 900 python bench.py --impl reference --steps 5 --warmup 2 > $OUT/bench_reference.json 2> $OUT/bench_reference.err ) 2> $OUT/bench_reference.time
 echo "bench reference rc=$?"; tail -3 $OUT/bench_reference.time
+timeout 300 python bench.py --mode slab --grid 256 --steps 5 --warmup 2 > $OUT/slab256_1gpu.json 2> $OUT/slab256_1gpu.err
+echo "slab mode on one GPU rc=$?"; python -c "import json; d=json.loads(open('$OUT/slab256_1gpu.json').readline()); print('slab 256 on 1 GPU: %.1f evals/s' % d['value'], d.get('leapfrog'))"
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r02_final/bench_default.json").readline())
