@@ -127,3 +127,49 @@ def test_e2e_chains_leg_never_raises_without_a_gpu():
     import bench
     out = bench.e2e_chains_leg(argparse.Namespace(grid=32, calc_h=0, steps=2, warmup=1, chains=2), timeout_s=120)
     assert set(out) == {"error"} and "no CUDA device" in out["error"]
+
+
+def test_kspace_leapfrog_algebra():
+    """The trajectory in k-space (api.cu leapfrog_kspace, kernels.cu kspace_drift_kernel / KspaceKickF), emulated with
+    numpy on the half grid, against the oracle's Hamiltonian_EoM (HMC.cc:251-369): with a Fourier-space mass the drift is
+    s^ += eps (V/N)/M p^ and the kick p^ += a FFT[gradpsi], the half kicks between steps merge, s and p are transformed
+    once at each end; momenta[0] for the run-away test is (1/N) sum_k w_k Re p^_k with w = 1 on the planes k_z = 0 and
+    N/2 (whose mirrors are stored) and 2 elsewhere."""
+    from oracle import barcode_oracle as bo
+    N, L = 16, 50.0
+    kw = dict(N1=N, L1=L, masskernel=1, likelihood=1, rsd_model=True, calc_h=0, mass_type=1, sfmodel=1)
+    p = bo.Params(**kw)
+    rng = np.random.default_rng(8)
+    kk = np.fft.fftfreq(N, d=L / N) * 2 * np.pi
+    k2 = kk[:, None, None] ** 2 + kk[None, :, None] ** 2 + kk[None, None, :] ** 2
+    power = np.where(k2 > 0, 2.0e3 / (1.0 + (np.sqrt(k2) / 0.2) ** 2), 0.0)
+    s0 = 0.3 * rng.standard_normal((N, N, N))
+    p0 = rng.standard_normal((N, N, N))
+    nobs = np.maximum(0.0, 1.0 + 0.3 * rng.standard_normal((N, N, N)))
+    ones = np.ones((N, N, N))
+    mass_f = np.where(power > 0, 1.0 / np.where(power > 0, power, 1.0), 0.0)   # mass_type 1 with factor 1
+    neps, eps = 3, 2e-3
+    s_ref, p_ref = bo.leapfrog(p, s0, p0, neps, eps, power, nobs, ones, ones, mass_f, None)
+
+    nzh = N // 2 + 1
+    normFS = L ** 3 / N ** 3
+    mf = mass_f[:, :, :nzh]
+    inv_mass = np.where(mf > 0, normFS / np.where(mf > 0, mf, 1.0), 0.0)    # launch_inverse_spectrum
+    shat, phat = np.fft.rfftn(s0), np.fft.rfftn(p0)
+    w = np.full(nzh, 2.0)
+    w[0] = w[-1] = 1.0
+
+    def kick(a):
+        g = bo.gradient_psi(p, np.fft.irfftn(shat, s=(N, N, N), axes=(0, 1, 2)), power, nobs, ones, ones)
+        return phat + a * np.fft.rfftn(g)          # = p^ + a ((V/N)/P s^ + norm h^): gradpsi's last sum, untransformed
+
+    phat = kick(-0.5 * eps)
+    for j in range(neps):
+        shat = shat + eps * inv_mass * phat
+        phat = kick(-0.5 * eps if j + 1 == neps else -eps)
+    s_k = np.fft.irfftn(shat, s=(N, N, N), axes=(0, 1, 2))
+    p_k = np.fft.irfftn(phat, s=(N, N, N), axes=(0, 1, 2))
+    assert np.abs(s_k - s_ref).max() < 1e-12 * np.abs(s_ref).max()
+    assert np.abs(p_k - p_ref).max() < 1e-12 * np.abs(p_ref).max()
+    p0_from_modes = float(np.sum(w * phat.real) / N ** 3)
+    assert abs(p0_from_modes - p_ref.flat[0]) < 1e-12 * np.abs(p_ref).max()
