@@ -55,6 +55,35 @@ def slab_irfftn(kslab, N, rank, world, dist):
     return np.fft.irfft(np.fft.ifft(zy, axis=1), n=N, axis=2)
 
 
+def slab_shared_inverse_pair(kslab, kfac_y, kfac_z, N, rank, world, dist):
+    """The shared x pass on slabs, inverse direction (fft_plan.cu xpass_shared_inverse_impl / c2r_yz_shared_impl):
+    ONE x pass and ONE all-to-all of `kslab` (a transposed k-space slab that already carries the x-pass functor with
+    k_c := 1), then per component the real multiplier on the y pass's load (K_MULK: k_y varies along the y pencil, k_z
+    along z) and the y and z passes.  kfac_y: [N], kfac_z: [N/2+1].  Returns the two real x-slabs
+    IFFT[k_y * kslab], IFFT[k_z * kslab] (1/N^3 included)."""
+    x0, Ns = slab.slab_range(N, rank, world)
+    tr = np.fft.ifft(kslab, axis=0)                                          # the shared x pass
+    blocks = [np.ascontiguousarray(tr[h * Ns:(h + 1) * Ns]) for h in range(world)]
+    recv = _all_to_all(blocks, rank, world, dist)                            # stays in the receive buffer ...
+    zy = np.concatenate(recv, axis=1)                                        # [x_l][y][z]
+    out = []
+    for mult in (kfac_y[None, :, None], kfac_z[None, None, :]):             # ... and is read once per component
+        out.append(np.fft.irfft(np.fft.ifft(mult * zy, axis=1), n=N, axis=2))
+    return out
+
+
+def slab_momenta0(phat_slab, N, world, dist):
+    """momenta[0] of a k-space trajectory on slabs (api.cu leapfrog_kspace, kernels.cu KspaceKickF): every rank sums
+    w_k Re p^_k / N^3 over ITS transposed slab (w = 1 on the planes k_z = 0 and N/2, 2 elsewhere), one all-reduce."""
+    import torch
+    nzh = N // 2 + 1
+    w = np.full(nzh, 2.0)
+    w[0] = w[-1] = 1.0
+    t = torch.tensor([float(np.sum(w * phat_slab.real)) / N ** 3], dtype=torch.float64)
+    dist.all_reduce(t)
+    return float(t[0])
+
+
 def slab_density(p: bo.Params, psi_local, rank, world, dist):
     """Mass assignment of this rank's particles into a halo-extended tile, halos added into the
     neighbours; returns (rho of the owned planes [Ns][N][N], halo width H)."""

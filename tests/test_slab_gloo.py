@@ -57,6 +57,17 @@ def _worker(rank, world, port, q):
         km0, pw0 = bo.measure_spectrum(p, a, 12)
         e_sp = max(np.abs(km - km0).max() / km0.max(), np.abs(pw - pw0).max() / pw0.max())
         assert e_V < 1e-13 and e_fd < 1e-14 and e_sp < 1e-13, (e_V, e_fd, e_sp)
+        # shared x pass on slabs (inverse direction): one transpose serves the y and the z component of a triple
+        kk = np.fft.fftfreq(N, d=L / N) * 2 * np.pi
+        nzh = N // 2 + 1
+        ky, kz = kk, kk[:nzh]
+        got_y, got_z = so.slab_shared_inverse_pair(k, ky, kz, N, rank, world, dist)
+        want_y = so.slab_irfftn(ky[None, x0:x0 + Ns, None] * k, N, rank, world, dist)   # the separate transforms
+        want_z = so.slab_irfftn(kz[None, None, :] * k, N, rank, world, dist)
+        e_sh = max(np.abs(got_y - want_y).max(), np.abs(got_z - want_z).max()) / np.abs(want_y).max()
+        # momenta[0] of a k-space trajectory: every rank's share of (1/N^3) sum_k p^_k, all-reduced
+        e_p0 = abs(so.slab_momenta0(k, N, world, dist) - a.flat[0])
+        assert e_sh < 1e-13 and e_p0 < 1e-13, (e_sh, e_p0)
         q.put((rank, e_fwd, e_inv, e_rho, H, float(rho.sum())))
     except Exception as exc:  # surface the failure instead of letting the parent wait for its timeout
         q.put((rank, repr(exc)))
