@@ -131,7 +131,7 @@ int bgpu_kinetic(bgpu_handle *h, const double *momenta, double *K);
  * Neps-step trajectory on the device, stopped where the reference stops it (|momenta[0]| > 1e50, :360-364).  With a
  * Fourier-space mass and the Zel'dovich model the trajectory runs in k-space (s^ and p^ updated on the half grid, s
  * and p transformed once at each end); otherwise in real space with the kicks merged into the gradient's last store.
- * Either form agrees with the reference's step-by-step form to rounding (1e-12 relative; tests/test_leapfrog_forms_gpu.py). */
+ * Either form agrees with the reference's step-by-step form to rounding (tests/test_leapfrog_forms_gpu.py). */
 int bgpu_leapfrog(bgpu_handle *h, const double *s_i, const double *p_i, uint64_t Neps, double epsilon,
                   double *s_f, double *p_f);
 /* S5 draw_momenta (HMC_momenta.cc:42-92) after the RNG: white = the 2*N doubles of
