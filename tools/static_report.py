@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from barcode_b200 import build as b  # noqa: E402
 
-MNEMONICS = ["UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "UBLKRED", "SYNCS", "LDGSTS", "RED.E.ADD.F64", "ATOMS",
+MNEMONICS = ["UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "UBLKRED", "SYNCS", "LDGSTS", "RED.E.ADD.F64", "REDG.E.ADD.F64", "ATOMS", "MUFU.RSQ64H",
              "SHFL", "DFMA", "DMUL", "DADD", "MUFU.RCP64H", "LDS", "STS", "LDG", "STG", "BAR.SYNC", "WARPSYNC"]
 
 
@@ -25,6 +25,7 @@ def demangle(names):
 
 
 def short(name):
+    name = name.replace("(anonymous namespace)::", "")
     name = re.sub(r"\(.*$", "", name)
     name = name.replace("bgpu::", "").replace("void ", "")
     return name if len(name) <= 110 else name[:107] + "..."
